@@ -1,0 +1,184 @@
+/*
+ * pydem_b200.h -- C ABI of the B200-native pyDEM hot path (libpydem_b200.so).
+ *
+ * Drop-in boundary for pyDEM's per-tile engine: the D-infinity slope/aspect stencil, the
+ * upstream-contributing-area (UCA) sweep and the TWI map, i.e. what
+ * pydem.dem_processing.DEMProcessor.calc_slopes_directions / calc_uca / calc_twi compute
+ * (reference dem_processing.py:587, 682, 1647) and what its only native seam,
+ * pydem/cyfuncs/cyutils.pyx (drain_area :78, drain_connections :35), accelerates.
+ *
+ * Plain C: pointers and sizes only, no torch / numpy types.  All grids are C-order
+ * [R][C] (row = latitude, row 0 = north), float64 unless stated, flat index i*C+j.
+ * Every function returns 0 on success and a non-zero pdm_status otherwise; the message
+ * is available from pdm_last_error() (thread-local).  There is NO CPU fallback: without
+ * a usable CUDA device every compute entry point fails with PDM_ERR_CUDA.
+ *
+ * Two layers:
+ *   1. tile handles (pdm_tile_*): fields live in HBM across calls, so the three stages
+ *      chain without host round trips and the graph is built once per tile;
+ *   2. one-shot host-buffer calls (pdm_slopes_directions, pdm_uca, pdm_uca_update,
+ *      pdm_twi): upload -> compute -> download, the exact shape of the reference calls.
+ */
+#ifndef PYDEM_B200_H
+#define PYDEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDM_ABI_VERSION 1
+
+typedef enum {
+    PDM_OK = 0,
+    PDM_ERR_ARG = 1,      /* bad argument (NULL, shape < 3x3, unknown field ...) */
+    PDM_ERR_CUDA = 2,     /* CUDA runtime / no device */
+    PDM_ERR_STATE = 3,    /* stage called before its inputs exist on the tile */
+    PDM_ERR_SECTION = 4,  /* direction outside [-pi/2, 2pi]: the reference raises IndexError
+                             (dem_processing.py:1068) */
+    PDM_ERR_NOMEM = 5
+} pdm_status;
+
+/* Fields of a tile (device-resident).  dtype in brackets. */
+typedef enum {
+    PDM_F_ELEV = 0,      /* [f64]  DEMProcessor.elev */
+    PDM_F_MAG = 1,       /* [f64]  .mag      (-1 on flats) */
+    PDM_F_DIR = 2,       /* [f64]  .direction (radians CCW from east, -1 on flats) */
+    PDM_F_FLATS = 3,     /* [u8]   .flats */
+    PDM_F_UCA = 4,       /* [f64]  .uca      (NaN on flats) */
+    PDM_F_TWI = 5,       /* [f64]  un-scaled twi (DEMProcessor.twi is 10x this) */
+    PDM_F_EDGE_TODO = 6, /* [u8]   .edge_todo */
+    PDM_F_EDGE_DONE = 7, /* [u8]   .edge_done */
+    PDM_F_SECTION = 8,   /* [i8]   DEMProcessor.section (debug attribute, dem_processing.py:137) */
+    PDM_F_PROP = 9,      /* [f64]  DEMProcessor.proportion */
+    PDM_F_TAINT = 10,    /* [f64]  propagated edge_todo weight (cyutils.pyx:163) */
+    PDM_F_COUNT_ = 11
+} pdm_field;
+
+/* Flags of DEMProcessor that act on the hot path (dem_processing.py:105-154). */
+typedef struct {
+    int32_t drain_pits;             /* default 1 */
+    int32_t drain_pits_min_border;  /* default 0 */
+    int64_t drain_pits_max_iter;    /* default 300 */
+    int64_t drain_pits_max_dist;    /* default 32; 0 = no index-distance filter */
+    double  drain_pits_max_dist_xy; /* default 0 (= None) */
+    int32_t apply_uca_limit_edges;  /* default 0 */
+    int32_t circular_ref_maxcount;  /* default 50 */
+    double  uca_saturation_limit;   /* default 32 */
+} pdm_uca_params;
+
+typedef struct {
+    int64_t n_cells;
+    int64_t n_sources;       /* cells nobody drains into (dem_processing.py:882-883) */
+    int64_t n_drained;       /* cells whose area was pushed downstream */
+    int64_t n_undone;        /* cells never reached (circular references) */
+    int64_t n_pits;          /* flats & elev>0 examined by the pit search */
+    int64_t n_pit_edges;
+    int64_t n_pits_undrained;
+    int64_t n_queue_items;   /* deferred (second-receiver) work items */
+    int64_t n_restarts;      /* circular-reference restarts (dem_processing.py:951-964) */
+    int64_t n_edge_todo;     /* border inflow cells */
+    double  min_area;        /* nanmin(dX2*dY2), dem_processing.py:898 */
+    float   ms_graph;        /* device time: section/proportion + receivers + pits + in-degree */
+    float   ms_sweep;        /* device time: accumulation sweep */
+    float   ms_total;
+} pdm_uca_stats;
+
+typedef struct {
+    double  twi_min_slope;            /* default 1e-3 */
+    double  twi_min_area;             /* DEMProcessor.twi_min_area after calc_uca */
+    double  uca_saturation_limit;     /* default 32 */
+    int32_t apply_twi_limits;         /* default 0 */
+    int32_t apply_twi_limits_on_uca;  /* default 0 */
+} pdm_twi_params;
+
+typedef struct pdm_tile pdm_tile;
+
+/* ---- library ------------------------------------------------------------------------- */
+int         pdm_abi_version(void);
+const char *pdm_last_error(void);
+/* Select the CUDA device for the calling thread's tiles (lazy context creation; safe to
+ * call after fork() in a ProcessManager worker, process_manager.py:1267). */
+int         pdm_init(int device);
+int         pdm_device_count(int *count);
+void        pdm_default_uca_params(pdm_uca_params *p);
+void        pdm_default_twi_params(pdm_twi_params *p);
+
+/* ---- tile handles ---------------------------------------------------------------------- */
+/* R x C tile on the current device.  stream: a cudaStream_t passed as void* (NULL = the
+ * legacy default stream); every kernel and copy of the tile is issued on it. */
+int pdm_tile_create(int64_t R, int64_t C, void *stream, pdm_tile **out);
+int pdm_tile_destroy(pdm_tile *t);
+/* Per-row spacing (DEMProcessor.dX, dY: R-1 "fence" values; dX2, dY2: R "post" values).
+ * thA/thB: optional (NULL -> computed with host atan2) per-fence facet angles
+ * atan2(dY,dX) / atan2(dX,dY) (dem_processing.py:1936) so a NumPy host can pass the
+ * values its own arctan2 produces. */
+int pdm_tile_set_spacing(pdm_tile *t, const double *dX, const double *dY,
+                         const double *dX2, const double *dY2,
+                         const double *thA, const double *thB);
+/* host <-> device for one field (sizes implied by the tile shape and the field dtype) */
+int pdm_tile_upload(pdm_tile *t, int field, const void *host);
+int pdm_tile_download(pdm_tile *t, int field, void *host);
+/* raw device pointer of a field (for zero-copy interop, e.g. NCCL halo exchange) */
+int pdm_tile_device_ptr(pdm_tile *t, int field, void **dev);
+/* declare a field valid after writing it through pdm_tile_device_ptr (device-side producers) */
+int pdm_tile_mark_resident(pdm_tile *t, int field);
+int pdm_tile_sync(pdm_tile *t);
+
+/* a1+a2: _tarboton_slopes_directions (dem_processing.py:1753-1903) + _find_flats_edges
+ * (657-680) + the stamping of flats (611-613).  In: ELEV.  Out: MAG, DIR, FLATS. */
+int pdm_tile_slopes_directions(pdm_tile *t);
+/* DEMProcessor.find_flats (305-306): FLATS = (MAG == -1). */
+int pdm_tile_find_flats(pdm_tile *t);
+/* a3..a7: _calc_uca_chunk (864-987) incl. _calc_uca_section_proportion (1021),
+ * _mk_adjacency_matrix (1072), _mk_connectivity_pits (1269) and cyutils.drain_area.
+ * In: ELEV, DIR, MAG, FLATS.  Out: UCA, EDGE_TODO, EDGE_DONE; MAG/FLATS updated at
+ * drained pits (1370-1371).  stats may be NULL. */
+int pdm_tile_uca(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *stats);
+/* a8: calc_uca(uca_init, edge_init_data) (719-744, 769-771) + _calc_uca_chunk_update
+ * (778-862).  UCA must hold uca_init.  Edge strips: left/right have R entries, top/bottom
+ * C entries; data f64, done/todo u8.  Out: UCA += delta, EDGE_TODO, EDGE_DONE. */
+int pdm_tile_uca_update(pdm_tile *t, const pdm_uca_params *p,
+                        const double *data_left, const double *data_right,
+                        const double *data_top, const double *data_bottom,
+                        const uint8_t *done_left, const uint8_t *done_right,
+                        const uint8_t *done_top, const uint8_t *done_bottom,
+                        const uint8_t *todo_left, const uint8_t *todo_right,
+                        const uint8_t *todo_top, const uint8_t *todo_bottom,
+                        pdm_uca_stats *stats);
+/* a9: calc_twi (1647-1677).  In: UCA, MAG.  Out: TWI (un-scaled). */
+int pdm_tile_twi(pdm_tile *t, const pdm_twi_params *p);
+
+/* ---- one-shot host-buffer calls ---------------------------------------------------------- */
+/* DEMProcessor.calc_slopes_directions with the conditioning flags off. */
+int pdm_slopes_directions(const double *elev, int64_t R, int64_t C,
+                          const double *dX, const double *dY,
+                          const double *thA, const double *thB,
+                          double *mag, double *direction, uint8_t *flats);
+/* DEMProcessor.calc_uca() full mode.  mag/flats are in-out (pit updates). */
+int pdm_uca(const double *elev, const double *direction, double *mag, uint8_t *flats,
+            int64_t R, int64_t C, const double *dX, const double *dY,
+            const double *dX2, const double *dY2, const double *thA, const double *thB,
+            const pdm_uca_params *p,
+            double *uca, uint8_t *edge_todo, uint8_t *edge_done, pdm_uca_stats *stats);
+/* DEMProcessor.calc_uca(uca_init=..., edge_init_data=[data, done, todo]) update mode.
+ * uca is in-out: uca_init on entry, uca_init + propagated edge deltas on return. */
+int pdm_uca_update(const double *elev, const double *direction, double *mag, uint8_t *flats, double *uca,
+                   int64_t R, int64_t C, const double *dX, const double *dY,
+                   const double *dX2, const double *dY2, const double *thA, const double *thB,
+                   const pdm_uca_params *p,
+                   const double *data_left, const double *data_right,
+                   const double *data_top, const double *data_bottom,
+                   const uint8_t *done_left, const uint8_t *done_right,
+                   const uint8_t *done_top, const uint8_t *done_bottom,
+                   const uint8_t *todo_left, const uint8_t *todo_right,
+                   const uint8_t *todo_top, const uint8_t *todo_bottom,
+                   uint8_t *edge_todo, uint8_t *edge_done);
+/* DEMProcessor.calc_twi(). */
+int pdm_twi(const double *uca, const double *mag, int64_t n, const pdm_twi_params *p, double *twi);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYDEM_B200_H */

@@ -1,0 +1,109 @@
+// drain_op.cuh -- the per-cell "drain" step of the accumulation sweep (cyutils.pyx:149-185)
+// as a work-list operator (worklist.cuh).
+//
+//   MODE 0: full sweep of _calc_uca_chunk: seeds = cells nobody drains into, the
+//           edge_todo taint travels with the area (cyutils.pyx:163).
+//   MODE 1: update sweep of _calc_uca_chunk_update (dem_processing.py:836-842): seeds = the
+//           border cells whose neighbour value became final (ST_START), `area` is the delta
+//           array, and pushes into a start cell are dropped -- the reference's
+//           "(skip_edge or done[r]) and r on the tile edge" rule (cyutils.pyx:157-159), which
+//           in update mode fires exactly for the start cells.
+#pragma once
+#include "worklist.cuh"
+
+// per-cell state byte of the update mode (t->flat0 is reused for it)
+#define ST_START 0x01     // ids: edge_done & edge_todo (dem_processing.py:798)
+#define ST_CONE 0x02      // downstream of a start cell (drain_connections, 823-824)
+#define ST_TODOSEED 0x04  // edge_todo & ~edge_done (799)
+#define ST_REACH 0x08     // downstream closure of the remaining todo cells (848-853)
+
+__device__ __forceinline__ uint32_t st_fetch_or(uint8_t *st, int32_t cell, uint32_t bits)
+{
+    uint32_t *w = reinterpret_cast<uint32_t *>(st) + (cell >> 2);
+    const int sh = (cell & 3) * 8;
+    const uint32_t old = atomicOr(w, bits << sh);
+    return (old >> sh) & 0xffu;
+}
+
+template <int MODE>
+struct DrainOp {
+    const uint8_t *link;
+    const double *prop;
+    double *area;
+    double *taint;
+    int32_t *indeg;
+    const uint8_t *st;
+    int32_t C;
+    const int32_t *pit_beg;
+    const int32_t *pit_end;
+    const int32_t *pit_dst;
+    const double *pit_w;
+
+    __device__ __forceinline__ bool is_seed(int32_t c) const
+    {
+        return MODE == 0 ? (link[c] & LK_SOURCE) != 0 : (st[c] & ST_START) != 0;
+    }
+    __device__ __forceinline__ bool skip(int32_t r) const { return MODE == 1 && (st[r] & ST_START); }
+
+    // Drain one ready cell; returns the receiver this lane continues with (or -1).
+    __device__ __forceinline__ int32_t process(int32_t i, const wl::Queue &q) const
+    {
+        using wl::dep_zero;
+        const uint8_t lk = link[i];
+        int32_t nxt = -1;
+        if (lk & LK_PIT) {
+            // long-range pit edges (_mk_connectivity_pits): rare, plain fence ordering
+            const double ai = __ldcg(area + i);
+            const double ti = MODE == 0 ? __ldcg(taint + i) : 0.0;
+            const int64_t slot = __double_as_longlong(prop[i]);
+            const int32_t e0 = pit_beg[slot], e1 = pit_end[slot];
+            for (int32_t e = e0; e < e1; e++) {
+                const int32_t r = pit_dst[e];
+                if (skip(r)) continue;
+                const double w = pit_w[e];
+                atomicAdd(area + r, __dmul_rn(ai, w));
+                if (MODE == 0 && ti != 0.0) atomicAdd(taint + r, __dmul_rn(ti, w));
+            }
+            __threadfence();
+            for (int32_t e = e0; e < e1; e++) {
+                const int32_t r = pit_dst[e];
+                if (skip(r)) continue;
+                if (atomicSub(indeg + r, 1) == 1) {
+                    if (nxt < 0) nxt = r; else q.push(r);
+                }
+            }
+            return nxt;
+        }
+        bool k1 = lk & LK_KEEP1, k2 = lk & LK_KEEP2;
+        if (!(k1 || k2)) return -1;
+        const int sec = lk & LK_SEC_MASK;
+        const double p = prop[i];
+        const int32_t r1 = i + wl::off_e1(sec, C), r2 = i + wl::off_e2(sec, C);
+        if (MODE == 1) {
+            if (k1 && skip(r1)) k1 = false;
+            if (k2 && skip(r2)) k2 = false;
+            if (!(k1 || k2)) return -1;
+        }
+        const double ai = __ldcg(area + i);
+        const double ti = MODE == 0 ? __ldcg(taint + i) : 0.0;
+        const double w2 = __dsub_rn(1.0, p);                                    // dem_processing.py:1082
+        int dep = 0;
+        if (k1) dep |= dep_zero(atomicAdd(area + r1, __dmul_rn(ai, p)));        // cyutils.pyx:161
+        if (k2) dep |= dep_zero(atomicAdd(area + r2, __dmul_rn(ai, w2)));
+        if (MODE == 0 && ti != 0.0) {                                           // cyutils.pyx:163-164
+            if (k1) dep |= dep_zero(atomicAdd(taint + r1, __dmul_rn(ti, p)));
+            if (k2) dep |= dep_zero(atomicAdd(taint + r2, __dmul_rn(ti, w2)));
+        }
+        const int one = 1 + dep;  // == 1, but only available once the adds above have returned
+        int o1 = 0, o2 = 0;
+        if (k1) o1 = atomicSub(indeg + r1, one);
+        if (k2) o2 = atomicSub(indeg + r2, one);
+        const bool rdy1 = k1 && o1 == 1, rdy2 = k2 && o2 == 1;
+        if (rdy1 && rdy2) {
+            // follow the larger share, hand the other receiver to an idle lane
+            if (p >= 0.5) { nxt = r1; q.push(r2); } else { nxt = r2; q.push(r1); }
+        } else if (rdy1) nxt = r1;
+        else if (rdy2) nxt = r2;
+        return nxt;
+    }
+};

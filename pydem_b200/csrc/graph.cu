@@ -1,0 +1,252 @@
+// graph.cu -- K3: drainage graph of a tile, never materialised as a sparse matrix.
+//
+// Reference behaviour: _calc_uca_section_proportion (dem_processing.py:1021-1070),
+// _mk_connectivity (1155-1267), the edge filter of _mk_adjacency_matrix (1136-1141), the
+// source / inflow-border bookkeeping of _calc_uca_chunk (882-937).
+//
+// Per cell the reference's CSC/CSR matrix rows reduce to one byte (facet index + which of
+// the two receivers survive the filter) and one double (share of the cardinal receiver);
+// the in-degree (CSR row length) is counted by looking at the 8 neighbours' bytes.
+//
+// Algorithmic traffic: link pass reads dir 8 + flats 1 + elev 8 (+2 neighbour elevations from
+// L1/L2), writes link 1 + prop 8; in-degree pass reads link 1, writes indeg 4 + area 8 + taint 8.
+#include "pdm_internal.cuh"
+
+namespace {
+
+__constant__ int g_e1r[8] = {0, -1, -1, 0, 0, 1, 1, 0};
+__constant__ int g_e1c[8] = {1, 0, 0, -1, -1, 0, 0, 1};
+__constant__ int g_e2r[8] = {-1, -1, -1, -1, 1, 1, 1, 1};
+__constant__ int g_e2c[8] = {1, 1, -1, -1, -1, -1, 1, 1};
+
+// section / proportion of one cell, exactly the reference's operation order.
+// Returns section in [-8, 7] or 127 if outside (the reference raises IndexError there).
+__device__ __forceinline__ int section_prop(double d, bool flat, double th, double &p_out)
+{
+    const double hp = PDM_PI / 2.0;
+    double qd = floor(__dmul_rn(__ddiv_rn(d, PDM_PI), 2.0));               // 1035
+    int q = (qd >= -128.0 && qd <= 127.0) ? (int)qd : 60;                   // int8 cast; NaN/out of range -> bad
+    double quad = __dsub_rn(d, __dmul_rn(hp, (double)q));                   // 1037
+    const double cth = __dsub_rn(hp, th);
+    const int odd = q & 1;                                                  // numpy modulo on int8
+    int sec = q * 2 + ((quad > th) && !odd) + ((quad > cth) && odd);        // 1040-1043
+    double p = __longlong_as_double(0x7ff8000000000000LL);
+    const bool I1 = (sec == 0) | (sec == 1) | (sec == 4) | (sec == 5);      // 1050
+    if (I1 && quad <= th) p = __ddiv_rn(quad, th);                          // 1052-1053
+    if (I1 && quad > th) p = __ddiv_rn(__dsub_rn(quad, th), cth);           // 1054-1056
+    if (!I1 && quad <= cth) p = __ddiv_rn(quad, cth);                       // 1057-1059
+    if (!I1 && quad > cth) p = __ddiv_rn(__dsub_rn(quad, cth), th);         // 1060-1062
+    if (flat) { sec = -1; p = __longlong_as_double(0x7ff8000000000000LL); } // 1064-1065
+    if (sec == 8) sec = 0;                                                  // 1067
+    if (sec < -8 || sec > 7) { p_out = p; return 127; }
+    const int idx = sec < 0 ? sec + 8 : sec;                                // python negative indexing
+    const double a = (idx & 1) ? -1.0 : 1.0;
+    p_out = __dsub_rn((1.0 + a) / 2.0, __dmul_rn(a, p));                    // 1068
+    return sec;
+}
+
+__global__ void __launch_bounds__(256)
+k_links(const double *__restrict__ E, const double *__restrict__ dir, const uint8_t *__restrict__ flats,
+        const double *__restrict__ th_row, int64_t R, int64_t C,
+        uint8_t *__restrict__ link, double *__restrict__ prop, uint8_t *__restrict__ pitmask,
+        unsigned long long *counters)
+{
+    const int64_t j = (int64_t)blockIdx.x * 32 + threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.y * 8 + threadIdx.y;
+    bool pit = false;
+    if (i < R && j < C) {
+        const int64_t n = i * C + j;
+        const bool fl = flats[n] != 0;
+        const double e0 = E[n];
+        double p;
+        int sec = section_prop(dir[n], fl, __ldg(th_row + i), p);
+        if (sec == 127) { atomicAdd(&counters[CT_BADSEC], 1ULL); sec = -1; }
+        uint8_t lk = LK_NOSEC;
+        if (sec >= 0) {
+            lk = (uint8_t)sec;
+            const int64_t i1 = i + g_e1r[sec], j1 = j + g_e1c[sec];
+            const int64_t i2 = i + g_e2r[sec], j2 = j + g_e2c[sec];
+            // _mk_connectivity: a receiver exists iff it is inside the tile; filter 1136-1137:
+            // weight not NaN, > 1e-8, and the receiver is not higher than the source
+            if (i1 >= 0 && i1 < R && j1 >= 0 && j1 < C) {
+                if (p > 1e-8 && __ldg(E + i1 * C + j1) <= e0) lk |= LK_KEEP1;
+            }
+            if (i2 >= 0 && i2 < R && j2 >= 0 && j2 < C) {
+                const double w2 = __dsub_rn(1.0, p);
+                if (w2 > 1e-8 && __ldg(E + i2 * C + j2) <= e0) lk |= LK_KEEP2;
+            }
+        }
+        link[n] = lk;
+        prop[n] = p;
+        pit = fl && (e0 > 0.0);                                             // pits_bool, 1284
+        pitmask[n] = pit ? 1 : 0;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, pit);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[CT_NPITS], (unsigned long long)__popc(m));
+}
+
+// export of DEMProcessor.section (int8) for tests / debugging
+__global__ void __launch_bounds__(256)
+k_section_export(const double *__restrict__ dir, const uint8_t *__restrict__ flats,
+                 const double *__restrict__ th_row, int64_t R, int64_t C, int8_t *__restrict__ section)
+{
+    const int64_t j = (int64_t)blockIdx.x * 32 + threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.y * 8 + threadIdx.y;
+    if (i >= R || j >= C) return;
+    double p;
+    int sec = section_prop(dir[i * C + j], flats[i * C + j] != 0, __ldg(th_row + i), p);
+    section[i * C + j] = (int8_t)sec;
+}
+
+// does neighbour byte `lk` at relative position (di,dj) drain into the centre cell?
+__device__ __forceinline__ int drains_in(uint8_t lk, uint8_t keepbit, uint32_t secmask)
+{
+    return ((lk & keepbit) && !(lk & (LK_NOSEC | LK_PIT)) && ((secmask >> (lk & LK_SEC_MASK)) & 1u)) ? 1 : 0;
+}
+
+// in-degree of every cell (+ pit in-edges already accumulated into indeg by the pit kernel),
+// source flag, and the initial state of the sweep: area = dX2*dY2 of the row, taint = 0.
+__global__ void __launch_bounds__(256)
+k_indeg(uint8_t *__restrict__ link, int64_t R, int64_t C, const double *__restrict__ row_area,
+        int32_t *__restrict__ indeg, double *__restrict__ area, double *__restrict__ taint,
+        unsigned long long *counters)
+{
+    const int64_t j = (int64_t)blockIdx.x * 32 + threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.y * 8 + threadIdx.y;
+    const bool in = (i < R && j < C);
+    int cnt = 0;
+    int64_t n = 0;
+    if (in) {
+        n = i * C + j;
+        const bool up = i > 0, dn = i < R - 1, lf = j > 0, rt = j < C - 1;
+        if (lf) cnt += drains_in(link[n - 1], LK_KEEP1, 0x81u);             // W neighbour: e1 = (0,+1)
+        if (rt) cnt += drains_in(link[n + 1], LK_KEEP1, 0x18u);             // E: e1 = (0,-1)
+        if (up) cnt += drains_in(link[n - C], LK_KEEP1, 0x60u);             // N: e1 = (+1,0)
+        if (dn) cnt += drains_in(link[n + C], LK_KEEP1, 0x06u);             // S: e1 = (-1,0)
+        if (up && lf) cnt += drains_in(link[n - C - 1], LK_KEEP2, 0xC0u);   // NW: e2 = (+1,+1)
+        if (up && rt) cnt += drains_in(link[n - C + 1], LK_KEEP2, 0x30u);   // NE: e2 = (+1,-1)
+        if (dn && lf) cnt += drains_in(link[n + C - 1], LK_KEEP2, 0x03u);   // SW: e2 = (-1,+1)
+        if (dn && rt) cnt += drains_in(link[n + C + 1], LK_KEEP2, 0x0Cu);   // SE: e2 = (-1,-1)
+        cnt += indeg[n];
+        indeg[n] = cnt;
+        area[n] = __ldg(row_area + i);                                      // 885, 901
+        taint[n] = 0.0;
+    }
+    const bool src = in && cnt == 0;
+    if (src) link[n] |= LK_SOURCE;                                          // 882-883
+    const unsigned m = __ballot_sync(0xffffffffu, src);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[CT_SOURCES], (unsigned long long)__popc(m));
+}
+
+__device__ __forceinline__ bool sec_in(int sec, uint32_t mask) { return sec >= 0 && ((mask >> sec) & 1u); }
+
+// inflow-border mask of _calc_uca_chunk 909-937; one thread per perimeter cell.
+// Also seeds taint (edge_todo as float, 944).
+__global__ void __launch_bounds__(256)
+k_border_todo(const double *__restrict__ E, const uint8_t *__restrict__ link, const double *__restrict__ prop,
+              int64_t R, int64_t C, const int32_t *__restrict__ pit_beg, const int32_t *__restrict__ pit_end, const double *__restrict__ pit_w,
+              const int32_t *__restrict__ pit_dst, int64_t n_pit_edges,
+              uint8_t *__restrict__ edge_todo, double *__restrict__ taint, unsigned long long *counters)
+{
+    const int64_t per = 2 * C + 2 * (R - 2);
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= per) return;
+    int64_t i, j;
+    if (t < C) { i = 0; j = t; }
+    else if (t < 2 * C) { i = R - 1; j = t - C; }
+    else { const int64_t u = t - 2 * C; i = 1 + (u >> 1); j = (u & 1) ? C - 1 : 0; }
+    const int64_t n = i * C + j;
+    const uint8_t lk = link[n];
+    const double TOL = 1e-2;
+    // column sum of A = total outflow weight that survived the filter (913-919)
+    double outflow = 0.0;
+    int sec = (lk & LK_NOSEC) ? -1 : (lk & LK_SEC_MASK);
+    if (lk & LK_PIT) {
+        const int64_t slot = __double_as_longlong(prop[n]);
+        for (int32_t e = pit_beg[slot]; e < pit_end[slot]; e++) outflow += pit_w[e];
+    } else {
+        const double p = prop[n];
+        // scipy sums a column's entries in row-index order; two terms commute
+        if (lk & LK_KEEP1) outflow += p;
+        if (lk & LK_KEEP2) outflow += __dsub_rn(1.0, p);
+    }
+    bool todo = false;
+    const bool big = outflow > TOL;
+    if (j == 0) todo = big && sec_in(sec, 0xC3u);                           // left: 6,7,0,1
+    if (j == C - 1) todo = big && sec_in(sec, 0x3Cu);                       // right: 2,3,4,5 (later assignment wins)
+    if (i == 0) todo = big && sec_in(sec, 0xF0u);                           // top: 4,5,6,7
+    if (i == R - 1) todo = big && sec_in(sec, 0x0Fu);                       // bottom: 0,1,2,3
+    if ((i == 0 || i == R - 1) && (j == 0 || j == C - 1)) {
+        // corners 924-930: |= outflow > TOL  |  inflow < TOL (row sum of A)
+        double inflow = 0.0;
+        for (int di = -1; di <= 1; di++)
+            for (int dj = -1; dj <= 1; dj++) {
+                const int64_t mi = i + di, mj = j + dj;
+                if ((di == 0 && dj == 0) || mi < 0 || mi >= R || mj < 0 || mj >= C) continue;
+                const uint8_t ml = link[mi * C + mj];
+                if (ml & (LK_NOSEC | LK_PIT)) continue;
+                const int ms = ml & LK_SEC_MASK;
+                if ((ml & LK_KEEP1) && g_e1r[ms] == -di && g_e1c[ms] == -dj) inflow += prop[mi * C + mj];
+                if ((ml & LK_KEEP2) && g_e2r[ms] == -di && g_e2c[ms] == -dj) inflow += __dsub_rn(1.0, prop[mi * C + mj]);
+            }
+        for (int64_t e = 0; e < n_pit_edges; e++)
+            if (pit_dst[e] == (int32_t)n) inflow += pit_w[e];
+        todo = todo || big || (inflow < TOL);
+    }
+    const double e0 = E[n];
+    if (e0 != e0) todo = false;                                             // 935
+    edge_todo[n] = todo ? 1 : 0;
+    if (todo) { taint[n] = 1.0; atomicAdd(&counters[CT_EDGE_TODO], 1ULL); }
+}
+
+}  // namespace
+
+
+// section/proportion + receivers + filter (k_links), then the pit drains.  Leaves indeg holding
+// only the pit in-edges.  Shared by the full sweep and the update mode (the reference rebuilds
+// both on every calc_uca call, dem_processing.py:787-793 / 873-879).
+int pdm_graph_links_pits(pdm_tile *t, const pdm_uca_params *p)
+{
+    dim3 block(32, 8);
+    dim3 grid((unsigned)((t->C + 31) / 32), (unsigned)((t->R + 7) / 8));
+    PDM_CUDA(cudaMemsetAsync(t->d_counters, 0, CT_N * sizeof(unsigned long long), t->stream));
+    PDM_CUDA(cudaMemsetAsync(t->indeg, 0, (size_t)t->N * sizeof(int32_t), t->stream));
+    k_links<<<grid, block, 0, t->stream>>>(t->elev, t->dir, t->flats, t->th_row, t->R, t->C, t->link, t->prop,
+                                           t->flat0, t->d_counters);
+    PDM_CUDA(cudaGetLastError());
+    t->n_pits = 0; t->n_pit_edges = 0;
+    if (p->drain_pits) {
+        int rc = pdm_launch_pits(t, p);
+        if (rc) return rc;
+    }
+    return PDM_OK;
+}
+
+int pdm_launch_graph(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *st)
+{
+    (void)st;
+    dim3 block(32, 8);
+    dim3 grid((unsigned)((t->C + 31) / 32), (unsigned)((t->R + 7) / 8));
+    int rc = pdm_graph_links_pits(t, p);
+    if (rc) return rc;
+    PDM_CUDA(cudaMemsetAsync(t->edge_todo, 0, (size_t)t->N, t->stream));
+    k_indeg<<<grid, block, 0, t->stream>>>(t->link, t->R, t->C, t->row_area, t->indeg, t->uca, t->taint,
+                                           t->d_counters);
+    PDM_CUDA(cudaGetLastError());
+    const int64_t per = 2 * t->C + 2 * (t->R - 2);
+    k_border_todo<<<(unsigned)((per + 255) / 256), 256, 0, t->stream>>>(
+        t->elev, t->link, t->prop, t->R, t->C, t->pit_beg, t->pit_end, t->pit_w, t->pit_dst, t->n_pit_edges,
+        t->edge_todo, t->taint, t->d_counters);
+    PDM_CUDA(cudaGetLastError());
+    return PDM_OK;
+}
+
+int pdm_launch_section_export(pdm_tile *t)
+{
+    if (!t->section) PDM_CUDA(cudaMalloc(&t->section, (size_t)t->N));
+    dim3 block(32, 8);
+    dim3 grid((unsigned)((t->C + 31) / 32), (unsigned)((t->R + 7) / 8));
+    k_section_export<<<grid, block, 0, t->stream>>>(t->dir, t->flats, t->th_row, t->R, t->C, t->section);
+    PDM_CUDA(cudaGetLastError());
+    return PDM_OK;
+}

@@ -1,0 +1,102 @@
+// pdm_internal.cuh -- shared declarations of libpydem_b200 (not part of the public ABI).
+//
+// Data layout in HBM (per tile, N = R*C cells, C-order, 32-bit cell indices):
+//   elev, mag, dir, uca, taint, prop, twi : f64[N]
+//   flats, flat0, link, edge_todo, edge_done : u8[N]
+//   indeg (i32[N], live in-degree counters), label (i32[N], flat-region union-find)
+//   queue (i32[N], deferred work items of the sweep)
+//   per-row geometry: dX,dY,dg,thA,thB : f64[R-1] (fences);  th_row,row_area : f64[R]
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/pydem_b200.h"
+
+#define PDM_PI 3.141592653589793
+
+// link byte written by the graph kernel (reference: section of
+// _calc_uca_section_proportion + the keep filter of _mk_adjacency_matrix 1136-1137)
+#define LK_SEC_MASK 0x07   // facet index 0..7 of the two receivers
+#define LK_KEEP1 0x08      // edge to the cardinal receiver e1 survives the filter
+#define LK_KEEP2 0x10      // edge to the diagonal receiver e2 survives the filter
+#define LK_PIT 0x20        // cell drains through a pit edge list (prop holds the slot)
+#define LK_NOSEC 0x40      // section outside 0..7 (flat / undefined): no receivers
+#define LK_SOURCE 0x80     // nobody drains into this cell (initial frontier)
+
+struct pdm_tile {
+    int64_t R, C, N;
+    int device;
+    cudaStream_t stream;
+    // fields
+    double *elev, *mag, *dir, *uca, *taint, *prop, *twi;
+    uint8_t *flats, *flat0, *link, *edge_todo, *edge_done;
+    int8_t *section;  // only materialised on download of PDM_F_SECTION
+    int32_t *indeg, *label, *queue;
+    // geometry
+    double *dX, *dY, *dg, *thA, *thB, *th_row, *row_area;
+    double min_area;
+    bool have_spacing, have_elev, have_slopes, have_flats, have_graph, have_uca;
+    // pit edge lists (device)
+    int32_t *pit_cell;     // [pit_cap] cells examined by the pit search (flats & elev > 0)
+    int32_t *pit_beg;      // [pit_cap] first / one-past-last edge of each pit in pit_dst/pit_w
+    int32_t *pit_end;
+    int32_t *pit_dst;      // [pit_edge_cap] receiving cell of each pit edge
+    double *pit_w;         // [pit_edge_cap] share of the pit's area
+    int32_t *pit_scratch_i;  // per-block border double buffers of the pit search
+    double *pit_scratch_d;
+    int64_t n_pits, n_pit_edges, pit_cap, pit_edge_cap, pit_scratch_blocks;
+    // staging of the update mode's edge strips: [left R][right R][top C][bottom C]
+    double *edge_buf_d;
+    uint8_t *edge_buf_b;
+    // small device scratch for counters (pinned host mirror for readback)
+    unsigned long long *d_counters;  // [32]
+    unsigned long long *h_counters;  // pinned
+    cudaEvent_t ev[4];
+};
+
+void pdm_set_error(const char *fmt, ...);
+int pdm_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define PDM_CUDA(call)                                                        \
+    do {                                                                      \
+        cudaError_t e__ = (call);                                             \
+        if (e__ != cudaSuccess) return pdm_cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+// kernels' launchers (each returns a pdm_status)
+int pdm_launch_geometry(pdm_tile *t);
+int pdm_launch_slopes(pdm_tile *t);
+int pdm_launch_flats(pdm_tile *t);
+int pdm_launch_find_flats(pdm_tile *t);
+int pdm_launch_graph(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *st);
+int pdm_launch_sweep_full(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *st);
+int pdm_launch_update(pdm_tile *t, const pdm_uca_params *p, const double *const data[4],
+                      const uint8_t *const done[4], const uint8_t *const todo[4], pdm_uca_stats *st);
+int pdm_launch_twi(pdm_tile *t, const pdm_twi_params *p);
+int pdm_launch_section_export(pdm_tile *t);
+int pdm_restart_rounds(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *st);
+int pdm_graph_links_pits(pdm_tile *t, const pdm_uca_params *p);
+int pdm_launch_pits(pdm_tile *t, const pdm_uca_params *p);
+
+// counters slots
+enum {
+    CT_QTAIL = 0,      // sweep queue: items produced
+    CT_QHEAD = 1,      // tickets handed out
+    CT_QDONE = 2,      // items completely processed
+    CT_PHASE1 = 3,     // warps that finished the source scan
+    CT_DRAINED = 4,    // cells drained
+    CT_SOURCES = 5,
+    CT_UNDONE = 6,
+    CT_BADSEC = 7,
+    CT_NPITS = 8,
+    CT_NPITEDGES = 9,
+    CT_PITS_UNDRAINED = 10,
+    CT_EDGE_TODO = 11,
+    CT_FLAG = 12,
+    CT_TMP0 = 13,
+    CT_TMP1 = 14,
+    CT_ABORT = 15,
+    CT_N = 32
+};

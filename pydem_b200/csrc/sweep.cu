@@ -1,0 +1,99 @@
+// sweep.cu -- K5: upstream-contributing-area accumulation (the "drain" sweep) and TWI.
+//
+// Reference behaviour: cyutils.drain_area (cyutils.pyx:78-187) driven by
+// _calc_uca_chunk (dem_processing.py:939-980).  The reference is level-synchronous and
+// rescans every cell 3-4x per level; here the same dependency order (a cell drains when
+// every cell draining into it has drained) is enforced by live in-degree counters:
+//
+//   * every cell with in-degree 0 is a source; a persistent grid scans for sources,
+//   * a thread drains a cell by pushing area*weight (and the edge_todo "taint") to its
+//     receivers with fp64 L2 atomics, then decrements the receivers' in-degree; the
+//     thread that brings a counter to 0 owns that receiver and continues with it
+//     (chain following, no level barrier).  A second ready receiver is handed to idle
+//     lanes through a global queue.
+//   * ordering: the area atomics are *returning* atomics; the in-degree decrement
+//     carries a data dependency on their return values, so a contribution is performed
+//     at L2 before the decrement that publishes it (no MEMBAR on the critical path).
+//
+// For an acyclic graph this visits every cell exactly once and yields the reference's
+// sums up to fp64 re-association (the reference adds in (level, source index) order).
+// Cells on cycles never reach in-degree 0; they are counted (n_undone) and handled by
+// the level-synchronous restart path below, which follows cyutils.pyx literally.
+//
+// Traffic per cell (sweep): link 1 + prop 8 + area 8 + taint 8 read, ~2 fp64 atomics +
+// 2 int atomics; the kernel is bound by L2 atomic latency along the longest flow path,
+// not by HBM bandwidth.
+#include "drain_op.cuh"
+
+namespace {
+
+// a6 epilogue: dem_processing.py:966-980
+__global__ void __launch_bounds__(256)
+k_uca_finalize(const double *__restrict__ E, const uint8_t *__restrict__ flats, const int32_t *__restrict__ indeg,
+               const double *__restrict__ taint, double *__restrict__ uca, uint8_t *__restrict__ edge_done,
+               int64_t N, int limit_edges, double limit_area, unsigned long long *counters)
+{
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool undone = false;
+    if (n < N) {
+        const double e = E[n];
+        double u = uca[n];
+        if (flats[n]) { u = __longlong_as_double(0x7ff8000000000000LL); uca[n] = u; }   // 972
+        bool ed = !(taint[n] != 0.0);                                                    // 969, 974
+        if (e != e) ed = true;                                                           // 975
+        if (limit_edges && u > limit_area) ed = true;                                    // 977-980
+        edge_done[n] = ed ? 1 : 0;
+        undone = indeg[n] > 0;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, undone);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[CT_UNDONE], (unsigned long long)__popc(m));
+}
+
+// a9: calc_twi dem_processing.py:1647-1677 (un-scaled)
+__global__ void __launch_bounds__(256)
+k_twi(const double *__restrict__ uca, const double *__restrict__ mag, double *__restrict__ twi, int64_t N,
+      double min_slope, double cap, int limit_uca, int limit_twi, double twi_sat)
+{
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    double u = uca[n];
+    if (limit_uca && u > cap) u = cap;                                       // 1663-1665
+    double t = log(__ddiv_rn(u, __dadd_rn(mag[n], min_slope)));              // 1667
+    if (limit_twi && t > twi_sat) t = twi_sat;                               // 1669-1672
+    twi[n] = t;
+}
+
+}  // namespace
+
+static int g_sweep_blocks = 0;
+
+int pdm_launch_sweep_full(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *st)
+{
+    (void)st;
+    if (!g_sweep_blocks) {
+        int rc = wl::grid_for(wl::k_worklist<DrainOp<0>, wl::DomainAll>, &g_sweep_blocks);
+        if (rc) return rc;
+    }
+    int rc = wl::reset_queue(t);
+    if (rc) return rc;
+    DrainOp<0> op{t->link, t->prop, t->uca, t->taint, t->indeg, nullptr, (int32_t)t->C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w};
+    wl::k_worklist<<<g_sweep_blocks, 256, 0, t->stream>>>(op, wl::DomainAll{t->N}, wl::Queue{t->queue, t->d_counters});
+    PDM_CUDA(cudaGetLastError());
+    const double limit_area = p->uca_saturation_limit * 2 * t->min_area;
+    k_uca_finalize<<<(unsigned)((t->N + 255) / 256), 256, 0, t->stream>>>(
+        t->elev, t->flats, t->indeg, t->taint, t->uca, t->edge_done, t->N, p->apply_uca_limit_edges, limit_area,
+        t->d_counters);
+    PDM_CUDA(cudaGetLastError());
+    return PDM_OK;
+}
+
+int pdm_launch_twi(pdm_tile *t, const pdm_twi_params *p)
+{
+    const double cap = p->uca_saturation_limit * p->twi_min_area;
+    const double twi_sat = log(p->uca_saturation_limit * p->twi_min_area / p->twi_min_slope);
+    k_twi<<<(unsigned)((t->N + 255) / 256), 256, 0, t->stream>>>(t->uca, t->mag, t->twi, t->N, p->twi_min_slope, cap,
+                                                                 p->apply_twi_limits_on_uca, p->apply_twi_limits,
+                                                                 twi_sat);
+    PDM_CUDA(cudaGetLastError());
+    return PDM_OK;
+}

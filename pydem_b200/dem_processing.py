@@ -1,0 +1,348 @@
+"""Drop-in ``DEMProcessor`` for pyDEM's hot path, backed by ``libpydem_b200.so``.
+
+Mirrors the operator surface of the reference ``pydem.dem_processing.DEMProcessor``
+(reference dem_processing.py:98-258): same constructor keywords, same attributes
+(``elev dX dY dX2 dY2 direction mag flats uca twi edge_todo edge_done twi_min_area`` and the
+behaviour flags of lines 105-154), same methods
+
+    calc_slopes_directions() -> (mag, direction)      reference :587
+    find_flats()                                      reference :305
+    calc_uca(plotflag=False, edge_init_data=None, uca_init=None) -> uca   reference :682
+    calc_twi() -> twi (un-scaled; self.twi = 10*twi)  reference :1647
+
+including the reference's in-place side effects (``mag``/``flats`` updated at drained pits,
+``twi_min_area`` lowered by ``calc_uca``).  Arrays are NumPy on the host side, exactly like
+the reference; all arithmetic happens on the GPU.  There is no CPU fallback: a missing
+library or device raises ``RuntimeError`` (the reference does the same when its Cython
+module is absent, dem_processing.py:714-715).
+
+Host<->device traffic: callers of the reference mutate the NumPy attributes between calls
+(``dp.dX[:] = 1`` in its tests, edge rows of ``direction`` in ``process_manager.calc_uca``),
+so every public ``calc_*`` call uploads its inputs from the attributes.  Stages that the
+reference chains internally (``calc_twi -> calc_uca -> calc_slopes_directions`` when the
+intermediate attribute is ``None``) stay resident in HBM and are downloaded once.
+"""
+import ctypes as ct
+import warnings
+
+import numpy as np
+
+from . import _lib
+
+FLAT_ID = np.nan
+FLAT_ID_INT = -1
+
+
+class DEMProcessor(object):
+    # behaviour flags and their reference defaults (dem_processing.py:105-154)
+    _DEFAULTS = dict(
+        fill_flats=True, fill_flats_below_sea=False, fill_flats_source_tol=1, fill_flats_peaks=True,
+        fill_flats_pits=True, fill_flats_max_iter=10,
+        drain_pits=True, drain_pits_path=True, drain_pits_min_border=False, drain_pits_spill=False,
+        drain_flats=False, drain_pits_max_iter=300, drain_pits_max_dist=32, drain_pits_max_dist_XY=None,
+        apply_uca_limit_edges=False, apply_twi_limits=False, apply_twi_limits_on_uca=False,
+        uca_saturation_limit=32.0, twi_min_slope=1e-3, twi_min_area=np.inf, circular_ref_maxcount=50,
+        maximum_pit_area=32.0, plotflag=False,
+    )
+    _ARRAYS = ("elev", "direction", "mag", "uca", "twi", "flats", "done", "dX", "dY", "dX2", "dY2")
+
+    def __init__(self, elev_fn=None, **kwargs):
+        if elev_fn:
+            kwds = _raster_kwargs(elev_fn)
+            kwds.update(kwargs)
+            kwargs = kwds
+        if kwargs.get("elev") is None:
+            raise ValueError("DEMProcessor needs `elev` (or an elevation file name)")
+        nrow = np.shape(kwargs["elev"])[0]
+        # scalar spacing -> per-row arrays (dem_processing.py:233-240)
+        if not isinstance(kwargs.get("dX"), np.ndarray):
+            if "dX2" not in kwargs:
+                kwargs["dX2"] = np.ones(nrow) * kwargs.get("dX", 1)
+            kwargs["dX"] = np.ones(nrow - 1) * kwargs.get("dX", 1)
+        if not isinstance(kwargs.get("dY"), np.ndarray):
+            if "dY2" not in kwargs:
+                kwargs["dY2"] = np.ones(nrow) * kwargs.get("dY", 1)
+            kwargs["dY"] = np.ones(nrow - 1) * kwargs.get("dY", 1)
+        for k, v in self._DEFAULTS.items():
+            setattr(self, k, kwargs.pop(k, v))
+        for k in self._ARRAYS:
+            v = kwargs.pop(k, None)
+            setattr(self, k, None if v is None else np.asarray(v))
+        if self.dX2 is None:
+            self.dX2 = np.ones(nrow)                                    # dem_processing.py:252-258
+        if self.dY2 is None:
+            self.dY2 = np.ones(nrow)
+        self.bounds = kwargs.pop("bounds", [])
+        self.transform = kwargs.pop("transform", [])
+        self.device = kwargs.pop("device", None)
+        if kwargs:
+            raise TypeError("DEMProcessor got unexpected keyword arguments %s" % sorted(kwargs))
+        self.edge_todo = None
+        self.edge_done = None
+        self.section = None
+        self.proportion = None
+        self.A = None            # the reference's sparse matrix is never materialised here
+        self.uca_stats = None    # pdm_uca_stats of the last calc_uca
+        self._tile = None
+        self._tile_shape = None
+        self._chain = 0          # >0 while stages are chained inside one public call
+        self._resident = set()   # fields valid in HBM during a chain
+
+    # ------------------------------------------------------------------------------------
+    # device plumbing
+    # ------------------------------------------------------------------------------------
+    def _lib(self):
+        L = _lib.load()
+        _lib.init(self.device)
+        return L
+
+    def _get_tile(self):
+        L = self._lib()
+        shape = tuple(self.elev.shape)
+        if self._tile is not None and self._tile_shape != shape:
+            self._free_tile()
+        if self._tile is None:
+            if len(shape) != 2:
+                raise ValueError("elev must be 2-D")
+            h = ct.c_void_p()
+            _lib.check(L.pdm_tile_create(shape[0], shape[1], None, ct.byref(h)))
+            self._tile, self._tile_shape = h, shape
+        return self._tile
+
+    def _free_tile(self):
+        if self._tile is not None:
+            try:
+                _lib.load().pdm_tile_destroy(self._tile)
+            except Exception:
+                pass
+            self._tile = None
+            self._resident = set()
+
+    def __del__(self):
+        self._free_tile()
+
+    def _up(self, field, arr):
+        """host -> HBM unless the field is already resident from a chained stage."""
+        if self._chain and field in self._resident:
+            return
+        a = np.ascontiguousarray(arr, dtype=_lib.FIELD_DTYPE[field])
+        if a.shape != self._tile_shape:
+            raise ValueError("field %d has shape %s, expected %s" % (field, a.shape, self._tile_shape))
+        _lib.check(_lib.load().pdm_tile_upload(self._get_tile(), field, _lib.ptr(a)))
+        self._resident.add(field)
+
+    def _down(self, field):
+        out = np.empty(self._tile_shape, dtype=_lib.FIELD_DTYPE[field])
+        _lib.check(_lib.load().pdm_tile_download(self._get_tile(), field, _lib.ptr(out)))
+        return out
+
+    def _spacing(self):
+        R = self.elev.shape[0]
+        dX = np.ascontiguousarray(self.dX, "float64"); dY = np.ascontiguousarray(self.dY, "float64")
+        dX2 = np.ascontiguousarray(self.dX2, "float64"); dY2 = np.ascontiguousarray(self.dY2, "float64")
+        if dX.shape != (R - 1,) or dY.shape != (R - 1,) or dX2.shape != (R,) or dY2.shape != (R,):
+            raise ValueError("dX, dY need %d entries and dX2, dY2 %d" % (R - 1, R))
+        # facet angles with NumPy's arctan2, as the reference computes them (dem_processing.py:1936)
+        thA = np.ascontiguousarray(np.arctan2(dY, dX)); thB = np.ascontiguousarray(np.arctan2(dX, dY))
+        _lib.check(_lib.load().pdm_tile_set_spacing(self._get_tile(), _lib.ptr(dX), _lib.ptr(dY), _lib.ptr(dX2),
+                                                    _lib.ptr(dY2), _lib.ptr(thA), _lib.ptr(thB)))
+
+    def _begin(self):
+        if self._chain == 0:
+            self._resident = set()
+        self._chain += 1
+
+    def _end(self):
+        self._chain -= 1
+        if self._chain == 0:
+            self._resident = set()
+
+    # ------------------------------------------------------------------------------------
+    # reference API
+    # ------------------------------------------------------------------------------------
+    def find_flats(self):
+        """dem_processing.py:305-306"""
+        self.flats = self.mag == FLAT_ID_INT
+
+    def calc_fill_flats(self):
+        raise NotImplementedError(
+            "elevation conditioning (calc_fill_flats, reference dem_processing.py:551-585) is outside the "
+            "accelerated hot path (SURVEY.md 8(f) rank 1); pass conditioned elevation with fill_flats=False")
+
+    def calc_pit_drain_paths(self):
+        raise NotImplementedError(
+            "elevation conditioning (calc_pit_drain_paths, reference dem_processing.py:428-548) is outside the "
+            "accelerated hot path (SURVEY.md 8(f) rank 1); pass conditioned elevation with drain_pits_path=False")
+
+    def calc_slopes_directions(self, plotflag=False):
+        """Magnitude and direction of slopes -> self.mag, self.direction, self.flats
+        (dem_processing.py:587-619)."""
+        if self.fill_flats:
+            self.calc_fill_flats()
+        if self.drain_pits_path:
+            self.calc_pit_drain_paths()
+        self._begin()
+        try:
+            L = self._lib()
+            t = self._get_tile()
+            self._spacing()
+            self._up(_lib.F_ELEV, self.elev)
+            _lib.check(L.pdm_tile_slopes_directions(t))
+            self._resident.update((_lib.F_MAG, _lib.F_DIR, _lib.F_FLATS))
+            self.mag = self._down(_lib.F_MAG)
+            self.direction = self._down(_lib.F_DIR)
+            self.flats = self._down(_lib.F_FLATS).astype(bool)
+        finally:
+            self._end()
+        return self.mag, self.direction
+
+    def _uca_params(self):
+        p = _lib.UcaParams()
+        _lib.load().pdm_default_uca_params(ct.byref(p))
+        if self.drain_flats and not self.drain_pits:
+            raise NotImplementedError("drain_flats is deprecated in the reference (README) and not accelerated")
+        if self.drain_pits_spill and not self.drain_pits:
+            raise NotImplementedError("drain_pits_spill ('not a great option', dem_processing.py:115) is not accelerated")
+        p.drain_pits = int(bool(self.drain_pits))
+        p.drain_pits_min_border = int(bool(self.drain_pits_min_border))
+        p.drain_pits_max_iter = int(self.drain_pits_max_iter)
+        p.drain_pits_max_dist = int(self.drain_pits_max_dist or 0)
+        p.drain_pits_max_dist_xy = float(self.drain_pits_max_dist_XY or 0.0)
+        p.apply_uca_limit_edges = int(bool(self.apply_uca_limit_edges))
+        p.circular_ref_maxcount = int(self.circular_ref_maxcount)
+        p.uca_saturation_limit = float(self.uca_saturation_limit)
+        return p
+
+    def calc_uca(self, plotflag=False, edge_init_data=None, uca_init=None):
+        """Upstream contributing area (dem_processing.py:682-776).
+
+        Full mode (``uca_init is None``) computes the tile's own UCA plus ``edge_todo`` /
+        ``edge_done``.  Update mode propagates only the difference between the neighbours'
+        finished edge values (``edge_init_data = [data, done, todo]``, dicts keyed
+        left/right/top/bottom) and ``uca_init``."""
+        self._begin()
+        try:
+            if self.direction is None:
+                self.calc_slopes_directions()
+            L = self._lib()
+            t = self._get_tile()
+            self._spacing()
+            self._up(_lib.F_ELEV, self.elev)
+            self._up(_lib.F_DIR, self.direction)
+            self._up(_lib.F_MAG, self.mag)
+            if self.flats is None:
+                raise ValueError("flats is not set: call calc_slopes_directions() or find_flats() first")
+            self._up(_lib.F_FLATS, self.flats)
+            p = self._uca_params()
+            st = _lib.UcaStats()
+            if uca_init is None:
+                _lib.check(L.pdm_tile_uca(t, ct.byref(p), ct.byref(st)))
+                # dem_processing.py:898-899
+                self.twi_min_area = min(self.twi_min_area, st.min_area)
+            else:
+                R, C = self._tile_shape
+                strips = _pack_edges(edge_init_data, R, C)
+                self._resident.discard(_lib.F_UCA)
+                self._up(_lib.F_UCA, np.asarray(uca_init).astype("float64"))       # 744
+                args = [_lib.ptr(a) for a in strips]
+                _lib.check(L.pdm_tile_uca_update(t, ct.byref(p), *args, ct.byref(st)))
+            self._resident.update((_lib.F_UCA, _lib.F_MAG, _lib.F_FLATS))
+            self.uca_stats = st.as_dict()
+            self.uca = self._down(_lib.F_UCA)
+            self.edge_todo = self._down(_lib.F_EDGE_TODO).astype(bool)
+            self.edge_done = self._down(_lib.F_EDGE_DONE).astype(bool)
+            if p.drain_pits and st.n_pits:
+                # _mk_connectivity_pits updates mag / flats of drained pits in place (1370-1371)
+                mag = self._down(_lib.F_MAG)
+                flats = self._down(_lib.F_FLATS).astype(bool)
+                if isinstance(self.mag, np.ndarray) and self.mag.dtype == np.float64 and self.mag.flags.writeable:
+                    self.mag[...] = mag
+                else:
+                    self.mag = mag
+                if isinstance(self.flats, np.ndarray) and self.flats.dtype == bool and self.flats.flags.writeable:
+                    self.flats[...] = flats
+                else:
+                    self.flats = flats
+                if st.n_pits_undrained:
+                    warnings.warn("Warning %d pits had no place to drain to in this chunk" % st.n_pits_undrained)
+            if st.n_undone:
+                warnings.warn("%d cells are on circular references and were not drained" % st.n_undone)
+        finally:
+            self._end()
+        return self.uca
+
+    def calc_twi(self):
+        """Topographic wetness index (dem_processing.py:1647-1677): returns the un-scaled
+        index and stores ``self.twi = 10 * twi``."""
+        self._begin()
+        try:
+            if self.uca is None:
+                self.calc_uca()
+            L = self._lib()
+            t = self._get_tile()
+            self._up(_lib.F_UCA, self.uca)
+            self._up(_lib.F_MAG, self.mag)
+            p = _lib.TwiParams()
+            L.pdm_default_twi_params(ct.byref(p))
+            p.twi_min_slope = float(self.twi_min_slope)
+            p.twi_min_area = float(self.twi_min_area)
+            p.uca_saturation_limit = float(self.uca_saturation_limit)
+            p.apply_twi_limits = int(bool(self.apply_twi_limits))
+            p.apply_twi_limits_on_uca = int(bool(self.apply_twi_limits_on_uca))
+            _lib.check(L.pdm_tile_twi(t, ct.byref(p)))
+            twi = self._down(_lib.F_TWI)
+            self.twi = twi * 10                                             # 1674
+        finally:
+            self._end()
+        return twi
+
+    # debugging attributes of the reference (dem_processing.py:137-139)
+    def calc_section_proportion(self):
+        """Fill ``self.section`` / ``self.proportion`` (reference _calc_uca_section_proportion :1021)
+        from the current direction / flats.  Test hook; not needed for calc_uca."""
+        self._begin()
+        try:
+            L = self._lib()
+            t = self._get_tile()
+            self._spacing()
+            self._up(_lib.F_ELEV, self.elev)
+            self._up(_lib.F_DIR, self.direction)
+            self._up(_lib.F_MAG, self.mag)
+            self._up(_lib.F_FLATS, self.flats)
+            self.section = self._down(_lib.F_SECTION)
+        finally:
+            self._end()
+        return self.section
+
+
+def _pack_edges(edge_init_data, R, C):
+    """[data, done, todo] dicts keyed left/right/top/bottom -> 12 contiguous strips in the
+    order the C ABI takes them (data x4, done x4, todo x4)."""
+    keys = ("left", "right", "top", "bottom")
+    lens = {"left": R, "right": R, "top": C, "bottom": C}
+    if edge_init_data is None:
+        data = {k: np.zeros(lens[k]) for k in keys}
+        done = {k: np.zeros(lens[k], bool) for k in keys}
+        todo = {k: np.zeros(lens[k], bool) for k in keys}
+    else:
+        data, done, todo = edge_init_data
+    out = []
+    for d, dt in ((data, np.float64), (done, np.uint8), (todo, np.uint8)):
+        for k in keys:
+            a = np.ascontiguousarray(np.asarray(d[k]).reshape(-1), dtype=dt)
+            if a.size != lens[k]:
+                raise ValueError("edge strip %r has %d entries, expected %d" % (k, a.size, lens[k]))
+            out.append(a)
+    return out
+
+
+def _raster_kwargs(fn):
+    """Elevation + per-row spacing from a raster file (reference utils.py:46-51).  Needs
+    rasterio/geopy, which are IO dependencies outside the hot path."""
+    try:
+        import rasterio  # noqa: F401
+    except ImportError as e:  # pragma: no cover
+        raise ImportError("reading %r needs rasterio (file IO is outside the accelerated hot path); "
+                          "pass elev=, dX=, dY= arrays instead" % fn) from e
+    from .raster_io import dem_processor_from_raster_kwargs  # pragma: no cover
+    return dem_processor_from_raster_kwargs(fn)  # pragma: no cover

@@ -1,0 +1,105 @@
+"""Shared helpers of the parity tests: case catalogue, oracle/GPU runners, comparison."""
+import io
+import contextlib
+import warnings
+
+import numpy as np
+
+from pydem_b200 import synth
+
+# tolerances of the parity bar (north_star: "stated float tolerance, integers bit-exact")
+DIR_ATOL = 1e-12     # radians; CUDA atan2 vs host libm/NumPy differ by <= 2 ulp
+MAG_RTOL = 1e-13     # sqrt/div are IEEE-exact on both sides; only pit mean-slopes re-associate
+UCA_RTOL = 1e-9      # fp64 atomics re-associate the reference's (level, index) summation order
+TWI_ATOL = 1e-9
+
+HOT = dict(fill_flats=False, drain_pits_path=False)
+
+
+def cases():
+    """name -> (elev, kwargs).  Sizes the oracle finishes in seconds."""
+    out = {}
+    card = np.repeat(np.arange(1.0, 6.0)[:, None], 5, 1)
+    diag = np.add.outer(np.arange(5.0), np.arange(5.0)) + 1.0
+    for nm, E in (("card", card), ("diag", diag)):
+        out[nm] = (E, {})
+        out[nm + "_rev"] = (E[::-1].copy(), {})
+        out[nm + "_T"] = (E.T.copy(), {})
+        out[nm + "_Trev"] = (E[::-1, ::-1].T.copy(), {})
+    out["cone32"] = (synth.cone_dem(32), {})
+    out["cone256"] = (synth.cone_dem(256), {})
+    out["cone256_nopits"] = (synth.cone_dem(256), dict(drain_pits=False))
+    out["frac128"] = (synth.fractal_dem(128, 1), {})
+    out["frac128_nopits"] = (synth.fractal_dem(128, 2), dict(drain_pits=False))
+    out["frac256_dx30"] = (synth.fractal_dem(256, 3), dict(dX=30.0, dY=30.0))
+    R = 200
+    out["frac_rect_vardx"] = (synth.fractal_dem(0, 4, shape=(R, 150)),
+                              dict(dX=np.linspace(20, 30, R - 1), dY=np.full(R - 1, 27.3),
+                                   dX2=np.linspace(20, 30, R), dY2=np.full(R, 27.3)))
+    E = synth.fractal_dem(128, 5); E[40:44, 50:53] = np.nan; E[80, 90] = np.nan; E[0, 5] = np.nan
+    out["nan_holes"] = (E, {})
+    out["quantized"] = (np.round(synth.fractal_dem(128, 6) / 20) * 20, {})
+    E = synth.fractal_dem(160, 7)
+    yy, xx = np.mgrid[0:160, 0:160]
+    for (cy, cx, r) in ((40, 40, 9), (100, 120, 14), (120, 30, 6)):
+        m = (yy - cy) ** 2 + (xx - cx) ** 2 <= r * r
+        E[m] = E[m].min()
+    out["lakes"] = (E, {})
+    out["lakes_minborder"] = (E, dict(drain_pits_min_border=True))
+    out["frac96_maxdist4"] = (synth.fractal_dem(96, 8), dict(drain_pits_max_dist=4, drain_pits_max_iter=20))
+    out["frac96_xy"] = (synth.fractal_dem(96, 9), dict(dX=30.0, dY=30.0, drain_pits_max_dist_XY=70.0))
+    out["odd_cols"] = (synth.fractal_dem(0, 10, shape=(67, 131)), dict(dX=10.0, dY=12.5))
+    out["tiny3"] = (np.array([[3.0, 2.0, 3.0], [2.0, 1.0, 2.0], [3.0, 2.5, 3.0]]), {})
+    out["frac512_limits"] = (synth.fractal_dem(512, 11), dict(dX=30.0, dY=30.0, apply_uca_limit_edges=True,
+                                                            apply_twi_limits=True, apply_twi_limits_on_uca=True))
+    return out
+
+
+def run(make, E, kw):
+    """Run the three stages on a processor factory; returns a dict of outputs."""
+    k = dict(HOT); k.update(kw)
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        dp = make(E, **k)
+        mag, direction = dp.calc_slopes_directions()
+        out = dict(mag0=np.array(mag), dir=np.array(direction), flats0=np.array(dp.flats))
+        out["uca"] = np.array(dp.calc_uca())
+        out["edge_todo"] = np.array(dp.edge_todo); out["edge_done"] = np.array(dp.edge_done)
+        out["mag"] = np.array(dp.mag); out["flats"] = np.array(dp.flats)
+        out["twi"] = np.array(dp.calc_twi()); out["twi10"] = np.array(dp.twi)
+        out["twi_min_area"] = dp.twi_min_area
+    return out
+
+
+def _nanmax(x):
+    x = x[np.isfinite(x)]
+    return float(x.max()) if x.size else 0.0
+
+
+def compare(ref, got):
+    """dict of error measures between two output dicts (ref = oracle / reference)."""
+    with np.errstate(invalid="ignore", divide="ignore"):
+        r = {}
+        for k in ("mag0", "mag", "dir", "uca", "twi", "twi10"):
+            a, b = np.asarray(ref[k], float), np.asarray(got[k], float)
+            r[k + "_nanpat"] = int((np.isnan(a) != np.isnan(b)).sum())
+            r[k + "_abs"] = _nanmax(np.abs(a - b))
+            r[k + "_rel"] = _nanmax(np.abs(a - b) / np.abs(a))
+            r[k + "_neq"] = int(((a != b) & ~(np.isnan(a) & np.isnan(b))).sum())
+        for k in ("flats0", "flats", "edge_todo", "edge_done"):
+            r[k + "_neq"] = int((np.asarray(ref[k], bool) != np.asarray(got[k], bool)).sum())
+        r["min_area_eq"] = bool(ref["twi_min_area"] == got["twi_min_area"])
+    return r
+
+
+def assert_parity(r, name=""):
+    msg = "%s: %s" % (name, r)
+    for k in ("flats0", "flats", "edge_todo", "edge_done"):
+        assert r[k + "_neq"] == 0, msg                       # integer/bool outputs bit-exact
+    for k in ("mag0", "mag", "dir", "uca", "twi", "twi10"):
+        assert r[k + "_nanpat"] == 0, msg
+    assert r["mag0_rel"] <= MAG_RTOL and r["mag_rel"] <= 1e-12, msg
+    assert r["dir_abs"] <= DIR_ATOL, msg
+    assert r["uca_rel"] <= UCA_RTOL, msg
+    assert r["twi_abs"] <= TWI_ATOL, msg
+    assert r["min_area_eq"], msg
