@@ -224,7 +224,8 @@ int orc_receivers(const int8_t *section, i64 R, i64 C, i64 *j1, i64 *j2)
 }
 
 /* numpy's pairwise float64 summation (numpy/_core/src/umath/loops_utils.h.src,
- * DOUBLE_pairwise_sum) and add.reduce = first element + pairwise(rest); third-party
+ * DOUBLE_pairwise_sum), which is what add.reduce applies to a contiguous float64 vector
+ * (checked against np.sum in tests/test_oracle_golden.py); third-party
  * arithmetic that np.mean/np.sum in _mk_connectivity_pits (1346-1370) rely on. */
 static double np_pairwise(const double *a, i64 n)
 {
@@ -243,7 +244,7 @@ static double np_pairwise(const double *a, i64 n)
 static double np_sum(const double *a, i64 n)
 {
     if (n == 0) return 0.0;
-    return a[0] + np_pairwise(a + 1, n - 1);
+    return np_pairwise(a, n);
 }
 double orc_np_sum(const double *a, i64 n) { return np_sum(a, n); }
 

@@ -39,8 +39,8 @@ struct PitArgs {
     int W;                    // window radius = max_iter + 1
 };
 
-// numpy pairwise summation (numpy/_core/src/umath/loops_utils.h.src) and
-// add.reduce = first element + pairwise(rest): what np.sum / np.mean do at 1346-1370.
+// numpy pairwise summation (numpy/_core/src/umath/loops_utils.h.src): what np.sum / np.mean
+// apply to the contiguous float64 vectors at 1346-1370.
 __device__ double np_pairwise(const double *a, int64_t n)
 {
     if (n < 8) {
@@ -66,7 +66,7 @@ __device__ double np_pairwise(const double *a, int64_t n)
 __device__ double np_sum(const double *a, int64_t n)
 {
     if (n == 0) return 0.0;
-    return __dadd_rn(a[0], np_pairwise(a + 1, n - 1));
+    return np_pairwise(a, n);
 }
 
 // NaN-propagating min (np.min) over a block; every thread passes its partial

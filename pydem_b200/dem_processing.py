@@ -47,6 +47,7 @@ class DEMProcessor(object):
     _ARRAYS = ("elev", "direction", "mag", "uca", "twi", "flats", "done", "dX", "dY", "dX2", "dY2")
 
     def __init__(self, elev_fn=None, **kwargs):
+        self._tile = None
         if elev_fn:
             kwds = _raster_kwargs(elev_fn)
             kwds.update(kwargs)

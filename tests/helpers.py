@@ -55,6 +55,33 @@ def cases():
     return out
 
 
+def golden_cases():
+    """Small catalogue whose reference outputs are committed under tests/golden/."""
+    out = {k: v for k, v in cases().items() if k.startswith(("card", "diag")) or k in ("cone32", "tiny3")}
+    out["frac48"] = (synth.fractal_dem(48, 31), {})
+    out["frac48_nopits"] = (synth.fractal_dem(48, 32), dict(drain_pits=False))
+    R = 40
+    out["rect_vardx"] = (synth.fractal_dem(0, 33, shape=(R, 30)),
+                         dict(dX=np.linspace(20, 30, R - 1), dY=np.full(R - 1, 27.3),
+                              dX2=np.linspace(20, 30, R), dY2=np.full(R, 27.3)))
+    E = synth.fractal_dem(48, 34); E[20:23, 30:32] = np.nan; E[40, 10] = np.nan; E[0, 5] = np.nan
+    out["nan48"] = (E, {})
+    out["quant48"] = (np.round(synth.fractal_dem(48, 35) / 20) * 20, {})
+    E = synth.fractal_dem(64, 36)
+    yy, xx = np.mgrid[0:64, 0:64]
+    for (cy, cx, r) in ((20, 20, 6), (45, 40, 8)):
+        m = (yy - cy) ** 2 + (xx - cx) ** 2 <= r * r
+        E[m] = E[m].min()
+    out["lakes64"] = (E, {})
+    out["lakes64_minborder"] = (E, dict(drain_pits_min_border=True))
+    out["maxdist40"] = (synth.fractal_dem(40, 37), dict(drain_pits_max_dist=4, drain_pits_max_iter=20))
+    out["xy40"] = (synth.fractal_dem(40, 38), dict(dX=30.0, dY=30.0, drain_pits_max_dist_XY=70.0))
+    out["odd37x51"] = (synth.fractal_dem(0, 39, shape=(37, 51)), dict(dX=10.0, dY=12.5))
+    out["limits48"] = (synth.fractal_dem(48, 40), dict(dX=30.0, dY=30.0, apply_uca_limit_edges=True,
+                                                       apply_twi_limits=True, apply_twi_limits_on_uca=True))
+    return out
+
+
 def run(make, E, kw):
     """Run the three stages on a processor factory; returns a dict of outputs."""
     k = dict(HOT); k.update(kw)
