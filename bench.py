@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- pyDEM hot path on B200: Mcells/s for slope+aspect -> UCA -> TWI.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--size 4096]
+
+One "step" = one pass of the hot path (calc_slopes_directions + calc_uca + calc_twi, conditioning
+flags off) over one synthetic fractal DEM.  N = 1 runs BASELINE.json configs[1] (4096 x 4096,
+f64, dX = dY = 30 m); N > 1 runs the row-sharded single-DEM path (pydem_b200.sharded: 4096 rows x
+4096 columns per GPU, halo rows exchanged over NCCL), weak scaling.
+
+Printed JSON line (rank 0):
+  value        whole-job Mcells/s with the elevation already resident in HBM (device-timed)
+  e2e          the same metric through the reference-facing operator
+               (DEMProcessor(elev=<pinned host array>).calc_twi()): H2D of the DEM and D2H of
+               mag/direction/uca/twi/flats/edge masks inside the timed region
+  roofline     dominant kernel (the UCA sweep) against the measured HBM peak
+  cpu_baseline the oracle port on one host core, bounded sample of the same DEM
+  --impl reference: the reference's CPU path on all host cores (see reference_arm()).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Mcells/s slope+aspect + UCA + TWI (D-infinity hot path, f64)"
+SPACING = 30.0
+BYTES_PER_CELL = 24.0   # read elev 8 + direction 8, write uca 8 (also 24 for the stencil)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU legs (oracle = checker; only this file's cpu_baseline / --impl reference legs may time it)
+# ----------------------------------------------------------------------------------------------
+def _cpu_hot_path(E, use_ref_sweep):
+    """One pass of the hot path on one host core.  use_ref_sweep: run the accumulation with the
+    reference's own compiled Cython kernel (oracle/_ref/cyutils*.so, built from
+    /root/reference/pydem/cyfuncs/cyutils.pyx) instead of the oracle's restatement of it."""
+    from oracle import oracle as orc
+    dp = orc.OracleDEMProcessor(E, dX=SPACING, dY=SPACING, fill_flats=False, drain_pits_path=False, drain_pits=False)
+    dp.calc_slopes_directions()
+    if not use_ref_sweep:
+        dp.calc_uca()
+    else:
+        from oracle import ref_harness
+        cy = ref_harness.load_ref_cyutils()
+        g, sec = dp._graph()
+        cptr, cidx, cdat, rptr, ridx = g.export()
+        inflow, _, _ = g.sums()
+        R, C = E.shape
+        area = np.full(R * C, SPACING * SPACING)
+        done = np.ascontiguousarray(inflow == 0)
+        ids = done.copy()
+        todo = np.zeros(R * C)
+        cy.drain_area(area, done, ids, cptr.astype(np.int32), cidx.astype(np.int32), cdat, rptr.astype(np.int32),
+                      ridx.astype(np.int32), R, C, todo, todo.copy())
+        area[dp.flats.ravel()] = np.nan
+        dp.uca = area.reshape(R, C)
+        dp.twi_min_area = SPACING * SPACING
+    dp.calc_twi()
+    return E.size
+
+
+def _ref_worker(args):
+    seed, n, use_ref = args
+    from pydem_b200 import synth
+    E = synth.fractal_dem(n, seed)
+    t = time.perf_counter()
+    cells = _cpu_hot_path(E, use_ref)
+    return cells, time.perf_counter() - t
+
+
+def cpu_baseline_leg(E_full, window=2048):
+    """Oracle port, one core, on the top-left window of the benchmark DEM."""
+    w = min(window, E_full.shape[0], E_full.shape[1])
+    E = np.ascontiguousarray(E_full[:w, :w])
+    _cpu_hot_path(E[:256, :256].copy(), False)   # builds/loads the oracle library
+    t = time.perf_counter()
+    cells = _cpu_hot_path(E, False)
+    dt = time.perf_counter() - t
+    return {"value": cells / dt / 1e6, "unit": "Mcells/s", "cores": 1, "kind": "port",
+            "sample": "oracle/pdm_oracle.c (C restatement, 1 core) on the %dx%d top-left window of the benchmark "
+                      "DEM, slope+aspect + UCA + TWI, %.1f s" % (w, w, dt)}
+
+
+def reference_arm(args):
+    """Reference CPU path on all host cores.  The reference has no intra-tile threading; its
+    ProcessManager runs one tile per process (process_manager.py:1251-1288).  The same here: every
+    core gets its own 1024x1024 window per step.  Only the reference's native piece can travel to
+    the GPU box (oracle/_ref: cyutils.pyx compiled with the reference's flags) -- it does the UCA
+    sweep, ~90% of the reference's time; the NumPy layers around it run as the oracle's C port
+    (faster than the reference's NumPy, i.e. optimistic for the reference)."""
+    import multiprocessing as mp
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc, ref_harness
+    orc.build()
+    use_ref = ref_harness.load_ref_cyutils() is not None
+    cores = os.cpu_count() or 1
+    win = 1024
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for _ in range(max(args.warmup, 0) and 1):
+            pool.map(_ref_worker, [(1000 + c, 256, use_ref) for c in range(cores)])
+        t0 = time.perf_counter()
+        cells = 0
+        for s in range(args.steps):
+            res = pool.map(_ref_worker, [(s * cores + c, win, use_ref) for c in range(cores)])
+            cells += sum(r[0] for r in res)
+        dt = time.perf_counter() - t0
+    val = cells / dt / 1e6
+    line = {"metric": METRIC, "value": val, "unit": "Mcells/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "fractal DEM, dX=dY=30 m, slope+aspect + UCA + TWI, fill_flats=False, "
+                                   "drain_pits_path=False, drain_pits=False; bounded sample: %d windows of %dx%d per "
+                                   "step (one per host core)" % (cores, win, win)},
+            "cpu_baseline": {"value": val, "unit": "Mcells/s", "cores": cores,
+                             "kind": "reference" if use_ref else "port",
+                             "sample": ("UCA sweep = the reference's compiled cyutils.drain_area (oracle/_ref); " if use_ref
+                                        else "UCA sweep = oracle restatement; ") +
+                                       "stencil/flats/graph/TWI = oracle C port; %d processes x %dx%d windows x %d steps"
+                                       % (cores, win, win, args.steps)},
+            "e2e": {"value": val, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from pydem_b200 import synth, _lib, _pinned, tile as T, DEMProcessor
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    _lib.init(local)
+    L = _lib.load()
+    n = args.size
+    peak_gbs, peak_src = measured_peak()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if world == 1:
+        E = synth.fractal_dem(n, 0)
+        stream = torch.cuda.current_stream().cuda_stream
+        dt = T.DeviceTile(n, n, stream=stream)
+        dt.set_spacing(SPACING, SPACING)
+        dt.upload(T.F_ELEV, E)
+        stats = {}
+
+        def step():
+            dt.slopes_directions()
+            st = dt.uca(drain_pits=0)
+            dt.twi()
+            stats.update(st)
+            return st
+        cells_per_step = n * n
+        workload = ("%dx%d fractal DEM (spectral synthesis, seed 0, H=0.8, 1..1001 m), dX=dY=30 m, "
+                    "slope+aspect + UCA + TWI, fill_flats=False, drain_pits_path=False, drain_pits=False "
+                    "(BASELINE.json configs[1], 'sinks' variant)" % (n, n))
+        parallelism = "1 GPU, single tile"
+    else:
+        from pydem_b200 import sharded
+        sh = sharded.ShardedDEM(rows_per_rank=n, cols=n, spacing=SPACING, seed=2)
+        stats = {}
+
+        def step():
+            st = sh.step()
+            stats.update(st)
+            return st
+        cells_per_step = n * n * world
+        workload = ("%dx%d value-noise DEM row-sharded over %d GPUs (%d rows each, halo rows over NCCL), dX=dY=30 m, "
+                    "slope+aspect + UCA + TWI, conditioning flags off, drain_pits=False" % (n * world, n, world, n))
+        parallelism = "row-block x%d" % world
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = L.pdm_launch_count()
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    sweep_ms, sweep_kernel_ms, slopes_ms = [], [], []
+    ev0.record()
+    for _ in range(args.steps):
+        st = step()
+        sweep_ms.append(st.get("ms_sweep", 0.0)); sweep_kernel_ms.append(st.get("ms_sweep_kernel", 0.0))
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = L.pdm_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    ms_per_step = ms / args.steps
+    value = cells_per_step / (ms_per_step * 1e-3) / 1e6
+
+    # ---- e2e through the reference-facing operator (host buffers, copies inside the timed region)
+    e2e = None
+    if world == 1:
+        Eh = _pinned.pinned_copy(E)
+        kw = dict(dX=SPACING, dY=SPACING, fill_flats=False, drain_pits_path=False, drain_pits=False)
+
+        def e2e_step():
+            dp = DEMProcessor(elev=Eh, **kw)
+            twi = dp.calc_twi()
+            chk = float(twi[n // 2, n // 2])   # the step's result is read on the host
+            dp._free_tile()
+            return chk
+        dt.close()
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        t_e2e = (time.perf_counter() - t0) / args.steps
+        e2e = {"value": cells_per_step / t_e2e / 1e6, "unit": "Mcells/s", "ms_per_step": t_e2e * 1e3,
+               "h2d_bytes_per_step": int(n * n * 8 + 4 * n * 8),
+               "d2h_bytes_per_step": int(n * n * (8 * 4 + 3))}
+    else:
+        e2e = sh.e2e(args.steps)
+
+    if rank != 0:
+        return
+    ms_sweep = float(np.mean(sweep_kernel_ms)) if sweep_kernel_ms and sweep_kernel_ms[0] else float(np.mean(sweep_ms))
+    cells_rank = cells_per_step / world
+    achieved = cells_rank * BYTES_PER_CELL / (ms_sweep * 1e-3) / 1e9 if ms_sweep else None
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mcells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload, "parallelism": parallelism,
+                   "l2": "inputs larger than L2 (elev %.0f MB, every intermediate field >= %.0f MB vs 126 MB L2)"
+                         % (n * n * 8 / 1e6, n * n / 1e6)},
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"kernel": "wl::k_worklist<DrainOp<0>> (UCA accumulation sweep)", "bound": "hbm",
+                     "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": (achieved / peak_gbs) if achieved else None,
+                     "traffic": PROFILE_TRAFFIC.get(n), "peak_source": peak_src,
+                     "algorithmic_bytes_per_cell": BYTES_PER_CELL, "cells_per_launch": int(cells_rank),
+                     "ms_per_launch": ms_sweep,
+                     "note": "dependency/latency-bound graph sweep; traffic = dram bytes of one ncu --set full capture"},
+        "stages": {k: stats.get(k) for k in ("ms_graph", "ms_sweep", "ms_sweep_scan", "ms_sweep_kernel", "n_sources",
+                                              "n_queue_items", "n_drained", "n_undone", "n_edge_todo")},
+    }
+    if world == 1:
+        line["cpu_baseline"] = cpu_baseline_leg(E)
+    print(json.dumps(line), flush=True)
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of the sweep kernel, one launch (profiles/, per size)
+PROFILE_TRAFFIC = {4096: 6.21e9}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=4096, help="rows (per GPU) = columns of the DEM")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

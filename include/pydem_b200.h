@@ -22,6 +22,7 @@
 #ifndef PYDEM_B200_H
 #define PYDEM_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -83,6 +84,8 @@ typedef struct {
     float   ms_graph;        /* device time: section/proportion + receivers + pits + in-degree */
     float   ms_sweep;        /* device time: accumulation sweep */
     float   ms_total;
+    float   ms_sweep_scan;   /* sweep kernel: until the last warp finished its source stripe */
+    float   ms_sweep_kernel; /* sweep kernel: first warp in to last warp out (globaltimer) */
 } pdm_uca_stats;
 
 typedef struct {
@@ -102,6 +105,11 @@ const char *pdm_last_error(void);
  * call after fork() in a ProcessManager worker, process_manager.py:1267). */
 int         pdm_init(int device);
 int         pdm_device_count(int *count);
+/* number of CUDA kernels this library has launched in this process (bench accounting) */
+unsigned long long pdm_launch_count(void);
+/* page-locked host buffers for the host-buffer entry points (full-rate PCIe copies) */
+int         pdm_host_alloc(size_t bytes, void **out);
+int         pdm_host_free(void *p);
 void        pdm_default_uca_params(pdm_uca_params *p);
 void        pdm_default_twi_params(pdm_twi_params *p);
 

@@ -31,7 +31,8 @@ class UcaStats(ct.Structure):
                 ("n_undone", ct.c_int64), ("n_pits", ct.c_int64), ("n_pit_edges", ct.c_int64),
                 ("n_pits_undrained", ct.c_int64), ("n_queue_items", ct.c_int64), ("n_restarts", ct.c_int64),
                 ("n_edge_todo", ct.c_int64), ("min_area", ct.c_double), ("ms_graph", ct.c_float),
-                ("ms_sweep", ct.c_float), ("ms_total", ct.c_float)]
+                ("ms_sweep", ct.c_float), ("ms_total", ct.c_float), ("ms_sweep_scan", ct.c_float),
+                ("ms_sweep_kernel", ct.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -46,7 +47,7 @@ class TwiParams(ct.Structure):
 # every symbol include/pydem_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "pdm_abi_version", "pdm_last_error", "pdm_init", "pdm_device_count", "pdm_default_uca_params",
-    "pdm_default_twi_params", "pdm_tile_create", "pdm_tile_destroy", "pdm_tile_set_spacing",
+    "pdm_default_twi_params", "pdm_launch_count", "pdm_host_alloc", "pdm_host_free", "pdm_tile_create", "pdm_tile_destroy", "pdm_tile_set_spacing",
     "pdm_tile_upload", "pdm_tile_download", "pdm_tile_device_ptr", "pdm_tile_mark_resident", "pdm_tile_sync",
     "pdm_tile_slopes_directions", "pdm_tile_find_flats", "pdm_tile_uca", "pdm_tile_uca_update",
     "pdm_tile_twi", "pdm_slopes_directions", "pdm_uca", "pdm_uca_update", "pdm_twi",
@@ -71,6 +72,9 @@ def load():
     L.pdm_last_error.restype = ct.c_char_p
     L.pdm_init.argtypes = [ct.c_int]
     L.pdm_device_count.argtypes = [ct.POINTER(ct.c_int)]
+    L.pdm_launch_count.restype = ct.c_ulonglong
+    L.pdm_host_alloc.argtypes = [ct.c_size_t, ct.POINTER(_vp)]
+    L.pdm_host_free.argtypes = [_vp]
     L.pdm_default_uca_params.argtypes = [ct.POINTER(UcaParams)]
     L.pdm_default_uca_params.restype = None
     L.pdm_default_twi_params.argtypes = [ct.POINTER(TwiParams)]

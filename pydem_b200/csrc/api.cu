@@ -10,6 +10,7 @@
 #include "pdm_internal.cuh"
 
 static thread_local char g_err[512] = "";
+unsigned long long g_pdm_launches = 0;
 
 void pdm_set_error(const char *fmt, ...)
 {
@@ -55,6 +56,21 @@ extern "C" {
 
 int pdm_abi_version(void) { return PDM_ABI_VERSION; }
 const char *pdm_last_error(void) { return g_err; }
+
+unsigned long long pdm_launch_count(void) { return g_pdm_launches; }
+
+int pdm_host_alloc(size_t bytes, void **out)
+{
+    if (!out) { pdm_set_error("pdm_host_alloc: NULL out"); return PDM_ERR_ARG; }
+    PDM_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return PDM_OK;
+}
+
+int pdm_host_free(void *p)
+{
+    if (p) PDM_CUDA(cudaFreeHost(p));
+    return PDM_OK;
+}
 
 int pdm_device_count(int *count)
 {
@@ -304,6 +320,8 @@ int pdm_tile_uca(pdm_tile *t, const pdm_uca_params *p_in, pdm_uca_stats *stats)
     st.n_pits = t->n_pits;
     st.n_pit_edges = t->n_pit_edges;
     st.n_pits_undrained = (int64_t)t->h_counters[CT_PITS_UNDRAINED];
+    st.ms_sweep_scan = (float)((double)(t->h_counters[CT_T_SCAN] - t->h_counters[CT_T_START]) * 1e-6);
+    st.ms_sweep_kernel = (float)((double)(t->h_counters[CT_T_END] - t->h_counters[CT_T_START]) * 1e-6);
     if (st.n_undone > 0) {
         // circular references: the reference restarts from the highest undone cells
         // (dem_processing.py:951-964); replayed level-synchronously.

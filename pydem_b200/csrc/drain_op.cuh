@@ -46,7 +46,7 @@ struct DrainOp {
     __device__ __forceinline__ bool skip(int32_t r) const { return MODE == 1 && (st[r] & ST_START); }
 
     // Drain one ready cell; returns the receiver this lane continues with (or -1).
-    __device__ __forceinline__ int32_t process(int32_t i, const wl::Queue &q) const
+    __device__ __forceinline__ int32_t process(int32_t i, const wl::Queue &q, int32_t &defer) const
     {
         using wl::dep_zero;
         const uint8_t lk = link[i];
@@ -101,7 +101,7 @@ struct DrainOp {
         const bool rdy1 = k1 && o1 == 1, rdy2 = k2 && o2 == 1;
         if (rdy1 && rdy2) {
             // follow the larger share, hand the other receiver to an idle lane
-            if (p >= 0.5) { nxt = r1; q.push(r2); } else { nxt = r2; q.push(r1); }
+            if (p >= 0.5) { nxt = r1; defer = r2; } else { nxt = r2; defer = r1; }
         } else if (rdy1) nxt = r1;
         else if (rdy2) nxt = r2;
         return nxt;

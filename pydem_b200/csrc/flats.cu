@@ -106,17 +106,17 @@ int pdm_launch_flats(pdm_tile *t)
     dim3 block(32, 8);
     dim3 grid((unsigned)((t->C + 31) / 32), (unsigned)((t->R + 7) / 8));
     k_ccl_merge<<<grid, block, 0, t->stream>>>(t->flat0, t->label, t->R, t->C);
-    PDM_CUDA(cudaGetLastError());
+    PDM_LAUNCHED();
     k_ccl_flatten<<<(unsigned)((t->N + 255) / 256), 256, 0, t->stream>>>(t->flat0, t->label, t->N);
-    PDM_CUDA(cudaGetLastError());
+    PDM_LAUNCHED();
     k_flats_extend<<<grid, block, 0, t->stream>>>(t->elev, t->flat0, t->label, t->R, t->C, t->flats, t->mag, t->dir);
-    PDM_CUDA(cudaGetLastError());
+    PDM_LAUNCHED();
     return PDM_OK;
 }
 
 int pdm_launch_find_flats(pdm_tile *t)
 {
     k_find_flats<<<(unsigned)((t->N + 255) / 256), 256, 0, t->stream>>>(t->mag, t->flats, t->N);
-    PDM_CUDA(cudaGetLastError());
+    PDM_LAUNCHED();
     return PDM_OK;
 }

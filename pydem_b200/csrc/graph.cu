@@ -213,7 +213,7 @@ int pdm_graph_links_pits(pdm_tile *t, const pdm_uca_params *p)
     PDM_CUDA(cudaMemsetAsync(t->indeg, 0, (size_t)t->N * sizeof(int32_t), t->stream));
     k_links<<<grid, block, 0, t->stream>>>(t->elev, t->dir, t->flats, t->th_row, t->R, t->C, t->link, t->prop,
                                            t->flat0, t->d_counters);
-    PDM_CUDA(cudaGetLastError());
+    PDM_LAUNCHED();
     t->n_pits = 0; t->n_pit_edges = 0;
     if (p->drain_pits) {
         int rc = pdm_launch_pits(t, p);
@@ -232,12 +232,12 @@ int pdm_launch_graph(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *st)
     PDM_CUDA(cudaMemsetAsync(t->edge_todo, 0, (size_t)t->N, t->stream));
     k_indeg<<<grid, block, 0, t->stream>>>(t->link, t->R, t->C, t->row_area, t->indeg, t->uca, t->taint,
                                            t->d_counters);
-    PDM_CUDA(cudaGetLastError());
+    PDM_LAUNCHED();
     const int64_t per = 2 * t->C + 2 * (t->R - 2);
     k_border_todo<<<(unsigned)((per + 255) / 256), 256, 0, t->stream>>>(
         t->elev, t->link, t->prop, t->R, t->C, t->pit_beg, t->pit_end, t->pit_w, t->pit_dst, t->n_pit_edges,
         t->edge_todo, t->taint, t->d_counters);
-    PDM_CUDA(cudaGetLastError());
+    PDM_LAUNCHED();
     return PDM_OK;
 }
 
@@ -247,6 +247,6 @@ int pdm_launch_section_export(pdm_tile *t)
     dim3 block(32, 8);
     dim3 grid((unsigned)((t->C + 31) / 32), (unsigned)((t->R + 7) / 8));
     k_section_export<<<grid, block, 0, t->stream>>>(t->dir, t->flats, t->th_row, t->R, t->C, t->section);
-    PDM_CUDA(cudaGetLastError());
+    PDM_LAUNCHED();
     return PDM_OK;
 }

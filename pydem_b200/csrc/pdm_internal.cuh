@@ -65,6 +65,14 @@ int pdm_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
         if (e__ != cudaSuccess) return pdm_cuda_fail(e__, #call, __FILE__, __LINE__); \
     } while (0)
 
+// every kernel launch goes through this: error check + launch accounting (pdm_launch_count)
+extern unsigned long long g_pdm_launches;
+#define PDM_LAUNCHED()                       \
+    do {                                     \
+        PDM_CUDA(cudaGetLastError());        \
+        g_pdm_launches++;                    \
+    } while (0)
+
 // kernels' launchers (each returns a pdm_status)
 int pdm_launch_geometry(pdm_tile *t);
 int pdm_launch_slopes(pdm_tile *t);
@@ -80,23 +88,29 @@ int pdm_restart_rounds(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *st);
 int pdm_graph_links_pits(pdm_tile *t, const pdm_uca_params *p);
 int pdm_launch_pits(pdm_tile *t, const pdm_uca_params *p);
 
-// counters slots
+// counters slots.  The queue counters are hammered by every warp (fetch-and-add tickets,
+// pushes, completion counts, termination polls): each lives on its own 128-byte line so the
+// L2 serialises them independently.
 enum {
     CT_QTAIL = 0,      // sweep queue: items produced
-    CT_QHEAD = 1,      // tickets handed out
-    CT_QDONE = 2,      // items completely processed
-    CT_PHASE1 = 3,     // warps that finished the source scan
-    CT_DRAINED = 4,    // cells drained
-    CT_SOURCES = 5,
-    CT_UNDONE = 6,
-    CT_BADSEC = 7,
-    CT_NPITS = 8,
-    CT_NPITEDGES = 9,
-    CT_PITS_UNDRAINED = 10,
-    CT_EDGE_TODO = 11,
-    CT_FLAG = 12,
-    CT_TMP0 = 13,
-    CT_TMP1 = 14,
-    CT_ABORT = 15,
-    CT_N = 32
+    CT_QHEAD = 16,     // tickets handed out
+    CT_QDONE = 32,     // items completely processed
+    CT_PHASE1 = 48,    // warps that finished the source scan
+    CT_DRAINED = 64,   // cells drained
+    CT_SOURCES = 80,
+    CT_UNDONE = 81,
+    CT_BADSEC = 82,
+    CT_NPITS = 83,
+    CT_NPITEDGES = 96,
+    CT_PITS_UNDRAINED = 97,
+    CT_EDGE_TODO = 84,
+    CT_FLAG = 98,
+    CT_TMP0 = 99,
+    CT_TMP1 = 100,
+    CT_ABORT = 101,
+    CT_T_START = 112,  // work-list timing (globaltimer ns): first warp in
+    CT_T_SCAN = 113,   // last warp finished its seed scan (+ scan-born chains)
+    CT_T_END = 114,    // last warp out
+    CT_N = 128
 };
+

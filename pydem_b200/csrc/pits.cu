@@ -372,7 +372,7 @@ int pdm_launch_pits(pdm_tile *t, const pdm_uca_params *p)
     }
     PDM_CUDA(cudaMemsetAsync(t->d_counters + CT_TMP0, 0, sizeof(unsigned long long), t->stream));
     k_pit_compact<<<(unsigned)((t->N + 255) / 256), 256, 0, t->stream>>>(t->flat0, t->N, t->pit_cell, t->d_counters);
-    PDM_CUDA(cudaGetLastError());
+    PDM_LAUNCHED();
     for (int attempt = 0; attempt < 8; attempt++) {
         PDM_CUDA(cudaMemsetAsync(t->d_counters + CT_NPITEDGES, 0, sizeof(unsigned long long), t->stream));
         PDM_CUDA(cudaMemsetAsync(t->d_counters + CT_PITS_UNDRAINED, 0, sizeof(unsigned long long), t->stream));
@@ -386,7 +386,7 @@ int pdm_launch_pits(pdm_tile *t, const pdm_uca_params *p)
         a.max_iter = (int)p->drain_pits_max_iter; a.max_dist = (int)p->drain_pits_max_dist;
         a.min_border = p->drain_pits_min_border; a.max_dist_xy = p->drain_pits_max_dist_xy; a.W = W;
         k_pit_search<<<(unsigned)blocks, PIT_THREADS, smem, t->stream>>>(a);
-        PDM_CUDA(cudaGetLastError());
+        PDM_LAUNCHED();
         rc = read_ctr(t);
         if (rc) return rc;
         if (t->h_counters[CT_ABORT]) {

@@ -132,7 +132,7 @@ int pdm_launch_geometry(pdm_tile *t)
 {
     int64_t n = t->R;
     k_geometry<<<(unsigned)((n + 255) / 256), 256, 0, t->stream>>>(t->dX, t->dY, t->thA, t->R, t->dg, t->th_row);
-    PDM_CUDA(cudaGetLastError());
+    PDM_LAUNCHED();
     return PDM_OK;
 }
 
@@ -142,6 +142,6 @@ int pdm_launch_slopes(pdm_tile *t)
     dim3 block(32, 8);
     dim3 grid((unsigned)((t->C + 31) / 32), (unsigned)((t->R + 7) / 8));
     k_slopes<<<grid, block, 0, t->stream>>>(t->elev, t->R, t->C, g, t->mag, t->dir, t->flat0, t->label);
-    PDM_CUDA(cudaGetLastError());
+    PDM_LAUNCHED();
     return PDM_OK;
 }

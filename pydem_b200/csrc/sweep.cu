@@ -77,13 +77,13 @@ int pdm_launch_sweep_full(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *s
     int rc = wl::reset_queue(t);
     if (rc) return rc;
     DrainOp<0> op{t->link, t->prop, t->uca, t->taint, t->indeg, nullptr, (int32_t)t->C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w};
-    wl::k_worklist<<<g_sweep_blocks, 256, 0, t->stream>>>(op, wl::DomainAll{t->N}, wl::Queue{t->queue, t->d_counters});
-    PDM_CUDA(cudaGetLastError());
+    wl::k_worklist<<<g_sweep_blocks, 256, 0, t->stream>>>(op, wl::DomainAll{t->N}, wl::Queue{t->queue, t->d_counters, (long long)t->N});
+    PDM_LAUNCHED();
     const double limit_area = p->uca_saturation_limit * 2 * t->min_area;
     k_uca_finalize<<<(unsigned)((t->N + 255) / 256), 256, 0, t->stream>>>(
         t->elev, t->flats, t->indeg, t->taint, t->uca, t->edge_done, t->N, p->apply_uca_limit_edges, limit_area,
         t->d_counters);
-    PDM_CUDA(cudaGetLastError());
+    PDM_LAUNCHED();
     return PDM_OK;
 }
 
@@ -94,6 +94,6 @@ int pdm_launch_twi(pdm_tile *t, const pdm_twi_params *p)
     k_twi<<<(unsigned)((t->N + 255) / 256), 256, 0, t->stream>>>(t->uca, t->mag, t->twi, t->N, p->twi_min_slope, cap,
                                                                  p->apply_twi_limits_on_uca, p->apply_twi_limits,
                                                                  twi_sat);
-    PDM_CUDA(cudaGetLastError());
+    PDM_LAUNCHED();
     return PDM_OK;
 }

@@ -90,7 +90,7 @@ struct FloodOp {
         }
         return !(st_fetch_or(st, r, ST_REACH) & ST_REACH);
     }
-    __device__ __forceinline__ int32_t process(int32_t i, const wl::Queue &q) const
+    __device__ __forceinline__ int32_t process(int32_t i, const wl::Queue &q, int32_t &defer) const
     {
         const uint8_t lk = link[i];
         int32_t nxt = -1;
@@ -109,7 +109,7 @@ struct FloodOp {
         }
         if (lk & LK_KEEP2) {
             const int32_t r = i + wl::off_e2(sec, C);
-            if (visit(r)) { if (nxt < 0) nxt = r; else q.push(r); }
+            if (visit(r)) { if (nxt < 0) nxt = r; else defer = r; }
         }
         return nxt;
     }
@@ -162,34 +162,34 @@ int pdm_launch_update(pdm_tile *t, const pdm_uca_params *p, const double *const 
     PDM_CUDA(cudaMemsetAsync(t->d_counters + CT_SOURCES, 0, sizeof(unsigned long long), t->stream));
     PDM_CUDA(cudaMemsetAsync(t->d_counters + CT_EDGE_TODO, 0, sizeof(unsigned long long), t->stream));
     k_upd_init<<<(unsigned)((t->N + 255) / 256), 256, 0, t->stream>>>(t->flats, t->N, delta, stt, t->indeg, t->edge_todo);
-    PDM_CUDA(cudaGetLastError());
+    PDM_LAUNCHED();
     const int64_t per = 2 * C + 2 * (R - 2);
     k_upd_border<<<(unsigned)((per + 255) / 256), 256, 0, t->stream>>>(t->edge_buf_d, t->edge_buf_b, t->edge_buf_b + per_all,
                                                                        t->uca, t->flats, R, C, delta, stt, t->edge_todo,
                                                                        t->d_counters);
-    PDM_CUDA(cudaGetLastError());
-    const wl::Queue q{t->queue, t->d_counters};
+    PDM_LAUNCHED();
+    const wl::Queue q{t->queue, t->d_counters, (long long)t->N};
     const wl::DomainBorder dom{R, C};
     // flood 1: cone + restricted in-degree (820-831)
     if ((rc = wl::reset_queue(t))) return rc;
     wl::k_worklist<<<g_blocks_flood0, 256, 0, t->stream>>>(
         FloodOp<0>{t->link, t->prop, stt, t->indeg, (int32_t)C, t->pit_beg, t->pit_end, t->pit_dst}, dom, q);
-    PDM_CUDA(cudaGetLastError());
+    PDM_LAUNCHED();
     // sweep of the deltas (836-842)
     if ((rc = wl::reset_queue(t))) return rc;
     wl::k_worklist<<<g_blocks_drain1, 256, 0, t->stream>>>(
         DrainOp<1>{t->link, t->prop, delta, nullptr, t->indeg, stt, (int32_t)C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w},
         dom, q);
-    PDM_CUDA(cudaGetLastError());
+    PDM_LAUNCHED();
     PDM_CUDA(cudaMemcpyAsync(t->h_counters + CT_DRAINED, t->d_counters + CT_DRAINED, sizeof(unsigned long long),
                              cudaMemcpyDeviceToHost, t->stream));
     // flood 2: remaining todo cells taint everything downstream (848-853)
     if ((rc = wl::reset_queue(t))) return rc;
     wl::k_worklist<<<g_blocks_flood1, 256, 0, t->stream>>>(
         FloodOp<1>{t->link, t->prop, stt, t->indeg, (int32_t)C, t->pit_beg, t->pit_end, t->pit_dst}, dom, q);
-    PDM_CUDA(cudaGetLastError());
+    PDM_LAUNCHED();
     k_upd_finalize<<<(unsigned)((t->N + 255) / 256), 256, 0, t->stream>>>(delta, stt, t->N, t->uca, t->edge_done);
-    PDM_CUDA(cudaGetLastError());
+    PDM_LAUNCHED();
     PDM_CUDA(cudaEventRecord(t->ev[2], t->stream));
     PDM_CUDA(cudaMemcpyAsync(t->h_counters + CT_SOURCES, t->d_counters + CT_SOURCES, sizeof(unsigned long long),
                              cudaMemcpyDeviceToHost, t->stream));

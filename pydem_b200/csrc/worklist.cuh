@@ -5,9 +5,10 @@
 // co-resident) runs until global quiescence:
 //   * seeds are found by scanning a domain (all cells, or just the tile perimeter) for
 //     Op::is_seed(cell),
-//   * Op::process(cell, push) handles one ready cell and returns the cell this lane
-//     continues with (chain following) or -1; additional ready cells are handed to idle
-//     lanes through a global queue (push),
+//   * Op::process(cell, queue, defer) handles one ready cell and returns the cell this lane
+//     continues with (chain following) or -1; one more ready cell can be returned in `defer`
+//     (pushed to the global queue with one warp-aggregated fetch-and-add), further ones are
+//     pushed directly (rare: pit drains),
 //   * termination: every warp has finished its scan and scan-born chains (CT_PHASE1 ==
 //     #warps) and every queued item has been completely processed (CT_QDONE == CT_QTAIL).
 //     Reading QDONE, then PHASE1, then QTAIL makes the test race-free: both counters are
@@ -37,9 +38,17 @@ __device__ __forceinline__ void st_volatile_i32(int32_t *p, int32_t v)
     asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 struct Queue {
     int32_t *slots;
     unsigned long long *ctr;
+    long long cap;  // number of slots (a cell is queued at most once per run: N suffices)
     __device__ __forceinline__ void push(int32_t cell) const
     {
         const unsigned long long slot = atomicAdd(&ctr[CT_QTAIL], 1ULL);
@@ -76,54 +85,45 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
     int64_t scan = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool scanning = scan < dsize;
     int32_t cur = -1;
-    int origin = 0;  // 1: chain started at a scanned seed, 2: at a queue item
+    long long ticket = -1;  // queue slot this lane is entitled to (fetch-and-add ticket, never fails)
+    int origin = 0;         // 1: chain started at a scanned seed, 2: at a queue item
     bool p1_reported = false;
     unsigned long long processed = 0;
-    unsigned iter = 0;
+    if (lane == 0) atomicMin(&q.ctr[CT_T_START], globaltimer_ns());
 
     for (;;) {
-        iter++;
-        // ---- acquire work: queue first (items on the critical path), then the next seed
-        bool want = cur < 0;
-        const unsigned want_mask = __ballot_sync(full, want);
-        const unsigned scan_mask = __ballot_sync(full, scanning);
-        if (want_mask) {
-            if (scan_mask == 0 || (iter & 3u) == 0) {
-                int32_t base = 0, got = 0;
-                if (lane == 0) {
-                    const unsigned long long h = ld_volatile_u64(q.ctr + CT_QHEAD);
-                    const unsigned long long t = ld_volatile_u64(q.ctr + CT_QTAIL);
-                    if (t > h) {
-                        unsigned long long k = (unsigned long long)__popc(want_mask);
-                        if (k > t - h) k = t - h;
-                        if (atomicCAS(&q.ctr[CT_QHEAD], h, h + k) == h) { base = (int32_t)h; got = (int32_t)k; }
-                    }
-                }
-                base = __shfl_sync(full, base, 0);
-                got = __shfl_sync(full, got, 0);
-                if (got) {
-                    const int rank = __popc(want_mask & ((1u << lane) - 1u));
-                    if (want && rank < got) {
-                        int32_t v;
-                        do { v = ld_volatile_i32(q.slots + base + rank); } while (v < 0);  // slot reserved, store in flight
-                        cur = v; origin = 2; want = false;
-                    }
-                }
+        // ---- acquire work: the next seed of this lane's scan stripe, or -- once the stripe is
+        //      exhausted -- a queue ticket.  Tickets are handed out with fetch-and-add, so
+        //      claiming never retries (a CAS-claimed queue serialises at one claim per L2 round
+        //      trip); a ticket whose slot is still empty simply waits for its producer.
+        if (cur < 0 && scanning) {
+            for (int s = 0; s < 8 && scan < dsize; s++) {
+                const int32_t c = dom.cell(scan);
+                scan += nthreads;
+                if (op.is_seed(c)) { cur = c; origin = 1; break; }
             }
-            if (want && scanning) {
-                for (int s = 0; s < 8 && scan < dsize; s++) {
-                    const int32_t c = dom.cell(scan);
-                    scan += nthreads;
-                    if (op.is_seed(c)) { cur = c; origin = 1; break; }
-                }
-                if (scan >= dsize) scanning = false;
-            }
+            if (scan >= dsize) scanning = false;
+        }
+        const bool need_ticket = cur < 0 && !scanning && ticket < 0;
+        const unsigned need_mask = __ballot_sync(full, need_ticket);
+        if (need_mask) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&q.ctr[CT_QHEAD], (unsigned long long)__popc(need_mask));
+            base = __shfl_sync(full, base, 0);
+            if (need_ticket) ticket = (long long)(base + __popc(need_mask & ((1u << lane) - 1u)));
+        }
+        if (cur < 0 && ticket >= 0 && ticket < q.cap) {
+            const int32_t v = ld_volatile_i32(q.slots + ticket);
+            if (v >= 0) { cur = v; origin = 2; ticket = -1; }
         }
         // ---- scan accounting: a warp reports once its scan and scan-born chains have ended
         if (!p1_reported) {
             const unsigned busy1 = __ballot_sync(full, scanning || (cur >= 0 && origin == 1));
             if (busy1 == 0) {
-                if (lane == 0) atomicAdd(&q.ctr[CT_PHASE1], 1ULL);
+                if (lane == 0) {
+                    atomicAdd(&q.ctr[CT_PHASE1], 1ULL);
+                    atomicMax(&q.ctr[CT_T_SCAN], globaltimer_ns());
+                }
                 p1_reported = true;
             }
         }
@@ -141,23 +141,34 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
                 }
                 term = __shfl_sync(full, term, 0);
                 if (term) break;
-                __nanosleep(200);
+                __nanosleep(100);
             }
             continue;
         }
         // ---- one step per working lane
         bool finished_q = false;
+        int32_t defer = -1;  // second ready receiver: handed to the queue, warp-aggregated below
         if (cur >= 0) {
             processed++;
-            const int32_t nxt = op.process(cur, q);
+            const int32_t nxt = op.process(cur, q, defer);
             cur = nxt;
             if (cur < 0) { finished_q = (origin == 2); origin = 0; }
+        }
+        const unsigned pm = __ballot_sync(full, defer >= 0);
+        if (pm) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&q.ctr[CT_QTAIL], (unsigned long long)__popc(pm));
+            base = __shfl_sync(full, base, 0);
+            if (defer >= 0) st_volatile_i32(q.slots + base + __popc(pm & ((1u << lane) - 1u)), defer);
         }
         const unsigned fq = __ballot_sync(full, finished_q);
         if (fq && lane == 0) atomicAdd(&q.ctr[CT_QDONE], (unsigned long long)__popc(fq));
     }
     for (int o = 16; o > 0; o >>= 1) processed += __shfl_down_sync(full, processed, o);
-    if (lane == 0 && processed) atomicAdd(&q.ctr[CT_DRAINED], processed);
+    if (lane == 0) {
+        if (processed) atomicAdd(&q.ctr[CT_DRAINED], processed);
+        atomicMax(&q.ctr[CT_T_END], globaltimer_ns());
+    }
 }
 
 // facet -> flat-index offsets of the cardinal (e1) and diagonal (e2) receiver
@@ -200,7 +211,9 @@ int grid_for(K kernel, int *blocks_out)
 inline int reset_queue(pdm_tile *t)
 {
     PDM_CUDA(cudaMemsetAsync(t->queue, 0xFF, (size_t)(t->N + 1) * sizeof(int32_t), t->stream));
-    PDM_CUDA(cudaMemsetAsync(t->d_counters, 0, 5 * sizeof(unsigned long long), t->stream));  // QTAIL..DRAINED
+    PDM_CUDA(cudaMemsetAsync(t->d_counters, 0, (CT_DRAINED + 1) * sizeof(unsigned long long), t->stream));  // QTAIL..DRAINED
+    PDM_CUDA(cudaMemsetAsync(t->d_counters + CT_T_START, 0xFF, sizeof(unsigned long long), t->stream));
+    PDM_CUDA(cudaMemsetAsync(t->d_counters + CT_T_SCAN, 0, 2 * sizeof(unsigned long long), t->stream));
     return PDM_OK;
 }
 

@@ -27,7 +27,7 @@ import warnings
 
 import numpy as np
 
-from . import _lib
+from . import _lib, _pinned
 
 FLAT_ID = np.nan
 FLAT_ID_INT = -1
@@ -97,6 +97,10 @@ class DEMProcessor(object):
         _lib.init(self.device)
         return L
 
+    # one parked device tile per shape: ProcessManager-style callers build a fresh DEMProcessor
+    # per tile and stage (process_manager.py:54-315), all of the same shape
+    _TILE_CACHE = {}
+
     def _get_tile(self):
         L = self._lib()
         shape = tuple(self.elev.shape)
@@ -105,19 +109,36 @@ class DEMProcessor(object):
         if self._tile is None:
             if len(shape) != 2:
                 raise ValueError("elev must be 2-D")
-            h = ct.c_void_p()
-            _lib.check(L.pdm_tile_create(shape[0], shape[1], None, ct.byref(h)))
+            key = (shape, _lib._device)
+            h = DEMProcessor._TILE_CACHE.pop(key, None)
+            if h is None:
+                h = ct.c_void_p()
+                _lib.check(L.pdm_tile_create(shape[0], shape[1], None, ct.byref(h)))
             self._tile, self._tile_shape = h, shape
         return self._tile
 
     def _free_tile(self):
         if self._tile is not None:
             try:
-                _lib.load().pdm_tile_destroy(self._tile)
+                key = (self._tile_shape, _lib._device)
+                if key not in DEMProcessor._TILE_CACHE:
+                    DEMProcessor._TILE_CACHE[key] = self._tile
+                else:
+                    _lib.load().pdm_tile_destroy(self._tile)
             except Exception:
                 pass
             self._tile = None
             self._resident = set()
+
+    @classmethod
+    def release_device_memory(cls):
+        """Free the parked device tiles."""
+        for h in cls._TILE_CACHE.values():
+            try:
+                _lib.load().pdm_tile_destroy(h)
+            except Exception:
+                pass
+        cls._TILE_CACHE.clear()
 
     def __del__(self):
         self._free_tile()
@@ -133,7 +154,7 @@ class DEMProcessor(object):
         self._resident.add(field)
 
     def _down(self, field):
-        out = np.empty(self._tile_shape, dtype=_lib.FIELD_DTYPE[field])
+        out = _pinned.empty(self._tile_shape, _lib.FIELD_DTYPE[field])
         _lib.check(_lib.load().pdm_tile_download(self._get_tile(), field, _lib.ptr(out)))
         return out
 

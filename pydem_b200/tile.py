@@ -1,0 +1,97 @@
+"""``DeviceTile``: thin Python handle over the ``pdm_tile_*`` C ABI -- fields stay in HBM
+between stages.  Used by bench.py (device-resident throughput), the sharded driver and the
+tests; ``DEMProcessor`` is the reference-compatible operator built on the same calls."""
+import ctypes as ct
+
+import numpy as np
+
+from . import _lib
+from ._lib import (F_DIR, F_EDGE_DONE, F_EDGE_TODO, F_ELEV, F_FLATS, F_MAG, F_PROP, F_SECTION, F_TAINT,  # noqa: F401
+                   F_TWI, F_UCA)
+
+
+class DeviceTile(object):
+    def __init__(self, R, C, device=None, stream=None):
+        self.L = _lib.load()
+        _lib.init(device)
+        self.R, self.C = int(R), int(C)
+        self.shape = (self.R, self.C)
+        h = ct.c_void_p()
+        _lib.check(self.L.pdm_tile_create(self.R, self.C, ct.c_void_p(stream or 0), ct.byref(h)))
+        self.h = h
+        self.min_area = None
+
+    def close(self):
+        if getattr(self, "h", None) is not None:
+            self.L.pdm_tile_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def set_spacing(self, dX, dY, dX2=None, dY2=None):
+        R = self.R
+        dX = np.ascontiguousarray(np.broadcast_to(np.asarray(dX, "float64"), (R - 1,)))
+        dY = np.ascontiguousarray(np.broadcast_to(np.asarray(dY, "float64"), (R - 1,)))
+        dX2 = np.ascontiguousarray(np.broadcast_to(np.asarray(dX[0] if dX2 is None else dX2, "float64"), (R,)))
+        dY2 = np.ascontiguousarray(np.broadcast_to(np.asarray(dY[0] if dY2 is None else dY2, "float64"), (R,)))
+        thA = np.ascontiguousarray(np.arctan2(dY, dX)); thB = np.ascontiguousarray(np.arctan2(dX, dY))
+        P = _lib.ptr
+        _lib.check(self.L.pdm_tile_set_spacing(self.h, P(dX), P(dY), P(dX2), P(dY2), P(thA), P(thB)))
+        self.min_area = float(np.nanmin(dX2 * dY2))
+
+    def upload(self, field, arr):
+        a = np.ascontiguousarray(arr, dtype=_lib.FIELD_DTYPE[field])
+        assert a.shape == self.shape, (a.shape, self.shape)
+        _lib.check(self.L.pdm_tile_upload(self.h, field, _lib.ptr(a)))
+
+    def download(self, field, out=None):
+        if out is None:
+            out = np.empty(self.shape, dtype=_lib.FIELD_DTYPE[field])
+        _lib.check(self.L.pdm_tile_download(self.h, field, _lib.ptr(out)))
+        return out
+
+    def device_ptr(self, field):
+        p = ct.c_void_p()
+        _lib.check(self.L.pdm_tile_device_ptr(self.h, field, ct.byref(p)))
+        return p.value
+
+    def as_torch(self, field):
+        """Zero-copy torch view of a field (for NCCL send/recv of halo rows)."""
+        import torch
+
+        class _CAI(object):
+            pass
+        o = _CAI()
+        dt = np.dtype(_lib.FIELD_DTYPE[field])
+        o.__cuda_array_interface__ = dict(shape=self.shape, typestr=dt.str, data=(self.device_ptr(field), False),
+                                          version=2, strides=None)
+        return torch.as_tensor(o, device="cuda")
+
+    def mark_resident(self, field):
+        _lib.check(self.L.pdm_tile_mark_resident(self.h, field))
+
+    def sync(self):
+        _lib.check(self.L.pdm_tile_sync(self.h))
+
+    def slopes_directions(self):
+        _lib.check(self.L.pdm_tile_slopes_directions(self.h))
+
+    def find_flats(self):
+        _lib.check(self.L.pdm_tile_find_flats(self.h))
+
+    def uca(self, **flags):
+        p = _lib.UcaParams()
+        self.L.pdm_default_uca_params(ct.byref(p))
+        for k, v in flags.items():
+            setattr(p, k, v)
+        st = _lib.UcaStats()
+        _lib.check(self.L.pdm_tile_uca(self.h, ct.byref(p), ct.byref(st)))
+        return st.as_dict()
+
+    def twi(self, twi_min_area=None, **flags):
+        p = _lib.TwiParams()
+        self.L.pdm_default_twi_params(ct.byref(p))
+        p.twi_min_area = self.min_area if twi_min_area is None else twi_min_area
+        for k, v in flags.items():
+            setattr(p, k, v)
+        _lib.check(self.L.pdm_tile_twi(self.h, ct.byref(p)))
