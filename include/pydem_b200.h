@@ -54,7 +54,9 @@ typedef enum {
     PDM_F_SECTION = 8,   /* [i8]   DEMProcessor.section (debug attribute, dem_processing.py:137) */
     PDM_F_PROP = 9,      /* [f64]  DEMProcessor.proportion */
     PDM_F_TAINT = 10,    /* [f64]  propagated edge_todo weight (cyutils.pyx:163) */
-    PDM_F_COUNT_ = 11
+    PDM_F_FLAT0 = 11,    /* [u8]   mag == -1 before the one-pixel extension (shard halo exchange) */
+    PDM_F_LINK = 12,     /* [u8]   facet index + kept-receiver bits of each cell (shard halo exchange) */
+    PDM_F_COUNT_ = 13
 } pdm_field;
 
 /* Flags of DEMProcessor that act on the hot path (dem_processing.py:105-154). */
@@ -157,6 +159,29 @@ int pdm_tile_uca_update(pdm_tile *t, const pdm_uca_params *p,
                         pdm_uca_stats *stats);
 /* a9: calc_twi (1647-1677).  In: UCA, MAG.  Out: TWI (un-scaled). */
 int pdm_tile_twi(pdm_tile *t, const pdm_twi_params *p);
+
+/* ---- row shards (one tile per GPU = a block of rows of one big DEM) --------------------------
+ * The tile has one halo row on every side where another rank continues the grid.  The host
+ * driver fills halo rows (elev, then flat0, then link) from the neighbouring ranks -- NCCL
+ * send/recv on the row views obtained with pdm_tile_device_ptr -- and calls the stages in this
+ * order: slopes, ccl, {label_pack / label_unpack until no rank changed}, flats_extend, links,
+ * indeg, {sweep, outbox_pack, inbox_begin, inbox_apply until no rank sent}, finalize.
+ * Equivalent of pyDEM's cross-tile edge resolution (process_manager.py:1090-1249) with true
+ * halo stencils, so the sharded result equals the single-tile result. */
+int pdm_tile_set_window(pdm_tile *t, int64_t row_off, int64_t R_global, int64_t own_lo, int64_t own_hi,
+                        const double *th_row);
+int pdm_shard_slopes(pdm_tile *t);
+int pdm_shard_ccl(pdm_tile *t);
+int pdm_shard_label_pack(pdm_tile *t, int64_t row, void *out_labels, void *out_elev);
+int pdm_shard_label_unpack(pdm_tile *t, int64_t row, const void *in_labels, const void *in_elev, void *changed);
+int pdm_shard_flats_extend(pdm_tile *t);
+int pdm_shard_links(pdm_tile *t, const pdm_uca_params *p);
+int pdm_shard_indeg(pdm_tile *t);
+int pdm_shard_sweep(pdm_tile *t, int first);
+int pdm_shard_outbox_pack(pdm_tile *t, int side, void *out_area, void *out_taint, void *out_count, void *nonzero);
+int pdm_shard_inbox_begin(pdm_tile *t);
+int pdm_shard_inbox_apply(pdm_tile *t, int side, const void *in_area, const void *in_taint, const void *in_count);
+int pdm_shard_finalize(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *stats);
 
 /* ---- one-shot host-buffer calls ---------------------------------------------------------- */
 /* DEMProcessor.calc_slopes_directions with the conditioning flags off. */

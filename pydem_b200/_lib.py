@@ -13,10 +13,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpydem_b200.so")
 
 # pdm_field
-F_ELEV, F_MAG, F_DIR, F_FLATS, F_UCA, F_TWI, F_EDGE_TODO, F_EDGE_DONE, F_SECTION, F_PROP, F_TAINT = range(11)
+(F_ELEV, F_MAG, F_DIR, F_FLATS, F_UCA, F_TWI, F_EDGE_TODO, F_EDGE_DONE, F_SECTION, F_PROP, F_TAINT, F_FLAT0,
+ F_LINK) = range(13)
 FIELD_DTYPE = {F_ELEV: np.float64, F_MAG: np.float64, F_DIR: np.float64, F_FLATS: np.uint8,
                F_UCA: np.float64, F_TWI: np.float64, F_EDGE_TODO: np.uint8, F_EDGE_DONE: np.uint8,
-               F_SECTION: np.int8, F_PROP: np.float64, F_TAINT: np.float64}
+               F_SECTION: np.int8, F_PROP: np.float64, F_TAINT: np.float64, F_FLAT0: np.uint8, F_LINK: np.uint8}
 
 
 class UcaParams(ct.Structure):
@@ -50,7 +51,10 @@ EXPORTS = [
     "pdm_default_twi_params", "pdm_launch_count", "pdm_host_alloc", "pdm_host_free", "pdm_tile_create", "pdm_tile_destroy", "pdm_tile_set_spacing",
     "pdm_tile_upload", "pdm_tile_download", "pdm_tile_device_ptr", "pdm_tile_mark_resident", "pdm_tile_sync",
     "pdm_tile_slopes_directions", "pdm_tile_find_flats", "pdm_tile_uca", "pdm_tile_uca_update",
-    "pdm_tile_twi", "pdm_slopes_directions", "pdm_uca", "pdm_uca_update", "pdm_twi",
+    "pdm_tile_twi", "pdm_tile_set_window", "pdm_shard_slopes", "pdm_shard_ccl", "pdm_shard_label_pack",
+    "pdm_shard_label_unpack", "pdm_shard_flats_extend", "pdm_shard_links", "pdm_shard_indeg", "pdm_shard_sweep",
+    "pdm_shard_outbox_pack", "pdm_shard_inbox_begin", "pdm_shard_inbox_apply", "pdm_shard_finalize",
+    "pdm_slopes_directions", "pdm_uca", "pdm_uca_update", "pdm_twi",
 ]
 
 _lib = None
@@ -92,6 +96,16 @@ def load():
     L.pdm_tile_uca.argtypes = [_vp, ct.POINTER(UcaParams), ct.POINTER(UcaStats)]
     L.pdm_tile_uca_update.argtypes = [_vp, ct.POINTER(UcaParams)] + [_vp] * 12 + [ct.POINTER(UcaStats)]
     L.pdm_tile_twi.argtypes = [_vp, ct.POINTER(TwiParams)]
+    L.pdm_tile_set_window.argtypes = [_vp, _i64, _i64, _i64, _i64, _vp]
+    for nm in ("pdm_shard_slopes", "pdm_shard_ccl", "pdm_shard_flats_extend", "pdm_shard_indeg", "pdm_shard_inbox_begin"):
+        getattr(L, nm).argtypes = [_vp]
+    L.pdm_shard_label_pack.argtypes = [_vp, _i64, _vp, _vp]
+    L.pdm_shard_label_unpack.argtypes = [_vp, _i64, _vp, _vp, _vp]
+    L.pdm_shard_links.argtypes = [_vp, ct.POINTER(UcaParams)]
+    L.pdm_shard_sweep.argtypes = [_vp, ct.c_int]
+    L.pdm_shard_outbox_pack.argtypes = [_vp, ct.c_int, _vp, _vp, _vp, _vp]
+    L.pdm_shard_inbox_apply.argtypes = [_vp, ct.c_int, _vp, _vp, _vp]
+    L.pdm_shard_finalize.argtypes = [_vp, ct.POINTER(UcaParams), ct.POINTER(UcaStats)]
     L.pdm_slopes_directions.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
     L.pdm_uca.argtypes = [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
                           ct.POINTER(UcaParams), _vp, _vp, _vp, ct.POINTER(UcaStats)]

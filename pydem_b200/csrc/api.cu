@@ -29,7 +29,8 @@ int pdm_cuda_fail(cudaError_t e, const char *what, const char *file, int line)
 static size_t field_elem_size(int field)
 {
     switch (field) {
-        case PDM_F_FLATS: case PDM_F_EDGE_TODO: case PDM_F_EDGE_DONE: case PDM_F_SECTION: return 1;
+        case PDM_F_FLATS: case PDM_F_EDGE_TODO: case PDM_F_EDGE_DONE: case PDM_F_SECTION:
+        case PDM_F_FLAT0: case PDM_F_LINK: return 1;
         default: return 8;
     }
 }
@@ -48,9 +49,13 @@ static void *field_ptr(pdm_tile *t, int field)
         case PDM_F_SECTION: return t->section;
         case PDM_F_PROP: return t->prop;
         case PDM_F_TAINT: return t->taint;
+        case PDM_F_FLAT0: return t->flat0;
+        case PDM_F_LINK: return t->link;
         default: return nullptr;
     }
 }
+
+static bool standalone(const pdm_tile *t) { return t->win.lo == 0 && t->win.hi == t->R && t->win.Rg == t->R && t->win.row_off == 0; }
 
 extern "C" {
 
@@ -122,6 +127,7 @@ int pdm_tile_create(int64_t R, int64_t C, void *stream, pdm_tile **out)
     pdm_tile *t = new pdm_tile();
     memset(t, 0, sizeof(*t));
     t->R = R; t->C = C; t->N = R * C;
+    t->win.R = R; t->win.C = C; t->win.row_off = 0; t->win.Rg = R; t->win.lo = 0; t->win.hi = R;
     t->stream = (cudaStream_t)stream;
     cudaError_t e = cudaGetDevice(&t->device);
     if (e != cudaSuccess) { delete t; return pdm_cuda_fail(e, "cudaGetDevice", __FILE__, __LINE__); }
@@ -163,7 +169,8 @@ int pdm_tile_destroy(pdm_tile *t)
     void *ptrs[] = {t->elev, t->mag, t->dir, t->uca, t->taint, t->prop, t->twi, t->flats, t->flat0, t->link,
                     t->edge_todo, t->edge_done, t->section, t->indeg, t->label, t->queue, t->dX, t->dY, t->dg,
                     t->thA, t->thB, t->th_row, t->row_area, t->d_counters, t->pit_cell, t->pit_beg, t->pit_end,
-                    t->pit_dst, t->pit_w, t->pit_scratch_i, t->pit_scratch_d, t->edge_buf_d, t->edge_buf_b};
+                    t->pit_dst, t->pit_w, t->pit_scratch_i, t->pit_scratch_d, t->edge_buf_d, t->edge_buf_b,
+                    t->glabel, t->glelev};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (t->h_counters) cudaFreeHost(t->h_counters);
     for (int k = 0; k < 4; k++) if (t->ev[k]) cudaEventDestroy(t->ev[k]);
@@ -176,11 +183,15 @@ int pdm_tile_set_spacing(pdm_tile *t, const double *dX, const double *dY, const 
 {
     if (!t || !dX || !dY || !dX2 || !dY2) { pdm_set_error("pdm_tile_set_spacing: NULL argument"); return PDM_ERR_ARG; }
     const int64_t R = t->R;
-    std::vector<double> a((size_t)R), b((size_t)R), area((size_t)R);
+    std::vector<double> a((size_t)R), b((size_t)R), area((size_t)R), thr((size_t)R);
     for (int64_t f = 0; f < R - 1; f++) {
         a[f] = thA ? thA[f] : atan2(dY[f], dX[f]);   // dem_processing.py:1936, facets 0,3,4,7
         b[f] = thB ? thB[f] : atan2(dX[f], dY[f]);   // facets 1,2,5,6
     }
+    // theta of _calc_uca_section_proportion for a stand-alone tile: facet-0 theta of fences
+    // 0..R-3 padded with its first and last entry (dem_processing.py:1031-1033); a shard gets
+    // its slice of the global array through pdm_tile_set_window
+    for (int64_t i = 0; i < R; i++) thr[i] = a[i == 0 ? 0 : (i == R - 1 ? R - 3 : i - 1)];
     double mn = NAN;
     for (int64_t i = 0; i < R; i++) {
         area[i] = dX2[i] * dY2[i];                    // 885
@@ -192,6 +203,7 @@ int pdm_tile_set_spacing(pdm_tile *t, const double *dX, const double *dY, const 
     PDM_CUDA(cudaMemcpyAsync(t->thA, a.data(), (size_t)(R - 1) * 8, cudaMemcpyHostToDevice, t->stream));
     PDM_CUDA(cudaMemcpyAsync(t->thB, b.data(), (size_t)(R - 1) * 8, cudaMemcpyHostToDevice, t->stream));
     PDM_CUDA(cudaMemcpyAsync(t->row_area, area.data(), (size_t)R * 8, cudaMemcpyHostToDevice, t->stream));
+    PDM_CUDA(cudaMemcpyAsync(t->th_row, thr.data(), (size_t)R * 8, cudaMemcpyHostToDevice, t->stream));
     int rc = pdm_launch_geometry(t);
     if (rc) return rc;
     PDM_CUDA(cudaStreamSynchronize(t->stream));  // the staging vectors die here
@@ -259,6 +271,7 @@ int pdm_tile_slopes_directions(pdm_tile *t)
 {
     if (!t) { pdm_set_error("NULL tile"); return PDM_ERR_ARG; }
     if (!t->have_elev || !t->have_spacing) { pdm_set_error("pdm_tile_slopes_directions: upload ELEV and set spacing first"); return PDM_ERR_STATE; }
+    if (!standalone(t)) { pdm_set_error("pdm_tile_slopes_directions: tile is a row shard; use the pdm_shard_* stages"); return PDM_ERR_STATE; }
     int rc = pdm_launch_slopes(t);
     if (rc) return rc;
     rc = pdm_launch_flats(t);
@@ -292,6 +305,7 @@ int pdm_tile_uca(pdm_tile *t, const pdm_uca_params *p_in, pdm_uca_stats *stats)
         pdm_set_error("pdm_tile_uca: needs ELEV, spacing, DIR/MAG and FLATS on the tile");
         return PDM_ERR_STATE;
     }
+    if (!standalone(t)) { pdm_set_error("pdm_tile_uca: tile is a row shard; use the pdm_shard_* stages"); return PDM_ERR_STATE; }
     pdm_uca_params p;
     if (p_in) p = *p_in; else pdm_default_uca_params(&p);
     pdm_uca_stats st;
@@ -349,6 +363,7 @@ int pdm_tile_uca_update(pdm_tile *t, const pdm_uca_params *p_in,
         pdm_set_error("pdm_tile_uca_update: needs ELEV, spacing, DIR/MAG, FLATS and UCA (= uca_init) on the tile");
         return PDM_ERR_STATE;
     }
+    if (!standalone(t)) { pdm_set_error("pdm_tile_uca_update: tile is a row shard"); return PDM_ERR_STATE; }
     pdm_uca_params p;
     if (p_in) p = *p_in; else pdm_default_uca_params(&p);
     pdm_uca_stats st;

@@ -25,6 +25,8 @@ __device__ __forceinline__ uint32_t st_fetch_or(uint8_t *st, int32_t cell, uint3
     return (old >> sh) & 0xffu;
 }
 
+//   MODE 2: resumed full sweep of a shard: like MODE 0, but the seeds come from an explicit list
+//           (cells whose last upstream contribution arrived from a neighbouring rank).
 template <int MODE>
 struct DrainOp {
     const uint8_t *link;
@@ -41,7 +43,7 @@ struct DrainOp {
 
     __device__ __forceinline__ bool is_seed(int32_t c) const
     {
-        return MODE == 0 ? (link[c] & LK_SOURCE) != 0 : (st[c] & ST_START) != 0;
+        return MODE == 0 ? (link[c] & LK_SOURCE) != 0 : (MODE == 2 ? true : (st[c] & ST_START) != 0);
     }
     __device__ __forceinline__ bool skip(int32_t r) const { return MODE == 1 && (st[r] & ST_START); }
 
@@ -54,7 +56,7 @@ struct DrainOp {
         if (lk & LK_PIT) {
             // long-range pit edges (_mk_connectivity_pits): rare, plain fence ordering
             const double ai = __ldcg(area + i);
-            const double ti = MODE == 0 ? __ldcg(taint + i) : 0.0;
+            const double ti = MODE != 1 ? __ldcg(taint + i) : 0.0;
             const int64_t slot = __double_as_longlong(prop[i]);
             const int32_t e0 = pit_beg[slot], e1 = pit_end[slot];
             for (int32_t e = e0; e < e1; e++) {
@@ -62,7 +64,7 @@ struct DrainOp {
                 if (skip(r)) continue;
                 const double w = pit_w[e];
                 atomicAdd(area + r, __dmul_rn(ai, w));
-                if (MODE == 0 && ti != 0.0) atomicAdd(taint + r, __dmul_rn(ti, w));
+                if (MODE != 1 && ti != 0.0) atomicAdd(taint + r, __dmul_rn(ti, w));
             }
             __threadfence();
             for (int32_t e = e0; e < e1; e++) {
@@ -85,12 +87,12 @@ struct DrainOp {
             if (!(k1 || k2)) return -1;
         }
         const double ai = __ldcg(area + i);
-        const double ti = MODE == 0 ? __ldcg(taint + i) : 0.0;
+        const double ti = MODE != 1 ? __ldcg(taint + i) : 0.0;
         const double w2 = __dsub_rn(1.0, p);                                    // dem_processing.py:1082
         int dep = 0;
         if (k1) dep |= dep_zero(atomicAdd(area + r1, __dmul_rn(ai, p)));        // cyutils.pyx:161
         if (k2) dep |= dep_zero(atomicAdd(area + r2, __dmul_rn(ai, w2)));
-        if (MODE == 0 && ti != 0.0) {                                           // cyutils.pyx:163-164
+        if (MODE != 1 && ti != 0.0) {                                           // cyutils.pyx:163-164
             if (k1) dep |= dep_zero(atomicAdd(taint + r1, __dmul_rn(ti, p)));
             if (k2) dep |= dep_zero(atomicAdd(taint + r2, __dmul_rn(ti, w2)));
         }

@@ -47,14 +47,15 @@ __device__ __forceinline__ int section_prop(double d, bool flat, double th, doub
 
 __global__ void __launch_bounds__(256)
 k_links(const double *__restrict__ E, const double *__restrict__ dir, const uint8_t *__restrict__ flats,
-        const double *__restrict__ th_row, int64_t R, int64_t C,
+        const double *__restrict__ th_row, Win w,
         uint8_t *__restrict__ link, double *__restrict__ prop, uint8_t *__restrict__ pitmask,
         unsigned long long *counters)
 {
+    const int64_t C = w.C;
     const int64_t j = (int64_t)blockIdx.x * 32 + threadIdx.x;
-    const int64_t i = (int64_t)blockIdx.y * 8 + threadIdx.y;
+    const int64_t i = w.lo + (int64_t)blockIdx.y * 8 + threadIdx.y;
     bool pit = false;
-    if (i < R && j < C) {
+    if (i < w.hi && j < C) {
         const int64_t n = i * C + j;
         const bool fl = flats[n] != 0;
         const double e0 = E[n];
@@ -66,12 +67,12 @@ k_links(const double *__restrict__ E, const double *__restrict__ dir, const uint
             lk = (uint8_t)sec;
             const int64_t i1 = i + g_e1r[sec], j1 = j + g_e1c[sec];
             const int64_t i2 = i + g_e2r[sec], j2 = j + g_e2c[sec];
-            // _mk_connectivity: a receiver exists iff it is inside the tile; filter 1136-1137:
+            // _mk_connectivity: a receiver exists iff it is inside the grid; filter 1136-1137:
             // weight not NaN, > 1e-8, and the receiver is not higher than the source
-            if (i1 >= 0 && i1 < R && j1 >= 0 && j1 < C) {
+            if (w.row_in_grid(i1) && j1 >= 0 && j1 < C) {
                 if (p > 1e-8 && __ldg(E + i1 * C + j1) <= e0) lk |= LK_KEEP1;
             }
-            if (i2 >= 0 && i2 < R && j2 >= 0 && j2 < C) {
+            if (w.row_in_grid(i2) && j2 >= 0 && j2 < C) {
                 const double w2 = __dsub_rn(1.0, p);
                 if (w2 > 1e-8 && __ldg(E + i2 * C + j2) <= e0) lk |= LK_KEEP2;
             }
@@ -92,7 +93,7 @@ k_section_export(const double *__restrict__ dir, const uint8_t *__restrict__ fla
 {
     const int64_t j = (int64_t)blockIdx.x * 32 + threadIdx.x;
     const int64_t i = (int64_t)blockIdx.y * 8 + threadIdx.y;
-    if (i >= R || j >= C) return;
+    if (i >= R || j >= C) return;  // all local rows
     double p;
     int sec = section_prop(dir[i * C + j], flats[i * C + j] != 0, __ldg(th_row + i), p);
     section[i * C + j] = (int8_t)sec;
@@ -104,35 +105,43 @@ __device__ __forceinline__ int drains_in(uint8_t lk, uint8_t keepbit, uint32_t s
     return ((lk & keepbit) && !(lk & (LK_NOSEC | LK_PIT)) && ((secmask >> (lk & LK_SEC_MASK)) & 1u)) ? 1 : 0;
 }
 
-// in-degree of every cell (+ pit in-edges already accumulated into indeg by the pit kernel),
-// source flag, and the initial state of the sweep: area = dX2*dY2 of the row, taint = 0.
+// in-degree of every owned cell (+ pit in-edges already accumulated into indeg by the pit
+// kernel), source flag, and the initial state of the sweep: area = dX2*dY2 of the row, taint = 0.
+// Halo rows of a shard (the out-boxes of the sweep) start at zero.
 __global__ void __launch_bounds__(256)
-k_indeg(uint8_t *__restrict__ link, int64_t R, int64_t C, const double *__restrict__ row_area,
+k_indeg(uint8_t *__restrict__ link, Win w, const double *__restrict__ row_area,
         int32_t *__restrict__ indeg, double *__restrict__ area, double *__restrict__ taint,
         unsigned long long *counters)
 {
+    const int64_t C = w.C;
     const int64_t j = (int64_t)blockIdx.x * 32 + threadIdx.x;
-    const int64_t i = (int64_t)blockIdx.y * 8 + threadIdx.y;
-    const bool in = (i < R && j < C);
+    const int64_t i = (int64_t)blockIdx.y * 8 + threadIdx.y;   // all local rows
+    const bool in = (i < w.R && j < C);
+    const bool own = in && i >= w.lo && i < w.hi;
     int cnt = 0;
     int64_t n = 0;
     if (in) {
         n = i * C + j;
-        const bool up = i > 0, dn = i < R - 1, lf = j > 0, rt = j < C - 1;
-        if (lf) cnt += drains_in(link[n - 1], LK_KEEP1, 0x81u);             // W neighbour: e1 = (0,+1)
-        if (rt) cnt += drains_in(link[n + 1], LK_KEEP1, 0x18u);             // E: e1 = (0,-1)
-        if (up) cnt += drains_in(link[n - C], LK_KEEP1, 0x60u);             // N: e1 = (+1,0)
-        if (dn) cnt += drains_in(link[n + C], LK_KEEP1, 0x06u);             // S: e1 = (-1,0)
-        if (up && lf) cnt += drains_in(link[n - C - 1], LK_KEEP2, 0xC0u);   // NW: e2 = (+1,+1)
-        if (up && rt) cnt += drains_in(link[n - C + 1], LK_KEEP2, 0x30u);   // NE: e2 = (+1,-1)
-        if (dn && lf) cnt += drains_in(link[n + C - 1], LK_KEEP2, 0x03u);   // SW: e2 = (-1,+1)
-        if (dn && rt) cnt += drains_in(link[n + C + 1], LK_KEEP2, 0x0Cu);   // SE: e2 = (-1,-1)
-        cnt += indeg[n];
-        indeg[n] = cnt;
-        area[n] = __ldg(row_area + i);                                      // 885, 901
+        if (own) {
+            const bool up = w.row_in_grid(i - 1), dn = w.row_in_grid(i + 1), lf = j > 0, rt = j < C - 1;
+            if (lf) cnt += drains_in(link[n - 1], LK_KEEP1, 0x81u);             // W neighbour: e1 = (0,+1)
+            if (rt) cnt += drains_in(link[n + 1], LK_KEEP1, 0x18u);             // E: e1 = (0,-1)
+            if (up) cnt += drains_in(link[n - C], LK_KEEP1, 0x60u);             // N: e1 = (+1,0)
+            if (dn) cnt += drains_in(link[n + C], LK_KEEP1, 0x06u);             // S: e1 = (-1,0)
+            if (up && lf) cnt += drains_in(link[n - C - 1], LK_KEEP2, 0xC0u);   // NW: e2 = (+1,+1)
+            if (up && rt) cnt += drains_in(link[n - C + 1], LK_KEEP2, 0x30u);   // NE: e2 = (+1,-1)
+            if (dn && lf) cnt += drains_in(link[n + C - 1], LK_KEEP2, 0x03u);   // SW: e2 = (-1,+1)
+            if (dn && rt) cnt += drains_in(link[n + C + 1], LK_KEEP2, 0x0Cu);   // SE: e2 = (-1,-1)
+            cnt += indeg[n];
+            indeg[n] = cnt;
+            area[n] = __ldg(row_area + i);                                      // 885, 901
+        } else {
+            indeg[n] = 0;
+            area[n] = 0.0;
+        }
         taint[n] = 0.0;
     }
-    const bool src = in && cnt == 0;
+    const bool src = own && cnt == 0;
     if (src) link[n] |= LK_SOURCE;                                          // 882-883
     const unsigned m = __ballot_sync(0xffffffffu, src);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[CT_SOURCES], (unsigned long long)__popc(m));
@@ -140,21 +149,28 @@ k_indeg(uint8_t *__restrict__ link, int64_t R, int64_t C, const double *__restri
 
 __device__ __forceinline__ bool sec_in(int sec, uint32_t mask) { return sec >= 0 && ((mask >> sec) & 1u); }
 
-// inflow-border mask of _calc_uca_chunk 909-937; one thread per perimeter cell.
-// Also seeds taint (edge_todo as float, 944).
+// inflow-border mask of _calc_uca_chunk 909-937 for the owned cells on the border of the global
+// grid.  Thread t < C: top-row candidate, t < 2C: bottom-row candidate, then two per owned row
+// (left / right column).  Also seeds taint (edge_todo as float, 944).
 __global__ void __launch_bounds__(256)
 k_border_todo(const double *__restrict__ E, const uint8_t *__restrict__ link, const double *__restrict__ prop,
-              int64_t R, int64_t C, const int32_t *__restrict__ pit_beg, const int32_t *__restrict__ pit_end, const double *__restrict__ pit_w,
+              Win w, const int32_t *__restrict__ pit_beg, const int32_t *__restrict__ pit_end, const double *__restrict__ pit_w,
               const int32_t *__restrict__ pit_dst, int64_t n_pit_edges,
               uint8_t *__restrict__ edge_todo, double *__restrict__ taint, unsigned long long *counters)
 {
-    const int64_t per = 2 * C + 2 * (R - 2);
+    const int64_t C = w.C;
+    const int64_t nown = w.hi - w.lo;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= per) return;
+    if (t >= 2 * C + 2 * nown) return;
     int64_t i, j;
-    if (t < C) { i = 0; j = t; }
-    else if (t < 2 * C) { i = R - 1; j = t - C; }
-    else { const int64_t u = t - 2 * C; i = 1 + (u >> 1); j = (u & 1) ? C - 1 : 0; }
+    if (t < C) { i = -w.row_off; j = t; }                                   // global row 0
+    else if (t < 2 * C) { i = w.Rg - 1 - w.row_off; j = t - C; }            // global last row
+    else {
+        const int64_t u = t - 2 * C;
+        i = w.lo + (u >> 1); j = (u & 1) ? C - 1 : 0;
+        if (w.top(i) || w.bottom(i)) return;                                // corners belong to the row threads
+    }
+    if (i < w.lo || i >= w.hi) return;                                      // that border row lives on another rank
     const int64_t n = i * C + j;
     const uint8_t lk = link[n];
     const double TOL = 1e-2;
@@ -172,17 +188,18 @@ k_border_todo(const double *__restrict__ E, const uint8_t *__restrict__ link, co
     }
     bool todo = false;
     const bool big = outflow > TOL;
+    const bool top = w.top(i), bot = w.bottom(i);
     if (j == 0) todo = big && sec_in(sec, 0xC3u);                           // left: 6,7,0,1
     if (j == C - 1) todo = big && sec_in(sec, 0x3Cu);                       // right: 2,3,4,5 (later assignment wins)
-    if (i == 0) todo = big && sec_in(sec, 0xF0u);                           // top: 4,5,6,7
-    if (i == R - 1) todo = big && sec_in(sec, 0x0Fu);                       // bottom: 0,1,2,3
-    if ((i == 0 || i == R - 1) && (j == 0 || j == C - 1)) {
+    if (top) todo = big && sec_in(sec, 0xF0u);                              // top: 4,5,6,7
+    if (bot) todo = big && sec_in(sec, 0x0Fu);                              // bottom: 0,1,2,3
+    if ((top || bot) && (j == 0 || j == C - 1)) {
         // corners 924-930: |= outflow > TOL  |  inflow < TOL (row sum of A)
         double inflow = 0.0;
         for (int di = -1; di <= 1; di++)
             for (int dj = -1; dj <= 1; dj++) {
                 const int64_t mi = i + di, mj = j + dj;
-                if ((di == 0 && dj == 0) || mi < 0 || mi >= R || mj < 0 || mj >= C) continue;
+                if ((di == 0 && dj == 0) || !w.row_in_grid(mi) || mj < 0 || mj >= C) continue;
                 const uint8_t ml = link[mi * C + mj];
                 if (ml & (LK_NOSEC | LK_PIT)) continue;
                 const int ms = ml & LK_SEC_MASK;
@@ -207,38 +224,52 @@ k_border_todo(const double *__restrict__ E, const uint8_t *__restrict__ link, co
 // both on every calc_uca call, dem_processing.py:787-793 / 873-879).
 int pdm_graph_links_pits(pdm_tile *t, const pdm_uca_params *p)
 {
+    const Win &w = t->win;
     dim3 block(32, 8);
-    dim3 grid((unsigned)((t->C + 31) / 32), (unsigned)((t->R + 7) / 8));
-    PDM_CUDA(cudaMemsetAsync(t->d_counters, 0, CT_N * sizeof(unsigned long long), t->stream));
+    dim3 grid((unsigned)((w.C + 31) / 32), (unsigned)((w.hi - w.lo + 7) / 8));
+    // stage counters only: the work-list counters below CT_SOURCES remember which queue slots are dirty
+    PDM_CUDA(cudaMemsetAsync(t->d_counters + CT_SOURCES, 0, (CT_N - CT_SOURCES) * sizeof(unsigned long long), t->stream));
     PDM_CUDA(cudaMemsetAsync(t->indeg, 0, (size_t)t->N * sizeof(int32_t), t->stream));
-    k_links<<<grid, block, 0, t->stream>>>(t->elev, t->dir, t->flats, t->th_row, t->R, t->C, t->link, t->prop,
+    k_links<<<grid, block, 0, t->stream>>>(t->elev, t->dir, t->flats, t->th_row, w, t->link, t->prop,
                                            t->flat0, t->d_counters);
     PDM_LAUNCHED();
     t->n_pits = 0; t->n_pit_edges = 0;
     if (p->drain_pits) {
+        if (w.lo != 0 || w.hi != t->R || w.Rg != t->R) {
+            pdm_set_error("drain_pits=True is not supported on a row shard yet (the pit search needs a %d-row halo); "
+                          "run the sharded path with drain_pits=False", (int)p->drain_pits_max_iter + 1);
+            return PDM_ERR_ARG;
+        }
         int rc = pdm_launch_pits(t, p);
         if (rc) return rc;
     }
     return PDM_OK;
 }
 
-int pdm_launch_graph(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *st)
+// in-degree + source flags + sweep state + inflow-border mask (after the neighbours' link rows
+// are in place on a shard)
+int pdm_launch_indeg_todo(pdm_tile *t)
 {
-    (void)st;
+    const Win &w = t->win;
     dim3 block(32, 8);
-    dim3 grid((unsigned)((t->C + 31) / 32), (unsigned)((t->R + 7) / 8));
-    int rc = pdm_graph_links_pits(t, p);
-    if (rc) return rc;
+    dim3 grid((unsigned)((w.C + 31) / 32), (unsigned)((t->R + 7) / 8));
     PDM_CUDA(cudaMemsetAsync(t->edge_todo, 0, (size_t)t->N, t->stream));
-    k_indeg<<<grid, block, 0, t->stream>>>(t->link, t->R, t->C, t->row_area, t->indeg, t->uca, t->taint,
-                                           t->d_counters);
+    k_indeg<<<grid, block, 0, t->stream>>>(t->link, w, t->row_area, t->indeg, t->uca, t->taint, t->d_counters);
     PDM_LAUNCHED();
-    const int64_t per = 2 * t->C + 2 * (t->R - 2);
+    const int64_t per = 2 * w.C + 2 * (w.hi - w.lo);
     k_border_todo<<<(unsigned)((per + 255) / 256), 256, 0, t->stream>>>(
-        t->elev, t->link, t->prop, t->R, t->C, t->pit_beg, t->pit_end, t->pit_w, t->pit_dst, t->n_pit_edges,
+        t->elev, t->link, t->prop, w, t->pit_beg, t->pit_end, t->pit_w, t->pit_dst, t->n_pit_edges,
         t->edge_todo, t->taint, t->d_counters);
     PDM_LAUNCHED();
     return PDM_OK;
+}
+
+int pdm_launch_graph(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *st)
+{
+    (void)st;
+    int rc = pdm_graph_links_pits(t, p);
+    if (rc) return rc;
+    return pdm_launch_indeg_todo(t);
 }
 
 int pdm_launch_section_export(pdm_tile *t)

@@ -25,8 +25,23 @@
 #define LK_NOSEC 0x40      // section outside 0..7 (flat / undefined): no receivers
 #define LK_SOURCE 0x80     // nobody drains into this cell (initial frontier)
 
+// Row window of a tile inside a (possibly larger, row-sharded) grid.  A stand-alone tile has
+// row_off = 0, Rg = R, lo = 0, hi = R.  A shard keeps halo rows around its owned rows [lo, hi);
+// "border" always means the border of the GLOBAL grid (rows 0 / Rg-1, columns 0 / C-1).
+struct Win {
+    int64_t R, C;        // local rows (owned + halo), columns
+    int64_t row_off;     // global row index of local row 0
+    int64_t Rg;          // rows of the global grid
+    int64_t lo, hi;      // owned local rows
+    __host__ __device__ __forceinline__ bool top(int64_t li) const { return li + row_off == 0; }
+    __host__ __device__ __forceinline__ bool bottom(int64_t li) const { return li + row_off == Rg - 1; }
+    // is local row li (possibly one step outside [0,R)) inside the global grid?
+    __host__ __device__ __forceinline__ bool row_in_grid(int64_t li) const { return li + row_off >= 0 && li + row_off < Rg; }
+};
+
 struct pdm_tile {
     int64_t R, C, N;
+    Win win;
     int device;
     cudaStream_t stream;
     // fields
@@ -34,10 +49,13 @@ struct pdm_tile {
     uint8_t *flats, *flat0, *link, *edge_todo, *edge_done;
     int8_t *section;  // only materialised on download of PDM_F_SECTION
     int32_t *indeg, *label, *queue;
+    long long *glabel;   // sharded mode: global minimum cell index of each flat region (at its local root)
+    double *glelev;      //               elevation of that cell
     // geometry
     double *dX, *dY, *dg, *thA, *thB, *th_row, *row_area;
     double min_area;
     bool have_spacing, have_elev, have_slopes, have_flats, have_graph, have_uca;
+    bool queue_ready;    // queue slots are all -1 except those the last work-list run used
     // pit edge lists (device)
     int32_t *pit_cell;     // [pit_cap] cells examined by the pit search (flats & elev > 0)
     int32_t *pit_beg;      // [pit_cap] first / one-past-last edge of each pit in pit_dst/pit_w

@@ -12,13 +12,17 @@
 // explicit _rn intrinsics), so mag is bit-identical and direction differs only by the
 // ulp-level difference between CUDA's atan2 and the host libm.
 //
+// Shards: the kernel runs over the owned rows of a window (Win); rows above/below come from
+// halo rows, and "border" means the border of the global grid, so a row-sharded run
+// computes exactly what one big tile would.
+//
 // Roofline: 8 B read (elev) + 16 B written (mag, direction) + 1 B (flat0) per cell.
 #include "pdm_internal.cuh"
 
 namespace {
 
 struct Geom {
-    const double *dX, *dY, *dg, *thA, *thB;
+    const double *dX, *dY, *dg, *thA, *thB;   // indexed by local fence (between local rows f, f+1)
 };
 
 // facet tables (dem_processing.py:173-193): cardinal neighbour e1, diagonal neighbour e2,
@@ -48,12 +52,14 @@ __device__ __forceinline__ void facet_update(double e0, double e1, double e2, do
     }
 }
 
-// All in-bounds facets of cell (i,j), ascending facet index, strict max (m2, dr in/out).
-// Upper facets (0-3) use fence i-1, lower facets (4-7) fence i (_get_d1_d2 1913-1934).
+// All in-grid facets of the cell at local row i, column j, ascending facet index, strict max
+// (m2, dr in/out).  Upper facets (0-3) use fence i-1, lower facets (4-7) fence i
+// (_get_d1_d2 1913-1934).
 template <bool INTERIOR>
-__device__ __forceinline__ void cell_facets(const double *__restrict__ E, int64_t R, int64_t C,
+__device__ __forceinline__ void cell_facets(const double *__restrict__ E, const Win &w,
                                             int64_t i, int64_t j, const Geom &g, double &m2, double &dr)
 {
+    const int64_t C = w.C;
     const double e0 = __ldg(E + i * C + j);
     const double HALF_PI_Q[8] = {0.0 * PDM_PI / 2, 1.0 * PDM_PI / 2, 1.0 * PDM_PI / 2, 2.0 * PDM_PI / 2,
                                  2.0 * PDM_PI / 2, 3.0 * PDM_PI / 2, 3.0 * PDM_PI / 2, 4.0 * PDM_PI / 2};
@@ -61,7 +67,7 @@ __device__ __forceinline__ void cell_facets(const double *__restrict__ E, int64_
     for (int k = 0; k < 8; k++) {
         const int64_t i1 = i + c_e1r[k], j1 = j + c_e1c[k], i2 = i + c_e2r[k], j2 = j + c_e2c[k];
         if (!INTERIOR) {
-            if (i1 < 0 || i1 >= R || j1 < 0 || j1 >= C || i2 < 0 || i2 >= R || j2 < 0 || j2 >= C) continue;
+            if (!w.row_in_grid(i1) || j1 < 0 || j1 >= C || !w.row_in_grid(i2) || j2 < 0 || j2 >= C) continue;
         }
         const int64_t f = (k < 4) ? i - 1 : i;
         const bool typeA = (k == 0 || k == 3 || k == 4 || k == 7);
@@ -75,34 +81,36 @@ __device__ __forceinline__ void cell_facets(const double *__restrict__ E, int64_
 }
 
 __global__ void __launch_bounds__(256)
-k_slopes(const double *__restrict__ E, int64_t R, int64_t C, Geom g,
+k_slopes(const double *__restrict__ E, Win w, Geom g,
          double *__restrict__ mag, double *__restrict__ dir, uint8_t *__restrict__ flat0,
          int32_t *__restrict__ label)
 {
+    const int64_t C = w.C;
     const int64_t j = (int64_t)blockIdx.x * 32 + threadIdx.x;
-    const int64_t i = (int64_t)blockIdx.y * 8 + threadIdx.y;
-    if (i >= R || j >= C) return;
+    const int64_t i = w.lo + (int64_t)blockIdx.y * 8 + threadIdx.y;
+    if (i >= w.hi || j >= C) return;
     double m2 = -1.0, dr = -1.0;
-    const bool border = (i == 0) | (j == 0) | (i == R - 1) | (j == C - 1);
+    const bool top = w.top(i), bot = w.bottom(i);
+    const bool border = top | bot | (j == 0) | (j == C - 1);
     if (!border) {
-        cell_facets<true>(E, R, C, i, j, g, m2, dr);
+        cell_facets<true>(E, w, i, j, g, m2, dr);
     } else {
         // copy-from-interior passes 1782-1795, resolved per border cell: the four
         // sequential whole-row/column copies mean an edge cell looks at its inward
         // neighbour and a corner at its diagonal interior neighbour through two tests.
         const double hp = PDM_PI / 2, thp = 3 * PDM_PI / 2, tp = 2 * PDM_PI;
-        const int64_t si = (i == 0) ? 1 : (i == R - 1 ? R - 2 : i);
+        const int64_t si = top ? i + 1 : (bot ? i - 1 : i);
         const int64_t sj = (j == 0) ? 1 : (j == C - 1 ? C - 2 : j);
         double sm = -1.0, sd_ = -1.0;
-        cell_facets<true>(E, R, C, si, sj, g, sm, sd_);
+        cell_facets<true>(E, w, si, sj, g, sm, sd_);
         bool take = true;
         if (j == 0) take = take && (sd_ > hp && sd_ < thp);
         if (j == C - 1) take = take && (sd_ < hp || sd_ > thp);
         // a column copy that did not happen leaves -1 in row 1 / R-2, which fails the row tests
-        if (i == 0) take = take && (sd_ > 0.0 && sd_ < PDM_PI);
-        if (i == R - 1) take = take && (sd_ > PDM_PI && sd_ < tp);
+        if (top) take = take && (sd_ > 0.0 && sd_ < PDM_PI);
+        if (bot) take = take && (sd_ > PDM_PI && sd_ < tp);
         if (take) { m2 = sm; dr = sd_; }
-        cell_facets<false>(E, R, C, i, j, g, m2, dr);
+        cell_facets<false>(E, w, i, j, g, m2, dr);
     }
     const int64_t n = i * C + j;
     const bool fl = (m2 == -1.0);
@@ -112,18 +120,11 @@ k_slopes(const double *__restrict__ E, int64_t R, int64_t C, Geom g,
     if (fl) label[n] = (int32_t)n;  // union-find root of the flat-region labelling (flats.cu)
 }
 
-__global__ void k_geometry(const double *__restrict__ dX, const double *__restrict__ dY,
-                           const double *__restrict__ thA, int64_t R,
-                           double *__restrict__ dg, double *__restrict__ th_row)
+__global__ void k_geometry(const double *__restrict__ dX, const double *__restrict__ dY, int64_t R,
+                           double *__restrict__ dg)
 {
     int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (f < R - 1) dg[f] = sqrt(__dadd_rn(__dmul_rn(dX[f], dX[f]), __dmul_rn(dY[f], dY[f])));  // 1962
-    if (f < R) {
-        // theta of _calc_uca_section_proportion: facet-0 theta of fences 0..R-3 padded with its
-        // first and last entry (dem_processing.py:1031-1033)
-        int64_t src = (f == 0) ? 0 : (f == R - 1 ? R - 3 : f - 1);
-        th_row[f] = thA[src];
-    }
 }
 
 }  // namespace
@@ -131,7 +132,7 @@ __global__ void k_geometry(const double *__restrict__ dX, const double *__restri
 int pdm_launch_geometry(pdm_tile *t)
 {
     int64_t n = t->R;
-    k_geometry<<<(unsigned)((n + 255) / 256), 256, 0, t->stream>>>(t->dX, t->dY, t->thA, t->R, t->dg, t->th_row);
+    k_geometry<<<(unsigned)((n + 255) / 256), 256, 0, t->stream>>>(t->dX, t->dY, t->R, t->dg);
     PDM_LAUNCHED();
     return PDM_OK;
 }
@@ -139,9 +140,10 @@ int pdm_launch_geometry(pdm_tile *t)
 int pdm_launch_slopes(pdm_tile *t)
 {
     Geom g{t->dX, t->dY, t->dg, t->thA, t->thB};
+    const Win &w = t->win;
     dim3 block(32, 8);
-    dim3 grid((unsigned)((t->C + 31) / 32), (unsigned)((t->R + 7) / 8));
-    k_slopes<<<grid, block, 0, t->stream>>>(t->elev, t->R, t->C, g, t->mag, t->dir, t->flat0, t->label);
+    dim3 grid((unsigned)((w.C + 31) / 32), (unsigned)((w.hi - w.lo + 7) / 8));
+    k_slopes<<<grid, block, 0, t->stream>>>(t->elev, w, g, t->mag, t->dir, t->flat0, t->label);
     PDM_LAUNCHED();
     return PDM_OK;
 }

@@ -27,15 +27,15 @@
 
 namespace {
 
-// a6 epilogue: dem_processing.py:966-980
+// a6 epilogue: dem_processing.py:966-980 (owned cells [n0, n1))
 __global__ void __launch_bounds__(256)
 k_uca_finalize(const double *__restrict__ E, const uint8_t *__restrict__ flats, const int32_t *__restrict__ indeg,
                const double *__restrict__ taint, double *__restrict__ uca, uint8_t *__restrict__ edge_done,
-               int64_t N, int limit_edges, double limit_area, unsigned long long *counters)
+               int64_t n0, int64_t n1, int limit_edges, double limit_area, unsigned long long *counters)
 {
-    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = n0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool undone = false;
-    if (n < N) {
+    if (n < n1) {
         const double e = E[n];
         double u = uca[n];
         if (flats[n]) { u = __longlong_as_double(0x7ff8000000000000LL); uca[n] = u; }   // 972
@@ -65,26 +65,59 @@ k_twi(const double *__restrict__ uca, const double *__restrict__ mag, double *__
 
 }  // namespace
 
-static int g_sweep_blocks = 0;
+static int g_sweep_blocks = 0, g_resume_blocks = 0;
 
-int pdm_launch_sweep_full(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *st)
+// first pass: every owned cell nobody drains into is a seed
+int pdm_launch_sweep_first(pdm_tile *t)
 {
-    (void)st;
     if (!g_sweep_blocks) {
-        int rc = wl::grid_for(wl::k_worklist<DrainOp<0>, wl::DomainAll>, &g_sweep_blocks);
+        int rc = wl::grid_for(wl::k_worklist<DrainOp<0>, wl::DomainRange>, &g_sweep_blocks);
         if (rc) return rc;
     }
     int rc = wl::reset_queue(t);
     if (rc) return rc;
+    const Win &w = t->win;
     DrainOp<0> op{t->link, t->prop, t->uca, t->taint, t->indeg, nullptr, (int32_t)t->C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w};
-    wl::k_worklist<<<g_sweep_blocks, 256, 0, t->stream>>>(op, wl::DomainAll{t->N}, wl::Queue{t->queue, t->d_counters, (long long)t->N});
+    wl::k_worklist<<<g_sweep_blocks, 256, 0, t->stream>>>(op, wl::DomainRange{w.lo * w.C, (w.hi - w.lo) * w.C},
+                                                          wl::Queue{t->queue, t->d_counters, (long long)t->N});
     PDM_LAUNCHED();
+    return PDM_OK;
+}
+
+// shard rounds: continue from the cells the in-box made ready (list in t->label, length in CT_TMP1)
+int pdm_launch_sweep_resume(pdm_tile *t)
+{
+    if (!g_resume_blocks) {
+        int rc = wl::grid_for(wl::k_worklist<DrainOp<2>, wl::DomainList>, &g_resume_blocks);
+        if (rc) return rc;
+    }
+    int rc = wl::reset_queue(t, 1);
+    if (rc) return rc;
+    DrainOp<2> op{t->link, t->prop, t->uca, t->taint, t->indeg, nullptr, (int32_t)t->C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w};
+    wl::k_worklist<<<g_resume_blocks, 256, 0, t->stream>>>(op, wl::DomainList{t->label, t->d_counters + CT_TMP1},
+                                                           wl::Queue{t->queue, t->d_counters, (long long)t->N});
+    PDM_LAUNCHED();
+    return PDM_OK;
+}
+
+int pdm_launch_uca_finalize(pdm_tile *t, const pdm_uca_params *p)
+{
+    const Win &w = t->win;
     const double limit_area = p->uca_saturation_limit * 2 * t->min_area;
-    k_uca_finalize<<<(unsigned)((t->N + 255) / 256), 256, 0, t->stream>>>(
-        t->elev, t->flats, t->indeg, t->taint, t->uca, t->edge_done, t->N, p->apply_uca_limit_edges, limit_area,
+    const int64_t n0 = w.lo * w.C, n1 = w.hi * w.C;
+    k_uca_finalize<<<(unsigned)((n1 - n0 + 255) / 256), 256, 0, t->stream>>>(
+        t->elev, t->flats, t->indeg, t->taint, t->uca, t->edge_done, n0, n1, p->apply_uca_limit_edges, limit_area,
         t->d_counters);
     PDM_LAUNCHED();
     return PDM_OK;
+}
+
+int pdm_launch_sweep_full(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *st)
+{
+    (void)st;
+    int rc = pdm_launch_sweep_first(t);
+    if (rc) return rc;
+    return pdm_launch_uca_finalize(t, p);
 }
 
 int pdm_launch_twi(pdm_tile *t, const pdm_twi_params *p)

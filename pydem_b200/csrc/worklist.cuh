@@ -62,6 +62,17 @@ struct DomainAll {
     __device__ __forceinline__ int64_t size() const { return N; }
     __device__ __forceinline__ int32_t cell(int64_t t) const { return (int32_t)t; }
 };
+struct DomainRange {   // cells [first, first + n): the owned rows of a shard
+    int64_t first, n;
+    __device__ __forceinline__ int64_t size() const { return n; }
+    __device__ __forceinline__ int32_t cell(int64_t t) const { return (int32_t)(first + t); }
+};
+struct DomainList {    // explicit seed list; its length lives in device memory
+    const int32_t *cells;
+    const unsigned long long *count;
+    __device__ __forceinline__ int64_t size() const { return (int64_t)*count; }
+    __device__ __forceinline__ int32_t cell(int64_t t) const { return cells[t]; }
+};
 struct DomainBorder {
     int64_t R, C;
     __device__ __forceinline__ int64_t size() const { return 2 * C + 2 * (R - 2); }
@@ -207,13 +218,33 @@ int grid_for(K kernel, int *blocks_out)
     return PDM_OK;
 }
 
-// host: reset the queue state before a run (slots to -1, the queue counters to 0)
-inline int reset_queue(pdm_tile *t)
+// wipe the slots the previous run used (they are the only ones that differ from -1)
+static __global__ void __launch_bounds__(256) k_queue_clean(int32_t *slots, const unsigned long long *ctr, long long cap)
 {
-    PDM_CUDA(cudaMemsetAsync(t->queue, 0xFF, (size_t)(t->N + 1) * sizeof(int32_t), t->stream));
-    PDM_CUDA(cudaMemsetAsync(t->d_counters, 0, (CT_DRAINED + 1) * sizeof(unsigned long long), t->stream));  // QTAIL..DRAINED
-    PDM_CUDA(cudaMemsetAsync(t->d_counters + CT_T_START, 0xFF, sizeof(unsigned long long), t->stream));
-    PDM_CUDA(cudaMemsetAsync(t->d_counters + CT_T_SCAN, 0, 2 * sizeof(unsigned long long), t->stream));
+    long long n = (long long)ctr[CT_QTAIL];
+    if (n > cap) n = cap;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        slots[i] = -1;
+}
+static __global__ void k_queue_zero(unsigned long long *ctr, int keep_drained)
+{
+    ctr[CT_QTAIL] = 0; ctr[CT_QHEAD] = 0; ctr[CT_QDONE] = 0; ctr[CT_PHASE1] = 0;
+    if (!keep_drained) ctr[CT_DRAINED] = 0;
+    ctr[CT_T_START] = ~0ULL; ctr[CT_T_SCAN] = 0; ctr[CT_T_END] = 0;
+}
+
+// host: reset the queue state before a run (slots to -1, the queue counters to 0)
+inline int reset_queue(pdm_tile *t, int keep_drained = 0)
+{
+    if (!t->queue_ready) {
+        PDM_CUDA(cudaMemsetAsync(t->queue, 0xFF, (size_t)(t->N + 1) * sizeof(int32_t), t->stream));
+        t->queue_ready = true;
+    } else {
+        k_queue_clean<<<296, 256, 0, t->stream>>>(t->queue, t->d_counters, (long long)t->N);
+        PDM_LAUNCHED();
+    }
+    k_queue_zero<<<1, 1, 0, t->stream>>>(t->d_counters, keep_drained);
+    PDM_LAUNCHED();
     return PDM_OK;
 }
 

@@ -1,0 +1,366 @@
+"""Row-sharded execution of the hot path over the GPUs of one box.
+
+One DEM of ``R x C`` cells is cut into contiguous row blocks, one per rank (one process per
+GPU, ``torch.distributed`` / NCCL).  Every rank keeps one halo row per interior side; halo rows
+travel between neighbouring ranks with NCCL send/recv (``Group.exchange``), everything else is
+local CUDA work through the ``pdm_shard_*`` C ABI (csrc/shard.cu):
+
+    elev halo -> slope/aspect (a1) -> flat0 halo -> region labels (+ label rounds) -> flats (a2)
+    -> links (a3/a4) -> link halo -> in-degree / inflow mask
+    -> { local sweep to quiescence ; exchange out-boxes ; apply in-boxes } until nobody sent
+    -> finalize -> TWI
+
+This is pyDEM's cross-tile UCA edge resolution (reference process_manager.py:1090-1249:
+tiles exchange edge strips and re-run calc_uca on the deltas until nothing changes) in its
+gating-free form: contributions that cross a shard boundary are accumulated in the halo row
+(out-box) together with the number of in-degree decrements they stand for.  Because every
+owned cell is computed from its true 3x3 neighbourhood and "border" means the border of the
+whole DEM, the sharded result equals the single-tile result.
+
+``Group`` hides where the ranks live: ``DistGroup`` = this process is one rank of a
+torch.distributed job; ``LocalGroup`` = all ranks live in this process (tests on one GPU, and
+the CPU tests of the exchange logic).
+"""
+import numpy as np
+
+from . import synth
+
+
+# ----------------------------------------------------------------------------------------------
+# partition
+# ----------------------------------------------------------------------------------------------
+def row_blocks(R, world):
+    """Contiguous, near-equal row blocks [r0, r1) per rank (every rank gets >= 2 rows)."""
+    if R < 2 * world:
+        raise ValueError("need at least 2 rows per rank")
+    edges = [(R * k) // world for k in range(world + 1)]
+    return [(edges[k], edges[k + 1]) for k in range(world)]
+
+
+def global_row_theta(dX, dY):
+    """theta of _calc_uca_section_proportion for the whole grid (dem_processing.py:1031-1033)."""
+    th = np.arctan2(np.asarray(dY, "float64"), np.asarray(dX, "float64"))
+    R = th.size + 1
+    idx = np.clip(np.arange(R) - 1, 0, R - 3)
+    return th[idx]
+
+
+class ShardSpec(object):
+    """Geometry of one rank's tile: owned global rows [r0, r1), local rows incl. halos."""
+
+    def __init__(self, R, C, rank, world):
+        self.R, self.C, self.rank, self.world = R, C, rank, world
+        self.r0, self.r1 = row_blocks(R, world)[rank]
+        self.halo_top = 1 if rank > 0 else 0
+        self.halo_bot = 1 if rank < world - 1 else 0
+        self.row_off = self.r0 - self.halo_top          # global row of local row 0
+        self.Rl = (self.r1 - self.r0) + self.halo_top + self.halo_bot
+        self.lo = self.halo_top
+        self.hi = self.lo + (self.r1 - self.r0)
+
+    def local_slice(self):
+        """global rows held locally (owned + halo)"""
+        return slice(self.row_off, self.row_off + self.Rl)
+
+
+# ----------------------------------------------------------------------------------------------
+# groups: neighbour exchange + sum-allreduce
+# ----------------------------------------------------------------------------------------------
+class LocalGroup(object):
+    """All ranks in this process.  ``exchange`` takes one dict per rank."""
+
+    def __init__(self, world):
+        self.world = world
+        self.local_ranks = list(range(world))
+
+    def exchange(self, bufs):
+        """bufs[k] = dict(send_up, send_down, recv_up, recv_down) of equally shaped tensors/arrays
+        (None where there is no neighbour).  Rank k's send_down lands in rank k+1's recv_up."""
+        for k in range(self.world - 1):
+            _copy(bufs[k + 1]["recv_up"], bufs[k]["send_down"])
+            _copy(bufs[k]["recv_down"], bufs[k + 1]["send_up"])
+
+    def allreduce_sum(self, values):
+        tot = sum(int(v) for v in values)
+        return [tot] * len(values)
+
+
+def _copy(dst, src):
+    if dst is None or src is None:
+        raise ValueError("exchange buffers missing on an interior boundary")
+    if hasattr(dst, "copy_"):
+        dst.copy_(src)
+    else:
+        dst[...] = src
+
+
+class DistGroup(object):
+    """This process is one rank of a torch.distributed job (NCCL on GPUs, gloo in CPU tests)."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank = dist.get_rank()
+        self.world = dist.get_world_size()
+        self.local_ranks = [self.rank]
+
+    def exchange(self, bufs):
+        dist = self.dist
+        b = bufs[0]
+        ops = []
+        if self.rank > 0:
+            ops.append(dist.P2POp(dist.isend, b["send_up"], self.rank - 1))
+            ops.append(dist.P2POp(dist.irecv, b["recv_up"], self.rank - 1))
+        if self.rank < self.world - 1:
+            ops.append(dist.P2POp(dist.isend, b["send_down"], self.rank + 1))
+            ops.append(dist.P2POp(dist.irecv, b["recv_down"], self.rank + 1))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):   # one ncclGroupStart/End with both neighbours
+                r.wait()
+
+    def allreduce_sum(self, values):
+        import torch
+        v = values[0]
+        t = v if hasattr(v, "device") else torch.tensor([int(v)], dtype=torch.int64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [int(t.item())]
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU engine of one rank
+# ----------------------------------------------------------------------------------------------
+class ShardEngine(object):
+    """One rank's tile on one GPU."""
+
+    def __init__(self, spec, dX, dY, dX2, dY2, device=None, stream=None):
+        import torch
+        from . import tile as T
+        self.T, self.torch, self.spec = T, torch, spec
+        s = spec
+        self.tile = T.DeviceTile(s.Rl, s.C, device=device, stream=stream)
+        fence = slice(s.row_off, s.row_off + s.Rl - 1)
+        self.tile.set_spacing(np.asarray(dX)[fence], np.asarray(dY)[fence], np.asarray(dX2)[s.local_slice()],
+                              np.asarray(dY2)[s.local_slice()])
+        self.tile.set_window(s.row_off, s.R, s.lo, s.hi, global_row_theta(dX, dY)[s.local_slice()])
+        self.tile.min_area = float(np.nanmin(np.asarray(dX2) * np.asarray(dY2)))   # of the whole DEM (898)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        C = s.C
+        mk = lambda dt: torch.zeros(C, dtype=dt, device=dev)
+        # packed exchange buffers: labels (int64 + f64) and out-boxes (f64 area, f64 taint, int32 count)
+        self.lab = {k: (mk(torch.int64), mk(torch.float64)) for k in ("send_up", "send_down", "recv_up", "recv_down")}
+        self.box = {k: torch.zeros(C * 5, dtype=torch.int32, device=dev) for k in ("send_up", "send_down", "recv_up", "recv_down")}
+        self.flag = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.views = {}
+
+    def rows(self, field):
+        if field not in self.views:
+            self.views[field] = self.tile.as_torch(field)
+        return self.views[field]
+
+    def halo_bufs(self, field):
+        """Row views for a plain halo exchange of one field: I send my first/last owned row and
+        receive into my halo rows."""
+        s, v = self.spec, self.rows(field)
+        return dict(send_up=v[s.lo] if s.halo_top else None, recv_up=v[s.lo - 1] if s.halo_top else None,
+                    send_down=v[s.hi - 1] if s.halo_bot else None, recv_down=v[s.hi] if s.halo_bot else None)
+
+    # packed label rows: [int64 labels | f64 elevations] travel as two tensors -> two exchanges
+    def label_pack(self):
+        s = self.spec
+        if s.halo_top:
+            self.tile.shard_stage("label_pack", s.lo, self.lab["send_up"][0].data_ptr(), self.lab["send_up"][1].data_ptr())
+        if s.halo_bot:
+            self.tile.shard_stage("label_pack", s.hi - 1, self.lab["send_down"][0].data_ptr(), self.lab["send_down"][1].data_ptr())
+
+    def label_unpack(self):
+        s = self.spec
+        self.flag.zero_()
+        if s.halo_top:
+            self.tile.shard_stage("label_unpack", s.lo - 1, self.lab["recv_up"][0].data_ptr(), self.lab["recv_up"][1].data_ptr(),
+                                  self.flag.data_ptr())
+        if s.halo_bot:
+            self.tile.shard_stage("label_unpack", s.hi, self.lab["recv_down"][0].data_ptr(), self.lab["recv_down"][1].data_ptr(),
+                                  self.flag.data_ptr())
+        return self.flag
+
+    def _box_ptrs(self, key):
+        b, C = self.box[key], self.spec.C
+        p = b.data_ptr()
+        return p, p + 8 * C, p + 16 * C   # area f64[C] | taint f64[C] | count i32[C]
+
+    def outbox_pack(self):
+        s = self.spec
+        self.flag.zero_()
+        if s.halo_top:
+            self.tile.shard_stage("outbox_pack", 0, *self._box_ptrs("send_up"), self.flag.data_ptr())
+        if s.halo_bot:
+            self.tile.shard_stage("outbox_pack", 1, *self._box_ptrs("send_down"), self.flag.data_ptr())
+        return self.flag
+
+    def inbox_apply(self):
+        s = self.spec
+        self.tile.shard_stage("inbox_begin")
+        if s.halo_top:
+            self.tile.shard_stage("inbox_apply", 0, *self._box_ptrs("recv_up"))
+        if s.halo_bot:
+            self.tile.shard_stage("inbox_apply", 1, *self._box_ptrs("recv_down"))
+
+    def box_bufs(self):
+        s = self.spec
+        return dict(send_up=self.box["send_up"] if s.halo_top else None, recv_up=self.box["recv_up"] if s.halo_top else None,
+                    send_down=self.box["send_down"] if s.halo_bot else None, recv_down=self.box["recv_down"] if s.halo_bot else None)
+
+    def lab_bufs(self, which):
+        s = self.spec
+        g = lambda k, ok: self.lab[k][which] if ok else None
+        return dict(send_up=g("send_up", s.halo_top), recv_up=g("recv_up", s.halo_top),
+                    send_down=g("send_down", s.halo_bot), recv_down=g("recv_down", s.halo_bot))
+
+
+def run_hot_path(engines, group, twi=True, **uca_flags):
+    """slope/aspect -> UCA -> TWI over all shards.  ``engines``: the engines of the ranks that
+    live in this process (group.local_ranks).  Returns per-engine stats dicts."""
+    T = engines[0].T
+    # a1: elevation halo, stencil
+    group.exchange([e.halo_bufs(T.F_ELEV) for e in engines])
+    for e in engines:
+        e.tile.shard_stage("slopes")
+    # a2: flat0 halo, region labels (+ cross-rank label rounds), one-pixel extension
+    group.exchange([e.halo_bufs(T.F_FLAT0) for e in engines])
+    for e in engines:
+        e.tile.shard_stage("ccl")
+    label_rounds = 0
+    if group.world > 1:
+        while True:
+            for e in engines:
+                e.label_pack()
+            group.exchange([e.lab_bufs(0) for e in engines])
+            group.exchange([e.lab_bufs(1) for e in engines])
+            changed = group.allreduce_sum([e.label_unpack() for e in engines])[0]
+            label_rounds += 1
+            if changed == 0:
+                break
+    for e in engines:
+        e.tile.shard_stage("flats_extend")
+    # a3/a4: links, link halo, in-degree + inflow-border mask
+    for e in engines:
+        e.tile.shard_links(**uca_flags)
+    group.exchange([e.halo_bufs(T.F_LINK) for e in engines])
+    for e in engines:
+        e.tile.shard_stage("indeg")
+    # a6/a7: local sweeps + out-box rounds
+    rounds, first = 0, 1
+    while True:
+        for e in engines:
+            e.tile.shard_stage("sweep", first)
+        first = 0
+        rounds += 1
+        if group.world == 1:
+            break
+        sent = group.allreduce_sum([e.outbox_pack() for e in engines])[0]
+        if sent == 0:
+            break
+        group.exchange([e.box_bufs() for e in engines])
+        for e in engines:
+            e.inbox_apply()
+    stats = []
+    for e in engines:
+        st = e.tile.shard_finalize()
+        st.update(sweep_rounds=rounds, label_rounds=label_rounds)
+        stats.append(st)
+        if twi:
+            e.tile.twi()
+    return stats
+
+
+# ----------------------------------------------------------------------------------------------
+# convenience drivers
+# ----------------------------------------------------------------------------------------------
+def run_local(E, world, dX=1.0, dY=1.0, dX2=None, dY2=None, **uca_flags):
+    """All ``world`` shards of ``E`` on the current GPU, one after the other (test helper and
+    single-GPU fallback for DEMs that do not fit one 32-bit-indexed tile).  Returns a dict of
+    assembled full-size arrays plus per-shard stats."""
+    import torch
+    from . import tile as T
+    R, C = E.shape
+    dXa = np.broadcast_to(np.asarray(dX, "float64"), (R - 1,)); dYa = np.broadcast_to(np.asarray(dY, "float64"), (R - 1,))
+    dX2a = np.broadcast_to(np.asarray(dXa[0] if dX2 is None else dX2, "float64"), (R,))
+    dY2a = np.broadcast_to(np.asarray(dYa[0] if dY2 is None else dY2, "float64"), (R,))
+    group = LocalGroup(world)
+    stream = torch.cuda.current_stream().cuda_stream
+    engines = []
+    for k in range(world):
+        spec = ShardSpec(R, C, k, world)
+        e = ShardEngine(spec, dXa, dYa, dX2a, dY2a, stream=stream)
+        loc = np.full((spec.Rl, C), np.nan)
+        loc[spec.lo:spec.hi] = E[spec.r0:spec.r1]            # halo rows arrive through the exchange
+        e.tile.upload(T.F_ELEV, loc)
+        engines.append(e)
+    stats = run_hot_path(engines, group, **uca_flags)
+    out = {}
+    for name, f in (("mag", T.F_MAG), ("direction", T.F_DIR), ("flats", T.F_FLATS), ("uca", T.F_UCA), ("twi", T.F_TWI),
+                    ("edge_todo", T.F_EDGE_TODO), ("edge_done", T.F_EDGE_DONE)):
+        full = np.empty((R, C), dtype=T._lib.FIELD_DTYPE[f])
+        for e in engines:
+            s = e.spec
+            full[s.r0:s.r1] = e.tile.download(f)[s.lo:s.hi]
+        out[name] = full.astype(bool) if full.dtype == np.uint8 else full
+    out["stats"] = stats
+    for e in engines:
+        e.tile.close()
+    return out
+
+
+class ShardedDEM(object):
+    """bench.py's N>1 workload: a value-noise DEM of (rows_per_rank * world) x cols, one row block
+    per rank of the torch.distributed job; ``step()`` runs the whole hot path once."""
+
+    def __init__(self, rows_per_rank, cols, spacing=30.0, seed=2):
+        import torch
+        from . import tile as T
+        self.T, self.torch = T, torch
+        self.group = DistGroup()
+        w, r = self.group.world, self.group.rank
+        R = rows_per_rank * w
+        self.spec = ShardSpec(R, cols, r, w)
+        s = self.spec
+        d = np.full(R - 1, float(spacing)); d2 = np.full(R, float(spacing))
+        self.engine = ShardEngine(s, d, d, d2, d2, stream=torch.cuda.current_stream().cuda_stream)
+        loc = np.full((s.Rl, cols), np.nan)
+        loc[s.lo:s.hi] = synth.value_noise_dem(s.r0, s.r1 - s.r0, cols, seed=seed)
+        self.host_elev = loc
+        self.engine.tile.upload(T.F_ELEV, loc)
+        self.cells = (s.r1 - s.r0) * cols
+
+    def step(self):
+        return run_hot_path([self.engine], self.group)[0]
+
+    def e2e(self, steps):
+        """Same metric with the rank's rows uploaded from pinned host memory and its results
+        (mag, direction, uca, twi, flats, edge masks) read back inside the timed region."""
+        import time
+        from . import _pinned
+        torch, T, s = self.torch, self.T, self.spec
+        Eh = _pinned.pinned_copy(self.host_elev)
+        outs = {f: _pinned.empty((s.Rl, s.C), T._lib.FIELD_DTYPE[f])
+                for f in (T.F_MAG, T.F_DIR, T.F_UCA, T.F_TWI, T.F_FLATS, T.F_EDGE_TODO, T.F_EDGE_DONE)}
+        dist = self.group.dist
+
+        def one():
+            self.engine.tile.upload(T.F_ELEV, Eh)
+            run_hot_path([self.engine], self.group)
+            for f, o in outs.items():
+                self.engine.tile.download(f, o)
+        one()
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one()
+        torch.cuda.synchronize(); dist.barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / steps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt.item())
+        cells = self.cells * self.group.world
+        return {"value": cells / dt / 1e6, "unit": "Mcells/s", "ms_per_step": dt * 1e3,
+                "h2d_bytes_per_step": int(s.Rl * s.C * 8 * self.group.world),
+                "d2h_bytes_per_step": int(s.Rl * s.C * (8 * 4 + 3) * self.group.world)}

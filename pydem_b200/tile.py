@@ -6,8 +6,8 @@ import ctypes as ct
 import numpy as np
 
 from . import _lib
-from ._lib import (F_DIR, F_EDGE_DONE, F_EDGE_TODO, F_ELEV, F_FLATS, F_MAG, F_PROP, F_SECTION, F_TAINT,  # noqa: F401
-                   F_TWI, F_UCA)
+from ._lib import (F_DIR, F_EDGE_DONE, F_EDGE_TODO, F_ELEV, F_FLAT0, F_FLATS, F_LINK, F_MAG, F_PROP,  # noqa: F401
+                   F_SECTION, F_TAINT, F_TWI, F_UCA)
 
 
 class DeviceTile(object):
@@ -66,6 +66,30 @@ class DeviceTile(object):
         o.__cuda_array_interface__ = dict(shape=self.shape, typestr=dt.str, data=(self.device_ptr(field), False),
                                           version=2, strides=None)
         return torch.as_tensor(o, device="cuda")
+
+    # ---- row shards (include/pydem_b200.h, "row shards") ------------------------------------
+    def set_window(self, row_off, R_global, own_lo, own_hi, th_row=None):
+        a = None if th_row is None else np.ascontiguousarray(th_row, "float64")
+        assert a is None or a.shape == (self.R,)
+        _lib.check(self.L.pdm_tile_set_window(self.h, int(row_off), int(R_global), int(own_lo), int(own_hi), _lib.ptr(a)))
+        self.own = (int(own_lo), int(own_hi))
+
+    def shard_stage(self, name, *args):
+        _lib.check(getattr(self.L, "pdm_shard_" + name)(self.h, *args))
+
+    def shard_links(self, **flags):
+        p = _lib.UcaParams()
+        self.L.pdm_default_uca_params(ct.byref(p))
+        p.drain_pits = 0
+        for k, v in flags.items():
+            setattr(p, k, v)
+        self._shard_params = p
+        _lib.check(self.L.pdm_shard_links(self.h, ct.byref(p)))
+
+    def shard_finalize(self):
+        st = _lib.UcaStats()
+        _lib.check(self.L.pdm_shard_finalize(self.h, ct.byref(self._shard_params), ct.byref(st)))
+        return st.as_dict()
 
     def mark_resident(self, field):
         _lib.check(self.L.pdm_tile_mark_resident(self.h, field))
