@@ -182,6 +182,14 @@ class DEMProcessor(object):
     # ------------------------------------------------------------------------------------
     # reference API
     # ------------------------------------------------------------------------------------
+    def _conditioning_flags(self):
+        """The flags the reference's conditioning routines read (for delegating them to the
+        reference implementation)."""
+        keys = ("fill_flats_below_sea", "fill_flats_source_tol", "fill_flats_peaks", "fill_flats_pits",
+                "fill_flats_max_iter", "drain_pits_max_iter", "drain_pits_max_dist", "drain_pits_max_dist_XY",
+                "maximum_pit_area")
+        return {k: getattr(self, k) for k in keys}
+
     def find_flats(self):
         """dem_processing.py:305-306"""
         self.flats = self.mag == FLAT_ID_INT

@@ -217,14 +217,42 @@ class ShardEngine(object):
                     send_down=g("send_down", s.halo_bot), recv_down=g("recv_down", s.halo_bot))
 
 
-def run_hot_path(engines, group, twi=True, **uca_flags):
+class _Timer(object):
+    """CUDA-event stage timer (only when profiling is requested)."""
+
+    def __init__(self, on):
+        self.on, self.marks = on, []
+        if on:
+            import torch
+            self.torch = torch
+            self.mark("start")
+
+    def mark(self, name):
+        if self.on:
+            ev = self.torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.marks.append((name, ev))
+
+    def result(self):
+        if not self.on:
+            return {}
+        self.torch.cuda.synchronize()
+        out = {}
+        for (n0, e0), (n1, e1) in zip(self.marks[:-1], self.marks[1:]):
+            out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+        return out
+
+
+def run_hot_path(engines, group, twi=True, profile=False, **uca_flags):
     """slope/aspect -> UCA -> TWI over all shards.  ``engines``: the engines of the ranks that
     live in this process (group.local_ranks).  Returns per-engine stats dicts."""
     T = engines[0].T
+    tm = _Timer(profile)
     # a1: elevation halo, stencil
     group.exchange([e.halo_bufs(T.F_ELEV) for e in engines])
     for e in engines:
         e.tile.shard_stage("slopes")
+    tm.mark("ms_slopes")
     # a2: flat0 halo, region labels (+ cross-rank label rounds), one-pixel extension
     group.exchange([e.halo_bufs(T.F_FLAT0) for e in engines])
     for e in engines:
@@ -242,27 +270,32 @@ def run_hot_path(engines, group, twi=True, **uca_flags):
                 break
     for e in engines:
         e.tile.shard_stage("flats_extend")
+    tm.mark("ms_flats")
     # a3/a4: links, link halo, in-degree + inflow-border mask
     for e in engines:
         e.tile.shard_links(**uca_flags)
     group.exchange([e.halo_bufs(T.F_LINK) for e in engines])
     for e in engines:
         e.tile.shard_stage("indeg")
+    tm.mark("ms_graph")
     # a6/a7: local sweeps + out-box rounds
     rounds, first = 0, 1
     while True:
         for e in engines:
             e.tile.shard_stage("sweep", first)
+        tm.mark("ms_sweep_first" if first else "ms_sweep_resume")
         first = 0
         rounds += 1
         if group.world == 1:
             break
         sent = group.allreduce_sum([e.outbox_pack() for e in engines])[0]
         if sent == 0:
+            tm.mark("ms_exchange")
             break
         group.exchange([e.box_bufs() for e in engines])
         for e in engines:
             e.inbox_apply()
+        tm.mark("ms_exchange")
     stats = []
     for e in engines:
         st = e.tile.shard_finalize()
@@ -270,6 +303,10 @@ def run_hot_path(engines, group, twi=True, **uca_flags):
         stats.append(st)
         if twi:
             e.tile.twi()
+    tm.mark("ms_finalize_twi")
+    prof = tm.result()
+    for st in stats:
+        st.update(prof)
     return stats
 
 
@@ -315,7 +352,7 @@ class ShardedDEM(object):
     """bench.py's N>1 workload: a value-noise DEM of (rows_per_rank * world) x cols, one row block
     per rank of the torch.distributed job; ``step()`` runs the whole hot path once."""
 
-    def __init__(self, rows_per_rank, cols, spacing=30.0, seed=2):
+    def __init__(self, rows_per_rank, cols, spacing=30.0, seed=0, profile=False):
         import torch
         from . import tile as T
         self.T, self.torch = T, torch
@@ -327,13 +364,17 @@ class ShardedDEM(object):
         d = np.full(R - 1, float(spacing)); d2 = np.full(R, float(spacing))
         self.engine = ShardEngine(s, d, d, d2, d2, stream=torch.cuda.current_stream().cuda_stream)
         loc = np.full((s.Rl, cols), np.nan)
-        loc[s.lo:s.hi] = synth.value_noise_dem(s.r0, s.r1 - s.r0, cols, seed=seed)
+        # every rank holds the same periodic spectral-synthesis block: stacked vertically the blocks
+        # join seamlessly (FFT fields are periodic), so per-GPU work is identical (weak scaling) and
+        # flow really crosses the shard boundaries
+        loc[s.lo:s.hi] = synth.fractal_dem(rows_per_rank, seed, shape=(rows_per_rank, cols))
+        self.profile = profile
         self.host_elev = loc
         self.engine.tile.upload(T.F_ELEV, loc)
         self.cells = (s.r1 - s.r0) * cols
 
     def step(self):
-        return run_hot_path([self.engine], self.group)[0]
+        return run_hot_path([self.engine], self.group, profile=self.profile)[0]
 
     def e2e(self, steps):
         """Same metric with the rank's rows uploaded from pinned host memory and its results

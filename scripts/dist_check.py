@@ -1,0 +1,46 @@
+"""Multi-GPU correctness under torchrun: the NCCL-sharded hot path vs the single-tile result.
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/dist_check.py [rows cols]
+Every rank computes the single-tile answer for the whole DEM on its own GPU and compares its
+owned rows of the sharded run against it."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+from pydem_b200 import _lib, sharded, synth, tile as T, DEMProcessor
+_lib.init(local)
+R = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+C = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+g = sharded.DistGroup()
+E = synth.value_noise_dem(0, R, C, seed=7)
+E[R // 2 - 3:R // 2 + 3, 100:400] = E[R // 2 - 3:R // 2 + 3, 100:400].min()     # a lake on a shard boundary
+spec = sharded.ShardSpec(R, C, g.rank, g.world)
+d = np.full(R - 1, 30.0); d2 = np.full(R, 30.0)
+eng = sharded.ShardEngine(spec, d, d, d2, d2, stream=torch.cuda.current_stream().cuda_stream)
+loc = np.full((spec.Rl, C), np.nan); loc[spec.lo:spec.hi] = E[spec.r0:spec.r1]
+eng.tile.upload(T.F_ELEV, loc)
+st = sharded.run_hot_path([eng], g)[0]
+dp = DEMProcessor(elev=E, dX=30.0, dY=30.0, fill_flats=False, drain_pits_path=False, drain_pits=False)
+dp.calc_twi()
+ok = True
+for name, f, exact in (("mag", T.F_MAG, True), ("direction", T.F_DIR, True), ("flats", T.F_FLATS, True),
+                       ("edge_todo", T.F_EDGE_TODO, True), ("edge_done", T.F_EDGE_DONE, True), ("uca", T.F_UCA, False)):
+    a = eng.tile.download(f)[spec.lo:spec.hi]
+    b = np.asarray(getattr(dp, name))[spec.r0:spec.r1]
+    if exact:
+        good = np.array_equal(a.astype(b.dtype), b, equal_nan=True) if a.dtype.kind == "f" else np.array_equal(a.astype(bool), b)
+    else:
+        good = np.allclose(a, b, rtol=1e-9, equal_nan=True)
+    ok = ok and good
+    if not good:
+        print("rank", g.rank, "MISMATCH", name, flush=True)
+flag = torch.tensor([0 if ok else 1], device="cuda")
+dist.all_reduce(flag)
+if g.rank == 0:
+    print("dist_check", "OK" if flag.item() == 0 else "FAILED", "world", g.world, "rows", R, "cols", C, st, flush=True)
+dist.destroy_process_group()
+sys.exit(0 if flag.item() == 0 else 1)
