@@ -52,8 +52,8 @@ typedef enum {
     PDM_F_EDGE_TODO = 6, /* [u8]   .edge_todo */
     PDM_F_EDGE_DONE = 7, /* [u8]   .edge_done */
     PDM_F_SECTION = 8,   /* [i8]   DEMProcessor.section (debug attribute, dem_processing.py:137) */
-    PDM_F_PROP = 9,      /* [f64]  DEMProcessor.proportion */
-    PDM_F_TAINT = 10,    /* [f64]  propagated edge_todo weight (cyutils.pyx:163) */
+    PDM_F_TWI10 = 9,     /* [f64]  10 * twi: what DEMProcessor.twi stores (dem_processing.py:1674) */
+    /* 10: reserved */
     PDM_F_FLAT0 = 11,    /* [u8]   mag == -1 before the one-pixel extension (shard halo exchange) */
     PDM_F_LINK = 12,     /* [u8]   facet index + kept-receiver bits of each cell (shard halo exchange) */
     PDM_F_COUNT_ = 13
@@ -157,7 +157,8 @@ int pdm_tile_uca_update(pdm_tile *t, const pdm_uca_params *p,
                         const uint8_t *todo_left, const uint8_t *todo_right,
                         const uint8_t *todo_top, const uint8_t *todo_bottom,
                         pdm_uca_stats *stats);
-/* a9: calc_twi (1647-1677).  In: UCA, MAG.  Out: TWI (un-scaled). */
+/* a9: calc_twi (1647-1677).  In: UCA, MAG.  Out: TWI (un-scaled, the return value) and TWI10
+ * (= 10 * twi, the attribute). */
 int pdm_tile_twi(pdm_tile *t, const pdm_twi_params *p);
 
 /* ---- row shards (one tile per GPU = a block of rows of one big DEM) --------------------------

@@ -47,8 +47,7 @@ static void *field_ptr(pdm_tile *t, int field)
         case PDM_F_EDGE_TODO: return t->edge_todo;
         case PDM_F_EDGE_DONE: return t->edge_done;
         case PDM_F_SECTION: return t->section;
-        case PDM_F_PROP: return t->prop;
-        case PDM_F_TAINT: return t->taint;
+        case PDM_F_TWI10: return t->twi10;
         case PDM_F_FLAT0: return t->flat0;
         case PDM_F_LINK: return t->link;
         default: return nullptr;
@@ -134,10 +133,10 @@ int pdm_tile_create(int64_t R, int64_t C, void *stream, pdm_tile **out)
     const size_t N = (size_t)t->N;
     struct { void **p; size_t bytes; } allocs[] = {
         {(void **)&t->elev, N * 8}, {(void **)&t->mag, N * 8}, {(void **)&t->dir, N * 8}, {(void **)&t->uca, N * 8},
-        {(void **)&t->taint, N * 8}, {(void **)&t->prop, N * 8}, {(void **)&t->twi, N * 8},
+        {(void **)&t->cell, N * sizeof(Cell)}, {(void **)&t->twi, N * 8},
         {(void **)&t->flats, N}, {(void **)&t->flat0, N + 8}, {(void **)&t->link, N}, {(void **)&t->edge_todo, N},
         {(void **)&t->edge_done, N},
-        {(void **)&t->indeg, N * 4}, {(void **)&t->label, N * 4}, {(void **)&t->queue, (N + 1) * 4},
+        {(void **)&t->label, N * 4}, {(void **)&t->queue, (N + 1) * 4},
         {(void **)&t->dX, (size_t)R * 8}, {(void **)&t->dY, (size_t)R * 8}, {(void **)&t->dg, (size_t)R * 8},
         {(void **)&t->thA, (size_t)R * 8}, {(void **)&t->thB, (size_t)R * 8}, {(void **)&t->th_row, (size_t)R * 8},
         {(void **)&t->row_area, (size_t)R * 8},
@@ -166,11 +165,11 @@ int pdm_tile_create(int64_t R, int64_t C, void *stream, pdm_tile **out)
 int pdm_tile_destroy(pdm_tile *t)
 {
     if (!t) return PDM_OK;
-    void *ptrs[] = {t->elev, t->mag, t->dir, t->uca, t->taint, t->prop, t->twi, t->flats, t->flat0, t->link,
-                    t->edge_todo, t->edge_done, t->section, t->indeg, t->label, t->queue, t->dX, t->dY, t->dg,
+    void *ptrs[] = {t->elev, t->mag, t->dir, t->uca, t->cell, t->twi, t->flats, t->flat0, t->link,
+                    t->edge_todo, t->edge_done, t->section, t->label, t->queue, t->dX, t->dY, t->dg,
                     t->thA, t->thB, t->th_row, t->row_area, t->d_counters, t->pit_cell, t->pit_beg, t->pit_end,
                     t->pit_dst, t->pit_w, t->pit_scratch_i, t->pit_scratch_d, t->edge_buf_d, t->edge_buf_b,
-                    t->glabel, t->glelev};
+                    t->glabel, t->glelev, t->twi10};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (t->h_counters) cudaFreeHost(t->h_counters);
     for (int k = 0; k < 4; k++) if (t->ev[k]) cudaEventDestroy(t->ev[k]);
@@ -383,6 +382,7 @@ int pdm_tile_uca_update(pdm_tile *t, const pdm_uca_params *p_in,
 int pdm_tile_twi(pdm_tile *t, const pdm_twi_params *p_in)
 {
     if (!t) { pdm_set_error("NULL tile"); return PDM_ERR_ARG; }
+    if (!t->twi10) PDM_CUDA(cudaMalloc(&t->twi10, (size_t)t->N * 8));
     if (!t->have_uca || !t->have_slopes) { pdm_set_error("pdm_tile_twi: needs UCA and MAG"); return PDM_ERR_STATE; }
     pdm_twi_params p;
     if (p_in) p = *p_in; else pdm_default_twi_params(&p);

@@ -29,11 +29,8 @@ __device__ __forceinline__ uint32_t st_fetch_or(uint8_t *st, int32_t cell, uint3
 //           (cells whose last upstream contribution arrived from a neighbouring rank).
 template <int MODE>
 struct DrainOp {
-    const uint8_t *link;
-    const double *prop;
-    double *area;
-    double *taint;
-    int32_t *indeg;
+    const uint8_t *link;   // SoA copy of the link bytes: only the seed scan reads it
+    Cell *cell;            // 32-byte sweep records
     const uint8_t *st;
     int32_t C;
     const int32_t *pit_beg;
@@ -51,26 +48,30 @@ struct DrainOp {
     __device__ __forceinline__ int32_t process(int32_t i, const wl::Queue &q, int32_t &defer) const
     {
         using wl::dep_zero;
-        const uint8_t lk = link[i];
+        // the cell's whole sweep state is one 32-byte sector: two 16-byte L2 loads
+        const double2 at = __ldcg(reinterpret_cast<const double2 *>(&cell[i].area));      // area, taint
+        const longlong2 pm = __ldcg(reinterpret_cast<const longlong2 *>(&cell[i].prop));  // prop | indeg, link
+        const double ai = at.x;
+        const double ti = MODE != 1 ? at.y : 0.0;
+        const double p = __longlong_as_double(pm.x);
+        const uint8_t lk = (uint8_t)((unsigned long long)pm.y >> 32);
         int32_t nxt = -1;
         if (lk & LK_PIT) {
             // long-range pit edges (_mk_connectivity_pits): rare, plain fence ordering
-            const double ai = __ldcg(area + i);
-            const double ti = MODE != 1 ? __ldcg(taint + i) : 0.0;
-            const int64_t slot = __double_as_longlong(prop[i]);
+            const int64_t slot = pm.x;
             const int32_t e0 = pit_beg[slot], e1 = pit_end[slot];
             for (int32_t e = e0; e < e1; e++) {
                 const int32_t r = pit_dst[e];
                 if (skip(r)) continue;
                 const double w = pit_w[e];
-                atomicAdd(area + r, __dmul_rn(ai, w));
-                if (MODE != 1 && ti != 0.0) atomicAdd(taint + r, __dmul_rn(ti, w));
+                atomicAdd(&cell[r].area, __dmul_rn(ai, w));
+                if (MODE != 1 && ti != 0.0) atomicAdd(&cell[r].taint, __dmul_rn(ti, w));
             }
             __threadfence();
             for (int32_t e = e0; e < e1; e++) {
                 const int32_t r = pit_dst[e];
                 if (skip(r)) continue;
-                if (atomicSub(indeg + r, 1) == 1) {
+                if (atomicSub(&cell[r].indeg, 1) == 1) {
                     if (nxt < 0) nxt = r; else q.push(r);
                 }
             }
@@ -79,27 +80,24 @@ struct DrainOp {
         bool k1 = lk & LK_KEEP1, k2 = lk & LK_KEEP2;
         if (!(k1 || k2)) return -1;
         const int sec = lk & LK_SEC_MASK;
-        const double p = prop[i];
         const int32_t r1 = i + wl::off_e1(sec, C), r2 = i + wl::off_e2(sec, C);
         if (MODE == 1) {
             if (k1 && skip(r1)) k1 = false;
             if (k2 && skip(r2)) k2 = false;
             if (!(k1 || k2)) return -1;
         }
-        const double ai = __ldcg(area + i);
-        const double ti = MODE != 1 ? __ldcg(taint + i) : 0.0;
         const double w2 = __dsub_rn(1.0, p);                                    // dem_processing.py:1082
         int dep = 0;
-        if (k1) dep |= dep_zero(atomicAdd(area + r1, __dmul_rn(ai, p)));        // cyutils.pyx:161
-        if (k2) dep |= dep_zero(atomicAdd(area + r2, __dmul_rn(ai, w2)));
+        if (k1) dep |= dep_zero(atomicAdd(&cell[r1].area, __dmul_rn(ai, p)));   // cyutils.pyx:161
+        if (k2) dep |= dep_zero(atomicAdd(&cell[r2].area, __dmul_rn(ai, w2)));
         if (MODE != 1 && ti != 0.0) {                                           // cyutils.pyx:163-164
-            if (k1) dep |= dep_zero(atomicAdd(taint + r1, __dmul_rn(ti, p)));
-            if (k2) dep |= dep_zero(atomicAdd(taint + r2, __dmul_rn(ti, w2)));
+            if (k1) dep |= dep_zero(atomicAdd(&cell[r1].taint, __dmul_rn(ti, p)));
+            if (k2) dep |= dep_zero(atomicAdd(&cell[r2].taint, __dmul_rn(ti, w2)));
         }
         const int one = 1 + dep;  // == 1, but only available once the adds above have returned
         int o1 = 0, o2 = 0;
-        if (k1) o1 = atomicSub(indeg + r1, one);
-        if (k2) o2 = atomicSub(indeg + r2, one);
+        if (k1) o1 = atomicSub(&cell[r1].indeg, one);
+        if (k2) o2 = atomicSub(&cell[r2].indeg, one);
         const bool rdy1 = k1 && o1 == 1, rdy2 = k2 && o2 == 1;
         if (rdy1 && rdy2) {
             // follow the larger share, hand the other receiver to an idle lane

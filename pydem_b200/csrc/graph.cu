@@ -9,7 +9,8 @@
 // the in-degree (CSR row length) is counted by looking at the 8 neighbours' bytes.
 //
 // Algorithmic traffic: link pass reads dir 8 + flats 1 + elev 8 (+2 neighbour elevations from
-// L1/L2), writes link 1 + prop 8; in-degree pass reads link 1, writes indeg 4 + area 8 + taint 8.
+// L1/L2), writes link 1 + prop 8 (scratch); in-degree pass reads link 1 + prop 8 and writes the
+// cell's 32-byte sweep record (Cell).
 #include "pdm_internal.cuh"
 
 namespace {
@@ -105,13 +106,12 @@ __device__ __forceinline__ int drains_in(uint8_t lk, uint8_t keepbit, uint32_t s
     return ((lk & keepbit) && !(lk & (LK_NOSEC | LK_PIT)) && ((secmask >> (lk & LK_SEC_MASK)) & 1u)) ? 1 : 0;
 }
 
-// in-degree of every owned cell (+ pit in-edges already accumulated into indeg by the pit
-// kernel), source flag, and the initial state of the sweep: area = dX2*dY2 of the row, taint = 0.
-// Halo rows of a shard (the out-boxes of the sweep) start at zero.
+// in-degree of every owned cell (+ pit in-edges counted by the pit kernel), source flag, and
+// the initial sweep record of the cell: area = dX2*dY2 of the row, taint = 0.  Halo rows of a
+// shard (the out-boxes of the sweep) start at zero.
 __global__ void __launch_bounds__(256)
-k_indeg(uint8_t *__restrict__ link, Win w, const double *__restrict__ row_area,
-        int32_t *__restrict__ indeg, double *__restrict__ area, double *__restrict__ taint,
-        unsigned long long *counters)
+k_indeg(uint8_t *__restrict__ link, Win w, const double *__restrict__ row_area, const double *__restrict__ prop,
+        const int32_t *__restrict__ pit_in, Cell *__restrict__ cell, unsigned long long *counters)
 {
     const int64_t C = w.C;
     const int64_t j = (int64_t)blockIdx.x * 32 + threadIdx.x;
@@ -122,6 +122,9 @@ k_indeg(uint8_t *__restrict__ link, Win w, const double *__restrict__ row_area,
     int64_t n = 0;
     if (in) {
         n = i * C + j;
+        Cell rec;
+        rec.taint = 0.0; rec.pad[0] = rec.pad[1] = rec.pad[2] = 0;
+        rec.link = link[n];
         if (own) {
             const bool up = w.row_in_grid(i - 1), dn = w.row_in_grid(i + 1), lf = j > 0, rt = j < C - 1;
             if (lf) cnt += drains_in(link[n - 1], LK_KEEP1, 0x81u);             // W neighbour: e1 = (0,+1)
@@ -132,14 +135,14 @@ k_indeg(uint8_t *__restrict__ link, Win w, const double *__restrict__ row_area,
             if (up && rt) cnt += drains_in(link[n - C + 1], LK_KEEP2, 0x30u);   // NE: e2 = (+1,-1)
             if (dn && lf) cnt += drains_in(link[n + C - 1], LK_KEEP2, 0x03u);   // SW: e2 = (-1,+1)
             if (dn && rt) cnt += drains_in(link[n + C + 1], LK_KEEP2, 0x0Cu);   // SE: e2 = (-1,-1)
-            cnt += indeg[n];
-            indeg[n] = cnt;
-            area[n] = __ldg(row_area + i);                                      // 885, 901
+            if (pit_in) cnt += pit_in[n];
+            rec.indeg = cnt;
+            rec.area = __ldg(row_area + i);                                     // 885, 901
+            rec.prop = prop[n];
         } else {
-            indeg[n] = 0;
-            area[n] = 0.0;
+            rec.indeg = 0; rec.area = 0.0; rec.prop = 0.0;
         }
-        taint[n] = 0.0;
+        cell[n] = rec;
     }
     const bool src = own && cnt == 0;
     if (src) link[n] |= LK_SOURCE;                                          // 882-883
@@ -153,10 +156,10 @@ __device__ __forceinline__ bool sec_in(int sec, uint32_t mask) { return sec >= 0
 // grid.  Thread t < C: top-row candidate, t < 2C: bottom-row candidate, then two per owned row
 // (left / right column).  Also seeds taint (edge_todo as float, 944).
 __global__ void __launch_bounds__(256)
-k_border_todo(const double *__restrict__ E, const uint8_t *__restrict__ link, const double *__restrict__ prop,
+k_border_todo(const double *__restrict__ E, const uint8_t *__restrict__ link, Cell *__restrict__ cell,
               Win w, const int32_t *__restrict__ pit_beg, const int32_t *__restrict__ pit_end, const double *__restrict__ pit_w,
               const int32_t *__restrict__ pit_dst, int64_t n_pit_edges,
-              uint8_t *__restrict__ edge_todo, double *__restrict__ taint, unsigned long long *counters)
+              uint8_t *__restrict__ edge_todo, unsigned long long *counters)
 {
     const int64_t C = w.C;
     const int64_t nown = w.hi - w.lo;
@@ -178,10 +181,10 @@ k_border_todo(const double *__restrict__ E, const uint8_t *__restrict__ link, co
     double outflow = 0.0;
     int sec = (lk & LK_NOSEC) ? -1 : (lk & LK_SEC_MASK);
     if (lk & LK_PIT) {
-        const int64_t slot = __double_as_longlong(prop[n]);
+        const int64_t slot = __double_as_longlong(cell[n].prop);
         for (int32_t e = pit_beg[slot]; e < pit_end[slot]; e++) outflow += pit_w[e];
     } else {
-        const double p = prop[n];
+        const double p = cell[n].prop;
         // scipy sums a column's entries in row-index order; two terms commute
         if (lk & LK_KEEP1) outflow += p;
         if (lk & LK_KEEP2) outflow += __dsub_rn(1.0, p);
@@ -203,8 +206,8 @@ k_border_todo(const double *__restrict__ E, const uint8_t *__restrict__ link, co
                 const uint8_t ml = link[mi * C + mj];
                 if (ml & (LK_NOSEC | LK_PIT)) continue;
                 const int ms = ml & LK_SEC_MASK;
-                if ((ml & LK_KEEP1) && g_e1r[ms] == -di && g_e1c[ms] == -dj) inflow += prop[mi * C + mj];
-                if ((ml & LK_KEEP2) && g_e2r[ms] == -di && g_e2c[ms] == -dj) inflow += __dsub_rn(1.0, prop[mi * C + mj]);
+                if ((ml & LK_KEEP1) && g_e1r[ms] == -di && g_e1c[ms] == -dj) inflow += cell[mi * C + mj].prop;
+                if ((ml & LK_KEEP2) && g_e2r[ms] == -di && g_e2c[ms] == -dj) inflow += __dsub_rn(1.0, cell[mi * C + mj].prop);
             }
         for (int64_t e = 0; e < n_pit_edges; e++)
             if (pit_dst[e] == (int32_t)n) inflow += pit_w[e];
@@ -213,7 +216,7 @@ k_border_todo(const double *__restrict__ E, const uint8_t *__restrict__ link, co
     const double e0 = E[n];
     if (e0 != e0) todo = false;                                             // 935
     edge_todo[n] = todo ? 1 : 0;
-    if (todo) { taint[n] = 1.0; atomicAdd(&counters[CT_EDGE_TODO], 1ULL); }
+    if (todo) { cell[n].taint = 1.0; atomicAdd(&counters[CT_EDGE_TODO], 1ULL); }
 }
 
 }  // namespace
@@ -229,8 +232,9 @@ int pdm_graph_links_pits(pdm_tile *t, const pdm_uca_params *p)
     dim3 grid((unsigned)((w.C + 31) / 32), (unsigned)((w.hi - w.lo + 7) / 8));
     // stage counters only: the work-list counters below CT_SOURCES remember which queue slots are dirty
     PDM_CUDA(cudaMemsetAsync(t->d_counters + CT_SOURCES, 0, (CT_N - CT_SOURCES) * sizeof(unsigned long long), t->stream));
-    PDM_CUDA(cudaMemsetAsync(t->indeg, 0, (size_t)t->N * sizeof(int32_t), t->stream));
-    k_links<<<grid, block, 0, t->stream>>>(t->elev, t->dir, t->flats, t->th_row, w, t->link, t->prop,
+    // proportion goes to scratch (the TWI buffer is free until calc_twi); k_indeg / the update
+    // mode assemble the 32-byte sweep records from it
+    k_links<<<grid, block, 0, t->stream>>>(t->elev, t->dir, t->flats, t->th_row, w, t->link, t->twi,
                                            t->flat0, t->d_counters);
     PDM_LAUNCHED();
     t->n_pits = 0; t->n_pit_edges = 0;
@@ -254,12 +258,13 @@ int pdm_launch_indeg_todo(pdm_tile *t)
     dim3 block(32, 8);
     dim3 grid((unsigned)((w.C + 31) / 32), (unsigned)((t->R + 7) / 8));
     PDM_CUDA(cudaMemsetAsync(t->edge_todo, 0, (size_t)t->N, t->stream));
-    k_indeg<<<grid, block, 0, t->stream>>>(t->link, w, t->row_area, t->indeg, t->uca, t->taint, t->d_counters);
+    k_indeg<<<grid, block, 0, t->stream>>>(t->link, w, t->row_area, t->twi, t->n_pits ? t->label : nullptr, t->cell,
+                                           t->d_counters);
     PDM_LAUNCHED();
     const int64_t per = 2 * w.C + 2 * (w.hi - w.lo);
     k_border_todo<<<(unsigned)((per + 255) / 256), 256, 0, t->stream>>>(
-        t->elev, t->link, t->prop, w, t->pit_beg, t->pit_end, t->pit_w, t->pit_dst, t->n_pit_edges,
-        t->edge_todo, t->taint, t->d_counters);
+        t->elev, t->link, t->cell, w, t->pit_beg, t->pit_end, t->pit_w, t->pit_dst, t->n_pit_edges,
+        t->edge_todo, t->d_counters);
     PDM_LAUNCHED();
     return PDM_OK;
 }

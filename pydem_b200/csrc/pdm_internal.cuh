@@ -1,9 +1,12 @@
 // pdm_internal.cuh -- shared declarations of libpydem_b200 (not part of the public ABI).
 //
 // Data layout in HBM (per tile, N = R*C cells, C-order, 32-bit cell indices):
-//   elev, mag, dir, uca, taint, prop, twi : f64[N]
+//   elev, mag, dir, uca, twi : f64[N]
 //   flats, flat0, link, edge_todo, edge_done : u8[N]
-//   indeg (i32[N], live in-degree counters), label (i32[N], flat-region union-find)
+//   cell : Cell[N] -- the sweep state of a cell packed into ONE 32-byte sector (area, taint,
+//          proportion, live in-degree, link byte): the sweep visits cells in flow order, i.e. at
+//          random, and every visit then costs one DRAM sector instead of five
+//   label (i32[N], flat-region union-find, later pit in-degree scratch / seed list)
 //   queue (i32[N], deferred work items of the sweep)
 //   per-row geometry: dX,dY,dg,thA,thB : f64[R-1] (fences);  th_row,row_area : f64[R]
 #pragma once
@@ -39,16 +42,28 @@ struct Win {
     __host__ __device__ __forceinline__ bool row_in_grid(int64_t li) const { return li + row_off >= 0 && li + row_off < Rg; }
 };
 
+// sweep state of one cell: exactly one 32-byte DRAM sector
+struct __align__(32) Cell {
+    double area;      // accumulated upstream area (cyutils.pyx:161); update mode: the delta
+    double taint;     // accumulated edge_todo weight (cyutils.pyx:163)
+    double prop;      // share of the cardinal receiver; for pit cells: slot of the pit edge list
+    int32_t indeg;    // receivers still waiting for this many sources; halo rows: -(decrements)
+    uint8_t link;     // LK_* byte (copy of link[])
+    uint8_t pad[3];
+};
+
 struct pdm_tile {
     int64_t R, C, N;
     Win win;
     int device;
     cudaStream_t stream;
     // fields
-    double *elev, *mag, *dir, *uca, *taint, *prop, *twi;
+    double *elev, *mag, *dir, *uca, *twi;
+    double *twi10;       // 10 * twi (what DEMProcessor.twi stores), allocated on first download request
+    Cell *cell;
     uint8_t *flats, *flat0, *link, *edge_todo, *edge_done;
     int8_t *section;  // only materialised on download of PDM_F_SECTION
-    int32_t *indeg, *label, *queue;
+    int32_t *label, *queue;
     long long *glabel;   // sharded mode: global minimum cell index of each flat region (at its local root)
     double *glelev;      //               elevation of that cell
     // geometry
@@ -115,6 +130,7 @@ enum {
     CT_QDONE = 32,     // items completely processed
     CT_PHASE1 = 48,    // warps that finished the source scan
     CT_DRAINED = 64,   // cells drained
+    CT_CHUNK = 72,     // next 32-entry chunk of the seed scan
     CT_SOURCES = 80,
     CT_UNDONE = 81,
     CT_BADSEC = 82,

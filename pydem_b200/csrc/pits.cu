@@ -31,8 +31,8 @@ struct PitArgs {
     int32_t *scratch_i;       // [blocks][2][PIT_CAP]
     double *scratch_d;        // [blocks][PIT_CAP]
     uint8_t *flats, *link;
-    double *mag, *prop;
-    int32_t *indeg;
+    double *mag, *prop;       // prop: proportion scratch (pit cells store their edge-list slot there)
+    int32_t *indeg;           // pit in-edges per receiving cell
     unsigned long long *ctr;
     int max_iter, max_dist, min_border;
     double max_dist_xy;
@@ -370,6 +370,8 @@ int pdm_launch_pits(pdm_tile *t, const pdm_uca_params *p)
         PDM_CUDA(cudaMalloc(&t->pit_dst, (size_t)t->pit_edge_cap * 4));
         PDM_CUDA(cudaMalloc(&t->pit_w, (size_t)t->pit_edge_cap * 8));
     }
+    // t->label (free after the flat labelling) counts the pit edges arriving at each cell
+    PDM_CUDA(cudaMemsetAsync(t->label, 0, (size_t)t->N * sizeof(int32_t), t->stream));
     PDM_CUDA(cudaMemsetAsync(t->d_counters + CT_TMP0, 0, sizeof(unsigned long long), t->stream));
     k_pit_compact<<<(unsigned)((t->N + 255) / 256), 256, 0, t->stream>>>(t->flat0, t->N, t->pit_cell, t->d_counters);
     PDM_LAUNCHED();
@@ -382,7 +384,7 @@ int pdm_launch_pits(pdm_tile *t, const pdm_uca_params *p)
         a.E = t->elev; a.pitmask = t->flat0; a.dX = t->dX; a.dY = t->dY; a.R = t->R; a.C = t->C; a.npits = npits;
         a.pit_cell = t->pit_cell; a.pit_beg = t->pit_beg; a.pit_end = t->pit_end; a.pit_dst = t->pit_dst; a.pit_w = t->pit_w;
         a.edge_cap = t->pit_edge_cap; a.scratch_i = t->pit_scratch_i; a.scratch_d = t->pit_scratch_d;
-        a.flats = t->flats; a.link = t->link; a.mag = t->mag; a.prop = t->prop; a.indeg = t->indeg; a.ctr = t->d_counters;
+        a.flats = t->flats; a.link = t->link; a.mag = t->mag; a.prop = t->twi; a.indeg = t->label; a.ctr = t->d_counters;
         a.max_iter = (int)p->drain_pits_max_iter; a.max_dist = (int)p->drain_pits_max_dist;
         a.min_border = p->drain_pits_min_border; a.max_dist_xy = p->drain_pits_max_dist_xy; a.W = W;
         k_pit_search<<<(unsigned)blocks, PIT_THREADS, smem, t->stream>>>(a);
@@ -403,7 +405,7 @@ int pdm_launch_pits(pdm_tile *t, const pdm_uca_params *p)
         t->pit_edge_cap = need + need / 4 + 1024;
         PDM_CUDA(cudaMalloc(&t->pit_dst, (size_t)t->pit_edge_cap * 4));
         PDM_CUDA(cudaMalloc(&t->pit_w, (size_t)t->pit_edge_cap * 8));
-        PDM_CUDA(cudaMemsetAsync(t->indeg, 0, (size_t)t->N * sizeof(int32_t), t->stream));
+        PDM_CUDA(cudaMemsetAsync(t->label, 0, (size_t)t->N * sizeof(int32_t), t->stream));
     }
     pdm_set_error("pit search: edge buffer kept overflowing");
     return PDM_ERR_NOMEM;

@@ -19,16 +19,16 @@
 namespace {
 
 __global__ void __launch_bounds__(256)
-k_outbox_pack(double *area, double *taint, int32_t *indeg, int64_t row, int64_t C,
+k_outbox_pack(Cell *cell, int64_t row, int64_t C,
               double *__restrict__ out_a, double *__restrict__ out_t, int32_t *__restrict__ out_c, long long *nonzero)
 {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool nz = false;
     if (j < C) {
-        const int64_t n = row * C + j;
-        const int32_t c = -indeg[n];
-        out_a[j] = area[n]; out_t[j] = taint[n]; out_c[j] = c;
-        area[n] = 0.0; taint[n] = 0.0; indeg[n] = 0;
+        Cell &x = cell[row * C + j];
+        const int32_t c = -x.indeg;
+        out_a[j] = x.area; out_t[j] = x.taint; out_c[j] = c;
+        x.area = 0.0; x.taint = 0.0; x.indeg = 0;
         nz = c != 0;
     }
     const unsigned m = __ballot_sync(0xffffffffu, nz);
@@ -36,7 +36,7 @@ k_outbox_pack(double *area, double *taint, int32_t *indeg, int64_t row, int64_t 
 }
 
 __global__ void __launch_bounds__(256)
-k_inbox_apply(double *area, double *taint, int32_t *indeg, int64_t row, int64_t C,
+k_inbox_apply(Cell *cell, int64_t row, int64_t C,
               const double *__restrict__ in_a, const double *__restrict__ in_t, const int32_t *__restrict__ in_c,
               int32_t *__restrict__ seeds, unsigned long long *ctr)
 {
@@ -45,10 +45,11 @@ k_inbox_apply(double *area, double *taint, int32_t *indeg, int64_t row, int64_t 
     const int32_t c = in_c[j];
     if (c == 0) return;
     const int64_t n = row * C + j;
-    area[n] = __dadd_rn(area[n], in_a[j]);
-    taint[n] = __dadd_rn(taint[n], in_t[j]);
-    const int32_t left = indeg[n] - c;
-    indeg[n] = left;
+    Cell &x = cell[n];
+    x.area = __dadd_rn(x.area, in_a[j]);
+    x.taint = __dadd_rn(x.taint, in_t[j]);
+    const int32_t left = x.indeg - c;
+    x.indeg = left;
     if (left == 0) seeds[atomicAdd(&ctr[CT_TMP1], 1ULL)] = (int32_t)n;
 }
 
@@ -170,7 +171,7 @@ int pdm_shard_outbox_pack(pdm_tile *t, int side, void *out_area, void *out_taint
     const Win &w = t->win;
     const int64_t row = side == 0 ? w.lo - 1 : w.hi;
     if (row < 0 || row >= t->R) { pdm_set_error("pdm_shard_outbox_pack: no halo row on side %d", side); return PDM_ERR_ARG; }
-    k_outbox_pack<<<(unsigned)((t->C + 255) / 256), 256, 0, t->stream>>>(t->uca, t->taint, t->indeg, row, t->C,
+    k_outbox_pack<<<(unsigned)((t->C + 255) / 256), 256, 0, t->stream>>>(t->cell, row, t->C,
                                                                          (double *)out_area, (double *)out_taint,
                                                                          (int32_t *)out_count, (long long *)nonzero);
     PDM_LAUNCHED();
@@ -191,7 +192,7 @@ int pdm_shard_inbox_apply(pdm_tile *t, int side, const void *in_area, const void
     if (!t) return PDM_ERR_ARG;
     const Win &w = t->win;
     const int64_t row = side == 0 ? w.lo : w.hi - 1;
-    k_inbox_apply<<<(unsigned)((t->C + 255) / 256), 256, 0, t->stream>>>(t->uca, t->taint, t->indeg, row, t->C,
+    k_inbox_apply<<<(unsigned)((t->C + 255) / 256), 256, 0, t->stream>>>(t->cell, row, t->C,
                                                                          (const double *)in_area, (const double *)in_taint,
                                                                          (const int32_t *)in_count, t->label, t->d_counters);
     PDM_LAUNCHED();

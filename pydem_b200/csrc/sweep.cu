@@ -20,30 +20,32 @@
 // Cells on cycles never reach in-degree 0; they are counted (n_undone) and handled by
 // the level-synchronous restart path below, which follows cyutils.pyx literally.
 //
-// Traffic per cell (sweep): link 1 + prop 8 + area 8 + taint 8 read, ~2 fp64 atomics +
-// 2 int atomics; the kernel is bound by L2 atomic latency along the longest flow path,
-// not by HBM bandwidth.
+// Traffic per cell (sweep): one 32-byte sector for the cell's own record and one per receiver
+// (fp64 atomic on .area + int atomic on .indeg of the same sector); the kernel is bound by
+// sector-granular DRAM access / L2 atomic latency, not by streaming bandwidth.
 #include "drain_op.cuh"
 
 namespace {
 
-// a6 epilogue: dem_processing.py:966-980 (owned cells [n0, n1))
+// a6 epilogue: dem_processing.py:966-980 (owned cells [n0, n1)): sweep records -> uca, edge_done
 __global__ void __launch_bounds__(256)
-k_uca_finalize(const double *__restrict__ E, const uint8_t *__restrict__ flats, const int32_t *__restrict__ indeg,
-               const double *__restrict__ taint, double *__restrict__ uca, uint8_t *__restrict__ edge_done,
+k_uca_finalize(const double *__restrict__ E, const uint8_t *__restrict__ flats, const Cell *__restrict__ cell,
+               double *__restrict__ uca, uint8_t *__restrict__ edge_done,
                int64_t n0, int64_t n1, int limit_edges, double limit_area, unsigned long long *counters)
 {
     const int64_t n = n0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool undone = false;
     if (n < n1) {
         const double e = E[n];
-        double u = uca[n];
-        if (flats[n]) { u = __longlong_as_double(0x7ff8000000000000LL); uca[n] = u; }   // 972
-        bool ed = !(taint[n] != 0.0);                                                    // 969, 974
+        const double2 at = *reinterpret_cast<const double2 *>(&cell[n].area);
+        double u = at.x;
+        if (flats[n]) u = __longlong_as_double(0x7ff8000000000000LL);                   // 972
+        uca[n] = u;
+        bool ed = !(at.y != 0.0);                                                        // 969, 974
         if (e != e) ed = true;                                                           // 975
         if (limit_edges && u > limit_area) ed = true;                                    // 977-980
         edge_done[n] = ed ? 1 : 0;
-        undone = indeg[n] > 0;
+        undone = cell[n].indeg > 0;
     }
     const unsigned m = __ballot_sync(0xffffffffu, undone);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[CT_UNDONE], (unsigned long long)__popc(m));
@@ -51,7 +53,8 @@ k_uca_finalize(const double *__restrict__ E, const uint8_t *__restrict__ flats, 
 
 // a9: calc_twi dem_processing.py:1647-1677 (un-scaled)
 __global__ void __launch_bounds__(256)
-k_twi(const double *__restrict__ uca, const double *__restrict__ mag, double *__restrict__ twi, int64_t N,
+k_twi(const double *__restrict__ uca, const double *__restrict__ mag, double *__restrict__ twi,
+      double *__restrict__ twi10, int64_t N,
       double min_slope, double cap, int limit_uca, int limit_twi, double twi_sat)
 {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -61,6 +64,7 @@ k_twi(const double *__restrict__ uca, const double *__restrict__ mag, double *__
     double t = log(__ddiv_rn(u, __dadd_rn(mag[n], min_slope)));              // 1667
     if (limit_twi && t > twi_sat) t = twi_sat;                               // 1669-1672
     twi[n] = t;
+    if (twi10) twi10[n] = __dmul_rn(t, 10.0);                                // 1674: DEMProcessor.twi
 }
 
 }  // namespace
@@ -77,7 +81,7 @@ int pdm_launch_sweep_first(pdm_tile *t)
     int rc = wl::reset_queue(t);
     if (rc) return rc;
     const Win &w = t->win;
-    DrainOp<0> op{t->link, t->prop, t->uca, t->taint, t->indeg, nullptr, (int32_t)t->C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w};
+    DrainOp<0> op{t->link, t->cell, nullptr, (int32_t)t->C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w};
     wl::k_worklist<<<g_sweep_blocks, 256, 0, t->stream>>>(op, wl::DomainRange{w.lo * w.C, (w.hi - w.lo) * w.C},
                                                           wl::Queue{t->queue, t->d_counters, (long long)t->N});
     PDM_LAUNCHED();
@@ -93,7 +97,7 @@ int pdm_launch_sweep_resume(pdm_tile *t)
     }
     int rc = wl::reset_queue(t, 1);
     if (rc) return rc;
-    DrainOp<2> op{t->link, t->prop, t->uca, t->taint, t->indeg, nullptr, (int32_t)t->C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w};
+    DrainOp<2> op{t->link, t->cell, nullptr, (int32_t)t->C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w};
     wl::k_worklist<<<g_resume_blocks, 256, 0, t->stream>>>(op, wl::DomainList{t->label, t->d_counters + CT_TMP1},
                                                            wl::Queue{t->queue, t->d_counters, (long long)t->N});
     PDM_LAUNCHED();
@@ -106,7 +110,7 @@ int pdm_launch_uca_finalize(pdm_tile *t, const pdm_uca_params *p)
     const double limit_area = p->uca_saturation_limit * 2 * t->min_area;
     const int64_t n0 = w.lo * w.C, n1 = w.hi * w.C;
     k_uca_finalize<<<(unsigned)((n1 - n0 + 255) / 256), 256, 0, t->stream>>>(
-        t->elev, t->flats, t->indeg, t->taint, t->uca, t->edge_done, n0, n1, p->apply_uca_limit_edges, limit_area,
+        t->elev, t->flats, t->cell, t->uca, t->edge_done, n0, n1, p->apply_uca_limit_edges, limit_area,
         t->d_counters);
     PDM_LAUNCHED();
     return PDM_OK;
@@ -124,7 +128,7 @@ int pdm_launch_twi(pdm_tile *t, const pdm_twi_params *p)
 {
     const double cap = p->uca_saturation_limit * p->twi_min_area;
     const double twi_sat = log(p->uca_saturation_limit * p->twi_min_area / p->twi_min_slope);
-    k_twi<<<(unsigned)((t->N + 255) / 256), 256, 0, t->stream>>>(t->uca, t->mag, t->twi, t->N, p->twi_min_slope, cap,
+    k_twi<<<(unsigned)((t->N + 255) / 256), 256, 0, t->stream>>>(t->uca, t->mag, t->twi, t->twi10, t->N, p->twi_min_slope, cap,
                                                                  p->apply_twi_limits_on_uca, p->apply_twi_limits,
                                                                  twi_sat);
     PDM_LAUNCHED();

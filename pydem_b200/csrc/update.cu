@@ -18,15 +18,20 @@
 
 namespace {
 
+// sweep records of the update mode: .area is the delta (0, NaN on flats: 802, 815), .indeg the
+// restricted in-degree counted by flood 1
 __global__ void __launch_bounds__(256)
-k_upd_init(const uint8_t *__restrict__ flats, int64_t N, double *__restrict__ delta, uint8_t *__restrict__ st,
-           int32_t *__restrict__ indeg, uint8_t *__restrict__ edge_todo)
+k_upd_init(const uint8_t *__restrict__ flats, const uint8_t *__restrict__ link, const double *__restrict__ prop,
+           int64_t N, Cell *__restrict__ cell, uint8_t *__restrict__ st, uint8_t *__restrict__ edge_todo)
 {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
-    delta[n] = flats[n] ? __longlong_as_double(0x7ff8000000000000LL) : 0.0;   // 802, 815
+    Cell rec;
+    rec.area = flats[n] ? __longlong_as_double(0x7ff8000000000000LL) : 0.0;
+    rec.taint = 0.0; rec.prop = prop[n]; rec.indeg = 0; rec.link = link[n];
+    rec.pad[0] = rec.pad[1] = rec.pad[2] = 0;
+    cell[n] = rec;
     st[n] = 0;
-    indeg[n] = 0;
     edge_todo[n] = 0;
 }
 
@@ -34,7 +39,7 @@ k_upd_init(const uint8_t *__restrict__ flats, int64_t N, double *__restrict__ de
 __global__ void __launch_bounds__(256)
 k_upd_border(const double *__restrict__ sdata, const uint8_t *__restrict__ sdone, const uint8_t *__restrict__ stodo,
              const double *__restrict__ uca0, const uint8_t *__restrict__ flats, int64_t R, int64_t C,
-             double *__restrict__ delta, uint8_t *__restrict__ st, uint8_t *__restrict__ edge_todo,
+             Cell *__restrict__ cell, uint8_t *__restrict__ st, uint8_t *__restrict__ edge_todo,
              unsigned long long *ctr)
 {
     const int64_t per = 2 * C + 2 * (R - 2);
@@ -55,7 +60,7 @@ k_upd_border(const double *__restrict__ sdata, const uint8_t *__restrict__ sdone
     if (!done) init = 0.0;                                                   // 738-739
     const bool start = done && todo;                                         // 798
     todo = todo && !done;                                                    // 799
-    if (done && !flats[n]) delta[n] = __dsub_rn(init, uca0[n]);             // 806-809 (flats stay NaN, 815)
+    if (done && !flats[n]) cell[n].area = __dsub_rn(init, uca0[n]);         // 806-809 (flats stay NaN, 815)
     st[n] = (start ? ST_START : 0) | (todo ? (ST_TODOSEED | ST_REACH) : 0);
     edge_todo[n] = todo ? 1 : 0;                                             // 817 (edge_todo_i)
     if (start) atomicAdd(&ctr[CT_SOURCES], 1ULL);
@@ -67,10 +72,8 @@ k_upd_border(const double *__restrict__ sdata, const uint8_t *__restrict__ sdone
 //   WHICH 1: seeds ST_TODOSEED, marks ST_REACH
 template <int WHICH>
 struct FloodOp {
-    const uint8_t *link;
-    const double *prop;
+    Cell *cell;
     uint8_t *st;
-    int32_t *indeg;
     int32_t C;
     const int32_t *pit_beg;
     const int32_t *pit_end;
@@ -85,17 +88,18 @@ struct FloodOp {
     {
         if (WHICH == 0) {
             if (st[r] & ST_START) return false;  // start bits are fixed before the flood
-            atomicAdd(indeg + r, 1);
+            atomicAdd(&cell[r].indeg, 1);
             return !(st_fetch_or(st, r, ST_CONE) & ST_CONE);
         }
         return !(st_fetch_or(st, r, ST_REACH) & ST_REACH);
     }
     __device__ __forceinline__ int32_t process(int32_t i, const wl::Queue &q, int32_t &defer) const
     {
-        const uint8_t lk = link[i];
+        const longlong2 pm = *reinterpret_cast<const longlong2 *>(&cell[i].prop);   // prop | indeg, link (link, prop fixed)
+        const uint8_t lk = (uint8_t)((unsigned long long)pm.y >> 32);
         int32_t nxt = -1;
         if (lk & LK_PIT) {
-            const int64_t slot = __double_as_longlong(prop[i]);
+            const int64_t slot = pm.x;
             for (int32_t e = pit_beg[slot]; e < pit_end[slot]; e++) {
                 const int32_t r = pit_dst[e];
                 if (visit(r)) { if (nxt < 0) nxt = r; else q.push(r); }
@@ -116,12 +120,12 @@ struct FloodOp {
 };
 
 __global__ void __launch_bounds__(256)
-k_upd_finalize(const double *__restrict__ delta, const uint8_t *__restrict__ st, int64_t N,
+k_upd_finalize(const Cell *__restrict__ cell, const uint8_t *__restrict__ st, int64_t N,
                double *__restrict__ uca, uint8_t *__restrict__ edge_done)
 {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
-    uca[n] = __dadd_rn(uca[n], delta[n]);                                    // 769
+    uca[n] = __dadd_rn(uca[n], cell[n].area);                                // 769
     edge_done[n] = (st[n] & ST_REACH) ? 0 : 1;                               // 856
 }
 
@@ -157,15 +161,14 @@ int pdm_launch_update(pdm_tile *t, const pdm_uca_params *p, const double *const 
         PDM_CUDA(cudaMemcpyAsync(t->edge_buf_b + per_all + off, todo[k], (size_t)len[k], cudaMemcpyHostToDevice, t->stream));
         off += len[k];
     }
-    double *delta = t->taint;
     uint8_t *stt = t->flat0;
     PDM_CUDA(cudaMemsetAsync(t->d_counters + CT_SOURCES, 0, sizeof(unsigned long long), t->stream));
     PDM_CUDA(cudaMemsetAsync(t->d_counters + CT_EDGE_TODO, 0, sizeof(unsigned long long), t->stream));
-    k_upd_init<<<(unsigned)((t->N + 255) / 256), 256, 0, t->stream>>>(t->flats, t->N, delta, stt, t->indeg, t->edge_todo);
+    k_upd_init<<<(unsigned)((t->N + 255) / 256), 256, 0, t->stream>>>(t->flats, t->link, t->twi, t->N, t->cell, stt, t->edge_todo);
     PDM_LAUNCHED();
     const int64_t per = 2 * C + 2 * (R - 2);
     k_upd_border<<<(unsigned)((per + 255) / 256), 256, 0, t->stream>>>(t->edge_buf_d, t->edge_buf_b, t->edge_buf_b + per_all,
-                                                                       t->uca, t->flats, R, C, delta, stt, t->edge_todo,
+                                                                       t->uca, t->flats, R, C, t->cell, stt, t->edge_todo,
                                                                        t->d_counters);
     PDM_LAUNCHED();
     const wl::Queue q{t->queue, t->d_counters, (long long)t->N};
@@ -173,12 +176,12 @@ int pdm_launch_update(pdm_tile *t, const pdm_uca_params *p, const double *const 
     // flood 1: cone + restricted in-degree (820-831)
     if ((rc = wl::reset_queue(t))) return rc;
     wl::k_worklist<<<g_blocks_flood0, 256, 0, t->stream>>>(
-        FloodOp<0>{t->link, t->prop, stt, t->indeg, (int32_t)C, t->pit_beg, t->pit_end, t->pit_dst}, dom, q);
+        FloodOp<0>{t->cell, stt, (int32_t)C, t->pit_beg, t->pit_end, t->pit_dst}, dom, q);
     PDM_LAUNCHED();
     // sweep of the deltas (836-842)
     if ((rc = wl::reset_queue(t))) return rc;
     wl::k_worklist<<<g_blocks_drain1, 256, 0, t->stream>>>(
-        DrainOp<1>{t->link, t->prop, delta, nullptr, t->indeg, stt, (int32_t)C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w},
+        DrainOp<1>{t->link, t->cell, stt, (int32_t)C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w},
         dom, q);
     PDM_LAUNCHED();
     PDM_CUDA(cudaMemcpyAsync(t->h_counters + CT_DRAINED, t->d_counters + CT_DRAINED, sizeof(unsigned long long),
@@ -186,9 +189,9 @@ int pdm_launch_update(pdm_tile *t, const pdm_uca_params *p, const double *const 
     // flood 2: remaining todo cells taint everything downstream (848-853)
     if ((rc = wl::reset_queue(t))) return rc;
     wl::k_worklist<<<g_blocks_flood1, 256, 0, t->stream>>>(
-        FloodOp<1>{t->link, t->prop, stt, t->indeg, (int32_t)C, t->pit_beg, t->pit_end, t->pit_dst}, dom, q);
+        FloodOp<1>{t->cell, stt, (int32_t)C, t->pit_beg, t->pit_end, t->pit_dst}, dom, q);
     PDM_LAUNCHED();
-    k_upd_finalize<<<(unsigned)((t->N + 255) / 256), 256, 0, t->stream>>>(delta, stt, t->N, t->uca, t->edge_done);
+    k_upd_finalize<<<(unsigned)((t->N + 255) / 256), 256, 0, t->stream>>>(t->cell, stt, t->N, t->uca, t->edge_done);
     PDM_LAUNCHED();
     PDM_CUDA(cudaEventRecord(t->ev[2], t->stream));
     PDM_CUDA(cudaMemcpyAsync(t->h_counters + CT_SOURCES, t->d_counters + CT_SOURCES, sizeof(unsigned long long),

@@ -3,8 +3,9 @@
 //
 // A grid of resident warps (one launch, sized by the occupancy API so that every block is
 // co-resident) runs until global quiescence:
-//   * seeds are found by scanning a domain (all cells, or just the tile perimeter) for
-//     Op::is_seed(cell),
+//   * seeds are found by scanning a domain (owned cells, a seed list, or just the tile
+//     perimeter) for Op::is_seed(cell): chunks of 32 consecutive entries are handed to warps by a
+//     global counter, tested with one coalesced load and dealt out to the warp's idle lanes,
 //   * Op::process(cell, queue, defer) handles one ready cell and returns the cell this lane
 //     continues with (chain following) or -1; one more ready cell can be returned in `defer`
 //     (pushed to the global queue with one warp-aggregated fetch-and-add), further ones are
@@ -90,47 +91,82 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
 {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     const unsigned long long nwarps = (unsigned long long)(nthreads >> 5);
     const int64_t dsize = dom.size();
-    int64_t scan = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool scanning = scan < dsize;
+    const long long nchunks = (long long)((dsize + 31) >> 5);
+    // seed scan state (warp-uniform): the scan domain is cut into chunks of 32 consecutive
+    // entries; a warp reserves a batch of CHUNK_BATCH chunks with one fetch-and-add (a per-chunk
+    // counter was the hottest address of the kernel), tests a chunk with one coalesced load,
+    // keeps the mask of seeds not yet given to a lane, and moves on when it is empty
+    const int CHUNK_BATCH = 16;
+    bool scanning = nchunks > 0;
+    long long ch_next = 0, ch_end = 0;   // current batch [ch_next, ch_end)
+    unsigned pend_mask = 0;  // lanes whose pend_cell is an unassigned seed
+    int32_t pend_cell = -1;
     int32_t cur = -1;
-    long long ticket = -1;  // queue slot this lane is entitled to (fetch-and-add ticket, never fails)
-    int origin = 0;         // 1: chain started at a scanned seed, 2: at a queue item
+    int32_t stash = -1;      // a second ready receiver kept for after the current chain (see below)
+    int chain_len = 0;
+    long long ticket = -1;   // queue slot this lane is entitled to (fetch-and-add ticket, never fails)
+    int origin = 0;          // 1: chain started at a scanned seed, 2: at a queue item
     bool p1_reported = false;
     unsigned long long processed = 0;
+    unsigned idle_polls = 0;
     if (lane == 0) atomicMin(&q.ctr[CT_T_START], globaltimer_ns());
 
     for (;;) {
-        // ---- acquire work: the next seed of this lane's scan stripe, or -- once the stripe is
-        //      exhausted -- a queue ticket.  Tickets are handed out with fetch-and-add, so
-        //      claiming never retries (a CAS-claimed queue serialises at one claim per L2 round
-        //      trip); a ticket whose slot is still empty simply waits for its producer.
-        if (cur < 0 && scanning) {
-            for (int s = 0; s < 8 && scan < dsize; s++) {
-                const int32_t c = dom.cell(scan);
-                scan += nthreads;
-                if (op.is_seed(c)) { cur = c; origin = 1; break; }
+        // ---- a finished chain first continues with the lane's own stashed cell
+        if (cur < 0 && stash >= 0) { cur = stash; stash = -1; chain_len = 0; }
+        // ---- acquire work, seeds first
+        unsigned idle_mask = __ballot_sync(full, cur < 0);
+        while (scanning && idle_mask) {
+            if (pend_mask == 0) {
+                if (ch_next >= ch_end) {
+                    long long b = 0;
+                    if (lane == 0) b = (long long)atomicAdd(&q.ctr[CT_CHUNK], (unsigned long long)CHUNK_BATCH);
+                    b = __shfl_sync(full, b, 0);
+                    if (b >= nchunks) { scanning = false; break; }
+                    ch_next = b;
+                    ch_end = b + CHUNK_BATCH < nchunks ? b + CHUNK_BATCH : nchunks;
+                }
+                const int64_t t = (ch_next << 5) + lane;
+                ch_next++;
+                pend_cell = t < dsize ? dom.cell(t) : -1;
+                pend_mask = __ballot_sync(full, pend_cell >= 0 && op.is_seed(pend_cell));
+                if (pend_mask == 0) continue;
             }
-            if (scan >= dsize) scanning = false;
+            // k-th idle lane takes the k-th pending seed
+            const int k = __popc(idle_mask & lt_mask);
+            const int npend = __popc(pend_mask);
+            const bool take = (cur < 0) && k < npend;
+            const int src = take ? (int)__fns(pend_mask, 0, k + 1) : 0;
+            const int32_t c = __shfl_sync(full, pend_cell, src);
+            if (take) { cur = c; origin = 1; chain_len = 0; }
+            int ntake = __popc(idle_mask);
+            if (ntake > npend) ntake = npend;
+            for (int i = 0; i < ntake; i++) pend_mask &= pend_mask - 1;   // drop the seeds just handed out
+            idle_mask = __ballot_sync(full, cur < 0);
         }
+        // ---- no more seeds for this warp: idle lanes take a queue ticket.  Tickets are handed out
+        //      with fetch-and-add, so claiming never retries (a CAS-claimed queue serialises at one
+        //      claim per L2 round trip); a ticket whose slot is still empty waits for its producer.
         const bool need_ticket = cur < 0 && !scanning && ticket < 0;
         const unsigned need_mask = __ballot_sync(full, need_ticket);
         if (need_mask) {
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(&q.ctr[CT_QHEAD], (unsigned long long)__popc(need_mask));
             base = __shfl_sync(full, base, 0);
-            if (need_ticket) ticket = (long long)(base + __popc(need_mask & ((1u << lane) - 1u)));
+            if (need_ticket) ticket = (long long)(base + __popc(need_mask & lt_mask));
         }
         if (cur < 0 && ticket >= 0 && ticket < q.cap) {
             const int32_t v = ld_volatile_i32(q.slots + ticket);
-            if (v >= 0) { cur = v; origin = 2; ticket = -1; }
+            if (v >= 0) { cur = v; origin = 2; ticket = -1; chain_len = 0; }
         }
         // ---- scan accounting: a warp reports once its scan and scan-born chains have ended
         if (!p1_reported) {
-            const unsigned busy1 = __ballot_sync(full, scanning || (cur >= 0 && origin == 1));
-            if (busy1 == 0) {
+            const unsigned busy1 = __ballot_sync(full, cur >= 0 && origin == 1);
+            if (!scanning && busy1 == 0) {
                 if (lane == 0) {
                     atomicAdd(&q.ctr[CT_PHASE1], 1ULL);
                     atomicMax(&q.ctr[CT_T_SCAN], globaltimer_ns());
@@ -141,18 +177,22 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
         // ---- nothing to do in this warp: terminate on global quiescence, else back off
         const unsigned work_mask = __ballot_sync(full, cur >= 0);
         if (work_mask == 0) {
-            const unsigned still_scanning = __ballot_sync(full, scanning);
-            if (still_scanning == 0) {
+            if (!scanning) {
+                // idle warps mostly watch their own ticket slots (distinct addresses); the shared
+                // counters are read only every 4th round so that polling does not slow the
+                // producers' atomics on the same lines
                 int term = 0;
-                if (lane == 0) {
-                    const unsigned long long d = ld_volatile_u64(q.ctr + CT_QDONE);
-                    const unsigned long long p1 = ld_volatile_u64(q.ctr + CT_PHASE1);
-                    const unsigned long long t = ld_volatile_u64(q.ctr + CT_QTAIL);
-                    term = (p1 == nwarps && d == t) ? 1 : 0;
+                if ((++idle_polls & 3u) == 0) {
+                    if (lane == 0) {
+                        const unsigned long long d = ld_volatile_u64(q.ctr + CT_QDONE);
+                        const unsigned long long p1 = ld_volatile_u64(q.ctr + CT_PHASE1);
+                        const unsigned long long t = ld_volatile_u64(q.ctr + CT_QTAIL);
+                        term = (p1 == nwarps && d == t) ? 1 : 0;
+                    }
+                    term = __shfl_sync(full, term, 0);
                 }
-                term = __shfl_sync(full, term, 0);
                 if (term) break;
-                __nanosleep(100);
+                __nanosleep(200);
             }
             continue;
         }
@@ -161,16 +201,23 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
         int32_t defer = -1;  // second ready receiver: handed to the queue, warp-aggregated below
         if (cur >= 0) {
             processed++;
+            chain_len++;
             const int32_t nxt = op.process(cur, q, defer);
             cur = nxt;
-            if (cur < 0) { finished_q = (origin == 2); origin = 0; }
+            // a second ready receiver waits in the lane's stash (no queue traffic) unless the
+            // stash is taken; a long chain hands its stash to the queue so that it cannot sit on
+            // the critical path behind it
+            if (defer >= 0 && stash < 0 && cur >= 0) { stash = defer; defer = -1; }
+            else if (defer >= 0 && cur < 0) { cur = defer; defer = -1; }
+            if (stash >= 0 && defer < 0 && chain_len > 12 && cur >= 0) { defer = stash; stash = -1; }
+            if (cur < 0 && stash < 0) { finished_q = (origin == 2); origin = 0; }
         }
         const unsigned pm = __ballot_sync(full, defer >= 0);
         if (pm) {
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(&q.ctr[CT_QTAIL], (unsigned long long)__popc(pm));
             base = __shfl_sync(full, base, 0);
-            if (defer >= 0) st_volatile_i32(q.slots + base + __popc(pm & ((1u << lane) - 1u)), defer);
+            if (defer >= 0) st_volatile_i32(q.slots + base + __popc(pm & lt_mask), defer);
         }
         const unsigned fq = __ballot_sync(full, finished_q);
         if (fq && lane == 0) atomicAdd(&q.ctr[CT_QDONE], (unsigned long long)__popc(fq));
@@ -228,7 +275,7 @@ static __global__ void __launch_bounds__(256) k_queue_clean(int32_t *slots, cons
 }
 static __global__ void k_queue_zero(unsigned long long *ctr, int keep_drained)
 {
-    ctr[CT_QTAIL] = 0; ctr[CT_QHEAD] = 0; ctr[CT_QDONE] = 0; ctr[CT_PHASE1] = 0;
+    ctr[CT_QTAIL] = 0; ctr[CT_QHEAD] = 0; ctr[CT_QDONE] = 0; ctr[CT_PHASE1] = 0; ctr[CT_CHUNK] = 0;
     if (!keep_drained) ctr[CT_DRAINED] = 0;
     ctr[CT_T_START] = ~0ULL; ctr[CT_T_SCAN] = 0; ctr[CT_T_END] = 0;
 }

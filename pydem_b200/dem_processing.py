@@ -147,7 +147,10 @@ class DEMProcessor(object):
         """host -> HBM unless the field is already resident from a chained stage."""
         if self._chain and field in self._resident:
             return
-        a = np.ascontiguousarray(arr, dtype=_lib.FIELD_DTYPE[field])
+        a = np.asarray(arr)
+        if a.dtype == np.bool_ and _lib.FIELD_DTYPE[field] == np.uint8:
+            a = a.view(np.uint8)                      # same bytes, no copy
+        a = np.ascontiguousarray(a, dtype=_lib.FIELD_DTYPE[field])
         if a.shape != self._tile_shape:
             raise ValueError("field %d has shape %s, expected %s" % (field, a.shape, self._tile_shape))
         _lib.check(_lib.load().pdm_tile_upload(self._get_tile(), field, _lib.ptr(a)))
@@ -221,7 +224,7 @@ class DEMProcessor(object):
             self._resident.update((_lib.F_MAG, _lib.F_DIR, _lib.F_FLATS))
             self.mag = self._down(_lib.F_MAG)
             self.direction = self._down(_lib.F_DIR)
-            self.flats = self._down(_lib.F_FLATS).astype(bool)
+            self.flats = self._down(_lib.F_FLATS).view(np.bool_)
         finally:
             self._end()
         return self.mag, self.direction
@@ -279,12 +282,12 @@ class DEMProcessor(object):
             self._resident.update((_lib.F_UCA, _lib.F_MAG, _lib.F_FLATS))
             self.uca_stats = st.as_dict()
             self.uca = self._down(_lib.F_UCA)
-            self.edge_todo = self._down(_lib.F_EDGE_TODO).astype(bool)
-            self.edge_done = self._down(_lib.F_EDGE_DONE).astype(bool)
+            self.edge_todo = self._down(_lib.F_EDGE_TODO).view(np.bool_)
+            self.edge_done = self._down(_lib.F_EDGE_DONE).view(np.bool_)
             if p.drain_pits and st.n_pits:
                 # _mk_connectivity_pits updates mag / flats of drained pits in place (1370-1371)
                 mag = self._down(_lib.F_MAG)
-                flats = self._down(_lib.F_FLATS).astype(bool)
+                flats = self._down(_lib.F_FLATS).view(np.bool_)
                 if isinstance(self.mag, np.ndarray) and self.mag.dtype == np.float64 and self.mag.flags.writeable:
                     self.mag[...] = mag
                 else:
@@ -321,7 +324,7 @@ class DEMProcessor(object):
             p.apply_twi_limits_on_uca = int(bool(self.apply_twi_limits_on_uca))
             _lib.check(L.pdm_tile_twi(t, ct.byref(p)))
             twi = self._down(_lib.F_TWI)
-            self.twi = twi * 10                                             # 1674
+            self.twi = self._down(_lib.F_TWI10)                             # 1674: 10 * twi, scaled on the GPU
         finally:
             self._end()
         return twi
