@@ -134,7 +134,13 @@ int pdm_tile_download(pdm_tile *t, int field, void *host);
 int pdm_tile_device_ptr(pdm_tile *t, int field, void **dev);
 /* declare a field valid after writing it through pdm_tile_device_ptr (device-side producers) */
 int pdm_tile_mark_resident(pdm_tile *t, int field);
+/* on != 0: use the literal 8 x (3 divisions + atan2) stencil formulation instead of the
+ * division-/atan2-saving one; both give bit-identical MAG/DIR (checked by the GPU tests) */
+int pdm_tile_set_stencil_parity(pdm_tile *t, int on);
 int pdm_tile_sync(pdm_tile *t);
+/* device self-test: the stencil's reciprocal-based division against IEEE division on n_pairs
+ * pseudo-random operand pairs; *mismatches must come back 0 */
+int pdm_selftest_division(unsigned long long seed, long long n_pairs, unsigned long long *mismatches);
 
 /* a1+a2: _tarboton_slopes_directions (dem_processing.py:1753-1903) + _find_flats_edges
  * (657-680) + the stamping of flats (611-613).  In: ELEV.  Out: MAG, DIR, FLATS. */

@@ -139,7 +139,8 @@ int pdm_tile_create(int64_t R, int64_t C, void *stream, pdm_tile **out)
         {(void **)&t->label, N * 4}, {(void **)&t->queue, (N + 1) * 4},
         {(void **)&t->dX, (size_t)R * 8}, {(void **)&t->dY, (size_t)R * 8}, {(void **)&t->dg, (size_t)R * 8},
         {(void **)&t->thA, (size_t)R * 8}, {(void **)&t->thB, (size_t)R * 8}, {(void **)&t->th_row, (size_t)R * 8},
-        {(void **)&t->row_area, (size_t)R * 8},
+        {(void **)&t->row_area, (size_t)R * 8}, {(void **)&t->rdX, (size_t)R * 8}, {(void **)&t->rdY, (size_t)R * 8},
+        {(void **)&t->rdg, (size_t)R * 8},
         {(void **)&t->d_counters, CT_N * sizeof(unsigned long long)},
     };
     for (auto &a : allocs) {
@@ -169,7 +170,7 @@ int pdm_tile_destroy(pdm_tile *t)
                     t->edge_todo, t->edge_done, t->section, t->label, t->queue, t->dX, t->dY, t->dg,
                     t->thA, t->thB, t->th_row, t->row_area, t->d_counters, t->pit_cell, t->pit_beg, t->pit_end,
                     t->pit_dst, t->pit_w, t->pit_scratch_i, t->pit_scratch_d, t->edge_buf_d, t->edge_buf_b,
-                    t->glabel, t->glelev, t->twi10};
+                    t->glabel, t->glelev, t->twi10, t->rdX, t->rdY, t->rdg};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (t->h_counters) cudaFreeHost(t->h_counters);
     for (int k = 0; k < 4; k++) if (t->ev[k]) cudaEventDestroy(t->ev[k]);
@@ -256,6 +257,21 @@ int pdm_tile_mark_resident(pdm_tile *t, int field)
     if (field == PDM_F_MAG || field == PDM_F_DIR) { t->have_slopes = true; t->have_graph = false; }
     if (field == PDM_F_FLATS) { t->have_flats = true; t->have_graph = false; }
     if (field == PDM_F_UCA) t->have_uca = true;
+    return PDM_OK;
+}
+
+int pdm_selftest_division(unsigned long long seed, long long n_pairs, unsigned long long *mismatches)
+{
+    if (!mismatches || n_pairs <= 0) { pdm_set_error("pdm_selftest_division: bad argument"); return PDM_ERR_ARG; }
+    const int blocks = 592;
+    long long per_thread = (n_pairs + blocks * 256 - 1) / (blocks * 256);
+    return pdm_launch_selftest_div(seed, blocks, per_thread, mismatches);
+}
+
+int pdm_tile_set_stencil_parity(pdm_tile *t, int on)
+{
+    if (!t) return PDM_ERR_ARG;
+    t->stencil_parity = on != 0;
     return PDM_OK;
 }
 

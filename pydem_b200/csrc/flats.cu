@@ -31,6 +31,16 @@ __device__ __forceinline__ int32_t uf_find(int32_t *label, int32_t x)
     return x;
 }
 
+// read-only find for the flatten pass: concurrent threads only ever store roots there, so a
+// walk that never writes cannot undo another thread's final label (path halving could: it may
+// store a stale grandparent over a root written in the meantime)
+__device__ __forceinline__ int32_t uf_find_ro(const int32_t *label, int32_t x)
+{
+    int32_t p = label[x];
+    while (p != x) { x = p; p = label[x]; }
+    return x;
+}
+
 __device__ __forceinline__ void uf_union(int32_t *label, int32_t a, int32_t b)
 {
     for (;;) {
@@ -68,7 +78,7 @@ k_ccl_flatten(const uint8_t *__restrict__ flat0, int32_t *label, int64_t n0, int
 {
     const int64_t n = n0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= n1 || !flat0[n]) return;
-    const int32_t r = uf_find(label, (int32_t)n);
+    const int32_t r = uf_find_ro(label, (int32_t)n);
     label[n] = r;
     if (gl && r == (int32_t)n) { gl[n] = (long long)n + goff; glE[n] = E[n]; }
 }

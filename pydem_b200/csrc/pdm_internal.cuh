@@ -68,8 +68,10 @@ struct pdm_tile {
     double *glelev;      //               elevation of that cell
     // geometry
     double *dX, *dY, *dg, *thA, *thB, *th_row, *row_area;
+    double *rdX, *rdY, *rdg;   // correctly rounded reciprocals of dX, dY, dg (fast stencil divisions)
     double min_area;
     bool have_spacing, have_elev, have_slopes, have_flats, have_graph, have_uca;
+    bool stencil_parity; // run the literal (slow) stencil formulation on this tile (tests)
     bool queue_ready;    // queue slots are all -1 except those the last work-list run used
     // pit edge lists (device)
     int32_t *pit_cell;     // [pit_cap] cells examined by the pit search (flats & elev > 0)
@@ -117,6 +119,7 @@ int pdm_launch_update(pdm_tile *t, const pdm_uca_params *p, const double *const 
                       const uint8_t *const done[4], const uint8_t *const todo[4], pdm_uca_stats *st);
 int pdm_launch_twi(pdm_tile *t, const pdm_twi_params *p);
 int pdm_launch_section_export(pdm_tile *t);
+int pdm_launch_selftest_div(unsigned long long seed, int blocks, long long per_thread, unsigned long long *mismatch_host);
 int pdm_restart_rounds(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *st);
 int pdm_graph_links_pits(pdm_tile *t, const pdm_uca_params *p);
 int pdm_launch_pits(pdm_tile *t, const pdm_uca_params *p);

@@ -17,13 +17,32 @@
 // computes exactly what one big tile would.
 //
 // Roofline: 8 B read (elev) + 16 B written (mag, direction) + 1 B (flat0) per cell.
+#include <stdlib.h>
+#include <string.h>
+
 #include "pdm_internal.cuh"
 
 namespace {
 
 struct Geom {
     const double *dX, *dY, *dg, *thA, *thB;   // indexed by local fence (between local rows f, f+1)
+    const double *rdX, *rdY, *rdg;            // correctly rounded reciprocals of dX, dY, dg
 };
+
+// a / b, correctly rounded, from the correctly rounded reciprocal rb = RN(1/b) (Markstein's
+// sequence: q <- q + (a - b q) rb, twice; the first pass makes q faithful, the second one is
+// then exact-residual + one rounding = IEEE quotient).  5 fp64 operations instead of the ~28 of
+// the generic division.  Preconditions (checked by the caller): a == 0 or 1e-150 <= |a| <= 1e150,
+// 1e-150 <= b <= 1e150, so nothing over/underflows.  pdm_selftest_division() compares it with
+// __ddiv_rn on the device.
+__device__ __forceinline__ double mdiv(double a, double b, double rb)
+{
+    double q = __dmul_rn(a, rb);
+    double r = __fma_rn(-q, b, a);
+    q = __fma_rn(r, rb, q);
+    r = __fma_rn(-q, b, a);
+    return __fma_rn(r, rb, q);
+}
 
 // facet tables (dem_processing.py:173-193): cardinal neighbour e1, diagonal neighbour e2,
 // direction = r * a + q * pi/2
@@ -80,8 +99,119 @@ __device__ __forceinline__ void cell_facets(const double *__restrict__ E, const 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Fast interior path.  Same result as cell_facets<true> bit for bit, with ~4x fewer fp64
+// instructions: the parity formulation spends 3 divisions, 1 atan2 and a dozen compares on
+// every one of the 8 facets, but
+//   * for positive spacings the signs of s1, s2, sd are the signs of the elevation
+//     differences, so a facet's case (unclamped / clamped to the cardinal / clamped to the
+//     diagonal / uphill) is known before any division and only the quotients that case needs
+//     are formed (uphill facets: none);
+//   * "r > theta" is decided by cross-multiplying (n2*d1^2 vs n1*d2^2); inside a 1e-8 relative
+//     guard band (exact ties on planar test surfaces) the whole cell takes the parity path, so
+//     the decision always agrees with comparing the computed angles;
+//   * the direction needs atan2 only for the facet that finally wins.
+// Every quotient that is formed uses the same IEEE operations as the parity path, so the
+// strict-greater tie-breaking between facets sees identical numbers.  Cells with a non-finite
+// neighbour, a tiny non-zero difference (quotient could underflow) or unusual spacing take the
+// parity path.
+// ------------------------------------------------------------------------------------------
+struct FacetBest {
+    double m2, dr;      // best squared magnitude and its direction (dr valid unless `lazy`)
+    double s1, s2;      // slopes of the best facet when its angle is still to be computed
+    double a, qpi2;
+    bool lazy;
+};
+
+// One facet, branch-free (lanes of a warp are in different cases, so per-case branches would
+// serialise).  n1 = e0-e1, n2 = e1-e2, nd = e0-e2, all finite; spacings > 0.  d1sq/d2sq = d1^2, d2^2.
+// Returns false when the "r > theta" test falls inside the guard band (the cell then takes the
+// parity path).
+__device__ __forceinline__ bool facet_fast(double n1, double n2, double nd, double d1, double d2, double dg,
+                                           double r1, double r2, double rg,
+                                           double d1sq, double d2sq, double th, double qpi2, double a, FacetBest &b)
+{
+    const bool p1 = n1 > 0.0, p2 = n2 > 0.0;
+    // r > theta  <=>  s2/s1 > d2/d1  <=>  n2*d1^2 > n1*d2^2   (s1, s2 > 0)
+    const double u = __dmul_rn(n2, d1sq), v = __dmul_rn(n1, d2sq);
+    const bool A = p1 && p2;
+    const bool band = A && !(fabs(u - v) > 1e-8 * v);
+    const bool over = u > v;
+    const bool a_under = A && !over;              // unclamped: rad2 = s1^2 + s2^2, r = atan2(s2, s1)
+    const bool use_s1 = a_under || (p1 && !p2);   // ... or clamped to the cardinal: rad2 = s1^2, r = 0
+    const bool use_sd = (A && over) || (!p1 && p2 && nd > 0.0);   // clamped to the diagonal: rad2 = sd^2, r = theta
+    const double q1 = mdiv(use_s1 ? n1 : nd, use_s1 ? d1 : dg, use_s1 ? r1 : rg);   // s1 or sd
+    const double q2 = mdiv(n2, d2, r2);                                              // s2 (only used when unclamped)
+    double rad2 = __dmul_rn(q1, q1);
+    if (a_under) rad2 = __dadd_rn(rad2, __dmul_rn(q2, q2));
+    if ((use_s1 || use_sd) && rad2 > b.m2) {
+        b.m2 = rad2;
+        b.lazy = a_under;
+        b.s1 = q1; b.s2 = q2; b.a = a; b.qpi2 = qpi2;
+        b.dr = __dadd_rn(__dmul_rn(use_sd ? th : 0.0, a), qpi2);
+    }
+    return !band;
+}
+
+// returns false when the cell must take the parity path
+__device__ __forceinline__ bool cell_fast(const double *__restrict__ E, const Win &w, int64_t i, int64_t j, const Geom &g,
+                                          double &m2, double &dr)
+{
+    const int64_t C = w.C;
+    const double *row = E + i * C + j;
+    const double c = __ldg(row), eE = __ldg(row + 1), eW = __ldg(row - 1);
+    const double eN = __ldg(row - C), eNE = __ldg(row - C + 1), eNW = __ldg(row - C - 1);
+    const double eS = __ldg(row + C), eSE = __ldg(row + C + 1), eSW = __ldg(row + C - 1);
+    const double dXu = __ldg(g.dX + i - 1), dYu = __ldg(g.dY + i - 1), dgu = __ldg(g.dg + i - 1);
+    const double dXl = __ldg(g.dX + i), dYl = __ldg(g.dY + i), dgl = __ldg(g.dg + i);
+    const double tAu = __ldg(g.thA + i - 1), tBu = __ldg(g.thB + i - 1), tAl = __ldg(g.thA + i), tBl = __ldg(g.thB + i);
+    const double rXu = __ldg(g.rdX + i - 1), rYu = __ldg(g.rdY + i - 1), rgu = __ldg(g.rdg + i - 1);
+    const double rXl = __ldg(g.rdX + i), rYl = __ldg(g.rdY + i), rgl = __ldg(g.rdg + i);
+    // spacing sanity (warp-uniform): 1e-150 < d < 1e150, aspect angle away from 0 and pi/2
+    const double lo = 1e-5, hi = PDM_PI / 2 - 1e-5;
+    bool ok = dXu > 1e-150 && dYu > 1e-150 && dXl > 1e-150 && dYl > 1e-150 && dgu < 1e150 && dgl < 1e150 &&
+              tAu > lo && tAu < hi && tBu > lo && tBu < hi && tAl > lo && tAl < hi && tBl > lo && tBl < hi;
+    // elevations: each is 0 or 1e-130 <= |e| <= 1e140 (exponent test on the integer pipe).  Then
+    // every non-zero difference of two of them is >= 2^-53 * 1e-130 > 1e-150 and < 1e150: no
+    // quotient below can underflow, overflow or see a NaN.
+    {
+        const double ev[9] = {c, eE, eW, eN, eNE, eNW, eS, eSE, eSW};
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            const unsigned hi32 = (unsigned)__double2hiint(ev[k]) & 0x7fffffffu;
+            const bool zero = (hi32 | (unsigned)__double2loint(ev[k])) == 0u;
+            ok = ok && (zero || (hi32 >= 0x25000000u && hi32 <= 0x5D000000u));   // 2^-431 .. 2^465
+        }
+    }
+    if (!ok) return false;
+    // differences: cardinal (c - e1), cardinal->diagonal (e1 - e2), diagonal (c - e2)
+    const double cE = __dsub_rn(c, eE), cN = __dsub_rn(c, eN), cW = __dsub_rn(c, eW), cS = __dsub_rn(c, eS);
+    const double cNE = __dsub_rn(c, eNE), cNW = __dsub_rn(c, eNW), cSW = __dsub_rn(c, eSW), cSE = __dsub_rn(c, eSE);
+    const double n2[8] = {__dsub_rn(eE, eNE), __dsub_rn(eN, eNE), __dsub_rn(eN, eNW), __dsub_rn(eW, eNW),
+                          __dsub_rn(eW, eSW), __dsub_rn(eS, eSW), __dsub_rn(eS, eSE), __dsub_rn(eE, eSE)};
+    const double n1[8] = {cE, cN, cN, cW, cW, cS, cS, cE};
+    const double ndv[8] = {cNE, cNE, cNW, cNW, cSW, cSW, cSE, cSE};
+    FacetBest b;
+    b.m2 = -1.0; b.dr = -1.0; b.s1 = 0.0; b.s2 = 0.0; b.a = 1.0; b.qpi2 = 0.0; b.lazy = false;
+    const double H = PDM_PI;
+    const double xu2 = __dmul_rn(dXu, dXu), yu2 = __dmul_rn(dYu, dYu), xl2 = __dmul_rn(dXl, dXl), yl2 = __dmul_rn(dYl, dYl);
+    bool sure = true;
+    sure &= facet_fast(n1[0], n2[0], ndv[0], dXu, dYu, dgu, rXu, rYu, rgu, xu2, yu2, tAu, 0.0 * H / 2, 1.0, b);
+    sure &= facet_fast(n1[1], n2[1], ndv[1], dYu, dXu, dgu, rYu, rXu, rgu, yu2, xu2, tBu, 1.0 * H / 2, -1.0, b);
+    sure &= facet_fast(n1[2], n2[2], ndv[2], dYu, dXu, dgu, rYu, rXu, rgu, yu2, xu2, tBu, 1.0 * H / 2, 1.0, b);
+    sure &= facet_fast(n1[3], n2[3], ndv[3], dXu, dYu, dgu, rXu, rYu, rgu, xu2, yu2, tAu, 2.0 * H / 2, -1.0, b);
+    sure &= facet_fast(n1[4], n2[4], ndv[4], dXl, dYl, dgl, rXl, rYl, rgl, xl2, yl2, tAl, 2.0 * H / 2, 1.0, b);
+    sure &= facet_fast(n1[5], n2[5], ndv[5], dYl, dXl, dgl, rYl, rXl, rgl, yl2, xl2, tBl, 3.0 * H / 2, -1.0, b);
+    sure &= facet_fast(n1[6], n2[6], ndv[6], dYl, dXl, dgl, rYl, rXl, rgl, yl2, xl2, tBl, 3.0 * H / 2, 1.0, b);
+    sure &= facet_fast(n1[7], n2[7], ndv[7], dXl, dYl, dgl, rXl, rYl, rgl, xl2, yl2, tAl, 4.0 * H / 2, -1.0, b);
+    if (!sure) return false;
+    m2 = b.m2;
+    dr = b.lazy ? __dadd_rn(__dmul_rn(atan2(b.s2, b.s1), b.a), b.qpi2) : b.dr;
+    return true;
+}
+
 __global__ void __launch_bounds__(256)
-k_slopes(const double *__restrict__ E, Win w, Geom g,
+k_slopes(const double *__restrict__ E, Win w, Geom g, int fast,
          double *__restrict__ mag, double *__restrict__ dir, uint8_t *__restrict__ flat0,
          int32_t *__restrict__ label)
 {
@@ -93,7 +223,10 @@ k_slopes(const double *__restrict__ E, Win w, Geom g,
     const bool top = w.top(i), bot = w.bottom(i);
     const bool border = top | bot | (j == 0) | (j == C - 1);
     if (!border) {
-        cell_facets<true>(E, w, i, j, g, m2, dr);
+        if (!(fast && cell_fast(E, w, i, j, g, m2, dr))) {
+            m2 = -1.0; dr = -1.0;
+            cell_facets<true>(E, w, i, j, g, m2, dr);
+        }
     } else {
         // copy-from-interior passes 1782-1795, resolved per border cell: the four
         // sequential whole-row/column copies mean an edge cell looks at its inward
@@ -121,10 +254,40 @@ k_slopes(const double *__restrict__ E, Win w, Geom g,
 }
 
 __global__ void k_geometry(const double *__restrict__ dX, const double *__restrict__ dY, int64_t R,
-                           double *__restrict__ dg)
+                           double *__restrict__ dg, double *__restrict__ rdX, double *__restrict__ rdY,
+                           double *__restrict__ rdg)
 {
     int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (f < R - 1) dg[f] = sqrt(__dadd_rn(__dmul_rn(dX[f], dX[f]), __dmul_rn(dY[f], dY[f])));  // 1962
+    if (f < R - 1) {
+        const double g = sqrt(__dadd_rn(__dmul_rn(dX[f], dX[f]), __dmul_rn(dY[f], dY[f])));  // 1962
+        dg[f] = g;
+        rdX[f] = __drcp_rn(dX[f]); rdY[f] = __drcp_rn(dY[f]); rdg[f] = __drcp_rn(g);
+    }
+}
+
+// device self-test of mdiv against the IEEE division: pseudo-random operands over the whole
+// admissible exponent range plus mantissas near 1, 2 and all-ones
+__global__ void k_selftest_div(unsigned long long seed, long long per_thread, unsigned long long *mismatch)
+{
+    unsigned long long x = seed ^ (0x9E3779B97F4A7C15ULL * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1));
+    unsigned long long bad = 0;
+    for (long long k = 0; k < per_thread; k++) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        unsigned long long ma = x & 0xFFFFFFFFFFFFFULL;
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        unsigned long long mb = x & 0xFFFFFFFFFFFFFULL;
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        const int mode = (int)(x & 7);
+        if (mode == 1) ma = 0; if (mode == 2) mb = 0xFFFFFFFFFFFFFULL; if (mode == 3) mb = 0; if (mode == 4) ma = 0xFFFFFFFFFFFFFULL;
+        if (mode == 5) mb &= 0xFFULL; if (mode == 6) ma &= 0xFFFULL;
+        const long long ea = 1023 - 480 + (long long)((x >> 8) % 960), eb = 1023 - 480 + (long long)((x >> 24) % 960);
+        const unsigned long long sa = (x >> 40) & 1;
+        const double a = __longlong_as_double((long long)((sa << 63) | ((unsigned long long)ea << 52) | ma));
+        const double b = __longlong_as_double((long long)(((unsigned long long)eb << 52) | mb));
+        const double q0 = __ddiv_rn(a, b), q1 = mdiv(a, b, __drcp_rn(b));
+        if (__double_as_longlong(q0) != __double_as_longlong(q1)) bad++;
+    }
+    if (bad) atomicAdd(mismatch, bad);
 }
 
 }  // namespace
@@ -132,18 +295,35 @@ __global__ void k_geometry(const double *__restrict__ dX, const double *__restri
 int pdm_launch_geometry(pdm_tile *t)
 {
     int64_t n = t->R;
-    k_geometry<<<(unsigned)((n + 255) / 256), 256, 0, t->stream>>>(t->dX, t->dY, t->R, t->dg);
+    k_geometry<<<(unsigned)((n + 255) / 256), 256, 0, t->stream>>>(t->dX, t->dY, t->R, t->dg, t->rdX, t->rdY, t->rdg);
     PDM_LAUNCHED();
     return PDM_OK;
 }
 
 int pdm_launch_slopes(pdm_tile *t)
 {
-    Geom g{t->dX, t->dY, t->dg, t->thA, t->thB};
+    Geom g{t->dX, t->dY, t->dg, t->thA, t->thB, t->rdX, t->rdY, t->rdg};
     const Win &w = t->win;
     dim3 block(32, 8);
     dim3 grid((unsigned)((w.C + 31) / 32), (unsigned)((w.hi - w.lo + 7) / 8));
-    k_slopes<<<grid, block, 0, t->stream>>>(t->elev, w, g, t->mag, t->dir, t->flat0, t->label);
+    // PYDEM_B200_STENCIL=parity runs the literal 8 x (3 div + atan2) formulation everywhere (tests
+    // compare both bit for bit)
+    static int fast = -1;
+    if (fast < 0) { const char *e = getenv("PYDEM_B200_STENCIL"); fast = (e && !strcmp(e, "parity")) ? 0 : 1; }
+    k_slopes<<<grid, block, 0, t->stream>>>(t->elev, w, g, t->stencil_parity ? 0 : fast, t->mag, t->dir, t->flat0, t->label);
     PDM_LAUNCHED();
+    return PDM_OK;
+}
+
+// number of (a, b) pairs out of blocks*256*per_thread for which mdiv(a,b) != a/b (must be 0)
+int pdm_launch_selftest_div(unsigned long long seed, int blocks, long long per_thread, unsigned long long *mismatch_host)
+{
+    unsigned long long *d = nullptr;
+    PDM_CUDA(cudaMalloc(&d, sizeof(unsigned long long)));
+    PDM_CUDA(cudaMemset(d, 0, sizeof(unsigned long long)));
+    k_selftest_div<<<blocks, 256>>>(seed, per_thread, d);
+    PDM_LAUNCHED();
+    PDM_CUDA(cudaMemcpy(mismatch_host, d, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    PDM_CUDA(cudaFree(d));
     return PDM_OK;
 }

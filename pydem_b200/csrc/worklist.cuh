@@ -46,6 +46,13 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
     return t;
 }
 
+// opaque zero that depends on x: orders a later load after the one that produced x
+__device__ __forceinline__ unsigned long long dep_zero_u64(unsigned long long x)
+{
+    asm volatile("and.b64 %0, %0, 0;" : "+l"(x));
+    return x;
+}
+
 struct Queue {
     int32_t *slots;
     unsigned long long *ctr;
@@ -184,9 +191,12 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
                 int term = 0;
                 if ((++idle_polls & 3u) == 0) {
                     if (lane == 0) {
+                        // the proof needs QDONE to be read before PHASE1 before QTAIL; the three
+                        // lines live in different L2 slices, so each address is made to depend on
+                        // the previous value (dependent loads cannot pass each other)
                         const unsigned long long d = ld_volatile_u64(q.ctr + CT_QDONE);
-                        const unsigned long long p1 = ld_volatile_u64(q.ctr + CT_PHASE1);
-                        const unsigned long long t = ld_volatile_u64(q.ctr + CT_QTAIL);
+                        const unsigned long long p1 = ld_volatile_u64(q.ctr + CT_PHASE1 + dep_zero_u64(d));
+                        const unsigned long long t = ld_volatile_u64(q.ctr + CT_QTAIL + dep_zero_u64(p1));
                         term = (p1 == nwarps && d == t) ? 1 : 0;
                     }
                     term = __shfl_sync(full, term, 0);

@@ -94,6 +94,9 @@ class DeviceTile(object):
     def mark_resident(self, field):
         _lib.check(self.L.pdm_tile_mark_resident(self.h, field))
 
+    def set_stencil_parity(self, on):
+        _lib.check(self.L.pdm_tile_set_stencil_parity(self.h, int(bool(on))))
+
     def sync(self):
         _lib.check(self.L.pdm_tile_sync(self.h))
 

@@ -168,3 +168,54 @@ def test_properties_at_4096(cuda_lib):
     # twi consistent with its definition on the host
     with np.errstate(invalid="ignore", divide="ignore"):
         np.testing.assert_allclose(dp.twi, 10 * np.log(uca / (dp.mag + 1e-3)), rtol=1e-12, equal_nan=True)
+
+
+@pytest.mark.parametrize("name", ["card", "diag", "cone256", "frac256_dx30", "frac_rect_vardx", "nan_holes", "quantized",
+                                  "lakes", "odd_cols", "tiny3", "frac512_limits"])
+def test_fast_stencil_equals_literal_stencil(cuda_lib, name):
+    """The division-/atan2-saving interior stencil must reproduce the literal 8 x (3 div + atan2)
+    formulation bit for bit (mag, direction, flats)."""
+    from pydem_b200 import tile as T
+    E, kw = helpers.cases()[name]
+    R, C = E.shape
+    out = []
+    for parity in (0, 1):
+        dt = T.DeviceTile(R, C)
+        dt.set_spacing(kw.get("dX", 1.0), kw.get("dY", 1.0), kw.get("dX2"), kw.get("dY2"))
+        dt.set_stencil_parity(parity)
+        dt.upload(T.F_ELEV, E)
+        dt.slopes_directions()
+        out.append((dt.download(T.F_MAG), dt.download(T.F_DIR), dt.download(T.F_FLATS)))
+        dt.close()
+    for a, b in zip(*out):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_fast_stencil_extreme_values(cuda_lib):
+    """Tiny / huge differences, exact ties and strongly anisotropic cells: the fast path must either
+    agree bit for bit or hand the cell to the literal path."""
+    from pydem_b200 import tile as T
+    rng = np.random.default_rng(3)
+    base = helpers.synth.fractal_dem(96, 50)
+    cases = [(base * 1e-160, 1.0, 1.0), (base * 1e140, 1.0, 1.0), (np.round(base), 1.0, 1.0), (np.round(base), 30.0, 10.0),
+             (base, 1e-3, 1e3), (base, 1.0, 1e-7), (np.floor(base / 7) + rng.integers(0, 2, base.shape) * 1e-300, 2.0, 3.0)]
+    for E, dX, dY in cases:
+        res = []
+        for parity in (0, 1):
+            dt = T.DeviceTile(*E.shape)
+            dt.set_spacing(dX, dY)
+            dt.set_stencil_parity(parity)
+            dt.upload(T.F_ELEV, E)
+            dt.slopes_directions()
+            res.append((dt.download(T.F_MAG), dt.download(T.F_DIR)))
+            dt.close()
+        np.testing.assert_array_equal(res[0][0], res[1][0])
+        np.testing.assert_array_equal(res[0][1], res[1][1])
+
+
+def test_reciprocal_division_is_ieee_exact(cuda_lib):
+    """The stencil's 5-operation division (Markstein sequence on a correctly rounded reciprocal)
+    against __ddiv_rn on 2e9 operand pairs incl. extreme mantissas/exponents: bit-identical."""
+    bad = ct.c_ulonglong(123)
+    cuda_lib.check(cuda_lib.load().pdm_selftest_division(2024, 2_000_000_000, ct.byref(bad)))
+    assert bad.value == 0
