@@ -46,7 +46,7 @@ def measured_peak():
 
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -54,16 +54,22 @@ class ClockSampler(object):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
-    def stop(self):
+    def mark(self):
+        """wall-clock stamp (nvidia-smi prints local time with ms)"""
+        import datetime
+        return datetime.datetime.now()
+
+    def stop(self, t0=None, t1=None):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -71,14 +77,20 @@ class ClockSampler(object):
             self.p.kill()
         self.f.flush(); self.f.seek(0)
         sm, mx, reasons = [], [], set()
+        rows = []
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
             if len(c) < 9:
                 continue
             try:
-                sm.append(float(c[1])); mx.append(float(c[2]))
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f")
+                rows.append((ts, float(c[1]), float(c[2]), c))
             except ValueError:
                 continue
+        inside = [r for r in rows if t0 is not None and t0 <= r[0] <= t1]
+        out["window"] = "timed region" if inside else "whole run (no sample fell inside the timed region)"
+        for ts, a, b, c in (inside or rows):
+            sm.append(a); mx.append(b)
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
@@ -87,8 +99,8 @@ class ClockSampler(object):
         except OSError:
             pass
         if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                   "samples": len(sm)}
+            out.update({"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                        "samples": len(sm)})
         return out
 
 
@@ -250,10 +262,11 @@ def gpu_arm(args):
                     % (n * world, n, n, n, world, world, n))
         parallelism = "row-block x%d" % world
 
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    t_begin = sampler.mark() if sampler else None
     launches0 = L.pdm_launch_count()
     ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
     sweep_ms, sweep_kernel_ms, slopes_ms = [], [], []
@@ -266,7 +279,7 @@ def gpu_arm(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = L.pdm_launch_count() - launches0
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_begin, sampler.mark()) if sampler else None
     if world > 1:
         tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -334,13 +347,13 @@ def gpu_arm(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the sweep kernel, one launch (profiles/, per size)
-PROFILE_TRAFFIC = {4096: 6.21e9}
+PROFILE_TRAFFIC = {4096: 1.388e9}   # profiles/r1_sweep_4096_ncu_full.csv: 868 MB read + 520 MB written
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=4096, help="rows (per GPU) = columns of the DEM")

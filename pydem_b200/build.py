@@ -58,6 +58,8 @@ def build(force=False, verbose=False):
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)
+    from . import synth
+    synth._host_lib()       # synthetic-data helper (gcc)
     return LIB
 
 

@@ -108,12 +108,21 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
     // counter was the hottest address of the kernel), tests a chunk with one coalesced load,
     // keeps the mask of seeds not yet given to a lane, and moves on when it is empty
     const int CHUNK_BATCH = 16;
-    bool scanning = nchunks > 0;
+    // Critical path.  All lanes of a warp advance in lock step, so a chain that shares its warp
+    // with 31 other busy lanes pays the slowest lane's memory latency three times per cell
+    // (measured ~7 us per cell against ~1 us alone).  Long flow paths (rivers of a conditioned
+    // DEM: thousands of cells) therefore run in EXPRESS mode: one chain per warp, lane 0 only.
+    //   * warp 0 of every block is express from the start (it never scans for seeds);
+    //   * every other warp becomes express when its seed scan is exhausted;
+    //   * a scanning warp hands a chain longer than HANDOFF cells to the queue.
+    const int HANDOFF = 16;
+    const bool express_only = (threadIdx.x >> 5) == 0 && gridDim.x * (blockDim.x >> 5) > 8;
+    bool scanning = nchunks > 0 && !express_only;
     long long ch_next = 0, ch_end = 0;   // current batch [ch_next, ch_end)
     unsigned pend_mask = 0;  // lanes whose pend_cell is an unassigned seed
     int32_t pend_cell = -1;
     int32_t cur = -1;
-    int32_t stash = -1;      // a second ready receiver kept for after the current chain (see below)
+    int32_t stash = -1, stash2 = -1, stash3 = -1;   // ready receivers kept for after the current chain (see below)
     int chain_len = 0;
     long long ticket = -1;   // queue slot this lane is entitled to (fetch-and-add ticket, never fails)
     int origin = 0;          // 1: chain started at a scanned seed, 2: at a queue item
@@ -124,7 +133,7 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
 
     for (;;) {
         // ---- a finished chain first continues with the lane's own stashed cell
-        if (cur < 0 && stash >= 0) { cur = stash; stash = -1; chain_len = 0; }
+        if (cur < 0 && stash >= 0) { cur = stash; stash = stash2; stash2 = stash3; stash3 = -1; chain_len = 0; }
         // ---- acquire work, seeds first
         unsigned idle_mask = __ballot_sync(full, cur < 0);
         while (scanning && idle_mask) {
@@ -158,7 +167,7 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
         // ---- no more seeds for this warp: idle lanes take a queue ticket.  Tickets are handed out
         //      with fetch-and-add, so claiming never retries (a CAS-claimed queue serialises at one
         //      claim per L2 round trip); a ticket whose slot is still empty waits for its producer.
-        const bool need_ticket = cur < 0 && !scanning && ticket < 0;
+        const bool need_ticket = cur < 0 && !scanning && ticket < 0 && lane == 0;   // express: one chain per warp
         const unsigned need_mask = __ballot_sync(full, need_ticket);
         if (need_mask) {
             unsigned long long base = 0;
@@ -217,9 +226,16 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
             // a second ready receiver waits in the lane's stash (no queue traffic) unless the
             // stash is taken; a long chain hands its stash to the queue so that it cannot sit on
             // the critical path behind it
-            if (defer >= 0 && stash < 0 && cur >= 0) { stash = defer; defer = -1; }
-            else if (defer >= 0 && cur < 0) { cur = defer; defer = -1; }
-            if (stash >= 0 && defer < 0 && chain_len > 12 && cur >= 0) { defer = stash; stash = -1; }
+            if (defer >= 0 && cur < 0) { cur = defer; defer = -1; }
+            else if (defer >= 0 && scanning && stash3 < 0) {
+                // bulk phase: a second ready receiver waits in the lane's stash (no queue traffic)
+                if (stash < 0) stash = defer; else if (stash2 < 0) stash2 = defer; else stash3 = defer;
+                defer = -1;
+            }
+            // bulk phase: a long chain moves to an express warp; its stash follows one cell per step
+            if (scanning && defer < 0 && chain_len > HANDOFF) {
+                if (cur >= 0) { defer = cur; cur = -1; chain_len = 0; }
+            }
             if (cur < 0 && stash < 0) { finished_q = (origin == 2); origin = 0; }
         }
         const unsigned pm = __ballot_sync(full, defer >= 0);
@@ -270,7 +286,7 @@ int grid_for(K kernel, int *blocks_out)
     PDM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     PDM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, 0));
     if (occ < 1) { pdm_set_error("work-list kernel does not fit on an SM"); return PDM_ERR_CUDA; }
-    if (occ > 4) occ = 4;
+    if (occ > 8) occ = 8;
     *blocks_out = sms * occ;
     return PDM_OK;
 }

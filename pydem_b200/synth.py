@@ -3,7 +3,13 @@ no network): the analytic cone of the reference's own fixtures and seeded fracta
 
 reference: pydem/utils_test_pydem.py:98-124 (case_cone), SURVEY.md section 8(d) (configs).
 """
+import ctypes as ct
+import os
+import subprocess
+
 import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def cone_dem(n=256):
@@ -59,3 +65,31 @@ def value_noise_dem(row0, nrows, ncols, seed=2, octaves=8, base=1024, lo=1.0, hi
         amp *= 0.55
     out /= norm
     return lo + (hi - lo) * out
+
+
+def _host_lib():
+    src = os.path.join(_HERE, "csrc_host", "priority_flood.c")
+    so = os.path.join(_HERE, "libpdm_synth.so")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-o", so, src])
+    L = ct.CDLL(so)
+    L.pdm_priority_flood_eps.restype = ct.c_int64
+    L.pdm_priority_flood_eps.argtypes = [np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS"), ct.c_int64, ct.c_int64,
+                                         ct.c_double]
+    return L
+
+
+def priority_flood(elev, eps=1e-3):
+    """Priority-flood + epsilon conditioning (in a copy): every cell gets a strictly descending
+    path to the border (no interior pits / flats)."""
+    E = np.array(elev, dtype=np.float64, order="C", copy=True)
+    n = _host_lib().pdm_priority_flood_eps(E, E.shape[0], E.shape[1], float(eps))
+    if n < 0:
+        raise MemoryError("priority_flood")
+    return E
+
+
+def conditioned_fractal_dem(n, seed=0, eps=1e-3, **kw):
+    """The fractal DEM after hydrological conditioning: long river networks draining to the border
+    (BASELINE.json configs[1] primary variant)."""
+    return priority_flood(fractal_dem(n, seed, **kw), eps)
