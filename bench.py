@@ -107,12 +107,12 @@ class ClockSampler(object):
 # ----------------------------------------------------------------------------------------------
 # CPU legs (oracle = checker; only this file's cpu_baseline / --impl reference legs may time it)
 # ----------------------------------------------------------------------------------------------
-def _cpu_hot_path(E, use_ref_sweep):
+def _cpu_hot_path(E, use_ref_sweep, drain_pits=False):
     """One pass of the hot path on one host core.  use_ref_sweep: run the accumulation with the
     reference's own compiled Cython kernel (oracle/_ref/cyutils*.so, built from
     /root/reference/pydem/cyfuncs/cyutils.pyx) instead of the oracle's restatement of it."""
     from oracle import oracle as orc
-    dp = orc.OracleDEMProcessor(E, dX=SPACING, dY=SPACING, fill_flats=False, drain_pits_path=False, drain_pits=False)
+    dp = orc.OracleDEMProcessor(E, dX=SPACING, dY=SPACING, fill_flats=False, drain_pits_path=False, drain_pits=drain_pits)
     dp.calc_slopes_directions()
     if not use_ref_sweep:
         dp.calc_uca()
@@ -137,15 +137,15 @@ def _cpu_hot_path(E, use_ref_sweep):
 
 
 def _ref_worker(args):
-    seed, n, use_ref = args
+    seed, n, use_ref, variant = args
     from pydem_b200 import synth
-    E = synth.fractal_dem(n, seed)
+    E = synth.conditioned_fractal_dem(n, seed) if variant == "conditioned" else synth.fractal_dem(n, seed)
     t = time.perf_counter()
     cells = _cpu_hot_path(E, use_ref)
     return cells, time.perf_counter() - t
 
 
-def cpu_baseline_leg(E_full, window=2048):
+def cpu_baseline_leg(E_full, window=1024):
     """Oracle port, one core, on the top-left window of the benchmark DEM."""
     w = min(window, E_full.shape[0], E_full.shape[1])
     E = np.ascontiguousarray(E_full[:w, :w])
@@ -173,24 +173,25 @@ def reference_arm(args):
     orc.build()
     use_ref = ref_harness.load_ref_cyutils() is not None
     cores = os.cpu_count() or 1
-    win = 1024
+    win = 1024 if args.steps <= 8 else 512      # bounded sample: the whole run stays within a few minutes
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         for _ in range(max(args.warmup, 0) and 1):
-            pool.map(_ref_worker, [(1000 + c, 256, use_ref) for c in range(cores)])
+            pool.map(_ref_worker, [(1000 + c, 256, use_ref, args.variant) for c in range(cores)])
         t0 = time.perf_counter()
         cells = 0
         for s in range(args.steps):
-            res = pool.map(_ref_worker, [(s * cores + c, win, use_ref) for c in range(cores)])
+            res = pool.map(_ref_worker, [(s * cores + c, win, use_ref, args.variant) for c in range(cores)])
             cells += sum(r[0] for r in res)
         dt = time.perf_counter() - t0
     val = cells / dt / 1e6
     line = {"metric": METRIC, "value": val, "unit": "Mcells/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "fractal DEM, dX=dY=30 m, slope+aspect + UCA + TWI, fill_flats=False, "
-                                   "drain_pits_path=False, drain_pits=False; bounded sample: %d windows of %dx%d per "
-                                   "step (one per host core)" % (cores, win, win)},
+            "config": {"workload": "%s fractal DEM, dX=dY=30 m, slope+aspect + UCA + TWI, fill_flats=False, "
+                                   "drain_pits_path=False, pit drains off in the CPU sweep; bounded sample: %d windows of "
+                                   "%dx%d per step (one per host core)"
+                                   % ("priority-flood conditioned" if args.variant == "conditioned" else "raw", cores, win, win)},
             "cpu_baseline": {"value": val, "unit": "Mcells/s", "cores": cores,
                              "kind": "reference" if use_ref else "port",
                              "sample": ("UCA sweep = the reference's compiled cyutils.drain_area (oracle/_ref); " if use_ref
@@ -205,6 +206,14 @@ def reference_arm(args):
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
+def _note(msg):
+    if os.environ.get("PDM_BENCH_VERBOSE"):
+        print("[bench rank %s %.1fs] %s" % (os.environ.get("RANK", "0"), time.perf_counter() - _T0, msg), file=sys.stderr, flush=True)
+
+
+_T0 = time.perf_counter()
+
+
 def gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -227,8 +236,16 @@ def gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    variant = args.variant
+    if variant == "conditioned":
+        # BASELINE.md primary variant: conditioned once on the host (priority-flood + eps; rows wrap so
+        # that the same block tiles vertically for the N>1 runs) -> long river networks, no interior pits
+        E = synth.conditioned_fractal_dem(n, 0, wrap_rows=True)
+    else:
+        E = synth.fractal_dem(n, 0)                      # secondary 'sinks' variant: raw fractal
+    pits_flag = 1 if (variant == "conditioned" and world == 1) else 0
+    flags_txt = ("fill_flats=False, drain_pits_path=False, drain_pits=%s" % bool(pits_flag))
     if world == 1:
-        E = synth.fractal_dem(n, 0)
         stream = torch.cuda.current_stream().cuda_stream
         dt = T.DeviceTile(n, n, stream=stream)
         dt.set_spacing(SPACING, SPACING)
@@ -237,18 +254,19 @@ def gpu_arm(args):
 
         def step():
             dt.slopes_directions()
-            st = dt.uca(drain_pits=0)
+            st = dt.uca(drain_pits=pits_flag)
             dt.twi()
             stats.update(st)
             return st
         cells_per_step = n * n
-        workload = ("%dx%d fractal DEM (spectral synthesis, seed 0, H=0.8, 1..1001 m), dX=dY=30 m, "
-                    "slope+aspect + UCA + TWI, fill_flats=False, drain_pits_path=False, drain_pits=False "
-                    "(BASELINE.json configs[1], 'sinks' variant)" % (n, n))
+        workload = ("%dx%d fractal DEM (spectral synthesis, seed 0, H=0.8, 1..1001 m%s), dX=dY=30 m, "
+                    "slope+aspect + UCA + TWI, %s (BASELINE.json configs[1], %s variant)"
+                    % (n, n, ", priority-flood+eps conditioned" if variant == "conditioned" else "", flags_txt,
+                       "primary" if variant == "conditioned" else "'sinks'"))
         parallelism = "1 GPU, single tile"
     else:
         from pydem_b200 import sharded
-        sh = sharded.ShardedDEM(rows_per_rank=n, cols=n, spacing=SPACING, seed=0, profile=True)
+        sh = sharded.ShardedDEM(rows_per_rank=n, cols=n, spacing=SPACING, seed=0, profile=True, block=E)
         stats = {}
 
         def step():
@@ -256,16 +274,19 @@ def gpu_arm(args):
             stats.update(st)
             return st
         cells_per_step = n * n * world
-        workload = ("%dx%d DEM = the %dx%d fractal block of the 1-GPU run repeated %d times vertically (periodic, "
+        workload = ("%dx%d DEM = the %dx%d block of the 1-GPU run (%s) repeated %d times vertically (periodic, "
                     "seamless), row-sharded over %d GPUs (%d rows each, halo rows over NCCL send/recv), dX=dY=30 m, "
-                    "slope+aspect + UCA + TWI, conditioning flags off, drain_pits=False"
-                    % (n * world, n, n, n, world, world, n))
+                    "slope+aspect + UCA + TWI, %s (pit drains are not available on shards)"
+                    % (n * world, n, n, n, "conditioned fractal" if variant == "conditioned" else "raw fractal", world,
+                       world, n, flags_txt))
         parallelism = "row-block x%d" % world
 
     sampler = ClockSampler(local) if rank == 0 else None
+    _note("setup done")
     for _ in range(args.warmup):
         step()
     barrier()
+    _note("warmup done")
     t_begin = sampler.mark() if sampler else None
     launches0 = L.pdm_launch_count()
     ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
@@ -278,6 +299,7 @@ def gpu_arm(args):
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
+    _note("timed loop done: %.1f ms" % ms)
     launches = L.pdm_launch_count() - launches0
     clocks = sampler.stop(t_begin, sampler.mark()) if sampler else None
     if world > 1:
@@ -291,7 +313,7 @@ def gpu_arm(args):
     e2e = None
     if world == 1:
         Eh = _pinned.pinned_copy(E)
-        kw = dict(dX=SPACING, dY=SPACING, fill_flats=False, drain_pits_path=False, drain_pits=False)
+        kw = dict(dX=SPACING, dY=SPACING, fill_flats=False, drain_pits_path=False, drain_pits=bool(pits_flag))
 
         def e2e_step():
             dp = DEMProcessor(elev=Eh, **kw)
@@ -313,6 +335,7 @@ def gpu_arm(args):
                "d2h_bytes_per_step": int(n * n * (8 * 4 + 3))}
     else:
         e2e = sh.e2e(args.steps)
+    _note("e2e done")
 
     if rank != 0:
         return
@@ -357,6 +380,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=4096, help="rows (per GPU) = columns of the DEM")
+    ap.add_argument("--variant", default="conditioned", choices=["conditioned", "sinks"],
+                    help="conditioned: priority-flood conditioned fractal, default flags (BASELINE.md primary); "
+                         "sinks: raw fractal with drain_pits=False")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -134,6 +134,7 @@ enum {
     CT_PHASE1 = 48,    // warps that finished the source scan
     CT_DRAINED = 64,   // cells drained
     CT_CHUNK = 72,     // next 32-entry chunk of the seed scan
+
     CT_SOURCES = 80,
     CT_UNDONE = 81,
     CT_BADSEC = 82,
@@ -145,6 +146,7 @@ enum {
     CT_TMP0 = 99,
     CT_TMP1 = 100,
     CT_ABORT = 101,
+    CT_WATCHDOG = 104, // set by a warp that saw no progress for seconds; sticky until the next graph build
     CT_T_START = 112,  // work-list timing (globaltimer ns): first warp in
     CT_T_SCAN = 113,   // last warp finished its seed scan (+ scan-born chains)
     CT_T_END = 114,    // last warp out

@@ -208,6 +208,12 @@ int pdm_shard_finalize(pdm_tile *t, const pdm_uca_params *p_in, pdm_uca_stats *s
     if (rc) return rc;
     rc = read_ctr(t);
     if (rc) return rc;
+    if (t->h_counters[CT_WATCHDOG]) {
+        pdm_set_error("pdm_shard_finalize: work-list watchdog fired (QTAIL=%llu QHEAD=%llu QDONE=%llu PHASE1=%llu DRAINED=%llu)",
+                      t->h_counters[CT_QTAIL], t->h_counters[CT_QHEAD], t->h_counters[CT_QDONE], t->h_counters[CT_PHASE1],
+                      t->h_counters[CT_DRAINED]);
+        return PDM_ERR_STATE;
+    }
     t->have_uca = true; t->have_graph = true;
     if (stats) {
         memset(stats, 0, sizeof(*stats));

@@ -198,7 +198,10 @@ int pdm_launch_update(pdm_tile *t, const pdm_uca_params *p, const double *const 
                              cudaMemcpyDeviceToHost, t->stream));
     PDM_CUDA(cudaMemcpyAsync(t->h_counters + CT_EDGE_TODO, t->d_counters + CT_EDGE_TODO, sizeof(unsigned long long),
                              cudaMemcpyDeviceToHost, t->stream));
+    PDM_CUDA(cudaMemcpyAsync(t->h_counters + CT_WATCHDOG, t->d_counters + CT_WATCHDOG, sizeof(unsigned long long),
+                             cudaMemcpyDeviceToHost, t->stream));
     PDM_CUDA(cudaStreamSynchronize(t->stream));
+    if (t->h_counters[CT_WATCHDOG]) { pdm_set_error("pdm_tile_uca_update: work-list watchdog fired"); return PDM_ERR_STATE; }
     if (st) {
         st->n_sources = (int64_t)t->h_counters[CT_SOURCES];
         st->n_drained = (int64_t)t->h_counters[CT_DRAINED];

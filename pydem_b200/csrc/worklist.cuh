@@ -128,7 +128,9 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
     int origin = 0;          // 1: chain started at a scanned seed, 2: at a queue item
     bool p1_reported = false;
     unsigned long long processed = 0;
-    unsigned idle_polls = 0;
+    unsigned idle_polls = 0, iters = 0;
+    unsigned long long idle_since = 0;   // watchdog: a warp that sees no progress for WATCHDOG_NS raises CT_WATCHDOG
+    const unsigned long long WATCHDOG_NS = 4000000000ULL;
     if (lane == 0) atomicMin(&q.ctr[CT_T_START], globaltimer_ns());
 
     for (;;) {
@@ -211,9 +213,27 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
                     term = __shfl_sync(full, term, 0);
                 }
                 if (term) break;
+                // watchdog (never fires in a correct run): instead of spinning forever on a lost
+                // item, give up loudly -- the host turns CT_WATCHDOG into an error
+                if ((idle_polls & 63u) == 0) {
+                    int quit = 0;
+                    if (lane == 0) {
+                        const unsigned long long now = globaltimer_ns();
+                        if (idle_since == 0) idle_since = now;
+                        else if (now - idle_since > WATCHDOG_NS) atomicExch(&q.ctr[CT_WATCHDOG], 1ULL);
+                        quit = ld_volatile_u64(q.ctr + CT_WATCHDOG) != 0;
+                    }
+                    if (__shfl_sync(full, quit, 0)) break;
+                }
                 __nanosleep(200);
             }
             continue;
+        }
+        idle_since = 0;
+        if ((++iters & 4095u) == 0) {
+            int quit = 0;
+            if (lane == 0) quit = ld_volatile_u64(q.ctr + CT_WATCHDOG) != 0;
+            if (__shfl_sync(full, quit, 0)) break;
         }
         // ---- one step per working lane
         bool finished_q = false;
@@ -304,6 +324,19 @@ static __global__ void k_queue_zero(unsigned long long *ctr, int keep_drained)
     ctr[CT_QTAIL] = 0; ctr[CT_QHEAD] = 0; ctr[CT_QDONE] = 0; ctr[CT_PHASE1] = 0; ctr[CT_CHUNK] = 0;
     if (!keep_drained) ctr[CT_DRAINED] = 0;
     ctr[CT_T_START] = ~0ULL; ctr[CT_T_SCAN] = 0; ctr[CT_T_END] = 0;
+}
+
+// host: after a run's counters were read back, turn a fired watchdog into an error
+inline int check_watchdog(pdm_tile *t)
+{
+    const unsigned long long *h = t->h_counters;
+    if (h[CT_WATCHDOG]) {
+        pdm_set_error("work-list watchdog fired: no progress for 4 s (QTAIL=%llu QHEAD=%llu QDONE=%llu PHASE1=%llu CHUNK=%llu "
+                      "DRAINED=%llu); results are incomplete", h[CT_QTAIL], h[CT_QHEAD], h[CT_QDONE], h[CT_PHASE1], h[CT_CHUNK],
+                      h[CT_DRAINED]);
+        return PDM_ERR_STATE;
+    }
+    return PDM_OK;
 }
 
 // host: reset the queue state before a run (slots to -1, the queue counters to 0)

@@ -34,8 +34,11 @@ static item pop(item *h, int64_t *n)
     return top;
 }
 
-/* in place; returns the number of raised cells, -1 on allocation failure */
-int64_t pdm_priority_flood_eps(double *E, int64_t R, int64_t C, double eps)
+/* in place; returns the number of raised cells, -1 on allocation failure.
+ * wrap_rows != 0: rows wrap around (row R-1 is adjacent to row 0) and only the left/right columns
+ * are outlets -- the conditioned block can then be stacked vertically any number of times into one
+ * seamless, already conditioned DEM (row-sharded weak-scaling runs). */
+int64_t pdm_priority_flood_eps2(double *E, int64_t R, int64_t C, double eps, int wrap_rows)
 {
     int64_t N = R * C, nh = 0, raised = 0;
     item *h = (item *)malloc((size_t)N * sizeof(item));
@@ -43,7 +46,7 @@ int64_t pdm_priority_flood_eps(double *E, int64_t R, int64_t C, double eps)
     if (!h || !closed) { free(h); free(closed); return -1; }
     for (int64_t i = 0; i < R; i++)
         for (int64_t j = 0; j < C; j++)
-            if (i == 0 || j == 0 || i == R - 1 || j == C - 1) {
+            if (j == 0 || j == C - 1 || (!wrap_rows && (i == 0 || i == R - 1))) {
                 item x = {E[i * C + j], i * C + j};
                 closed[i * C + j] = 1; push(h, &nh, x);
             }
@@ -53,6 +56,7 @@ int64_t pdm_priority_flood_eps(double *E, int64_t R, int64_t C, double eps)
         for (int di = -1; di <= 1; di++)
             for (int dj = -1; dj <= 1; dj++) {
                 int64_t ni = ci + di, nj = cj + dj;
+                if (wrap_rows) ni = (ni + R) % R;
                 if ((!di && !dj) || ni < 0 || ni >= R || nj < 0 || nj >= C) continue;
                 int64_t n = ni * C + nj;
                 if (closed[n]) continue;
@@ -64,4 +68,9 @@ int64_t pdm_priority_flood_eps(double *E, int64_t R, int64_t C, double eps)
     }
     free(h); free(closed);
     return raised;
+}
+
+int64_t pdm_priority_flood_eps(double *E, int64_t R, int64_t C, double eps)
+{
+    return pdm_priority_flood_eps2(E, R, C, eps, 0);
 }

@@ -352,7 +352,7 @@ class ShardedDEM(object):
     """bench.py's N>1 workload: a value-noise DEM of (rows_per_rank * world) x cols, one row block
     per rank of the torch.distributed job; ``step()`` runs the whole hot path once."""
 
-    def __init__(self, rows_per_rank, cols, spacing=30.0, seed=0, profile=False):
+    def __init__(self, rows_per_rank, cols, spacing=30.0, seed=0, profile=False, block=None):
         import torch
         from . import tile as T
         self.T, self.torch = T, torch
@@ -364,10 +364,12 @@ class ShardedDEM(object):
         d = np.full(R - 1, float(spacing)); d2 = np.full(R, float(spacing))
         self.engine = ShardEngine(s, d, d, d2, d2, stream=torch.cuda.current_stream().cuda_stream)
         loc = np.full((s.Rl, cols), np.nan)
-        # every rank holds the same periodic spectral-synthesis block: stacked vertically the blocks
-        # join seamlessly (FFT fields are periodic), so per-GPU work is identical (weak scaling) and
-        # flow really crosses the shard boundaries
-        loc[s.lo:s.hi] = synth.fractal_dem(rows_per_rank, seed, shape=(rows_per_rank, cols))
+        # every rank holds the same periodic block (spectral synthesis, conditioned with wrapping
+        # rows): stacked vertically the blocks join seamlessly, so per-GPU work is identical (weak
+        # scaling) and rivers really cross the shard boundaries
+        if block is None:
+            block = synth.conditioned_fractal_dem(rows_per_rank, seed, shape=(rows_per_rank, cols), wrap_rows=True)
+        loc[s.lo:s.hi] = block
         self.profile = profile
         self.host_elev = loc
         self.engine.tile.upload(T.F_ELEV, loc)

@@ -73,23 +73,25 @@ def _host_lib():
     if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
         subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-o", so, src])
     L = ct.CDLL(so)
-    L.pdm_priority_flood_eps.restype = ct.c_int64
-    L.pdm_priority_flood_eps.argtypes = [np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS"), ct.c_int64, ct.c_int64,
-                                         ct.c_double]
+    L.pdm_priority_flood_eps2.restype = ct.c_int64
+    L.pdm_priority_flood_eps2.argtypes = [np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS"), ct.c_int64, ct.c_int64,
+                                          ct.c_double, ct.c_int]
     return L
 
 
-def priority_flood(elev, eps=1e-3):
+def priority_flood(elev, eps=1e-3, wrap_rows=False):
     """Priority-flood + epsilon conditioning (in a copy): every cell gets a strictly descending
-    path to the border (no interior pits / flats)."""
+    path to the border (no interior pits / flats).  ``wrap_rows``: rows wrap around and only the
+    left/right columns are outlets, so the block can be stacked vertically into one seamless,
+    conditioned DEM."""
     E = np.array(elev, dtype=np.float64, order="C", copy=True)
-    n = _host_lib().pdm_priority_flood_eps(E, E.shape[0], E.shape[1], float(eps))
+    n = _host_lib().pdm_priority_flood_eps2(E, E.shape[0], E.shape[1], float(eps), int(bool(wrap_rows)))
     if n < 0:
         raise MemoryError("priority_flood")
     return E
 
 
-def conditioned_fractal_dem(n, seed=0, eps=1e-3, **kw):
+def conditioned_fractal_dem(n, seed=0, eps=1e-3, wrap_rows=False, **kw):
     """The fractal DEM after hydrological conditioning: long river networks draining to the border
     (BASELINE.json configs[1] primary variant)."""
-    return priority_flood(fractal_dem(n, seed, **kw), eps)
+    return priority_flood(fractal_dem(n, seed, **kw), eps, wrap_rows)
