@@ -130,8 +130,8 @@ int pdm_launch_pits(pdm_tile *t, const pdm_uca_params *p);
 enum {
     CT_QTAIL = 0,      // sweep queue: items produced
     CT_QHEAD = 16,     // tickets handed out
-    CT_QDONE = 32,     // items completely processed
-    CT_PHASE1 = 48,    // warps that finished the source scan
+    CT_QDONE = 32,     // chains (seed- or queue-born) that have completely ended
+    CT_PHASE1 = 48,    // (unused)
     CT_DRAINED = 64,   // cells drained
     CT_CHUNK = 72,     // next 32-entry chunk of the seed scan
 

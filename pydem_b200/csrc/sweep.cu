@@ -83,7 +83,7 @@ int pdm_launch_sweep_first(pdm_tile *t)
     const Win &w = t->win;
     DrainOp<0> op{t->link, t->cell, nullptr, (int32_t)t->C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w};
     wl::k_worklist<<<g_sweep_blocks, 256, 0, t->stream>>>(op, wl::DomainRange{w.lo * w.C, (w.hi - w.lo) * w.C},
-                                                          wl::Queue{t->queue, t->d_counters, (long long)t->N});
+                                                          wl::Queue{t->queue, t->d_counters, (long long)t->N, t->d_counters + CT_SOURCES});
     PDM_LAUNCHED();
     return PDM_OK;
 }
@@ -99,7 +99,7 @@ int pdm_launch_sweep_resume(pdm_tile *t)
     if (rc) return rc;
     DrainOp<2> op{t->link, t->cell, nullptr, (int32_t)t->C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w};
     wl::k_worklist<<<g_resume_blocks, 256, 0, t->stream>>>(op, wl::DomainList{t->label, t->d_counters + CT_TMP1},
-                                                           wl::Queue{t->queue, t->d_counters, (long long)t->N});
+                                                           wl::Queue{t->queue, t->d_counters, (long long)t->N, t->d_counters + CT_TMP1});
     PDM_LAUNCHED();
     return PDM_OK;
 }

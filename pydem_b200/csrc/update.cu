@@ -171,7 +171,8 @@ int pdm_launch_update(pdm_tile *t, const pdm_uca_params *p, const double *const 
                                                                        t->uca, t->flats, R, C, t->cell, stt, t->edge_todo,
                                                                        t->d_counters);
     PDM_LAUNCHED();
-    const wl::Queue q{t->queue, t->d_counters, (long long)t->N};
+    const wl::Queue q{t->queue, t->d_counters, (long long)t->N, t->d_counters + CT_SOURCES};       // seeds: start cells
+    const wl::Queue q2{t->queue, t->d_counters, (long long)t->N, t->d_counters + CT_EDGE_TODO};    // seeds: remaining todo cells
     const wl::DomainBorder dom{R, C};
     // flood 1: cone + restricted in-degree (820-831)
     if ((rc = wl::reset_queue(t))) return rc;
@@ -189,7 +190,7 @@ int pdm_launch_update(pdm_tile *t, const pdm_uca_params *p, const double *const 
     // flood 2: remaining todo cells taint everything downstream (848-853)
     if ((rc = wl::reset_queue(t))) return rc;
     wl::k_worklist<<<g_blocks_flood1, 256, 0, t->stream>>>(
-        FloodOp<1>{t->cell, stt, (int32_t)C, t->pit_beg, t->pit_end, t->pit_dst}, dom, q);
+        FloodOp<1>{t->cell, stt, (int32_t)C, t->pit_beg, t->pit_end, t->pit_dst}, dom, q2);
     PDM_LAUNCHED();
     k_upd_finalize<<<(unsigned)((t->N + 255) / 256), 256, 0, t->stream>>>(t->cell, stt, t->N, t->uca, t->edge_done);
     PDM_LAUNCHED();

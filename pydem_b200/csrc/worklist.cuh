@@ -10,12 +10,12 @@
 //     continues with (chain following) or -1; one more ready cell can be returned in `defer`
 //     (pushed to the global queue with one warp-aggregated fetch-and-add), further ones are
 //     pushed directly (rare: pit drains),
-//   * termination: every warp has finished its scan and scan-born chains (CT_PHASE1 ==
-//     #warps) and every queued item has been completely processed (CT_QDONE == CT_QTAIL).
-//     Reading QDONE, then PHASE1, then QTAIL makes the test race-free: both counters are
-//     monotonic and QDONE <= QTAIL always, so equality observed in that order means there
-//     was an instant with no active chain and an empty queue, after which nothing can be
-//     produced.
+//   * termination: the number of seeds S is known before the launch (the kernels that flag
+//     the seeds count them), every chain -- whether it started at a seed or at a queue item --
+//     bumps CT_QDONE when it has completely ended, and every queue push bumps CT_QTAIL.  Always
+//     QDONE <= seeds dealt + QTAIL <= S + QTAIL, all monotonic; so reading QDONE first and QTAIL
+//     second and finding QDONE == S + QTAIL proves that at the first read every seed had been
+//     dealt and every started chain had ended: nothing can be produced any more.
 // Every cell may enter the queue at most once per run, so a queue of N+1 slots suffices.
 #pragma once
 #include "pdm_internal.cuh"
@@ -57,6 +57,7 @@ struct Queue {
     int32_t *slots;
     unsigned long long *ctr;
     long long cap;  // number of slots (a cell is queued at most once per run: N suffices)
+    const unsigned long long *nseeds;  // device counter: exact number of seeds in the scan domain
     __device__ __forceinline__ void push(int32_t cell) const
     {
         const unsigned long long slot = atomicAdd(&ctr[CT_QTAIL], 1ULL);
@@ -100,7 +101,6 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-    const unsigned long long nwarps = (unsigned long long)(nthreads >> 5);
     const int64_t dsize = dom.size();
     const long long nchunks = (long long)((dsize + 31) >> 5);
     // seed scan state (warp-uniform): the scan domain is cut into chunks of 32 consecutive
@@ -125,8 +125,9 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
     int32_t stash = -1, stash2 = -1, stash3 = -1;   // ready receivers kept for after the current chain (see below)
     int chain_len = 0;
     long long ticket = -1;   // queue slot this lane is entitled to (fetch-and-add ticket, never fails)
-    int origin = 0;          // 1: chain started at a scanned seed, 2: at a queue item
-    bool p1_reported = false;
+    bool active = false;     // this lane owns an unfinished chain (current cell and/or stash)
+    bool scan_stamped = false;
+    const unsigned long long nseeds = *q.nseeds;
     unsigned long long processed = 0;
     unsigned idle_polls = 0, iters = 0;
     unsigned long long idle_since = 0;   // watchdog: a warp that sees no progress for WATCHDOG_NS raises CT_WATCHDOG
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
             const bool take = (cur < 0) && k < npend;
             const int src = take ? (int)__fns(pend_mask, 0, k + 1) : 0;
             const int32_t c = __shfl_sync(full, pend_cell, src);
-            if (take) { cur = c; origin = 1; chain_len = 0; }
+            if (take) { cur = c; active = true; chain_len = 0; }
             int ntake = __popc(idle_mask);
             if (ntake > npend) ntake = npend;
             for (int i = 0; i < ntake; i++) pend_mask &= pend_mask - 1;   // drop the seeds just handed out
@@ -179,18 +180,12 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
         }
         if (cur < 0 && ticket >= 0 && ticket < q.cap) {
             const int32_t v = ld_volatile_i32(q.slots + ticket);
-            if (v >= 0) { cur = v; origin = 2; ticket = -1; chain_len = 0; }
+            if (v >= 0) { cur = v; active = true; ticket = -1; chain_len = 0; }
         }
-        // ---- scan accounting: a warp reports once its scan and scan-born chains have ended
-        if (!p1_reported) {
-            const unsigned busy1 = __ballot_sync(full, cur >= 0 && origin == 1);
-            if (!scanning && busy1 == 0) {
-                if (lane == 0) {
-                    atomicAdd(&q.ctr[CT_PHASE1], 1ULL);
-                    atomicMax(&q.ctr[CT_T_SCAN], globaltimer_ns());
-                }
-                p1_reported = true;
-            }
+        // ---- statistics only: when did the last warp run out of seeds
+        if (!scanning && !scan_stamped) {
+            if (lane == 0) atomicMax(&q.ctr[CT_T_SCAN], globaltimer_ns());
+            scan_stamped = true;
         }
         // ---- nothing to do in this warp: terminate on global quiescence, else back off
         const unsigned work_mask = __ballot_sync(full, cur >= 0);
@@ -202,13 +197,12 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
                 int term = 0;
                 if ((++idle_polls & 3u) == 0) {
                     if (lane == 0) {
-                        // the proof needs QDONE to be read before PHASE1 before QTAIL; the three
-                        // lines live in different L2 slices, so each address is made to depend on
-                        // the previous value (dependent loads cannot pass each other)
+                        // the proof needs QDONE to be read before QTAIL; the two lines live in
+                        // different L2 slices, so the second address is made to depend on the first
+                        // value (dependent loads cannot pass each other)
                         const unsigned long long d = ld_volatile_u64(q.ctr + CT_QDONE);
-                        const unsigned long long p1 = ld_volatile_u64(q.ctr + CT_PHASE1 + dep_zero_u64(d));
-                        const unsigned long long t = ld_volatile_u64(q.ctr + CT_QTAIL + dep_zero_u64(p1));
-                        term = (p1 == nwarps && d == t) ? 1 : 0;
+                        const unsigned long long t = ld_volatile_u64(q.ctr + CT_QTAIL + dep_zero_u64(d));
+                        term = (d == nseeds + t) ? 1 : 0;
                     }
                     term = __shfl_sync(full, term, 0);
                 }
@@ -235,6 +229,30 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
             if (lane == 0) quit = ld_volatile_u64(q.ctr + CT_WATCHDOG) != 0;
             if (__shfl_sync(full, quit, 0)) break;
         }
+        // ---- express fast path: lane 0 is the only lane with work and the warp has no seeds left
+        //      to deal -> follow the chain to its end in a tight single-lane loop (no warp
+        //      collectives between cells: the critical path pays memory round trips only)
+        if (!scanning && work_mask == 1u) {
+            if (lane == 0) {
+                unsigned spin = 0;
+                while (cur >= 0) {
+                    processed++;
+                    int32_t d2 = -1;
+                    const int32_t nxt = op.process(cur, q, d2);
+                    if (d2 >= 0) q.push(d2);           // the other ready receiver: another express warp takes it
+                    cur = nxt;
+                    // cells stashed while the warp was still scanning belong to this chain: they must
+                    // be finished before the chain counts as ended
+                    if (cur < 0 && stash >= 0) { cur = stash; stash = stash2; stash2 = stash3; stash3 = -1; }
+                    if ((++spin & 8191u) == 0 && ld_volatile_u64(q.ctr + CT_WATCHDOG) != 0) break;
+                }
+                atomicAdd(&q.ctr[CT_QDONE], 1ULL);
+                active = false;
+                cur = -1;
+            }
+            __syncwarp(full);
+            continue;
+        }
         // ---- one step per working lane
         bool finished_q = false;
         int32_t defer = -1;  // second ready receiver: handed to the queue, warp-aggregated below
@@ -256,7 +274,7 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
             if (scanning && defer < 0 && chain_len > HANDOFF) {
                 if (cur >= 0) { defer = cur; cur = -1; chain_len = 0; }
             }
-            if (cur < 0 && stash < 0) { finished_q = (origin == 2); origin = 0; }
+            if (cur < 0 && stash < 0) { finished_q = active; active = false; }
         }
         const unsigned pm = __ballot_sync(full, defer >= 0);
         if (pm) {
