@@ -332,7 +332,7 @@ def gpu_arm(args):
         t_e2e = (time.perf_counter() - t0) / args.steps
         e2e = {"value": cells_per_step / t_e2e / 1e6, "unit": "Mcells/s", "ms_per_step": t_e2e * 1e3,
                "h2d_bytes_per_step": int(n * n * 8 + 4 * n * 8),
-               "d2h_bytes_per_step": int(n * n * (8 * 4 + 3))}
+               "d2h_bytes_per_step": int(n * n * (8 * 5 + 3))}   # mag, direction, uca, twi, 10*twi + 3 masks
     else:
         e2e = sh.e2e(args.steps)
     _note("e2e done")

@@ -130,6 +130,9 @@ int pdm_tile_set_spacing(pdm_tile *t, const double *dX, const double *dY,
 /* host <-> device for one field (sizes implied by the tile shape and the field dtype) */
 int pdm_tile_upload(pdm_tile *t, int field, const void *host);
 int pdm_tile_download(pdm_tile *t, int field, void *host);
+/* like pdm_tile_download, but the copy runs on a side stream after the work queued so far and
+ * overlaps later stages; the host buffer (page-locked: pdm_host_alloc) is valid after pdm_tile_sync */
+int pdm_tile_download_async(pdm_tile *t, int field, void *host);
 /* raw device pointer of a field (for zero-copy interop, e.g. NCCL halo exchange) */
 int pdm_tile_device_ptr(pdm_tile *t, int field, void **dev);
 /* declare a field valid after writing it through pdm_tile_device_ptr (device-side producers) */
@@ -152,6 +155,11 @@ int pdm_tile_find_flats(pdm_tile *t);
  * In: ELEV, DIR, MAG, FLATS.  Out: UCA, EDGE_TODO, EDGE_DONE; MAG/FLATS updated at
  * drained pits (1370-1371).  stats may be NULL. */
 int pdm_tile_uca(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *stats);
+/* The cells the last pdm_tile_uca examined as pits (flats & elev > 0) with their MAG / FLATS values
+ * after the search -- the only cells of MAG / FLATS that calc_uca changes (dem_processing.py:1370-1371),
+ * so a host mirror can patch its arrays in place without downloading whole fields.  Call with
+ * capacity 0 to learn *n (= pdm_uca_stats.n_pits). */
+int pdm_tile_pit_updates(pdm_tile *t, int64_t capacity, int32_t *cells, double *mag, uint8_t *flats, int64_t *n);
 /* a8: calc_uca(uca_init, edge_init_data) (719-744, 769-771) + _calc_uca_chunk_update
  * (778-862).  UCA must hold uca_init.  Edge strips: left/right have R entries, top/bottom
  * C entries; data f64, done/todo u8.  Out: UCA += delta, EDGE_TODO, EDGE_DONE. */

@@ -49,8 +49,8 @@ class TwiParams(ct.Structure):
 EXPORTS = [
     "pdm_abi_version", "pdm_last_error", "pdm_init", "pdm_device_count", "pdm_default_uca_params",
     "pdm_default_twi_params", "pdm_launch_count", "pdm_host_alloc", "pdm_host_free", "pdm_tile_create", "pdm_tile_destroy", "pdm_tile_set_spacing",
-    "pdm_tile_upload", "pdm_tile_download", "pdm_tile_device_ptr", "pdm_tile_mark_resident", "pdm_tile_set_stencil_parity", "pdm_tile_sync", "pdm_selftest_division",
-    "pdm_tile_slopes_directions", "pdm_tile_find_flats", "pdm_tile_uca", "pdm_tile_uca_update",
+    "pdm_tile_upload", "pdm_tile_download", "pdm_tile_download_async", "pdm_tile_device_ptr", "pdm_tile_mark_resident", "pdm_tile_set_stencil_parity", "pdm_tile_sync", "pdm_selftest_division",
+    "pdm_tile_slopes_directions", "pdm_tile_find_flats", "pdm_tile_uca", "pdm_tile_pit_updates", "pdm_tile_uca_update",
     "pdm_tile_twi", "pdm_tile_set_window", "pdm_shard_slopes", "pdm_shard_ccl", "pdm_shard_label_pack",
     "pdm_shard_label_unpack", "pdm_shard_flats_extend", "pdm_shard_links", "pdm_shard_indeg", "pdm_shard_sweep",
     "pdm_shard_outbox_pack", "pdm_shard_inbox_begin", "pdm_shard_inbox_apply", "pdm_shard_finalize",
@@ -88,6 +88,7 @@ def load():
     L.pdm_tile_set_spacing.argtypes = [_vp] + [_vp] * 6
     L.pdm_tile_upload.argtypes = [_vp, ct.c_int, _vp]
     L.pdm_tile_download.argtypes = [_vp, ct.c_int, _vp]
+    L.pdm_tile_download_async.argtypes = [_vp, ct.c_int, _vp]
     L.pdm_tile_device_ptr.argtypes = [_vp, ct.c_int, ct.POINTER(_vp)]
     L.pdm_tile_mark_resident.argtypes = [_vp, ct.c_int]
     L.pdm_tile_set_stencil_parity.argtypes = [_vp, ct.c_int]
@@ -96,6 +97,7 @@ def load():
     L.pdm_tile_slopes_directions.argtypes = [_vp]
     L.pdm_tile_find_flats.argtypes = [_vp]
     L.pdm_tile_uca.argtypes = [_vp, ct.POINTER(UcaParams), ct.POINTER(UcaStats)]
+    L.pdm_tile_pit_updates.argtypes = [_vp, _i64, _vp, _vp, _vp, ct.POINTER(_i64)]
     L.pdm_tile_uca_update.argtypes = [_vp, ct.POINTER(UcaParams)] + [_vp] * 12 + [ct.POINTER(UcaStats)]
     L.pdm_tile_twi.argtypes = [_vp, ct.POINTER(TwiParams)]
     L.pdm_tile_set_window.argtypes = [_vp, _i64, _i64, _i64, _i64, _vp]

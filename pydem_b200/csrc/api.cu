@@ -158,6 +158,9 @@ int pdm_tile_create(int64_t R, int64_t C, void *stream, pdm_tile **out)
         if (e != cudaSuccess) { pdm_cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__); pdm_tile_destroy(t); return PDM_ERR_CUDA; }
     }
     cudaMemsetAsync(t->d_counters, 0, CT_N * sizeof(unsigned long long), t->stream);
+    e = cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->copy_ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) { pdm_cuda_fail(e, "copy stream", __FILE__, __LINE__); pdm_tile_destroy(t); return PDM_ERR_CUDA; }
     t->min_area = INFINITY;
     *out = t;
     return PDM_OK;
@@ -174,6 +177,8 @@ int pdm_tile_destroy(pdm_tile *t)
     for (void *p : ptrs) if (p) cudaFree(p);
     if (t->h_counters) cudaFreeHost(t->h_counters);
     for (int k = 0; k < 4; k++) if (t->ev[k]) cudaEventDestroy(t->ev[k]);
+    if (t->copy_stream) { cudaStreamSynchronize(t->copy_stream); cudaStreamDestroy(t->copy_stream); }
+    if (t->copy_ev) cudaEventDestroy(t->copy_ev);
     delete t;
     return PDM_OK;
 }
@@ -240,6 +245,21 @@ int pdm_tile_download(pdm_tile *t, int field, void *host)
     return PDM_OK;
 }
 
+// device -> host copy of one field, ordered after everything queued on the tile so far but not
+// blocking the tile's stream: the copy overlaps the next stage.  The host buffer (page-locked
+// for a truly asynchronous copy) is valid after pdm_tile_sync().
+int pdm_tile_download_async(pdm_tile *t, int field, void *host)
+{
+    if (!t || !host) { pdm_set_error("pdm_tile_download_async: NULL argument"); return PDM_ERR_ARG; }
+    if (field == PDM_F_SECTION) return pdm_tile_download(t, field, host);
+    void *d = field_ptr(t, field);
+    if (!d) { pdm_set_error("pdm_tile_download_async: unknown field %d", field); return PDM_ERR_ARG; }
+    PDM_CUDA(cudaEventRecord(t->copy_ev, t->stream));
+    PDM_CUDA(cudaStreamWaitEvent(t->copy_stream, t->copy_ev, 0));
+    PDM_CUDA(cudaMemcpyAsync(host, d, (size_t)t->N * field_elem_size(field), cudaMemcpyDeviceToHost, t->copy_stream));
+    return PDM_OK;
+}
+
 int pdm_tile_device_ptr(pdm_tile *t, int field, void **dev)
 {
     if (!t || !dev) { pdm_set_error("pdm_tile_device_ptr: NULL argument"); return PDM_ERR_ARG; }
@@ -279,6 +299,7 @@ int pdm_tile_sync(pdm_tile *t)
 {
     if (!t) return PDM_ERR_ARG;
     PDM_CUDA(cudaStreamSynchronize(t->stream));
+    PDM_CUDA(cudaStreamSynchronize(t->copy_stream));
     return PDM_OK;
 }
 
@@ -400,6 +421,15 @@ int pdm_tile_uca_update(pdm_tile *t, const pdm_uca_params *p_in,
     if (rc) return rc;
     if (stats) *stats = st;
     return PDM_OK;
+}
+
+int pdm_tile_pit_updates(pdm_tile *t, int64_t capacity, int32_t *cells, double *mag, uint8_t *flats, int64_t *n)
+{
+    if (!t || !n) { pdm_set_error("pdm_tile_pit_updates: NULL argument"); return PDM_ERR_ARG; }
+    *n = t->n_pits;
+    if (t->n_pits == 0) return PDM_OK;
+    if (capacity < t->n_pits || !cells || !mag || !flats) { pdm_set_error("pdm_tile_pit_updates: need room for %lld pits", (long long)t->n_pits); return PDM_ERR_ARG; }
+    return pdm_launch_pit_readback(t, cells, mag, flats);
 }
 
 int pdm_tile_twi(pdm_tile *t, const pdm_twi_params *p_in)

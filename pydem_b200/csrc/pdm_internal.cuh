@@ -89,6 +89,8 @@ struct pdm_tile {
     unsigned long long *d_counters;  // [32]
     unsigned long long *h_counters;  // pinned
     cudaEvent_t ev[4];
+    cudaStream_t copy_stream;   // device->host copies that overlap the next stage (pdm_tile_download_async)
+    cudaEvent_t copy_ev;
 };
 
 void pdm_set_error(const char *fmt, ...);
@@ -119,6 +121,7 @@ int pdm_launch_update(pdm_tile *t, const pdm_uca_params *p, const double *const 
                       const uint8_t *const done[4], const uint8_t *const todo[4], pdm_uca_stats *st);
 int pdm_launch_twi(pdm_tile *t, const pdm_twi_params *p);
 int pdm_launch_section_export(pdm_tile *t);
+int pdm_launch_pit_readback(pdm_tile *t, int32_t *cells, double *mag, uint8_t *flats);
 int pdm_launch_selftest_div(unsigned long long seed, int blocks, long long per_thread, unsigned long long *mismatch_host);
 int pdm_restart_rounds(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *st);
 int pdm_graph_links_pits(pdm_tile *t, const pdm_uca_params *p);

@@ -318,7 +318,38 @@ k_pit_compact(const uint8_t *__restrict__ pitmask, int64_t N, int32_t *__restric
     if (is) pit_cell[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)n;
 }
 
+// after the search: what changed at each examined pit (for sparse host-side updates)
+__global__ void __launch_bounds__(256)
+k_pit_gather(const int32_t *__restrict__ pit_cell, int64_t npits, const double *__restrict__ mag,
+             const uint8_t *__restrict__ flats, double *__restrict__ out_mag, uint8_t *__restrict__ out_flat)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= npits) return;
+    const int32_t c = pit_cell[k];
+    out_mag[k] = mag[c];
+    out_flat[k] = flats[c];
+}
+
 }  // namespace
+
+// cells examined by the last pit search with their current mag / flats values (host buffers of
+// t->n_pits entries each)
+int pdm_launch_pit_readback(pdm_tile *t, int32_t *cells, double *mag, uint8_t *flats)
+{
+    const int64_t n = t->n_pits;
+    if (n == 0) return PDM_OK;
+    double *d_mag = nullptr; uint8_t *d_fl = nullptr;
+    PDM_CUDA(cudaMalloc(&d_mag, (size_t)n * 8));
+    PDM_CUDA(cudaMalloc(&d_fl, (size_t)n));
+    k_pit_gather<<<(unsigned)((n + 255) / 256), 256, 0, t->stream>>>(t->pit_cell, n, t->mag, t->flats, d_mag, d_fl);
+    PDM_LAUNCHED();
+    PDM_CUDA(cudaMemcpyAsync(cells, t->pit_cell, (size_t)n * 4, cudaMemcpyDeviceToHost, t->stream));
+    PDM_CUDA(cudaMemcpyAsync(mag, d_mag, (size_t)n * 8, cudaMemcpyDeviceToHost, t->stream));
+    PDM_CUDA(cudaMemcpyAsync(flats, d_fl, (size_t)n, cudaMemcpyDeviceToHost, t->stream));
+    PDM_CUDA(cudaStreamSynchronize(t->stream));
+    cudaFree(d_mag); cudaFree(d_fl);
+    return PDM_OK;
+}
 
 static int read_ctr(pdm_tile *t)
 {

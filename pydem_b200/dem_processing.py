@@ -157,9 +157,21 @@ class DEMProcessor(object):
         self._resident.add(field)
 
     def _down(self, field):
+        """HBM -> page-locked host array.  The copy is queued behind the stage that produced the
+        field and overlaps the following stages; `_end()` of the outermost public call waits."""
         out = _pinned.empty(self._tile_shape, _lib.FIELD_DTYPE[field])
-        _lib.check(_lib.load().pdm_tile_download(self._get_tile(), field, _lib.ptr(out)))
+        _lib.check(_lib.load().pdm_tile_download_async(self._get_tile(), field, _lib.ptr(out)))
         return out
+
+    @staticmethod
+    def _patched(arr, cells, values, dtype):
+        """arr.flat[cells] = values, in place when arr is a writable C-contiguous array of the right
+        dtype (the reference mutates the caller's array), else on a converted copy."""
+        a = arr
+        if not (isinstance(a, np.ndarray) and a.dtype == dtype and a.flags.writeable and a.flags.c_contiguous):
+            a = np.array(arr, dtype=dtype, order="C")
+        a.reshape(-1)[cells] = values
+        return a
 
     def _spacing(self):
         R = self.elev.shape[0]
@@ -181,6 +193,8 @@ class DEMProcessor(object):
         self._chain -= 1
         if self._chain == 0:
             self._resident = set()
+            if self._tile is not None:
+                _lib.check(_lib.load().pdm_tile_sync(self._tile))      # all queued downloads have landed
 
     # ------------------------------------------------------------------------------------
     # reference API
@@ -286,16 +300,15 @@ class DEMProcessor(object):
             self.edge_done = self._down(_lib.F_EDGE_DONE).view(np.bool_)
             if p.drain_pits and st.n_pits:
                 # _mk_connectivity_pits updates mag / flats of drained pits in place (1370-1371)
-                mag = self._down(_lib.F_MAG)
-                flats = self._down(_lib.F_FLATS).view(np.bool_)
-                if isinstance(self.mag, np.ndarray) and self.mag.dtype == np.float64 and self.mag.flags.writeable:
-                    self.mag[...] = mag
-                else:
-                    self.mag = mag
-                if isinstance(self.flats, np.ndarray) and self.flats.dtype == bool and self.flats.flags.writeable:
-                    self.flats[...] = flats
-                else:
-                    self.flats = flats
+                # _mk_connectivity_pits changes mag / flats only at the examined pits: patch the host
+                # arrays in place (like the reference) from a sparse readback
+                _lib.check(L.pdm_tile_sync(t))      # earlier mag / flats downloads must have landed before patching
+                npit = int(st.n_pits)
+                cells = np.empty(npit, np.int32); pmag = np.empty(npit, np.float64); pfl = np.empty(npit, np.uint8)
+                got = ct.c_int64(0)
+                _lib.check(L.pdm_tile_pit_updates(t, npit, _lib.ptr(cells), _lib.ptr(pmag), _lib.ptr(pfl), ct.byref(got)))
+                self.mag = self._patched(self.mag, cells, pmag, np.float64)
+                self.flats = self._patched(self.flats, cells, pfl.view(np.bool_), np.bool_)
                 if st.n_pits_undrained:
                     warnings.warn("Warning %d pits had no place to drain to in this chunk" % st.n_pits_undrained)
             if st.n_undone:
@@ -342,7 +355,7 @@ class DEMProcessor(object):
             self._up(_lib.F_DIR, self.direction)
             self._up(_lib.F_MAG, self.mag)
             self._up(_lib.F_FLATS, self.flats)
-            self.section = self._down(_lib.F_SECTION)
+            self.section = self._down(_lib.F_SECTION)    # (synchronous: computed on demand)
         finally:
             self._end()
         return self.section
