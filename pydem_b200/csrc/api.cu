@@ -359,9 +359,10 @@ int pdm_tile_uca(pdm_tile *t, const pdm_uca_params *p_in, pdm_uca_stats *stats)
     if (rc) return rc;
     if (t->h_counters[CT_WATCHDOG]) {
         pdm_set_error("pdm_tile_uca: work-list watchdog fired (QTAIL=%llu QHEAD=%llu QDONE=%llu PHASE1=%llu CHUNK=%llu DRAINED=%llu "
-                      "SOURCES=%llu)",
+                      "SOURCES=%llu DEALT=%llu TAKEN=%llu EXITS=%llu)",
                       t->h_counters[CT_QTAIL], t->h_counters[CT_QHEAD], t->h_counters[CT_QDONE], t->h_counters[CT_PHASE1],
-                      t->h_counters[CT_CHUNK], t->h_counters[CT_DRAINED], t->h_counters[CT_SOURCES]);
+                      t->h_counters[CT_CHUNK], t->h_counters[CT_DRAINED], t->h_counters[CT_SOURCES], t->h_counters[CT_DBG_DEALT],
+                      t->h_counters[CT_DBG_TAKEN], t->h_counters[CT_DBG_EXITS]);
         return PDM_ERR_STATE;
     }
     if (t->h_counters[CT_BADSEC]) {

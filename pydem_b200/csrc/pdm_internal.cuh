@@ -149,6 +149,9 @@ enum {
     CT_TMP0 = 99,
     CT_TMP1 = 100,
     CT_ABORT = 101,
+    CT_DBG_DEALT = 73,  // diagnostics: seeds dealt / queue items consumed / warps that left through the termination test
+    CT_DBG_TAKEN = 74,
+    CT_DBG_EXITS = 75,
     CT_WATCHDOG = 104, // set by a warp that saw no progress for seconds; sticky until the next graph build
     CT_T_START = 112,  // work-list timing (globaltimer ns): first warp in
     CT_T_SCAN = 113,   // last warp finished its seed scan (+ scan-born chains)

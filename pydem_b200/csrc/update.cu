@@ -93,6 +93,12 @@ struct FloodOp {
         }
         return !(st_fetch_or(st, r, ST_REACH) & ST_REACH);
     }
+    __device__ __forceinline__ unsigned long long chain(int32_t i, const wl::Queue &q) const
+    {
+        unsigned long long n = 0;
+        while (i >= 0) { int32_t d = -1; n++; const int32_t nx = process(i, q, d); if (d >= 0) q.push(d); i = nx; }
+        return n;
+    }
     __device__ __forceinline__ int32_t process(int32_t i, const wl::Queue &q, int32_t &defer) const
     {
         const longlong2 pm = *reinterpret_cast<const longlong2 *>(&cell[i].prop);   // prop | indeg, link (link, prop fixed)

@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
             if (take) { cur = c; active = true; chain_len = 0; }
             int ntake = __popc(idle_mask);
             if (ntake > npend) ntake = npend;
+            if (lane == 0) atomicAdd(&q.ctr[CT_DBG_DEALT], (unsigned long long)ntake);
             for (int i = 0; i < ntake; i++) pend_mask &= pend_mask - 1;   // drop the seeds just handed out
             idle_mask = __ballot_sync(full, cur < 0);
         }
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
         }
         if (cur < 0 && ticket >= 0 && ticket < q.cap) {
             const int32_t v = ld_volatile_i32(q.slots + ticket);
-            if (v >= 0) { cur = v; active = true; ticket = -1; chain_len = 0; }
+            if (v >= 0) { cur = v; active = true; ticket = -1; chain_len = 0; atomicAdd(&q.ctr[CT_DBG_TAKEN], 1ULL); }
         }
         // ---- statistics only: when did the last warp run out of seeds
         if (!scanning && !scan_stamped) {
@@ -197,16 +198,27 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
                 int term = 0;
                 if ((++idle_polls & 3u) == 0) {
                     if (lane == 0) {
-                        // the proof needs QDONE to be read before QTAIL; the two lines live in
-                        // different L2 slices, so the second address is made to depend on the first
-                        // value (dependent loads cannot pass each other)
+                        // the proof needs QDONE to be read before QTAIL.  The cheap filter reads both
+                        // with plain volatile loads (the second address depends on the first value);
+                        // the two lines live in different L2 slices -- on different dies -- and a
+                        // load may be served from a copy that lags the slice the atomics are performed
+                        // in (seen once per ~2000 sweeps: a stale QTAIL made 37 warps leave early and
+                        // orphaned a ticket).  So an apparent quiescence is CONFIRMED with two
+                        // read-modify-writes, which are performed at the counters themselves, each
+                        // issued only after the previous one returned.
                         const unsigned long long d = ld_volatile_u64(q.ctr + CT_QDONE);
                         const unsigned long long t = ld_volatile_u64(q.ctr + CT_QTAIL + dep_zero_u64(d));
-                        term = (d == nseeds + t) ? 1 : 0;
+                        if (d == nseeds + t) {
+                            __threadfence();
+                            const unsigned long long d2 = atomicAdd(&q.ctr[CT_QDONE], 0ULL);
+                            __threadfence();
+                            const unsigned long long t2 = atomicAdd(&q.ctr[CT_QTAIL + dep_zero_u64(d2)], 0ULL);
+                            term = (d2 == nseeds + t2) ? 1 : 0;
+                        }
                     }
                     term = __shfl_sync(full, term, 0);
                 }
-                if (term) break;
+                if (term) { if (lane == 0) atomicAdd(&q.ctr[CT_DBG_EXITS], 1ULL); break; }
                 // watchdog (never fires in a correct run): instead of spinning forever on a lost
                 // item, give up loudly -- the host turns CT_WATCHDOG into an error
                 if ((idle_polls & 63u) == 0) {
@@ -234,18 +246,15 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
         //      collectives between cells: the critical path pays memory round trips only)
         if (!scanning && work_mask == 1u) {
             if (lane == 0) {
-                unsigned spin = 0;
-                while (cur >= 0) {
-                    processed++;
-                    int32_t d2 = -1;
-                    const int32_t nxt = op.process(cur, q, d2);
-                    if (d2 >= 0) q.push(d2);           // the other ready receiver: another express warp takes it
-                    cur = nxt;
-                    // cells stashed while the warp was still scanning belong to this chain: they must
-                    // be finished before the chain counts as ended
-                    if (cur < 0 && stash >= 0) { cur = stash; stash = stash2; stash2 = stash3; stash3 = -1; }
-                    if ((++spin & 8191u) == 0 && ld_volatile_u64(q.ctr + CT_WATCHDOG) != 0) break;
+                // the chain (and whatever this lane stashed while its warp was still scanning: those
+                // cells belong to the same chain's accounting) runs to its end
+                for (;;) {
+                    processed += op.chain(cur, q);
+                    if (stash < 0) break;
+                    cur = stash; stash = stash2; stash2 = stash3; stash3 = -1;
                 }
+                // every push of this chain was a returning atomic whose result the slot store waited
+                // for, so it has been performed before this (in-order issued) increment leaves the SM
                 atomicAdd(&q.ctr[CT_QDONE], 1ULL);
                 active = false;
                 cur = -1;
@@ -277,14 +286,16 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
             if (cur < 0 && stash < 0) { finished_q = active; active = false; }
         }
         const unsigned pm = __ballot_sync(full, defer >= 0);
+        unsigned long long base = 0;
         if (pm) {
-            unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(&q.ctr[CT_QTAIL], (unsigned long long)__popc(pm));
             base = __shfl_sync(full, base, 0);
             if (defer >= 0) st_volatile_i32(q.slots + base + __popc(pm & lt_mask), defer);
         }
         const unsigned fq = __ballot_sync(full, finished_q);
-        if (fq && lane == 0) atomicAdd(&q.ctr[CT_QDONE], (unsigned long long)__popc(fq));
+        // the QDONE increment carries a data dependency on the push counter's returned value: a chain's
+        // pushes are performed before its end is counted (a fence here cost 20-160 % of the sweep)
+        if (fq && lane == 0) atomicAdd(&q.ctr[CT_QDONE], (unsigned long long)__popc(fq) + dep_zero_u64(base));
     }
     for (int o = 16; o > 0; o >>= 1) processed += __shfl_down_sync(full, processed, o);
     if (lane == 0) {
@@ -341,7 +352,7 @@ static __global__ void k_queue_zero(unsigned long long *ctr, int keep_drained)
 {
     ctr[CT_QTAIL] = 0; ctr[CT_QHEAD] = 0; ctr[CT_QDONE] = 0; ctr[CT_PHASE1] = 0; ctr[CT_CHUNK] = 0;
     if (!keep_drained) ctr[CT_DRAINED] = 0;
-    ctr[CT_T_START] = ~0ULL; ctr[CT_T_SCAN] = 0; ctr[CT_T_END] = 0;
+    ctr[CT_T_START] = ~0ULL; ctr[CT_T_SCAN] = 0; ctr[CT_T_END] = 0; ctr[CT_DBG_DEALT] = 0; ctr[CT_DBG_TAKEN] = 0; ctr[CT_DBG_EXITS] = 0;
 }
 
 // host: after a run's counters were read back, turn a fired watchdog into an error
