@@ -212,7 +212,8 @@ def twi(uca, mag, min_slope, min_area, sat_limit=32.0, limit_uca=False, limit_tw
 class OracleDEMProcessor(object):
     """Same attribute / method surface as the reference DEMProcessor for the hot path."""
 
-    _FLAGS = dict(fill_flats=True, drain_pits=True, drain_pits_path=True, drain_pits_min_border=False,
+    _FLAGS = dict(fill_flats=True, fill_flats_below_sea=False, fill_flats_source_tol=1, fill_flats_peaks=True,
+                  fill_flats_pits=True, maximum_pit_area=32.0, drain_pits=True, drain_pits_path=True, drain_pits_min_border=False,
                   drain_pits_max_iter=300, drain_pits_max_dist=32, drain_pits_max_dist_XY=None,
                   apply_uca_limit_edges=False, apply_twi_limits=False, apply_twi_limits_on_uca=False,
                   uca_saturation_limit=32.0, twi_min_slope=1e-3, twi_min_area=np.inf,
@@ -245,10 +246,25 @@ class OracleDEMProcessor(object):
     def find_flats(self):
         self.flats = self.mag == -1
 
+    def calc_fill_flats(self):
+        from . import conditioning
+        self.elev = conditioning.fill_flats(self.elev, self.fill_flats_below_sea, self.fill_flats_source_tol,
+                                            self.fill_flats_peaks, self.fill_flats_pits, self.maximum_pit_area)
+
+    def calc_pit_drain_paths(self):
+        from . import conditioning
+        self.elev, n_bad, _ = conditioning.pit_drain_paths(self.elev, self.dX, self.dY, self.fill_flats_below_sea,
+                                                           self.drain_pits_max_iter, self.drain_pits_max_dist,
+                                                           self.drain_pits_max_dist_XY)
+        self.stats["pits_without_drain_path"] = n_bad
+        return self.elev
+
     def calc_slopes_directions(self):
-        if self.fill_flats or self.drain_pits_path:
-            raise NotImplementedError("oracle restates the hot path only; pass conditioned elevation "
-                                      "with fill_flats=False, drain_pits_path=False")
+        # conditioning (601-609): restated in oracle/conditioning.py
+        if self.fill_flats:
+            self.calc_fill_flats()
+        if self.drain_pits_path:
+            self.calc_pit_drain_paths()
         mag, direction = slopes_directions(self.elev, self.dX, self.dY)
         flats = find_flats_edges(self.elev, mag)
         direction[flats] = -1; mag[flats] = -1                          # 611-612

@@ -164,7 +164,9 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
             if (take) { cur = c; active = true; chain_len = 0; }
             int ntake = __popc(idle_mask);
             if (ntake > npend) ntake = npend;
+#ifdef PDM_WL_DEBUG   // diagnostics (hot address: costs ~40 % of a seed-heavy sweep)
             if (lane == 0) atomicAdd(&q.ctr[CT_DBG_DEALT], (unsigned long long)ntake);
+#endif
             for (int i = 0; i < ntake; i++) pend_mask &= pend_mask - 1;   // drop the seeds just handed out
             idle_mask = __ballot_sync(full, cur < 0);
         }
@@ -181,7 +183,12 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
         }
         if (cur < 0 && ticket >= 0 && ticket < q.cap) {
             const int32_t v = ld_volatile_i32(q.slots + ticket);
-            if (v >= 0) { cur = v; active = true; ticket = -1; chain_len = 0; atomicAdd(&q.ctr[CT_DBG_TAKEN], 1ULL); }
+            if (v >= 0) {
+                cur = v; active = true; ticket = -1; chain_len = 0;
+#ifdef PDM_WL_DEBUG
+                atomicAdd(&q.ctr[CT_DBG_TAKEN], 1ULL);
+#endif
+            }
         }
         // ---- statistics only: when did the last warp run out of seeds
         if (!scanning && !scan_stamped) {

@@ -9,6 +9,10 @@ where /root/reference exists):
   edge_done, twi, section, the post-uca mag/flats) for the small cases of tests/helpers.golden_cases().
 * ref_update.npz        : a row-tiled edge-update sequence (calc_uca(uca_init, edge_init_data))
   driven through the reference, every call's inputs and outputs.
+* ref_conditioning.npz  : reference calc_fill_pit_artifacts / calc_fill_flats /
+  calc_pit_drain_paths outputs for tests/helpers.conditioning_cases() (stored as sparse
+  differences from the input).  `<case>_paths_tiefree` records whether the reference's pit order
+  is free of elevation ties that change the result (np.argsort's tie order is platform-defined).
 """
 import contextlib
 import importlib.util
@@ -80,8 +84,34 @@ def update_sequence():
     np.savez_compressed(os.path.join(HERE, "ref_update.npz"), **out)
 
 
+def _sparse(out, key, new, old):
+    idx = np.flatnonzero(new.ravel() != old.ravel())
+    out[key + "_idx"] = idx.astype("int32"); out[key + "_val"] = new.ravel()[idx]
+
+
+def conditioning():
+    from oracle import conditioning as oc
+    out = {}
+    for nm, (E, dX, dY) in helpers.conditioning_cases().items():
+        def run(meth, elev):
+            dp = rh.ref_processor(elev, dX=dX, dY=dY)
+            with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                getattr(dp, meth)()
+            return np.array(dp.elev)
+        art = run("calc_fill_pit_artifacts", E)
+        fill = run("calc_fill_flats", E)
+        paths = run("calc_pit_drain_paths", fill)
+        _sparse(out, nm + "_art", art, E); _sparse(out, nm + "_fill", fill, E); _sparse(out, nm + "_paths", paths, fill)
+        mine = oc.pit_drain_paths(fill, dX, dY)[0]
+        out[nm + "_paths_tiefree"] = np.array(np.array_equal(mine, paths))
+        print(nm, "art", len(out[nm + "_art_idx"]), "fill", len(out[nm + "_fill_idx"]), "paths", len(out[nm + "_paths_idx"]),
+              "tiefree", bool(out[nm + "_paths_tiefree"]))
+    np.savez_compressed(os.path.join(HERE, "ref_conditioning.npz"), **out)
+
+
 if __name__ == "__main__":
-    known_answers(); case_outputs(); update_sequence()
+    known_answers(); case_outputs(); update_sequence(); conditioning()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -130,3 +130,37 @@ def assert_parity(r, name=""):
     assert r["uca_rel"] <= UCA_RTOL, msg
     assert r["twi_abs"] <= TWI_ATOL, msg
     assert r["min_area_eq"], msg
+
+
+def conditioning_cases():
+    """name -> (elev, dX, dY): inputs of the elevation-conditioning parity tests (fill_flats,
+    pit artifacts, pit drain paths).  Small enough for the reference/oracle Python loops."""
+    rng = np.random.default_rng(5)
+    out = {}
+    out["fractal96"] = synth.fractal_dem(96, 3)
+    out["quant96"] = np.round(synth.fractal_dem(96, 3) / 8.0) + 1        # coarse quantisation: flats, artifacts, tied pits
+    out["quant_fine80"] = np.round(synth.fractal_dem(80, 4) / 2.0) + 1
+    g = synth.fractal_dem(128, 7).copy()
+    yy, xx = np.mgrid[:128, :128]
+    for (ci, cj, r) in ((40, 40, 12), (90, 70, 9), (20, 100, 6), (0, 64, 10), (127, 20, 8)):   # two lakes cross the array edge
+        m = (yy - ci) ** 2 + (xx - cj) ** 2 <= r * r
+        g[m] = g[m].min()
+    out["lakes128"] = g
+    out["noise_int"] = np.round(rng.random((40, 56)) * 6) + 1
+    p = synth.fractal_dem(64, 9).copy()
+    p[20:30, 20:30] = p.max() + 5; p[40:44, 10:30] = p.max() + 7               # plateaus: the "peak" branch
+    out["peaks64"] = p
+    out["rect50x90"] = np.round(synth.fractal_dem(0, 11, shape=(50, 90)) / 5.0) + 2
+    s = synth.fractal_dem(72, 12).copy(); s[s < np.percentile(s, 20)] = 0.0    # sea (elev == 0) is masked out
+    out["sea72"] = s
+    a = np.round(synth.fractal_dem(64, 13) / 3.0) + 5                           # planted quantisation artifacts
+    for (ci, cj, h, w) in ((10, 10, 1, 1), (20, 30, 2, 3), (40, 15, 5, 6), (45, 45, 6, 6), (30, 50, 1, 4), (55, 8, 3, 3)):
+        v = a[ci, cj]
+        a[ci - 1:ci + h + 1, cj - 1:cj + w + 1] = v + 1
+        a[ci:ci + h, cj:cj + w] = v
+    out["artifacts64"] = a
+    res = {}
+    for k, E in out.items():
+        R = E.shape[0]
+        res[k] = (E, 30.0 + np.linspace(0, 3, R - 1), np.full(R - 1, 28.0))
+    return res
