@@ -98,6 +98,28 @@ typedef struct {
     int32_t apply_twi_limits_on_uca;  /* default 0 */
 } pdm_twi_params;
 
+/* elevation conditioning (the reference's fill_flats* / drain_pits_path traits, dem_processing.py:105-119, 154) */
+typedef struct {
+    int32_t fill_flats_below_sea;   /* default 0: cells with elev <= 0 are sea and never conditioned */
+    int32_t fill_flats_source_tol;  /* default 1 */
+    int32_t fill_flats_peaks;       /* default 1 */
+    int32_t fill_flats_pits;        /* default 1 */
+    double  maximum_pit_area;       /* default 32 cells; 0 disables calc_fill_pit_artifacts */
+    int32_t drain_pits_max_iter;    /* default 300 */
+    int32_t drain_pits_max_dist;    /* default 32 cells; 0 = no limit */
+    double  drain_pits_max_dist_xy; /* default 0 = None */
+} pdm_cond_params;
+
+typedef struct {
+    int64_t n_artifact_regions;     /* locally-minimal regions examined by the artifact pass */
+    int64_t n_artifacts_filled;     /* regions raised by one unit */
+    int64_t n_flat_regions;         /* regions handed to _fill_flat */
+    int64_t distance_sweeps;        /* Jacobi sweeps of utils.get_distance (all regions together) */
+    int64_t n_pits;                 /* strict local minima visited by calc_pit_drain_paths */
+    int64_t n_pits_undrained;       /* the reference's "pits had no place to drain to" warning count */
+    int64_t path_max_iter;          /* the reference's printed maxiter */
+} pdm_cond_stats;
+
 typedef struct pdm_tile pdm_tile;
 
 /* ---- library ------------------------------------------------------------------------- */
@@ -114,6 +136,7 @@ int         pdm_host_alloc(size_t bytes, void **out);
 int         pdm_host_free(void *p);
 void        pdm_default_uca_params(pdm_uca_params *p);
 void        pdm_default_twi_params(pdm_twi_params *p);
+void        pdm_default_cond_params(pdm_cond_params *p);
 
 /* ---- tile handles ---------------------------------------------------------------------- */
 /* R x C tile on the current device.  stream: a cudaStream_t passed as void* (NULL = the
@@ -174,6 +197,19 @@ int pdm_tile_uca_update(pdm_tile *t, const pdm_uca_params *p,
 /* a9: calc_twi (1647-1677).  In: UCA, MAG.  Out: TWI (un-scaled, the return value) and TWI10
  * (= 10 * twi, the attribute). */
 int pdm_tile_twi(pdm_tile *t, const pdm_twi_params *p);
+
+/* ---- elevation conditioning: what calc_slopes_directions runs first when
+ * fill_flats / drain_pits_path are on (dem_processing.py:601-609).  In/out: ELEV, modified in
+ * place on the device; every derived field of the tile is invalidated.  Bit-identical to the
+ * reference on NaN-free elevation (pits of equal elevation are visited in raster order; the
+ * reference's np.argsort tie order is platform-defined).  Not available on a row shard. */
+/* calc_fill_pit_artifacts (396-426) */
+int pdm_tile_fill_pit_artifacts(pdm_tile *t, const pdm_cond_params *p, pdm_cond_stats *stats);
+/* calc_fill_flats (551-585) -> _fill_flat (308-394); runs the artifact pass first when
+ * maximum_pit_area != 0, as the reference does */
+int pdm_tile_fill_flats(pdm_tile *t, const pdm_cond_params *p, pdm_cond_stats *stats);
+/* calc_pit_drain_paths (428-548); needs the spacing (dX, dY) */
+int pdm_tile_pit_drain_paths(pdm_tile *t, const pdm_cond_params *p, pdm_cond_stats *stats);
 
 /* ---- row shards (one tile per GPU = a block of rows of one big DEM) --------------------------
  * The tile has one halo row on every side where another rank continues the grid.  The host

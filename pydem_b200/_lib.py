@@ -45,6 +45,18 @@ class TwiParams(ct.Structure):
                 ("apply_twi_limits_on_uca", ct.c_int32)]
 
 
+class CondParams(ct.Structure):
+    _fields_ = [("fill_flats_below_sea", ct.c_int32), ("fill_flats_source_tol", ct.c_int32),
+                ("fill_flats_peaks", ct.c_int32), ("fill_flats_pits", ct.c_int32),
+                ("maximum_pit_area", ct.c_double), ("drain_pits_max_iter", ct.c_int32),
+                ("drain_pits_max_dist", ct.c_int32), ("drain_pits_max_dist_xy", ct.c_double)]
+
+
+class CondStats(ct.Structure):
+    _fields_ = [(k, ct.c_int64) for k in ("n_artifact_regions", "n_artifacts_filled", "n_flat_regions",
+                                          "distance_sweeps", "n_pits", "n_pits_undrained", "path_max_iter")]
+
+
 # every symbol include/pydem_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "pdm_abi_version", "pdm_last_error", "pdm_init", "pdm_device_count", "pdm_default_uca_params",
@@ -55,6 +67,7 @@ EXPORTS = [
     "pdm_shard_label_unpack", "pdm_shard_flats_extend", "pdm_shard_links", "pdm_shard_indeg", "pdm_shard_sweep",
     "pdm_shard_outbox_pack", "pdm_shard_inbox_begin", "pdm_shard_inbox_apply", "pdm_shard_finalize",
     "pdm_slopes_directions", "pdm_uca", "pdm_uca_update", "pdm_twi",
+    "pdm_default_cond_params", "pdm_tile_fill_pit_artifacts", "pdm_tile_fill_flats", "pdm_tile_pit_drain_paths",
 ]
 
 _lib = None
@@ -100,6 +113,10 @@ def load():
     L.pdm_tile_pit_updates.argtypes = [_vp, _i64, _vp, _vp, _vp, ct.POINTER(_i64)]
     L.pdm_tile_uca_update.argtypes = [_vp, ct.POINTER(UcaParams)] + [_vp] * 12 + [ct.POINTER(UcaStats)]
     L.pdm_tile_twi.argtypes = [_vp, ct.POINTER(TwiParams)]
+    L.pdm_default_cond_params.argtypes = [ct.POINTER(CondParams)]
+    L.pdm_default_cond_params.restype = None
+    for nm in ("pdm_tile_fill_pit_artifacts", "pdm_tile_fill_flats", "pdm_tile_pit_drain_paths"):
+        getattr(L, nm).argtypes = [_vp, ct.POINTER(CondParams), ct.POINTER(CondStats)]
     L.pdm_tile_set_window.argtypes = [_vp, _i64, _i64, _i64, _i64, _vp]
     for nm in ("pdm_shard_slopes", "pdm_shard_ccl", "pdm_shard_flats_extend", "pdm_shard_indeg", "pdm_shard_inbox_begin"):
         getattr(L, nm).argtypes = [_vp]

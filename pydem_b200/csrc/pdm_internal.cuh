@@ -115,6 +115,7 @@ int pdm_launch_geometry(pdm_tile *t);
 int pdm_launch_slopes(pdm_tile *t);
 int pdm_launch_flats(pdm_tile *t);
 int pdm_launch_find_flats(pdm_tile *t);
+int pdm_launch_ccl(pdm_tile *t);   // union-find labels of the mask in flat0 (label[] must hold own indices)
 int pdm_launch_graph(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *st);
 int pdm_launch_sweep_full(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *st);
 int pdm_launch_update(pdm_tile *t, const pdm_uca_params *p, const double *const data[4],

@@ -130,6 +130,8 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
     const unsigned long long nseeds = *q.nseeds;
     unsigned long long processed = 0;
     unsigned idle_polls = 0, iters = 0;
+    unsigned long long push_dep = 0;
+    unsigned done_acc = 0;   // chains this warp has finished but not yet added to CT_QDONE (warp-uniform)
     unsigned long long idle_since = 0;   // watchdog: a warp that sees no progress for WATCHDOG_NS raises CT_WATCHDOG
     const unsigned long long WATCHDOG_NS = 4000000000ULL;
     if (lane == 0) atomicMin(&q.ctr[CT_T_START], globaltimer_ns());
@@ -198,6 +200,14 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
         // ---- nothing to do in this warp: terminate on global quiescence, else back off
         const unsigned work_mask = __ballot_sync(full, cur >= 0);
         if (work_mask == 0) {
+            // finished chains are counted lazily: one add when the warp runs dry instead of one per
+            // step (every seed-born chain counts, and a per-step add to the one QDONE address cost
+            // ~40 % of a source-rich sweep).  QDONE only has to be complete at quiescence, and a warp
+            // that still holds uncounted chains is by construction not idle yet.
+            if (done_acc) {
+                if (lane == 0) atomicAdd(&q.ctr[CT_QDONE], (unsigned long long)done_acc + dep_zero_u64(push_dep));
+                done_acc = 0;
+            }
             if (!scanning) {
                 // idle warps mostly watch their own ticket slots (distinct addresses); the shared
                 // counters are read only every 4th round so that polling does not slow the
@@ -262,10 +272,11 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
                 }
                 // every push of this chain was a returning atomic whose result the slot store waited
                 // for, so it has been performed before this (in-order issued) increment leaves the SM
-                atomicAdd(&q.ctr[CT_QDONE], 1ULL);
+                atomicAdd(&q.ctr[CT_QDONE], 1ULL + done_acc);
                 active = false;
                 cur = -1;
             }
+            done_acc = 0;
             __syncwarp(full);
             continue;
         }
@@ -300,9 +311,11 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
             if (defer >= 0) st_volatile_i32(q.slots + base + __popc(pm & lt_mask), defer);
         }
         const unsigned fq = __ballot_sync(full, finished_q);
-        // the QDONE increment carries a data dependency on the push counter's returned value: a chain's
-        // pushes are performed before its end is counted (a fence here cost 20-160 % of the sweep)
-        if (fq && lane == 0) atomicAdd(&q.ctr[CT_QDONE], (unsigned long long)__popc(fq) + dep_zero_u64(base));
+        // counted later (see done_acc); the eventual QDONE add carries a data dependency on the last
+        // push counter value this warp received: a chain's pushes are performed before its end is
+        // counted (a fence here cost 20-160 % of the sweep)
+        done_acc += __popc(fq);
+        if (pm) push_dep = base;
     }
     for (int o = 16; o > 0; o >>= 1) processed += __shfl_down_sync(full, processed, o);
     if (lane == 0) {

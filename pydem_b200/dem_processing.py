@@ -211,24 +211,66 @@ class DEMProcessor(object):
         """dem_processing.py:305-306"""
         self.flats = self.mag == FLAT_ID_INT
 
+    def _cond_params(self):
+        p = _lib.CondParams()
+        _lib.load().pdm_default_cond_params(ct.byref(p))
+        p.fill_flats_below_sea = int(bool(self.fill_flats_below_sea))
+        p.fill_flats_source_tol = int(self.fill_flats_source_tol)
+        p.fill_flats_peaks = int(bool(self.fill_flats_peaks))
+        p.fill_flats_pits = int(bool(self.fill_flats_pits))
+        p.maximum_pit_area = float(self.maximum_pit_area or 0.0)
+        p.drain_pits_max_iter = int(self.drain_pits_max_iter)
+        p.drain_pits_max_dist = int(self.drain_pits_max_dist or 0)
+        p.drain_pits_max_dist_xy = float(self.drain_pits_max_dist_XY or 0.0)
+        return p
+
+    def _condition(self, stages):
+        """Run conditioning stages on the device copy of ``elev`` (uploaded once) and bring the
+        conditioned elevation back: the reference rebinds ``self.elev`` (425, 548, 580)."""
+        self._begin()
+        try:
+            L = self._lib()
+            t = self._get_tile()
+            self._spacing()
+            self._up(_lib.F_ELEV, np.asarray(self.elev, dtype="float64"))
+            p = self._cond_params()
+            stats = {}
+            for name in stages:
+                st = _lib.CondStats()
+                _lib.check(getattr(L, "pdm_tile_" + name)(t, ct.byref(p), ct.byref(st)))
+                stats.update({k: getattr(st, k) for k, _ in st._fields_ if getattr(st, k)})
+            self._resident = {_lib.F_ELEV}            # every derived field of the tile is stale now
+            self.elev = self._down(_lib.F_ELEV)
+            self.cond_stats = stats
+            if stats.get("n_pits_undrained"):
+                warnings.warn("Warning %d pits had no place to drain to in this chunk" % stats["n_pits_undrained"])
+        finally:
+            self._end()
+        return self.elev
+
+    def calc_fill_pit_artifacts(self):
+        """dem_processing.py:396-426"""
+        self._condition(["fill_pit_artifacts"])
+
     def calc_fill_flats(self):
-        raise NotImplementedError(
-            "elevation conditioning (calc_fill_flats, reference dem_processing.py:551-585) is outside the "
-            "accelerated hot path (SURVEY.md 8(f) rank 1); pass conditioned elevation with fill_flats=False")
+        """dem_processing.py:551-585 (includes calc_fill_pit_artifacts when maximum_pit_area is set)"""
+        self._condition(["fill_flats"])
 
     def calc_pit_drain_paths(self):
-        raise NotImplementedError(
-            "elevation conditioning (calc_pit_drain_paths, reference dem_processing.py:428-548) is outside the "
-            "accelerated hot path (SURVEY.md 8(f) rank 1); pass conditioned elevation with drain_pits_path=False")
+        """dem_processing.py:428-548"""
+        return self._condition(["pit_drain_paths"])
 
     def calc_slopes_directions(self, plotflag=False):
         """Magnitude and direction of slopes -> self.mag, self.direction, self.flats
-        (dem_processing.py:587-619)."""
-        if self.fill_flats:
-            self.calc_fill_flats()
-        if self.drain_pits_path:
-            self.calc_pit_drain_paths()
+        (dem_processing.py:587-619), after the elevation conditioning the flags ask for (601-609)."""
         self._begin()
+        try:
+            stages = (["fill_flats"] if self.fill_flats else []) + (["pit_drain_paths"] if self.drain_pits_path else [])
+            if stages:
+                self._condition(stages)
+        except Exception:
+            self._end()
+            raise
         try:
             L = self._lib()
             t = self._get_tile()

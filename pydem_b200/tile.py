@@ -106,6 +106,16 @@ class DeviceTile(object):
     def find_flats(self):
         _lib.check(self.L.pdm_tile_find_flats(self.h))
 
+    def condition(self, stage, **flags):
+        """stage: 'fill_pit_artifacts' | 'fill_flats' | 'pit_drain_paths' (ELEV modified in HBM)."""
+        p = _lib.CondParams()
+        self.L.pdm_default_cond_params(ct.byref(p))
+        for k, v in flags.items():
+            setattr(p, k, v)
+        st = _lib.CondStats()
+        _lib.check(getattr(self.L, "pdm_tile_" + stage)(self.h, ct.byref(p), ct.byref(st)))
+        return {k: getattr(st, k) for k, _ in st._fields_}
+
     def uca(self, **flags):
         p = _lib.UcaParams()
         self.L.pdm_default_uca_params(ct.byref(p))

@@ -78,5 +78,7 @@ def test_operator_surface_matches_reference():
         assert getattr(dp, flag) == default
     with pytest.raises(TypeError):
         DEMProcessor(elev=np.zeros((5, 5)), not_a_flag=1)
-    with pytest.raises(NotImplementedError):
-        DEMProcessor(elev=np.zeros((5, 5))).calc_slopes_directions()   # conditioning flags default to True
+    for meth in ("calc_fill_flats", "calc_fill_pit_artifacts", "calc_pit_drain_paths", "find_flats"):
+        assert list(inspect.signature(getattr(DEMProcessor, meth)).parameters) == ["self"]
+    with pytest.raises(RuntimeError):                                   # no device here, and no CPU fallback
+        DEMProcessor(elev=np.ones((5, 5))).calc_slopes_directions()      # default flags: conditioning runs first
