@@ -380,6 +380,14 @@ int pdm_tile_uca(pdm_tile *t, const pdm_uca_params *p_in, pdm_uca_stats *stats)
     st.n_pits_undrained = (int64_t)t->h_counters[CT_PITS_UNDRAINED];
     st.ms_sweep_scan = (float)((double)(t->h_counters[CT_T_SCAN] - t->h_counters[CT_T_START]) * 1e-6);
     st.ms_sweep_kernel = (float)((double)(t->h_counters[CT_T_END] - t->h_counters[CT_T_START]) * 1e-6);
+    if (getenv("PYDEM_B200_WL_DEBUG")) {
+        const unsigned long long *h = t->h_counters;
+        fprintf(stderr, "[wl] kernel %.3f ms scan %.3f ms | scan-phase cells %llu | chains: calls %llu cells %llu avg %.0f ns/cell | "
+                "team: lane-steps %llu avg %.0f ns | idle polls %llu | queue items %llu\n",
+                st.ms_sweep_kernel, st.ms_sweep_scan, h[CT_X_SCAN_CELLS], h[CT_X_CHAIN_CALLS], h[CT_X_CHAIN_CELLS],
+                h[CT_X_CHAIN_CELLS] ? (double)h[CT_X_CHAIN_NS] / (double)h[CT_X_CHAIN_CELLS] : 0.0, h[CT_X_TEAM_LANES],
+                h[CT_X_TEAM_LANES] ? (double)h[CT_X_TEAM_NS] / (double)h[CT_X_TEAM_LANES] : 0.0, h[CT_X_POLLS], h[CT_QTAIL]);
+    }
     if (st.n_undone > 0) {
         // circular references: the reference restarts from the highest undone cells
         // (dem_processing.py:951-964); replayed level-synchronously.

@@ -37,6 +37,7 @@ struct DrainOp {
     const int32_t *pit_end;
     const int32_t *pit_dst;
     const double *pit_w;
+    int32_t strict;        // hold the decrements back until the adds have returned (see process())
 
     __device__ __forceinline__ bool is_seed(int32_t c) const
     {
@@ -47,7 +48,6 @@ struct DrainOp {
     // Drain one ready cell; returns the receiver this lane continues with (or -1).
     __device__ __forceinline__ int32_t process(int32_t i, const wl::Queue &q, int32_t &defer) const
     {
-        using wl::dep_zero;
         // the cell's whole sweep state is one 32-byte sector: two 16-byte L2 loads
         const double2 at = __ldcg(reinterpret_cast<const double2 *>(&cell[i].area));      // area, taint
         const longlong2 pm = __ldcg(reinterpret_cast<const longlong2 *>(&cell[i].prop));  // prop | indeg, link
@@ -87,14 +87,28 @@ struct DrainOp {
             if (!(k1 || k2)) return -1;
         }
         const double w2 = __dsub_rn(1.0, p);                                    // dem_processing.py:1082
-        int dep = 0;
-        if (k1) dep |= dep_zero(atomicAdd(&cell[r1].area, __dmul_rn(ai, p)));   // cyutils.pyx:161
-        if (k2) dep |= dep_zero(atomicAdd(&cell[r2].area, __dmul_rn(ai, w2)));
+        // Ordering: a receiver's area must contain this contribution before the decrement that may
+        // publish it.  The adds and the decrement of one receiver go to the SAME 32-byte sector and
+        // are issued in program order by one thread, so they travel the same SM -> L2-slice path
+        // and are performed in issue order; no fence, no waiting for the adds (a MEMBAR.GPU here
+        // cost 20-160 % of the sweep).  That is how the hardware behaves (scripts/stress.py: 1200
+        // sweeps + sharded runs, every result compared), not a PTX memory-model guarantee, so
+        // `strict` (PYDEM_B200_SWEEP_STRICT=1) makes the decrement's operand depend on the adds'
+        // return values -- a comparison ptxas cannot fold -- for cross-checking: one more round
+        // trip per cell.
+        double a1 = 0.0, a2 = 0.0, u1 = 0.0, u2 = 0.0;
+        if (k1) a1 = atomicAdd(&cell[r1].area, __dmul_rn(ai, p));               // cyutils.pyx:161
+        if (k2) a2 = atomicAdd(&cell[r2].area, __dmul_rn(ai, w2));
         if (MODE != 1 && ti != 0.0) {                                           // cyutils.pyx:163-164
-            if (k1) dep |= dep_zero(atomicAdd(&cell[r1].taint, __dmul_rn(ti, p)));
-            if (k2) dep |= dep_zero(atomicAdd(&cell[r2].taint, __dmul_rn(ti, w2)));
+            if (k1) u1 = atomicAdd(&cell[r1].taint, __dmul_rn(ti, p));
+            if (k2) u2 = atomicAdd(&cell[r2].taint, __dmul_rn(ti, w2));
         }
-        const int one = 1 + dep;  // == 1, but only available once the adds above have returned
+        int one = 1;
+        if (strict) {
+            const int NEVER = 0x7ff4dead;   // high word of a signalling NaN no sum produces
+            one += (__double2hiint(a1) == NEVER) | (__double2hiint(a2) == NEVER) | (__double2hiint(u1) == NEVER) |
+                   (__double2hiint(u2) == NEVER);
+        }
         int o1 = 0, o2 = 0;
         if (k1) o1 = atomicSub(&cell[r1].indeg, one);
         if (k2) o2 = atomicSub(&cell[r2].indeg, one);
@@ -107,20 +121,31 @@ struct DrainOp {
         return nxt;
     }
 
-    // Express chain (single lane, the critical path of the sweep): follow the flow path from cell
-    // `i` until no receiver becomes ready; returns the number of cells drained.  (A variant that
-    // pre-loaded the receivers' records and skipped the returning atomics when a receiver's
-    // in-degree was already 1 gained only ~7 % and is not kept.)
-    __device__ __forceinline__ unsigned long long chain(int32_t i, const wl::Queue &q) const
+    // Express chain (single lane, the critical path of the sweep): follow the flow path from `cur`
+    // until it ends (cur = -1) or forks, i.e. both receivers became ready at once (cur = the
+    // receiver with the larger share, other = the second one).  The caller gives `other` to an idle
+    // lane of the same warp so that both branches advance together.  Returns the cells drained.
+    //
+    // The chain pays dependent memory round trips only: load the cell's record, then add + decrement
+    // on the receivers.  scripts/ubench/lat.cu on B200: L2-hit ld.cg 209 ns, returning atomic
+    // 260-310 ns, +130-230 ns when the sector comes from DRAM (river cells were last touched by
+    // their tributaries, long before); measured here 1.0 us per cell on the 4096^2 conditioned DEM.
+    // Three ideas to shorten it were built, measured at 4096^2 and dropped (all bit-compatible, none
+    // faster): (1) a look-ahead walker on one-byte link hints prefetching the receivers' records
+    // into L2 -- its own dependent loads miss L2 and cost more than the DRAM latency they save
+    // (1.03 -> 1.41 us per cell); (2) taking the final area from the add's return value when the
+    // receiver's in-degree is already 1 -- needs that in-degree first, still two round trips;
+    // (3) reading the receivers' records speculatively right behind the decrement (one round trip) --
+    // the extra operations on the same sector serialise at L2 (1.03 -> 1.26 us per cell).
+    __device__ __forceinline__ unsigned long long chain(int32_t &cur, int32_t &other, const wl::Queue &q) const
     {
         unsigned long long n = 0;
-        while (i >= 0) {
-            int32_t d = -1;
+        int32_t i = cur;
+        while (i >= 0 && other < 0) {
             n++;
-            const int32_t nx = process(i, q, d);
-            if (d >= 0) q.push(d);   // the other ready receiver: another express warp takes it
-            i = nx;
+            i = process(i, q, other);
         }
+        cur = i;
         return n;
     }
 };

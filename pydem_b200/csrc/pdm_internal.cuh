@@ -157,6 +157,10 @@ enum {
     CT_T_START = 112,  // work-list timing (globaltimer ns): first warp in
     CT_T_SCAN = 113,   // last warp finished its seed scan (+ scan-born chains)
     CT_T_END = 114,    // last warp out
+    CT_X_FIRST = 116,  // diagnostics of a work-list run (PYDEM_B200_WL_DEBUG)
+    CT_X_CHAIN_CALLS = 116, CT_X_CHAIN_CELLS = 117, CT_X_CHAIN_NS = 118, CT_X_TEAM_LANES = 119, CT_X_TEAM_NS = 120,
+    CT_X_POLLS = 121, CT_X_SCAN_CELLS = 122,
+    CT_X_LAST = 122,
     CT_N = 128
 };
 

@@ -11,9 +11,10 @@
 //     thread that brings a counter to 0 owns that receiver and continues with it
 //     (chain following, no level barrier).  A second ready receiver is handed to idle
 //     lanes through a global queue.
-//   * ordering: the area atomics are *returning* atomics; the in-degree decrement
-//     carries a data dependency on their return values, so a contribution is performed
-//     at L2 before the decrement that publishes it (no MEMBAR on the critical path).
+//   * ordering: a receiver's area adds and its in-degree decrement hit the same 32-byte
+//     sector in program order from one thread and are performed in that order at L2
+//     (no MEMBAR on the critical path; drain_op.cuh explains, PYDEM_B200_SWEEP_STRICT=1
+//     cross-checks with a true data dependency).
 //
 // For an acyclic graph this visits every cell exactly once and yields the reference's
 // sums up to fp64 re-association (the reference adds in (level, source index) order).
@@ -23,6 +24,8 @@
 // Traffic per cell (sweep): one 32-byte sector for the cell's own record and one per receiver
 // (fp64 atomic on .area + int atomic on .indeg of the same sector); the kernel is bound by
 // sector-granular DRAM access / L2 atomic latency, not by streaming bandwidth.
+#include <stdlib.h>
+
 #include "drain_op.cuh"
 
 namespace {
@@ -71,6 +74,13 @@ k_twi(const double *__restrict__ uca, const double *__restrict__ mag, double *__
 
 static int g_sweep_blocks = 0, g_resume_blocks = 0;
 
+static int sweep_strict()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("PYDEM_B200_SWEEP_STRICT"); v = (e && atoi(e)) ? 1 : 0; }
+    return v;
+}
+
 // first pass: every owned cell nobody drains into is a seed
 int pdm_launch_sweep_first(pdm_tile *t)
 {
@@ -81,9 +91,9 @@ int pdm_launch_sweep_first(pdm_tile *t)
     int rc = wl::reset_queue(t);
     if (rc) return rc;
     const Win &w = t->win;
-    DrainOp<0> op{t->link, t->cell, nullptr, (int32_t)t->C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w};
+    DrainOp<0> op{t->link, t->cell, nullptr, (int32_t)t->C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w, sweep_strict()};
     wl::k_worklist<<<g_sweep_blocks, 256, 0, t->stream>>>(op, wl::DomainRange{w.lo * w.C, (w.hi - w.lo) * w.C},
-                                                          wl::Queue{t->queue, t->d_counters, (long long)t->N, t->d_counters + CT_SOURCES});
+                                                          wl::tuned(wl::Queue{t->queue, t->d_counters, (long long)t->N, t->d_counters + CT_SOURCES}));
     PDM_LAUNCHED();
     return PDM_OK;
 }
@@ -97,9 +107,9 @@ int pdm_launch_sweep_resume(pdm_tile *t)
     }
     int rc = wl::reset_queue(t, 1);
     if (rc) return rc;
-    DrainOp<2> op{t->link, t->cell, nullptr, (int32_t)t->C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w};
+    DrainOp<2> op{t->link, t->cell, nullptr, (int32_t)t->C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w, sweep_strict()};
     wl::k_worklist<<<g_resume_blocks, 256, 0, t->stream>>>(op, wl::DomainList{t->label, t->d_counters + CT_TMP1},
-                                                           wl::Queue{t->queue, t->d_counters, (long long)t->N, t->d_counters + CT_TMP1});
+                                                           wl::tuned(wl::Queue{t->queue, t->d_counters, (long long)t->N, t->d_counters + CT_TMP1}));
     PDM_LAUNCHED();
     return PDM_OK;
 }

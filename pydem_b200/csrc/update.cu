@@ -93,10 +93,13 @@ struct FloodOp {
         }
         return !(st_fetch_or(st, r, ST_REACH) & ST_REACH);
     }
-    __device__ __forceinline__ unsigned long long chain(int32_t i, const wl::Queue &q) const
+    // single-lane chain (worklist.cuh): runs until the chain ends or forks
+    __device__ __forceinline__ unsigned long long chain(int32_t &cur, int32_t &other, const wl::Queue &q) const
     {
         unsigned long long n = 0;
-        while (i >= 0) { int32_t d = -1; n++; const int32_t nx = process(i, q, d); if (d >= 0) q.push(d); i = nx; }
+        int32_t i = cur;
+        while (i >= 0 && other < 0) { n++; i = process(i, q, other); }
+        cur = i;
         return n;
     }
     __device__ __forceinline__ int32_t process(int32_t i, const wl::Queue &q, int32_t &defer) const
@@ -188,7 +191,7 @@ int pdm_launch_update(pdm_tile *t, const pdm_uca_params *p, const double *const 
     // sweep of the deltas (836-842)
     if ((rc = wl::reset_queue(t))) return rc;
     wl::k_worklist<<<g_blocks_drain1, 256, 0, t->stream>>>(
-        DrainOp<1>{t->link, t->cell, stt, (int32_t)C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w},
+        DrainOp<1>{t->link, t->cell, stt, (int32_t)C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w, 0},
         dom, q);
     PDM_LAUNCHED();
     PDM_CUDA(cudaMemcpyAsync(t->h_counters + CT_DRAINED, t->d_counters + CT_DRAINED, sizeof(unsigned long long),

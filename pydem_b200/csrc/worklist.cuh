@@ -18,6 +18,8 @@
 //     dealt and every started chain had ended: nothing can be produced any more.
 // Every cell may enter the queue at most once per run, so a queue of N+1 slots suffices.
 #pragma once
+#include <stdlib.h>
+
 #include "pdm_internal.cuh"
 
 namespace wl {
@@ -46,7 +48,11 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
     return t;
 }
 
-// opaque zero that depends on x: orders a later load after the one that produced x
+// zero derived from x.  NOTE: ptxas folds "x & 0", so this does NOT hold the consumer back until x
+// has arrived (checked in SASS); it only keeps the source order explicit.  Nothing relies on it:
+// the termination test is confirmed with fenced read-modify-writes, and a chain's queue pushes
+// are complete before its end is counted because the slot store consumed the push counter's
+// return value (in-order issue).
 __device__ __forceinline__ unsigned long long dep_zero_u64(unsigned long long x)
 {
     asm volatile("and.b64 %0, %0, 0;" : "+l"(x));
@@ -58,6 +64,8 @@ struct Queue {
     unsigned long long *ctr;
     long long cap;  // number of slots (a cell is queued at most once per run: N suffices)
     const unsigned long long *nseeds;  // device counter: exact number of seeds in the scan domain
+    int32_t backoff_max;   // longest sleep of an idle warp between polls, ns (0: default)
+    int32_t dbg;           // collect the CT_X_* diagnostics (PYDEM_B200_WL_DEBUG)
     __device__ __forceinline__ void push(int32_t cell) const
     {
         const unsigned long long slot = atomicAdd(&ctr[CT_QTAIL], 1ULL);
@@ -134,6 +142,10 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
     unsigned done_acc = 0;   // chains this warp has finished but not yet added to CT_QDONE (warp-uniform)
     unsigned long long idle_since = 0;   // watchdog: a warp that sees no progress for WATCHDOG_NS raises CT_WATCHDOG
     const unsigned long long WATCHDOG_NS = 4000000000ULL;
+    unsigned backoff = 200;
+    const unsigned backoff_max = q.backoff_max > 0 ? (unsigned)q.backoff_max : 200u;
+    unsigned long long x_polls = 0, x_chain_ns = 0, x_chain_cells = 0, x_chain_calls = 0, x_team_ns = 0, x_team_steps = 0,
+                       x_team_lanes = 0;
     if (lane == 0) atomicMin(&q.ctr[CT_T_START], globaltimer_ns());
 
     for (;;) {
@@ -175,7 +187,9 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
         // ---- no more seeds for this warp: idle lanes take a queue ticket.  Tickets are handed out
         //      with fetch-and-add, so claiming never retries (a CAS-claimed queue serialises at one
         //      claim per L2 round trip); a ticket whose slot is still empty waits for its producer.
-        const bool need_ticket = cur < 0 && !scanning && ticket < 0 && lane == 0;   // express: one chain per warp
+        // express: one queue item per warp at a time (its forks stay in the warp, see below)
+        const bool warp_idle = __ballot_sync(full, cur >= 0 || stash >= 0) == 0;
+        const bool need_ticket = warp_idle && !scanning && ticket < 0 && lane == 0;
         const unsigned need_mask = __ballot_sync(full, need_ticket);
         if (need_mask) {
             unsigned long long base = 0;
@@ -195,6 +209,7 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
         // ---- statistics only: when did the last warp run out of seeds
         if (!scanning && !scan_stamped) {
             if (lane == 0) atomicMax(&q.ctr[CT_T_SCAN], globaltimer_ns());
+            if (q.dbg) atomicAdd(&q.ctr[CT_X_SCAN_CELLS], processed);
             scan_stamped = true;
         }
         // ---- nothing to do in this warp: terminate on global quiescence, else back off
@@ -248,45 +263,43 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
                     }
                     if (__shfl_sync(full, quit, 0)) break;
                 }
-                __nanosleep(200);
+                // idle warps back off: thousands of them polling the same few lines slow the L2
+                // slices the working chains' atomics go through
+                __nanosleep(backoff);
+                if (backoff < backoff_max) backoff <<= 1;
+                if (q.dbg && lane == 0) x_polls++;
             }
             continue;
         }
         idle_since = 0;
+        backoff = 200;
         if ((++iters & 4095u) == 0) {
             int quit = 0;
             if (lane == 0) quit = ld_volatile_u64(q.ctr + CT_WATCHDOG) != 0;
             if (__shfl_sync(full, quit, 0)) break;
         }
-        // ---- express fast path: lane 0 is the only lane with work and the warp has no seeds left
-        //      to deal -> follow the chain to its end in a tight single-lane loop (no warp
-        //      collectives between cells: the critical path pays memory round trips only)
-        if (!scanning && work_mask == 1u) {
-            if (lane == 0) {
-                // the chain (and whatever this lane stashed while its warp was still scanning: those
-                // cells belong to the same chain's accounting) runs to its end
-                for (;;) {
-                    processed += op.chain(cur, q);
-                    if (stash < 0) break;
-                    cur = stash; stash = stash2; stash2 = stash3; stash3 = -1;
-                }
-                // every push of this chain was a returning atomic whose result the slot store waited
-                // for, so it has been performed before this (in-order issued) increment leaves the SM
-                atomicAdd(&q.ctr[CT_QDONE], 1ULL + done_acc);
-                active = false;
-                cur = -1;
-            }
-            done_acc = 0;
-            __syncwarp(full);
-            continue;
-        }
         // ---- one step per working lane
         bool finished_q = false;
-        int32_t defer = -1;  // second ready receiver: handed to the queue, warp-aggregated below
-        if (cur >= 0) {
+        int32_t defer = -1;  // second ready receiver: dealt to an idle lane of this warp or handed to the queue
+        if (!scanning && (work_mask & (work_mask - 1)) == 0) {
+            // express fast path: one lane has work and the warp has no seeds left to deal -> it
+            // follows the chain in a tight single-lane loop (no warp collectives between cells:
+            // the critical path pays memory round trips only) until the chain ends or forks
+            if (cur >= 0) {
+                const unsigned long long t0 = q.dbg ? globaltimer_ns() : 0;
+                const unsigned long long nc = op.chain(cur, defer, q);
+                processed += nc;
+                if (q.dbg) { x_chain_ns += globaltimer_ns() - t0; x_chain_cells += nc; x_chain_calls++; }
+                if (cur < 0 && defer >= 0) { cur = defer; defer = -1; }
+                if (cur < 0 && stash < 0) { finished_q = active; active = false; }
+            }
+            __syncwarp(full);
+        } else if (cur >= 0) {
             processed++;
             chain_len++;
+            const unsigned long long t0 = (q.dbg && !scanning) ? globaltimer_ns() : 0;
             const int32_t nxt = op.process(cur, q, defer);
+            if (q.dbg && !scanning) { x_team_ns += globaltimer_ns() - t0; x_team_lanes++; }
             cur = nxt;
             // a second ready receiver waits in the lane's stash (no queue traffic) unless the
             // stash is taken; a long chain hands its stash to the queue so that it cannot sit on
@@ -303,6 +316,28 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
             }
             if (cur < 0 && stash < 0) { finished_q = active; active = false; }
         }
+        // ---- express team: a flow path that forks (both receivers became ready at once) keeps both
+        //      branches in this warp -- the k-th forking lane gives its second receiver to the k-th
+        //      idle lane, which drains it in lock step.  Through the global queue the branch would
+        //      wait for an idle warp to notice its ticket (~1 us, more than draining two cells),
+        //      and the branches of a D-infinity flow path re-join a few cells later, so that wait
+        //      sat on the critical path of nearly every level.  A dealt cell is not a queue item:
+        //      it belongs to the giving chain's accounting, which is only reported when the whole
+        //      warp has run dry.
+        if (!scanning) {
+            const unsigned dm = __ballot_sync(full, defer >= 0);
+            if (dm) {
+                const bool idle = cur < 0 && stash < 0 && ticket < 0;
+                const unsigned im = __ballot_sync(full, idle);
+                const int nd = __popc(dm), ni = __popc(im);
+                const int k = __popc(im & lt_mask);
+                const bool take = idle && k < nd;
+                const int src = take ? (int)__fns(dm, 0, k + 1) : 0;
+                const int32_t c = __shfl_sync(full, defer, src);
+                if (defer >= 0 && __popc(dm & lt_mask) < ni) defer = -1;   // given away
+                if (take) { cur = c; chain_len = 0; }
+            }
+        }
         const unsigned pm = __ballot_sync(full, defer >= 0);
         unsigned long long base = 0;
         if (pm) {
@@ -311,11 +346,21 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
             if (defer >= 0) st_volatile_i32(q.slots + base + __popc(pm & lt_mask), defer);
         }
         const unsigned fq = __ballot_sync(full, finished_q);
-        // counted later (see done_acc); the eventual QDONE add carries a data dependency on the last
-        // push counter value this warp received: a chain's pushes are performed before its end is
-        // counted (a fence here cost 20-160 % of the sweep)
+        // counted later (see done_acc).  A chain's pushes are performed before its end is counted: the
+        // push counter add is returning and its value addressed the slot store above, so it was
+        // back before anything after it issued (a fence here cost 20-160 % of the sweep)
         done_acc += __popc(fq);
         if (pm) push_dep = base;
+    }
+    if (q.dbg) {
+        // diagnostics: single-lane chains (calls, cells, ns), team steps (lane-steps, lane-ns), idle polls
+        atomicAdd(&q.ctr[CT_X_CHAIN_CALLS], x_chain_calls);
+        atomicAdd(&q.ctr[CT_X_CHAIN_CELLS], x_chain_cells);
+        atomicAdd(&q.ctr[CT_X_CHAIN_NS], x_chain_ns);
+        atomicAdd(&q.ctr[CT_X_TEAM_LANES], x_team_lanes);
+        atomicAdd(&q.ctr[CT_X_TEAM_NS], x_team_ns);
+        atomicAdd(&q.ctr[CT_X_POLLS], x_polls);
+        (void)x_team_steps;
     }
     for (int o = 16; o > 0; o >>= 1) processed += __shfl_down_sync(full, processed, o);
     if (lane == 0) {
@@ -338,12 +383,25 @@ __device__ __forceinline__ int32_t off_e2(int sec, int32_t C)
     const int c = (sec <= 1 || sec >= 6) ? 1 : -1;
     return r * C + c;
 }
-// opaque zero that depends on x (a true data dependency the compiler cannot fold)
-__device__ __forceinline__ int dep_zero(double x)
+// host: tunables / diagnostics of a run (environment, read once)
+inline Queue tuned(Queue q)
 {
-    int z = __double2hiint(x);
-    asm volatile("and.b32 %0, %0, 0;" : "+r"(z));
-    return z;
+    static int backoff = -1, dbg = 0;
+    if (backoff < 0) {
+        const char *e = getenv("PYDEM_B200_WL_BACKOFF");
+        backoff = e ? atoi(e) : 0;
+        const char *d = getenv("PYDEM_B200_WL_DEBUG");
+        dbg = d ? atoi(d) : 0;
+    }
+    q.backoff_max = backoff;
+    q.dbg = dbg;
+    return q;
+}
+inline int max_blocks_per_sm()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("PYDEM_B200_WL_OCC"); v = e ? atoi(e) : 8; if (v < 1) v = 1; }
+    return v;
 }
 
 // host: persistent grid size (all blocks co-resident) for a given instantiation
@@ -355,7 +413,7 @@ int grid_for(K kernel, int *blocks_out)
     PDM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     PDM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, 0));
     if (occ < 1) { pdm_set_error("work-list kernel does not fit on an SM"); return PDM_ERR_CUDA; }
-    if (occ > 8) occ = 8;
+    if (occ > max_blocks_per_sm()) occ = max_blocks_per_sm();
     *blocks_out = sms * occ;
     return PDM_OK;
 }
@@ -372,6 +430,7 @@ static __global__ void k_queue_zero(unsigned long long *ctr, int keep_drained)
 {
     ctr[CT_QTAIL] = 0; ctr[CT_QHEAD] = 0; ctr[CT_QDONE] = 0; ctr[CT_PHASE1] = 0; ctr[CT_CHUNK] = 0;
     if (!keep_drained) ctr[CT_DRAINED] = 0;
+    for (int k = CT_X_FIRST; k <= CT_X_LAST; k++) ctr[k] = 0;
     ctr[CT_T_START] = ~0ULL; ctr[CT_T_SCAN] = 0; ctr[CT_T_END] = 0; ctr[CT_DBG_DEALT] = 0; ctr[CT_DBG_TAKEN] = 0; ctr[CT_DBG_EXITS] = 0;
 }
 

@@ -1,0 +1,49 @@
+"""A/B of the sweep tunables on the conditioned and raw fractal: one subprocess per setting (the
+environment is read once per process).  A setting is a comma list of strict= (PYDEM_B200_SWEEP_STRICT),
+backoff= (.._WL_BACKOFF, ns), occ= (.._WL_OCC, blocks per SM), dbg= (.._WL_DEBUG).
+    python scripts/sweep_ab.py [n] opt=0 opt=0,backoff=3200 opt=2,occ=4,dbg=1 ..."""
+import sys, os, json, subprocess
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+
+if len(sys.argv) > 1 and sys.argv[1] == "--child":
+    import torch
+    from pydem_b200 import tile as T
+    n = int(sys.argv[2])
+    for kind, drain_pits in (("cond", 1), ("raw", 0)):
+        E = np.load("/tmp/ab_%s_%d.npy" % (kind, n))
+        dt = T.DeviceTile(n, n, stream=torch.cuda.current_stream().cuda_stream)
+        dt.set_spacing(30.0, 30.0); dt.upload(T.F_ELEV, E)
+        best = None
+        for rep in range(6):
+            dt.slopes_directions()
+            st = dt.uca(drain_pits=drain_pits)
+            assert st["n_drained"] == n * n and st["n_undone"] == 0, st
+            if rep and (best is None or st["ms_sweep"] < best["ms_sweep"]): best = st
+        u = dt.download(T.F_UCA)
+        np.save("/tmp/ab_uca_%s_%s.npy" % (kind, os.environ["AB_TAG"]), u)
+        print(json.dumps(dict(cfg=os.environ["AB_TAG"], kind=kind, n=n, ms_graph=round(best["ms_graph"], 3),
+                              ms_sweep=round(best["ms_sweep"], 3), ms_sweep_scan=round(best.get("ms_sweep_scan", 0), 3),
+                              n_queue_items=best.get("n_queue_items"))), flush=True)
+        dt.close()
+    sys.exit(0)
+
+from pydem_b200 import synth
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+opts = sys.argv[2:] or ["strict=0", "strict=1"]
+KEYS = {"strict": "PYDEM_B200_SWEEP_STRICT", "backoff": "PYDEM_B200_WL_BACKOFF", "occ": "PYDEM_B200_WL_OCC", "dbg": "PYDEM_B200_WL_DEBUG"}
+np.save("/tmp/ab_cond_%d.npy" % n, synth.conditioned_fractal_dem(n, 0))
+np.save("/tmp/ab_raw_%d.npy" % n, synth.fractal_dem(n, 0))
+for o in opts:
+    env = dict(os.environ, AB_TAG=o)
+    for kv in o.split(","):
+        k, v = kv.split("=")
+        env[KEYS[k]] = v
+    subprocess.run([sys.executable, os.path.abspath(__file__), "--child", str(n)], env=env, check=False)
+for kind in ("cond", "raw"):
+    ref = np.load("/tmp/ab_uca_%s_%s.npy" % (kind, opts[0]))
+    for o in opts[1:]:
+        u = np.load("/tmp/ab_uca_%s_%s.npy" % (kind, o))
+        m = np.isfinite(ref)
+        print(kind, "opt", o, "vs", opts[0], "max rel diff %.3e" % np.max(np.abs(u[m] - ref[m]) / np.abs(ref[m])), "nan pattern equal", bool(np.array_equal(np.isnan(u), np.isnan(ref))))
