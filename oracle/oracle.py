@@ -259,7 +259,7 @@ class OracleDEMProcessor(object):
         self.stats["pits_without_drain_path"] = n_bad
         return self.elev
 
-    def calc_slopes_directions(self):
+    def calc_slopes_directions(self, plotflag=False):
         # conditioning (601-609): restated in oracle/conditioning.py
         if self.fill_flats:
             self.calc_fill_flats()
@@ -285,7 +285,7 @@ class OracleDEMProcessor(object):
         self.section, self.proportion = sec, prop
         return Graph(self.elev, j1, j2, prop, *pit), sec
 
-    def calc_uca(self, edge_init_data=None, uca_init=None):
+    def calc_uca(self, plotflag=False, edge_init_data=None, uca_init=None):
         if self.direction is None:
             self.calc_slopes_directions()
         if uca_init is None:

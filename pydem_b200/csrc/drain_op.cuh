@@ -130,13 +130,17 @@ struct DrainOp {
     // on the receivers.  scripts/ubench/lat.cu on B200: L2-hit ld.cg 209 ns, returning atomic
     // 260-310 ns, +130-230 ns when the sector comes from DRAM (river cells were last touched by
     // their tributaries, long before); measured here 1.0 us per cell on the 4096^2 conditioned DEM.
-    // Three ideas to shorten it were built, measured at 4096^2 and dropped (all bit-compatible, none
+    // Four ideas to shorten it were built, measured at 4096^2 and dropped (all bit-compatible, none
     // faster): (1) a look-ahead walker on one-byte link hints prefetching the receivers' records
     // into L2 -- its own dependent loads miss L2 and cost more than the DRAM latency they save
     // (1.03 -> 1.41 us per cell); (2) taking the final area from the add's return value when the
     // receiver's in-degree is already 1 -- needs that in-degree first, still two round trips;
     // (3) reading the receivers' records speculatively right behind the decrement (one round trip) --
-    // the extra operations on the same sector serialise at L2 (1.03 -> 1.26 us per cell).
+    // the extra operations on the same sector serialise at L2 (1.03 -> 1.26 us per cell); (4) keeping the
+    // receivers' link bytes in the record and prefetching the receivers' receivers one cell ahead
+    // without any dependent load -- no measurable change (7.30 vs 7.33 ms): DRAM latency is not what
+    // the chain waits for.  What is left is the number of dependent L2 operations per level; the
+    // next step is to keep a flow path's cells in shared memory ("what comes next").
     __device__ __forceinline__ unsigned long long chain(int32_t &cur, int32_t &other, const wl::Queue &q) const
     {
         unsigned long long n = 0;

@@ -1,0 +1,368 @@
+"""In-memory tile orchestrator for mosaics: the caller of the DEM hot path.
+
+Mirrors the semantics of the reference's ``pydem.process_manager.ProcessManager`` -- grid and
+overlap geometry (process_manager.py:517-740), the per-tile workers ``calc_elev_cond`` (:54),
+``calc_aspect_slope`` (:73), ``calc_uca`` (:94, including the one-pixel-overlap patch of edge
+directions), ``calc_uca_ec_metrics`` (:199), ``calc_uca_ec`` (:224, including the corner
+double-count rule) and ``calc_twi`` (:296), and the serial scheduling loop of
+``process_uca_edges`` (:1090-1189) -- with two differences of form, not of result:
+
+* no zarr store and no GeoTIFF files: tiles are NumPy arrays handed in with their pixel box in
+  the mosaic; every tile keeps its own result arrays, and a neighbour's edge strip is read from
+  the neighbour's arrays at the pixel the reference's ``edge_data`` slice addresses;
+* the ``DEMProcessor`` is this package's CUDA operator (any class with the reference's operator
+  surface can be passed, which is how the CPU tests run the same orchestrator on the oracle).
+
+The reference's own orchestrator, run unmodified over in-memory stand-ins for zarr/rasterio
+(``oracle/ref_pm_harness.py``), produced ``tests/golden/ref_pm.npz``; ``tests/test_process_manager.py``
+compares this module against it array by array (aspect, slope, uca, uca_edges, edge masks, twi,
+and the order in which tiles were corrected).
+"""
+import numpy as np
+
+SIDES = ("left", "right", "top", "bottom")
+CORNERS = ("top-left", "top-right", "bottom-left", "bottom-right")
+# where a tile's own edge lives inside its arrays (process_manager.py:41-50)
+EDGE = {
+    "left": (slice(0, None), 0), "right": (slice(0, None), -1), "top": (0, slice(0, None)), "bottom": (-1, slice(0, None)),
+    "top-left": (0, 0), "top-right": (0, -1), "bottom-left": (-1, 0), "bottom-right": (-1, -1),
+}
+# direction ranges (radians CCW from east) that leave the tile through a side (process_manager.py:102-107)
+DOWNSTREAM = {"left": (np.pi / 2, 3 * np.pi / 2), "right": (2 * np.pi - np.pi / 2, np.pi / 2), "top": (0.0, np.pi), "bottom": (np.pi, 2 * np.pi)}
+
+
+def split_mosaic(shape, ny_grid, nx_grid, overlap):
+    """Pixel boxes (r0, r1, c0, c1) of an ny_grid x nx_grid tiling of a ``shape`` raster whose
+    neighbouring tiles share ``overlap`` pixels, row-major.  Same cut as the reference's test
+    generator (utils_test_pydem.mk_test_multifile :359-408): interior seams are centred on the
+    regular grid lines."""
+    def cuts(n, k):
+        step = -(-n // k)
+        starts = [s for s in range(0, n - overlap, step)]
+        lo = [starts[0]] + [s - overlap // 2 for s in starts[1:]]
+        hi = [s + (overlap + 1) // 2 for s in starts[1:]] + [n]
+        return list(zip(lo, [min(h, n) for h in hi]))
+    return [(r0, r1, c0, c1) for (r0, r1) in cuts(shape[0], ny_grid) for (c0, c1) in cuts(shape[1], nx_grid)]
+
+
+class _Tile(object):
+    __slots__ = ("box", "gi", "gj", "elev", "dX", "dY", "dX2", "dY2", "aspect", "slope", "uca", "uca_edges",
+                 "edge_todo", "edge_done", "twi", "trim", "edge_src")
+
+
+class ProcessManager(object):
+    """tiles: list of elevation arrays; boxes: their (r0, r1, c0, c1) pixel boxes in the mosaic, in
+    processing order (the reference processes its source files in sorted-name order).
+    spacing: dict(dX=, dY=, dX2=, dY2=) of scalars applied to every tile (the reference derives
+    per-row arrays from each GeoTIFF; its tests force 1 everywhere), or a list of such dicts of
+    per-tile arrays.  dem_proc_kwargs: flags forwarded to every DEMProcessor (reference trait of
+    the same name).  dem_processor: operator class (default: the CUDA DEMProcessor)."""
+
+    def __init__(self, tiles, boxes, spacing=None, dem_proc_kwargs=None, dem_processor=None, n_workers=1):
+        if dem_processor is None:
+            from .dem_processing import DEMProcessor as dem_processor
+        self.DEMProcessor = dem_processor
+        self.dem_proc_kwargs = dict(dem_proc_kwargs or {})
+        self.n_workers = int(n_workers)
+        if len(tiles) != len(boxes) or not tiles:
+            raise ValueError("need one pixel box per tile")
+        self.tiles = []
+        for k, (e, b) in enumerate(zip(tiles, boxes)):
+            t = _Tile()
+            t.box = tuple(int(v) for v in b)
+            t.elev = np.array(e, dtype="float64")
+            if t.elev.shape != (t.box[1] - t.box[0], t.box[3] - t.box[2]):
+                raise ValueError("tile %d: shape %s does not match its box %s" % (k, t.elev.shape, t.box))
+            sp = (spacing[k] if isinstance(spacing, (list, tuple)) else spacing) or {}
+            R = t.elev.shape[0]
+            t.dX = np.ones(R - 1) * sp.get("dX", 1.0); t.dY = np.ones(R - 1) * sp.get("dY", 1.0)
+            t.dX2 = np.ones(R) * sp.get("dX2", sp.get("dX", 1.0)) if not isinstance(sp.get("dX2"), np.ndarray) else sp["dX2"]
+            t.dY2 = np.ones(R) * sp.get("dY2", sp.get("dY", 1.0)) if not isinstance(sp.get("dY2"), np.ndarray) else sp["dY2"]
+            for nm in ("aspect", "slope", "uca", "uca_edges", "edge_todo", "edge_done", "twi"):
+                setattr(t, nm, None)
+            self.tiles.append(t)
+        self.n_inputs = len(self.tiles)
+        self.uca_edge_metrics = np.zeros((self.n_inputs, 2))
+        self.success = np.zeros((self.n_inputs, 4), bool)
+        self.correction_log = []       # tiles in the order process_uca_edges corrected them
+        self.compute_grid()
+        self.compute_grid_overlaps()
+
+    # ------------------------------------------------------------------------------------
+    # geometry (process_manager.py:517-740)
+    # ------------------------------------------------------------------------------------
+    def compute_grid(self):
+        """Place every tile in the (row, column) grid of the mosaic: tiles that start on the same
+        mosaic row / column form a grid row / column (the reference does this with the rounded
+        top/left bounds of the files)."""
+        r0s = sorted(set(t.box[0] for t in self.tiles)); c0s = sorted(set(t.box[2] for t in self.tiles))
+        self.grid_shape = (len(r0s), len(c0s))
+        self.grid_id2i = -np.ones(self.grid_shape, dtype=int)
+        for i, t in enumerate(self.tiles):
+            t.gi, t.gj = r0s.index(t.box[0]), c0s.index(t.box[2])
+            if self.grid_id2i[t.gi, t.gj] >= 0:
+                raise ValueError("two tiles start at mosaic pixel (%d, %d)" % (t.box[0], t.box[2]))
+            self.grid_id2i[t.gi, t.gj] = i
+        for i, t in enumerate(self.tiles):      # a grid row has one height, a grid column one width (:537-545)
+            for o in self.tiles:
+                if o.gi == t.gi and o.elev.shape[0] != t.elev.shape[0] or o.gj == t.gj and o.elev.shape[1] != t.elev.shape[1]:
+                    raise ValueError("tiles of one grid row / column must have the same number of rows / columns")
+
+    def _nb(self, t, di, dj):
+        i, j = t.gi + di, t.gj + dj
+        if i < 0 or j < 0 or i >= self.grid_shape[0] or j >= self.grid_shape[1]:
+            return None
+        k = self.grid_id2i[i, j]
+        return None if k < 0 else self.tiles[k]
+
+    @staticmethod
+    def _overlap(shared, tie):
+        """(pixels this tile gives up on that side, distance of the neighbour's copy of my edge
+        from the neighbour's own edge) for `shared` common pixels (_calc_overlap :567-599)."""
+        return int(np.round((shared + tie - 0.01) / 2)), max(int(np.round(shared)), 1)
+
+    def compute_grid_overlaps(self):
+        for t in self.tiles:
+            R, C = t.elev.shape
+            lf, rt, up, dn = self._nb(t, 0, -1), self._nb(t, 0, 1), self._nb(t, -1, 0), self._nb(t, 1, 0)
+            c_lo, c_lo_e = self._overlap(lf.box[3] - t.box[2], 0) if lf else (0, 0)
+            c_hi, c_hi_e = self._overlap(t.box[3] - rt.box[2], 1) if rt else (0, 0)
+            r_lo, r_lo_e = self._overlap(up.box[1] - t.box[0], 0) if up else (0, 0)
+            r_hi, r_hi_e = self._overlap(t.box[1] - dn.box[0], 1) if dn else (0, 0)
+            t.trim = (r_lo, r_hi, c_lo, c_hi)
+            # Where the values for my edges come from: (tile, row index/slice, column index/slice).
+            # The reference addresses its side-by-side store one step outside the tile's block
+            # (edge_data :700-711); with no neighbour on a side that step is zero and the edge
+            # data are the tile's own edge.
+            def src(di, dj, rows, cols):
+                o = self._nb(t, di, dj) if (di or dj) else t
+                return (o if o is not None else None, rows, cols)
+            tl = 1 if (t.gj > 0 and t.gi > 0) else 0
+            bl = 1 if (t.gj > 0 and t.gi < self.grid_shape[0] - 1) else 0
+            tr = 1 if (t.gj < self.grid_shape[1] - 1 and t.gi > 0) else 0
+            br = 1 if (t.gj < self.grid_shape[1] - 1 and t.gi < self.grid_shape[0] - 1) else 0
+
+            def corner(on, di, dj, re, ce, own_r, own_c):
+                # the block one step up/down by `re` and left/right by `ce` (each may be 0)
+                sdi = di if (on and re) else 0; sdj = dj if (on and ce) else 0
+                o = self._nb(t, sdi, sdj) if (sdi or sdj) else t
+                if o is None:
+                    return (None, 0, 0)
+                oR, oC = o.elev.shape
+                rr = (oR - re if di < 0 else re - 1) if sdi else own_r
+                cc = (oC - ce if dj < 0 else ce - 1) if sdj else own_c
+                return (o, rr, cc)
+            t.edge_src = {
+                "left": src(0, -1 if c_lo_e else 0, slice(0, None), (lf.elev.shape[1] - c_lo_e) if c_lo_e else 0),
+                "right": src(0, 1 if c_hi_e else 0, slice(0, None), (c_hi_e - 1) if c_hi_e else C - 1),
+                "top": src(-1 if r_lo_e else 0, 0, (up.elev.shape[0] - r_lo_e) if r_lo_e else 0, slice(0, None)),
+                "bottom": src(1 if r_hi_e else 0, 0, (r_hi_e - 1) if r_hi_e else R - 1, slice(0, None)),
+                "top-left": corner(tl, -1, -1, r_lo_e, c_lo_e, 0, 0),
+                "top-right": corner(tr, -1, 1, r_lo_e, c_hi_e, 0, C - 1),
+                "bottom-left": corner(bl, 1, -1, r_hi_e, c_lo_e, R - 1, 0),
+                "bottom-right": corner(br, 1, 1, r_hi_e, c_hi_e, R - 1, C - 1),
+            }
+            t_one = {}
+            # check_1overlap (:286-294): is the source exactly one step outside my block?
+            for key, (o, rr, cc) in t.edge_src.items():
+                steps = []
+                if key in ("left", "top-left", "bottom-left"): steps.append(c_lo_e if (key == "left" or (tl if key == "top-left" else bl)) else 0)
+                if key in ("right", "top-right", "bottom-right"): steps.append(c_hi_e if (key == "right" or (tr if key == "top-right" else br)) else 0)
+                if key in ("top", "top-left", "top-right"): steps.append(r_lo_e if (key == "top" or (tl if key == "top-left" else tr)) else 0)
+                if key in ("bottom", "bottom-left", "bottom-right"): steps.append(r_hi_e if (key == "bottom" or (bl if key == "bottom-left" else br)) else 0)
+                t_one[key] = any(s == 1 for s in steps)
+            t.edge_src["_one"] = t_one
+
+    def _edge(self, t, key, field):
+        """The reference's ``store[field][edge_slice[key]]`` for tile t (a copy)."""
+        o, rr, cc = t.edge_src[key]
+        if o is None:
+            return np.zeros((), dtype=getattr(t, field).dtype)[()] if key in CORNERS else np.zeros(
+                t.elev.shape[0] if key in ("left", "right") else t.elev.shape[1], dtype=getattr(t, field).dtype)
+        a = getattr(o, field)
+        v = a[rr, cc]
+        return np.array(v) if isinstance(v, np.ndarray) else v
+
+    def _dp(self, t, **kw):
+        k = dict(elev=t.elev.copy(), dX=t.dX.copy(), dY=t.dY.copy(), dX2=t.dX2.copy(), dY2=t.dY2.copy())
+        k.update(kw)
+        k.update(self.dem_proc_kwargs)
+        return self.DEMProcessor(**k)
+
+    # ------------------------------------------------------------------------------------
+    # workers
+    # ------------------------------------------------------------------------------------
+    def _elev_cond(self, t):                                    # calc_elev_cond :54-71
+        dp = self._dp(t)
+        dp.calc_fill_flats()
+        dp.calc_pit_drain_paths()
+        t.elev = np.array(dp.elev, dtype="float64")
+
+    def _aspect_slope(self, t):                                 # calc_aspect_slope :73-92
+        dp = self._dp(t, fill_flats=False)
+        dp.calc_slopes_directions()
+        t.aspect = np.array(dp.direction, dtype="float64"); t.slope = np.array(dp.mag, dtype="float64")
+
+    @staticmethod
+    def _leaves(d, key):
+        lo, hi = DOWNSTREAM[key]
+        if key == "right":
+            return ((d >= lo) | (d <= hi)) & (d >= 0)
+        return (d >= lo) & (d <= hi)
+
+    @staticmethod
+    def _east_west(d):
+        return ((d < 1e-6) & (d >= 0)) | (np.abs(d - np.pi * 2) < 1e-6)
+
+    def _uca(self, t):                                          # calc_uca :94-197
+        direction = t.aspect.copy(); mag = t.slope.copy()
+        one = t.edge_src["_one"]
+        for key in SIDES:
+            if not one[key]:
+                continue
+            d = direction[EDGE[key]]                            # a view: edits land in `direction`
+            ids = self._leaves(d, key)                          # only edges the flow leaves through
+            if key in ("top", "bottom"):
+                ids = ids | self._east_west(d)
+            ids = ids | (d == -1)                               # and flats
+            other = ("top", "bottom") if key in ("left", "right") else ("left", "right")
+            # the two end cells belong to the corner rule below when they also leave through the adjacent side
+            ids[0] = ids[0] & (not bool(self._leaves(d[0:1], other[0])[0]))
+            ids[-1] = ids[-1] & (not bool(self._leaves(d[-1:], other[1])[0]))
+            nb_a = self._edge(t, key, "aspect"); nb_s = self._edge(t, key, "slope")
+            m = mag[EDGE[key]]
+            d[ids] = nb_a[ids]; m[ids] = nb_s[ids]
+            t.aspect[EDGE[key]] = d; t.slope[EDGE[key]] = m     # the stored fields are patched too (:149-150)
+        for key in CORNERS:
+            if not one[key]:
+                continue
+            ktb, klr = key.split("-")
+            d = direction[EDGE[key]]
+            da = np.array([d])
+            ids = bool((self._leaves(da, klr) & (self._leaves(da, ktb) | self._east_west(da)))[0])
+            if not ids:
+                continue
+            direction[EDGE[key]] = self._edge(t, key, "aspect"); mag[EDGE[key]] = self._edge(t, key, "slope")
+            t.aspect[EDGE[key]] = direction[EDGE[key]]; t.slope[EDGE[key]] = mag[EDGE[key]]
+        dp = self._dp(t, direction=direction, mag=mag, fill_flats=False)
+        dp.find_flats()
+        dp.calc_uca()
+        t.uca = np.array(dp.uca, dtype="float64")
+        t.edge_todo = np.array(dp.edge_todo, dtype=bool); t.edge_done = np.array(dp.edge_done, dtype=bool)
+        if t.uca_edges is None:
+            t.uca_edges = np.zeros_like(t.uca)
+
+    def _metrics(self, t):                                      # calc_uca_ec_metrics :199-221
+        n_done = 0; p_done = 0
+        for key in SIDES + ("top-left", "top-right", "bottom-left", "bottom-right"):
+            et = t.edge_todo[EDGE[key]]
+            edn = self._edge(t, key, "edge_done")
+            n_done += np.sum(et & edn); p_done += np.sum(et)
+        return (n_done / (1e-16 + p_done), n_done)
+
+    def _uca_ec(self, t):                                       # calc_uca_ec :224-284
+        dp = self._dp(t, direction=t.aspect.copy(), mag=t.slope.copy(), fill_flats=False)
+        dp.find_flats()
+        uca_init = t.uca.copy(); edges_init = t.uca_edges.copy()
+        data = {k: self._edge(t, k, "uca") + self._edge(t, k, "uca_edges") for k in SIDES}
+        done = {k: self._edge(t, k, "edge_done") for k in SIDES}
+        todo = {k: np.array(t.edge_todo[EDGE[k]]) for k in SIDES}
+        todo_nb = {k: self._edge(t, k, "edge_todo") for k in SIDES}
+        # a corner cell sits on two strips; when both neighbours have finished it, one of them is
+        # dropped so that its inflow is not counted twice, and the diagonal neighbour's value is
+        # preferred where that neighbour really is one step away and done (:257-270)
+        for key in ("top-left", "bottom-right", "top-right", "bottom-left"):
+            ktb, klr = key.split("-")
+            ir, ic = EDGE[key]
+            if done[ktb][ic] & done[klr][ir]:
+                done[ktb][ic] = False
+                if t.edge_src["_one"][key] and self._edge(t, key, "edge_done"):
+                    v = self._edge(t, key, "uca") + self._edge(t, key, "uca_edges")
+                    data[klr][ir] = v; data[ktb][ic] = v
+        todo = {k: v & (todo_nb[k] == False) for k, v in todo.items()}  # noqa: E712 (:274)
+        dp.calc_uca(uca_init=uca_init + edges_init, edge_init_data=[data, done, todo])
+        t.uca_edges = np.array(dp.uca, dtype="float64") - uca_init
+        t.edge_todo = np.array(dp.edge_todo, dtype=bool); t.edge_done = np.array(dp.edge_done, dtype=bool)
+
+    def _twi(self, t):                                          # calc_twi :296-315
+        dp = self._dp(t, direction=t.aspect.copy(), mag=t.slope.copy(), fill_flats=False, uca=t.uca + t.uca_edges)
+        dp.find_flats()
+        dp.calc_twi()
+        t.twi = np.array(dp.twi, dtype="float64")
+
+    # ------------------------------------------------------------------------------------
+    # stages (process_manager.py:993-1316)
+    # ------------------------------------------------------------------------------------
+    def _stage(self, fn, col):
+        for i, t in enumerate(self.tiles):
+            if not self.success[i, col]:
+                fn(t)
+                self.success[i, col] = True
+        return self.success[:, col].copy()
+
+    def process_elevation(self):
+        return self._stage(self._elev_cond, 0)
+
+    def process_aspect_slope(self):
+        return self._stage(self._aspect_slope, 1)
+
+    def process_uca(self):
+        return self._stage(self._uca, 2)
+
+    def update_uca_edge_metrics(self, index=None):
+        for i in (range(self.n_inputs) if index is None else index):
+            self.uca_edge_metrics[i] = self._metrics(self.tiles[i])
+        return self.uca_edge_metrics.copy()
+
+    def _order(self, mets, mets_type):
+        if mets.shape[0] == 1:
+            return np.zeros(1, int)
+        return np.argpartition(-mets[:, mets_type], min(self.n_workers * 2, mets.shape[0] - 1))
+
+    def process_uca_edges(self, mets_type=0, max_count=100000):
+        """Serial correction loop (:1090-1189, n_workers == 1): correct the tile whose inflow edges
+        are most complete, refresh the metrics of that tile and its four neighbours, stop when the
+        ranking no longer changes."""
+        mets = self.update_uca_edge_metrics()
+        I = self._order(mets, mets_type)
+        I_old = np.zeros_like(I)
+        count = 0
+        while np.any(I_old != I) and count < max_count:
+            count += 1
+            k = int(I[0])
+            self._uca_ec(self.tiles[k])
+            self.correction_log.append(k)
+            I_old = I.copy()
+            t = self.tiles[k]
+            chk = {k}
+            for (di, dj) in ((0, -1), (0, 1), (-1, 0), (1, 0)):
+                o = self._nb(t, di, dj)
+                if o is not None:
+                    chk.add(self.tiles.index(o))
+            mets = self.update_uca_edge_metrics(sorted(chk))
+            I = self._order(mets, mets_type)
+        return mets
+
+    def process_twi(self):
+        self.process_elevation()
+        self.process_aspect_slope()
+        self.process_uca()
+        self.process_uca_edges()
+        return self._stage(self._twi, 3)
+
+    # ------------------------------------------------------------------------------------
+    # results
+    # ------------------------------------------------------------------------------------
+    def mosaic(self, key):
+        """The non-overlapping mosaic of a result (save_non_overlap_data :742-784): every tile
+        contributes the part it does not share, `uca` includes the edge corrections."""
+        R = max(t.box[1] for t in self.tiles); C = max(t.box[3] for t in self.tiles)
+        out = np.full((R, C), np.nan)
+        for t in self.tiles:
+            a = getattr(t, key)
+            if key == "uca":
+                a = a + t.uca_edges
+            r_lo, r_hi, c_lo, c_hi = t.trim
+            nr, nc = t.elev.shape
+            out[t.box[0] + r_lo:t.box[1] - r_hi, t.box[2] + c_lo:t.box[3] - c_hi] = a[r_lo:nr - r_hi, c_lo:nc - c_hi]
+        return out

@@ -164,3 +164,39 @@ def conditioning_cases():
         R = E.shape[0]
         res[k] = (E, 30.0 + np.linspace(0, 3, R - 1), np.full(R - 1, 28.0))
     return res
+
+
+def pm_cases():
+    """name -> (DEM, nx_grid, ny_grid, overlap, dem_proc_kwargs) for the tile-orchestrator tests:
+    the reference's own multi-file tilings of the 32x32 cone (test_end_to_end.py:86-149) and a
+    rough fractal."""
+    x, y = np.mgrid[-1:1:32j, -1:1:32j]
+    cone = 1 - np.sqrt(x ** 2 + y ** 2) / np.sqrt(2)              # utils_test_pydem.py:98-103
+    frac = synth.fractal_dem(64, 3)
+    c = {}
+    for (nx, ny, ov) in ((3, 3, 2), (5, 4, 2), (5, 4, 3), (3, 3, 1), (3, 4, 1)):
+        c["cone_%dx%d_%doverlap" % (nx, ny, ov)] = (cone, nx, ny, ov, {})
+    c["fractal_3x3_2overlap"] = (frac, 3, 3, 2, {})
+    c["fractal_2x3_1overlap"] = (frac, 2, 3, 1, {})
+    return c
+
+
+def pm_compare(pm, G, name):
+    """Our ProcessManager's per-tile arrays against the reference's side-by-side store (golden
+    dict G).  Returns the worst deviation per field (bool fields: number of differing cells)."""
+    worst = {}
+    gs = G[name + "_grid_slice"]
+    for i, t in enumerate(pm.tiles):
+        sl = (slice(gs[i][0], gs[i][1]), slice(gs[i][2], gs[i][3]))
+        for key in ("elev", "aspect", "slope", "uca", "uca_edges", "edge_todo", "edge_done", "twi"):
+            a = G["%s_%s" % (name, key)][sl]; b = getattr(t, key)
+            if a.dtype == bool:
+                d = float((a != b).sum())
+            else:
+                with np.errstate(invalid="ignore"):
+                    d = np.where(np.isnan(a) & np.isnan(b), 0.0, np.where(np.isnan(a) != np.isnan(b), np.inf, np.abs(a - b)))
+                    if key in ("uca", "uca_edges"):
+                        d = d / np.maximum(1.0, np.abs(np.nan_to_num(a)))
+                d = float(d.max())
+            worst[key] = max(worst.get(key, 0.0), d)
+    return worst

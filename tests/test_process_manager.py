@@ -1,0 +1,104 @@
+"""Tile orchestrator (pydem_b200.process_manager) on the CPU:
+* the orchestrator driving the ORACLE operator reproduces the unmodified reference
+  ProcessManager array by array (golden fixture tests/golden/ref_pm.npz, made by
+  tests/golden/make_golden_pm.py) including the order in which tiles were corrected;
+* where the reference tree is present: the reference's ProcessManager runs live over the
+  in-memory store, (a) with its own DEMProcessor and (b) with the oracle operator swapped in at
+  ``pydem.process_manager.DEMProcessor`` -- the drop-in point INTEGRATION.md names."""
+import contextlib
+import io
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+import helpers
+from oracle.oracle import OracleDEMProcessor
+from oracle import ref_harness
+from pydem_b200.process_manager import ProcessManager, split_mosaic
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_pm.npz"))
+CASES = helpers.pm_cases()
+# oracle operator vs reference operator: direction 8.9e-16, uca rel 8e-15, masks exact
+TOL = dict(elev=0.0, slope=1e-13, aspect=1e-12, uca=1e-9, uca_edges=1e-9, edge_todo=0, edge_done=0, twi=1e-8)
+
+
+def oracle_factory(**k):
+    return OracleDEMProcessor(k.pop("elev"), **k)
+
+
+def run_pm(E, boxes, kw, factory):
+    tiles = [E[b[0]:b[1], b[2]:b[3]] for b in boxes]
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        pm = ProcessManager(tiles, boxes, dem_proc_kwargs=kw, dem_processor=factory)
+        pm.process_twi()
+    return pm
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_split_matches_reference_generator(name):
+    E, nx, ny, ov, kw = CASES[name]
+    assert sorted(split_mosaic(E.shape, ny, nx, ov)) == sorted(map(tuple, G[name + "_boxes"].tolist()))
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_orchestrator_equals_reference_process_manager(name):
+    E, nx, ny, ov, kw = CASES[name]
+    np.testing.assert_array_equal(E, G[name + "_E"])
+    boxes = [tuple(b) for b in G[name + "_boxes"].tolist()]
+    pm = run_pm(E, boxes, kw, oracle_factory)
+    worst = helpers.pm_compare(pm, G, name)
+    for k, tol in TOL.items():
+        assert worst[k] <= tol, (name, worst)
+    assert pm.correction_log == G[name + "_order"].tolist(), name          # same scheduling decisions
+    assert pm.success.all()
+    m = pm.mosaic("uca"); c = G[name + "_compact_uca"]
+    assert m.shape == c.shape
+    np.testing.assert_allclose(m, c, rtol=1e-9, equal_nan=True)
+    np.testing.assert_allclose(pm.mosaic("twi"), G[name + "_compact_twi"], atol=1e-8, equal_nan=True)
+
+
+def test_reference_criterion_on_the_cone():
+    """test_end_to_end.py:96: the mosaic's uca equals the single-tile uca away from the rim."""
+    E, nx, ny, ov, kw = CASES["cone_5x4_2overlap"]
+    pm = run_pm(E, split_mosaic(E.shape, ny, nx, ov), kw, oracle_factory)
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        dp = OracleDEMProcessor(E.copy(), dX=1.0, dY=1.0)
+        dp.calc_twi()
+    np.testing.assert_array_almost_equal(dp.uca[1:-1, 1:-1], pm.mosaic("uca")[1:-1, 1:-1])
+
+
+def test_rejects_inconsistent_tiles():
+    E = CASES["cone_3x3_2overlap"][0]
+    with pytest.raises(ValueError):
+        ProcessManager([E[:10, :10]], [(0, 12, 0, 10)], dem_processor=oracle_factory)
+    with pytest.raises(ValueError):
+        ProcessManager([E[:10, :10], E[:12, 8:20]], [(0, 10, 0, 10), (0, 12, 8, 20)], dem_processor=oracle_factory)
+
+
+@pytest.mark.skipif(not ref_harness.reference_available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("name", ["cone_3x3_1overlap", "fractal_3x3_2overlap"])
+def test_operator_drops_in_under_the_reference_process_manager(name):
+    """The UNMODIFIED reference ProcessManager with this repo's operator interface swapped in at
+    pydem.process_manager.DEMProcessor (the oracle stands in for the CUDA operator on the CPU;
+    tests/test_gpu_process_manager.py runs the CUDA operator through the same orchestration)."""
+    from oracle import ref_pm_harness as H
+    E, nx, ny, ov, kw = CASES[name]
+
+    class Adapter(OracleDEMProcessor):
+        def __init__(self, **k):
+            k.pop("bounds", None); k.pop("transform", None)
+            super().__init__(k.pop("elev"), **k)
+
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        r = H.run_reference_pm(E, nx, ny, ov, "dropin_" + name, dem_processor=Adapter, dem_proc_kwargs=kw)
+    assert r["success"].all()
+    assert r["correction_order"] == G[name + "_order"].tolist()
+    for key in ("elev", "slope", "edge_todo", "edge_done"):
+        np.testing.assert_array_equal(r[key], G["%s_%s" % (name, key)])
+    np.testing.assert_allclose(r["aspect"], G[name + "_aspect"], atol=1e-12)
+    np.testing.assert_allclose(r["uca"] + r["uca_edges"], G[name + "_uca"] + G[name + "_uca_edges"], rtol=1e-9, equal_nan=True)
