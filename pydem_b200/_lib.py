@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpydem_b200.so")
+LIB_PATH = os.environ.get("PYDEM_B200_LIB") or os.path.join(_HERE, "libpydem_b200.so")   # override: A/B of library builds
 
 # pdm_field
 (F_ELEV, F_MAG, F_DIR, F_FLATS, F_UCA, F_TWI, F_EDGE_TODO, F_EDGE_DONE, F_SECTION, F_TWI10, F_RESERVED, F_FLAT0,

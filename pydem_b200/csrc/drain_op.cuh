@@ -27,19 +27,6 @@ __device__ __forceinline__ uint32_t st_fetch_or(uint8_t *st, int32_t cell, uint3
 
 //   MODE 2: resumed full sweep of a shard: like MODE 0, but the seeds come from an explicit list
 //           (cells whose last upstream contribution arrived from a neighbouring rank).
-// one 32-byte sweep record read with a single 256-bit load (one point in time for all fields)
-struct Rec32 { double area, taint, prop; int32_t indeg; uint8_t link; };
-__device__ __forceinline__ Rec32 ld_rec(const Cell *c)
-{
-    unsigned long long a, b, p, d;
-    asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(p), "=l"(d) : "l"(c) : "memory");
-    Rec32 r;
-    r.area = __longlong_as_double((long long)a); r.taint = __longlong_as_double((long long)b);
-    r.prop = __longlong_as_double((long long)p);
-    r.indeg = (int32_t)(d & 0xffffffffULL); r.link = (uint8_t)(d >> 32);
-    return r;
-}
-
 template <int MODE>
 struct DrainOp {
     const uint8_t *link;   // SoA copy of the link bytes: only the seed scan reads it
@@ -51,7 +38,6 @@ struct DrainOp {
     const int32_t *pit_dst;
     const double *pit_w;
     int32_t strict;        // hold the decrements back until the adds have returned (see process())
-    int32_t spec;          // the tail reads the receivers' records behind the decrement (see step())
 
     __device__ __forceinline__ bool is_seed(int32_t c) const
     {
@@ -59,46 +45,20 @@ struct DrainOp {
     }
     __device__ __forceinline__ bool skip(int32_t r) const { return MODE == 1 && (st[r] & ST_START); }
 
-    // What a lane carries from one step to the next: the record of the cell it is about to drain,
-    // when it was read behind the decrement that made that cell ready (see step()).
-    struct State {
-        int32_t cell;     // the cell the fields below belong to (-1: nothing carried)
-        double area, taint, prop;
-        uint8_t link;
-        __device__ State() : cell(-1), area(0.0), taint(0.0), prop(0.0), link(0) {}
-    };
-
     // Drain one ready cell; returns the receiver this lane continues with (or -1).
-    //
-    // read_behind (the latency-bound tail of the sweep; off in the bandwidth-bound bulk phase): both
-    // receivers' records are read with one 256-bit load each, issued right BEHIND their
-    // decrements.  Adds, decrement and load of one receiver target the same 32-byte sector and are
-    // performed in issue order (the ordering the sweep relies on anyway, see below), so when a
-    // decrement turns out to have been the last one, the record read behind it already holds the
-    // receiver's final area and taint, and the next step starts without loading it: ONE dependent
-    // round trip per cell instead of two.  scripts/ubench/chain.cu (cold synthetic river, B200):
-    // 932 -> 485 ns per cell ("snapshot before the decrement" 520 ns and "preload one level
-    // ahead" 554 ns are the measured alternatives).  PYDEM_B200_SWEEP_SPEC=0 turns it off.
-    // Tried and dropped: a look-ahead walker on one-byte link hints prefetching records into L2 (its
-    // own dependent loads cost more than the DRAM latency they save) and prefetching the
-    // receivers' receivers from link bytes kept in the record (no measurable change).
-    __device__ __forceinline__ int32_t step(int32_t i, const wl::Queue &q, int32_t &defer, State &st, bool read_behind) const
+    __device__ __forceinline__ int32_t process(int32_t i, const wl::Queue &q, int32_t &defer) const
     {
-        double ai, ti, p;
-        uint8_t lk;
-        if (st.cell == i) {
-            ai = st.area; ti = st.taint; p = st.prop; lk = st.link;
-        } else {
-            // the cell's whole sweep state is one 32-byte sector
-            const Rec32 me = ld_rec(&cell[i]);
-            ai = me.area; ti = me.taint; p = me.prop; lk = me.link;
-        }
-        st.cell = -1;
-        if (MODE == 1) ti = 0.0;
+        // the cell's whole sweep state is one 32-byte sector: two 16-byte L2 loads
+        const double2 at = __ldcg(reinterpret_cast<const double2 *>(&cell[i].area));      // area, taint
+        const longlong2 pm = __ldcg(reinterpret_cast<const longlong2 *>(&cell[i].prop));  // prop | indeg, link
+        const double ai = at.x;
+        const double ti = MODE != 1 ? at.y : 0.0;
+        const double p = __longlong_as_double(pm.x);
+        const uint8_t lk = (uint8_t)((unsigned long long)pm.y >> 32);
         int32_t nxt = -1;
         if (lk & LK_PIT) {
             // long-range pit edges (_mk_connectivity_pits): rare, plain fence ordering
-            const int64_t slot = __double_as_longlong(p);
+            const int64_t slot = pm.x;
             const int32_t e0 = pit_beg[slot], e1 = pit_end[slot];
             for (int32_t e = e0; e < e1; e++) {
                 const int32_t r = pit_dst[e];
@@ -152,48 +112,49 @@ struct DrainOp {
         int o1 = 0, o2 = 0;
         if (k1) o1 = atomicSub(&cell[r1].indeg, one);
         if (k2) o2 = atomicSub(&cell[r2].indeg, one);
-        Rec32 s1, s2;
-        const bool rb = MODE != 1 && read_behind && spec && !strict;
-        if (rb) {
-            if (k1) s1 = ld_rec(&cell[r1]);     // behind the decrement of the same sector
-            if (k2) s2 = ld_rec(&cell[r2]);
-        }
         const bool rdy1 = k1 && o1 == 1, rdy2 = k2 && o2 == 1;
         if (rdy1 && rdy2) {
             // follow the larger share, hand the other receiver to an idle lane
             if (p >= 0.5) { nxt = r1; defer = r2; } else { nxt = r2; defer = r1; }
         } else if (rdy1) nxt = r1;
         else if (rdy2) nxt = r2;
-        if (rb && nxt >= 0) {
-            const Rec32 &s = (nxt == r1) ? s1 : s2;
-            st.cell = nxt; st.area = s.area; st.taint = s.taint; st.prop = s.prop; st.link = s.link;
-        }
         return nxt;
-    }
-
-    // bulk phase: one cell, nothing carried, no read-behind
-    __device__ __forceinline__ int32_t process(int32_t i, const wl::Queue &q, int32_t &defer) const
-    {
-        State st;
-        return step(i, q, defer, st, false);
     }
 
     // Express chain (single lane, the critical path of the sweep): follow the flow path from `cur`
     // until it ends (cur = -1) or forks, i.e. both receivers became ready at once (cur = the
-    // receiver with the larger share, other = the second one; the caller gives `other` to an idle
-    // lane of the same warp so that both branches advance together).  The next cell's record is
-    // carried in registers (step(), read-behind).  Returns the cells drained.
-    // Measured and dropped at 4096^2: running the lanes of a team through bounded chains of this
-    // kind to give them the carried record too (6.5 -> 8.3 ms), and draining a whole front of up
-    // to four ready cells per iteration from one lane (front kept in local memory: 12+ ms).
+    // receiver with the larger share, other = the second one).  The caller gives `other` to an idle
+    // lane of the same warp so that both branches advance together.  Returns the cells drained.
+    //
+    // The chain pays dependent memory round trips only: load the cell's record, then add + decrement
+    // on the receivers.  scripts/ubench/lat.cu on B200: L2-hit ld.cg 209 ns, returning atomic
+    // 260-310 ns, +130-230 ns when the sector comes from DRAM (river cells were last touched by
+    // their tributaries, long before); measured here 1.0 us per cell on the 4096^2 conditioned DEM.
+    // Ideas to shorten it that were built, measured at 4096^2 and dropped (all bit-compatible):
+    // (1) a look-ahead walker on one-byte link hints prefetching the receivers' records into L2 --
+    //     its own dependent loads miss L2 and cost more than the DRAM latency they save
+    //     (1.03 -> 1.41 us per cell);
+    // (2) taking the final area from the add's return value when the receiver's in-degree is
+    //     already 1 -- needs that in-degree first, still two round trips;
+    // (3) reading both receivers' records with one 256-bit load each right behind the decrement and
+    //     carrying the next cell's record in registers (one round trip per cell).  In isolation
+    //     this halves the latency (scripts/ubench/chain.cu, cold synthetic river: 932 -> 485 ns per
+    //     cell); inside the sweep it moved the 4096^2 conditioned case by -14 % on one box and
+    //     +8 % on another (median of 15 sweeps each, builds alternated on the same GPU), and its
+    //     16 extra registers cost the bulk phase a resident block per SM (scan 0.98 -> 1.12 ms);
+    // (4) the same for the lanes of a team (bounded chains): slower (6.5 -> 8.3 ms); draining a whole
+    //     front of up to four ready cells per iteration from one lane (local-memory front): 12+ ms;
+    // (5) keeping the receivers' link bytes in the record and prefetching the receivers' receivers
+    //     one cell ahead without a dependent load: no measurable change.
+    // What is left is the number of dependent L2 operations per level; the next step is to keep a
+    // flow path's cells in shared memory ("what comes next").
     __device__ __forceinline__ unsigned long long chain(int32_t &cur, int32_t &other, const wl::Queue &q) const
     {
         unsigned long long n = 0;
         int32_t i = cur;
-        State st;
         while (i >= 0 && other < 0) {
             n++;
-            i = step(i, q, other, st, true);
+            i = process(i, q, other);
         }
         cur = i;
         return n;

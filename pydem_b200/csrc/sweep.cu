@@ -74,12 +74,6 @@ k_twi(const double *__restrict__ uca, const double *__restrict__ mag, double *__
 
 static int g_sweep_blocks = 0, g_resume_blocks = 0;
 
-static int sweep_spec()
-{
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("PYDEM_B200_SWEEP_SPEC"); v = e ? (atoi(e) ? 1 : 0) : 1; }
-    return v;
-}
 static int sweep_strict()
 {
     static int v = -1;
@@ -97,7 +91,7 @@ int pdm_launch_sweep_first(pdm_tile *t)
     int rc = wl::reset_queue(t);
     if (rc) return rc;
     const Win &w = t->win;
-    DrainOp<0> op{t->link, t->cell, nullptr, (int32_t)t->C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w, sweep_strict(), sweep_spec()};
+    DrainOp<0> op{t->link, t->cell, nullptr, (int32_t)t->C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w, sweep_strict()};
     wl::k_worklist<<<g_sweep_blocks, 256, 0, t->stream>>>(op, wl::DomainRange{w.lo * w.C, (w.hi - w.lo) * w.C},
                                                           wl::tuned(wl::Queue{t->queue, t->d_counters, (long long)t->N, t->d_counters + CT_SOURCES}));
     PDM_LAUNCHED();
@@ -113,7 +107,7 @@ int pdm_launch_sweep_resume(pdm_tile *t)
     }
     int rc = wl::reset_queue(t, 1);
     if (rc) return rc;
-    DrainOp<2> op{t->link, t->cell, nullptr, (int32_t)t->C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w, sweep_strict(), sweep_spec()};
+    DrainOp<2> op{t->link, t->cell, nullptr, (int32_t)t->C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w, sweep_strict()};
     wl::k_worklist<<<g_resume_blocks, 256, 0, t->stream>>>(op, wl::DomainList{t->label, t->d_counters + CT_TMP1},
                                                            wl::tuned(wl::Queue{t->queue, t->d_counters, (long long)t->N, t->d_counters + CT_TMP1}));
     PDM_LAUNCHED();

@@ -191,7 +191,7 @@ int pdm_launch_update(pdm_tile *t, const pdm_uca_params *p, const double *const 
     // sweep of the deltas (836-842)
     if ((rc = wl::reset_queue(t))) return rc;
     wl::k_worklist<<<g_blocks_drain1, 256, 0, t->stream>>>(
-        DrainOp<1>{t->link, t->cell, stt, (int32_t)C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w, 0, 0},
+        DrainOp<1>{t->link, t->cell, stt, (int32_t)C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w, 0},
         dom, q);
     PDM_LAUNCHED();
     PDM_CUDA(cudaMemcpyAsync(t->h_counters + CT_DRAINED, t->d_counters + CT_DRAINED, sizeof(unsigned long long),

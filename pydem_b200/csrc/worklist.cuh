@@ -283,9 +283,8 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
         int32_t defer = -1;  // second ready receiver: dealt to an idle lane of this warp or handed to the queue
         if (!scanning && (work_mask & (work_mask - 1)) == 0) {
             // express fast path: one lane has work and the warp has no seeds left to deal -> it
-            // follows the chain in a tight single-lane loop (no warp collectives between cells, the
-            // next cell's record carried in registers: the critical path pays one memory round trip
-            // per cell, DrainOp::step) until the chain ends or forks
+            // follows the chain in a tight single-lane loop (no warp collectives between cells:
+            // the critical path pays memory round trips only) until the chain ends or forks
             if (cur >= 0) {
                 const unsigned long long t0 = q.dbg ? globaltimer_ns() : 0;
                 const unsigned long long nc = op.chain(cur, defer, q);

@@ -1,0 +1,53 @@
+"""BASELINE.json configs[4] in miniature on one GPU: a ny x nx mosaic of tiles cut (with overlap)
+from one conditioned fractal, run through pydem_b200.process_manager.ProcessManager (the
+reference's ProcessManager semantics: per-tile stages + process_uca_edges corrections) with the
+CUDA operator.  Reports stage times and how the mosaic compares with the single-DEM result.
+    python scripts/run_mosaic.py [n=4096] [grid=4] [overlap=2] [--out gpurun_out/mosaic.json]"""
+import json, os, sys, time, warnings
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+from pydem_b200 import synth, DEMProcessor
+from pydem_b200.process_manager import ProcessManager, split_mosaic
+
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+n = int(args[0]) if len(args) > 0 else 4096
+grid = int(args[1]) if len(args) > 1 else 4
+ov = int(args[2]) if len(args) > 2 else 2
+out = os.path.join(ROOT, "gpurun_out", "mosaic.json")
+E = synth.conditioned_fractal_dem(n, 0)
+boxes = split_mosaic(E.shape, grid, grid, ov)
+kw = dict(fill_flats=False, drain_pits_path=False)
+sp = dict(dX=30.0, dY=30.0)
+res = dict(workload="%dx%d mosaic of %d tiles (%d px overlap) cut from the %dx%d conditioned fractal, fill_flats=False, "
+                    "drain_pits_path=False, drain_pits=True" % (grid, grid, len(boxes), ov, n, n), cells=int(E.size))
+with warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    for rep in range(2):            # first pass warms the pinned pools and the per-shape device tiles
+        pm = ProcessManager([E[b[0]:b[1], b[2]:b[3]] for b in boxes], boxes, spacing=sp, dem_proc_kwargs=kw)
+        pm.success[:, 0] = True     # elevation is already conditioned (what the reference's first stage would do)
+        t = {}
+        for name, fn in (("aspect_slope", pm.process_aspect_slope), ("uca", pm.process_uca), ("uca_edges", pm.process_uca_edges),
+                         ("twi", lambda: pm._stage(pm._twi, 3))):
+            torch.cuda.synchronize(); t0 = time.perf_counter(); fn(); torch.cuda.synchronize()
+            t[name] = (time.perf_counter() - t0) * 1e3
+    dp = DEMProcessor(elev=E, dX=30.0, dY=30.0, **kw)
+    torch.cuda.synchronize(); t0 = time.perf_counter(); dp.calc_twi(); torch.cuda.synchronize()
+    t_single = (time.perf_counter() - t0) * 1e3
+res["ms"] = t
+res["ms_total"] = sum(t.values())
+res["Mcells_s"] = E.size / res["ms_total"] / 1e3
+res["corrections"] = len(pm.correction_log)
+res["ms_single_tile_calc_twi"] = t_single
+m = pm.mosaic("uca")
+with np.errstate(invalid="ignore", divide="ignore"):
+    rel = np.abs(m - dp.uca) / np.abs(dp.uca)
+inner = rel[1:-1, 1:-1]
+res["mosaic_vs_single"] = dict(cells_within_1e9=float(np.mean(inner[np.isfinite(inner)] <= 1e-9)), max_rel=float(np.nanmax(inner)),
+                               note="the reference's tile-edge approximation makes the mosaic differ from the single-DEM "
+                                    "result on rough terrain (SURVEY.md 8e); equality holds on smooth surfaces (tests)")
+res["edge_todo_left"] = int(sum(int(tl.edge_todo.sum()) for tl in pm.tiles))
+print(json.dumps(res))
+os.makedirs(os.path.dirname(out), exist_ok=True)
+json.dump(res, open(out, "w"), indent=1)
