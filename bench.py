@@ -252,12 +252,28 @@ def gpu_arm(args):
         dt.upload(T.F_ELEV, E)
         stats = {}
 
+        sev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        stage_ms = {"slopes": [], "uca": [], "twi": []}
+
         def step():
+            sev[0].record()
             dt.slopes_directions()
-            st = dt.uca(drain_pits=pits_flag)
+            sev[1].record()
+            st = dt.uca(drain_pits=pits_flag)      # synchronises the stream (reads the sweep's counters)
+            sev[2].record()
             dt.twi()
+            sev[3].record()
             stats.update(st)
+            stage_ms["_pending"] = True
             return st
+
+        def collect_stage_times():
+            # called after the step's work has completed (the next uca() call or the final barrier syncs)
+            if stage_ms.pop("_pending", False):
+                sev[3].synchronize()
+                stage_ms["slopes"].append(sev[0].elapsed_time(sev[1]))
+                stage_ms["uca"].append(sev[1].elapsed_time(sev[2]))
+                stage_ms["twi"].append(sev[2].elapsed_time(sev[3]))
         cells_per_step = n * n
         workload = ("%dx%d fractal DEM (spectral synthesis, seed 0, H=0.8, 1..1001 m%s), dX=dY=30 m, "
                     "slope+aspect + UCA + TWI, %s (BASELINE.json configs[1], %s variant)"
@@ -294,6 +310,8 @@ def gpu_arm(args):
     ev0.record()
     for _ in range(args.steps):
         st = step()
+        if world == 1:
+            collect_stage_times()      # waits for the step's last (0.1 ms) kernel: steps are serial anyway
         sweep_ms.append(st.get("ms_sweep", 0.0) or (st.get("ms_sweep_first", 0.0) + st.get("ms_sweep_resume", 0.0)))
         sweep_kernel_ms.append(st.get("ms_sweep_kernel", 0.0))
     ev1.record()
@@ -365,6 +383,22 @@ def gpu_arm(args):
                                               "n_queue_items", "n_drained", "n_undone", "n_edge_todo") if k in stats},
     }
     if world == 1:
+        ms_sl, ms_u, ms_t = (float(np.mean(stage_ms[k])) for k in ("slopes", "uca", "twi"))
+        # BASELINE.json's metric names the stages separately: slope+aspect (calc_slopes_directions incl. the flat
+        # mask), UCA (graph + pit drains + sweep), TWI -- device-resident, CUDA events in the timed loop
+        line["per_stage"] = {
+            "slope_aspect": {"Mcells_s": cells_per_step / ms_sl / 1e3, "ms": ms_sl,
+                             "hbm_GBs_algorithmic": cells_per_step * 25.0 / (ms_sl * 1e-3) / 1e9,
+                             "frac_of_hbm_peak": cells_per_step * 25.0 / (ms_sl * 1e-3) / 1e9 / peak_gbs,
+                             "note": "25 B/cell: read elev 8, write mag 8 + direction 8 + flats 1; k_slopes is fp64-issue bound"},
+            "uca": {"Mcells_s": cells_per_step / ms_u / 1e3, "ms": ms_u,
+                    "hbm_GBs_algorithmic": cells_per_step * BYTES_PER_CELL / (ms_u * 1e-3) / 1e9,
+                    "frac_of_hbm_peak": cells_per_step * BYTES_PER_CELL / (ms_u * 1e-3) / 1e9 / peak_gbs},
+            "twi": {"Mcells_s": cells_per_step / ms_t / 1e3, "ms": ms_t,
+                    "hbm_GBs_algorithmic": cells_per_step * 32.0 / (ms_t * 1e-3) / 1e9,
+                    "frac_of_hbm_peak": cells_per_step * 32.0 / (ms_t * 1e-3) / 1e9 / peak_gbs,
+                    "note": "32 B/cell: read uca 8 + mag 8, write twi 8 + 10*twi 8"},
+        }
         line["cpu_baseline"] = cpu_baseline_leg(E)
     print(json.dumps(line), flush=True)
 

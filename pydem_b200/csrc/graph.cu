@@ -127,14 +127,20 @@ k_indeg(uint8_t *__restrict__ link, Win w, const double *__restrict__ row_area, 
         rec.link = link[n];
         if (own) {
             const bool up = w.row_in_grid(i - 1), dn = w.row_in_grid(i + 1), lf = j > 0, rt = j < C - 1;
-            if (lf) cnt += drains_in(link[n - 1], LK_KEEP1, 0x81u);             // W neighbour: e1 = (0,+1)
-            if (rt) cnt += drains_in(link[n + 1], LK_KEEP1, 0x18u);             // E: e1 = (0,-1)
-            if (up) cnt += drains_in(link[n - C], LK_KEEP1, 0x60u);             // N: e1 = (+1,0)
-            if (dn) cnt += drains_in(link[n + C], LK_KEEP1, 0x06u);             // S: e1 = (-1,0)
-            if (up && lf) cnt += drains_in(link[n - C - 1], LK_KEEP2, 0xC0u);   // NW: e2 = (+1,+1)
-            if (up && rt) cnt += drains_in(link[n - C + 1], LK_KEEP2, 0x30u);   // NE: e2 = (+1,-1)
-            if (dn && lf) cnt += drains_in(link[n + C - 1], LK_KEEP2, 0x03u);   // SW: e2 = (-1,+1)
-            if (dn && rt) cnt += drains_in(link[n + C + 1], LK_KEEP2, 0x0Cu);   // SE: e2 = (-1,-1)
+            // all eight neighbour bytes are loaded unconditionally (a missing neighbour reads the
+            // cell's own byte and is masked out), so the loads are independent and in flight together
+            // instead of eight load -> test -> branch round trips (0.44 -> 0.2x ms at 4096^2)
+            const int64_t dW = lf ? -1 : 0, dE = rt ? 1 : 0, dN = up ? -C : 0, dS = dn ? C : 0;
+            const uint8_t bW = link[n + dW], bE = link[n + dE], bN = link[n + dN], bS = link[n + dS];
+            const uint8_t bNW = link[n + dN + dW], bNE = link[n + dN + dE], bSW = link[n + dS + dW], bSE = link[n + dS + dE];
+            cnt += lf ? drains_in(bW, LK_KEEP1, 0x81u) : 0;                     // W neighbour: e1 = (0,+1)
+            cnt += rt ? drains_in(bE, LK_KEEP1, 0x18u) : 0;                     // E: e1 = (0,-1)
+            cnt += up ? drains_in(bN, LK_KEEP1, 0x60u) : 0;                     // N: e1 = (+1,0)
+            cnt += dn ? drains_in(bS, LK_KEEP1, 0x06u) : 0;                     // S: e1 = (-1,0)
+            cnt += (up && lf) ? drains_in(bNW, LK_KEEP2, 0xC0u) : 0;            // NW: e2 = (+1,+1)
+            cnt += (up && rt) ? drains_in(bNE, LK_KEEP2, 0x30u) : 0;            // NE: e2 = (+1,-1)
+            cnt += (dn && lf) ? drains_in(bSW, LK_KEEP2, 0x03u) : 0;            // SW: e2 = (-1,+1)
+            cnt += (dn && rt) ? drains_in(bSE, LK_KEEP2, 0x0Cu) : 0;            // SE: e2 = (-1,-1)
             if (pit_in) cnt += pit_in[n];
             rec.indeg = cnt;
             rec.area = __ldg(row_area + i);                                     // 885, 901

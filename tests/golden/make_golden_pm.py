@@ -35,7 +35,7 @@ def main():
         with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
             warnings.simplefilter("ignore")
             r = H.run_reference_pm(E, nx, ny, ov, name, dem_proc_kwargs=kw)
-            if name.startswith("cone"):
+            if name.startswith("cone") and ov >= 1:      # the reference's own tilings all overlap
                 dp = ref.DEMProcessor(elev=E.copy(), **kw)
                 dp.dX[:] = 1; dp.dY[:] = 1; dp.dX2[:] = 1; dp.dY2[:] = 1
                 dp.calc_twi()

@@ -178,6 +178,13 @@ def pm_cases():
         c["cone_%dx%d_%doverlap" % (nx, ny, ov)] = (cone, nx, ny, ov, {})
     c["fractal_3x3_2overlap"] = (frac, 3, 3, 2, {})
     c["fractal_2x3_1overlap"] = (frac, 2, 3, 1, {})
+    # beyond the reference's own tilings: no overlap at all, single rows / columns of tiles, wide overlap, flags
+    c["cone_3x3_0overlap"] = (cone, 3, 3, 0, {})
+    c["fractal_2x2_0overlap"] = (frac, 2, 2, 0, {})
+    c["fractal_4x1_2overlap"] = (frac, 4, 1, 2, {})
+    c["fractal_1x3_4overlap"] = (frac, 1, 3, 4, {})
+    c["fractal_3x3_2overlap_nopits"] = (frac, 3, 3, 2, dict(drain_pits=False))
+    c["fractal_2x2_2overlap_limits"] = (frac, 2, 2, 2, dict(apply_uca_limit_edges=True, apply_twi_limits=True, apply_twi_limits_on_uca=True))
     return c
 
 
