@@ -96,15 +96,27 @@ struct DrainOp {
         // `strict` (PYDEM_B200_SWEEP_STRICT=1) makes the decrement's operand depend on the adds'
         // return values -- a comparison ptxas cannot fold -- for cross-checking: one more round
         // trip per cell.
-        double a1 = 0.0, a2 = 0.0, u1 = 0.0, u2 = 0.0;
-        if (k1) a1 = atomicAdd(&cell[r1].area, __dmul_rn(ai, p));               // cyutils.pyx:161
-        if (k2) a2 = atomicAdd(&cell[r2].area, __dmul_rn(ai, w2));
-        if (MODE != 1 && ti != 0.0) {                                           // cyutils.pyx:163-164
-            if (k1) u1 = atomicAdd(&cell[r1].taint, __dmul_rn(ti, p));
-            if (k2) u2 = atomicAdd(&cell[r2].taint, __dmul_rn(ti, w2));
-        }
         int one = 1;
-        if (strict) {
+        if (!strict) {
+            // results unused: nothing waits for the adds (they must not share code with the strict
+            // branch -- a returning add whose value is touched only under `if (strict)` still had
+            // its high word moved right behind it by the compiler, which made every step wait for
+            // the add before issuing the decrement: three round trips instead of two, seen in the
+            // ncu source view as a stall on the move, 1.03 -> 1.43 us per chain cell)
+            if (k1) atomicAdd(&cell[r1].area, __dmul_rn(ai, p));                // cyutils.pyx:161
+            if (k2) atomicAdd(&cell[r2].area, __dmul_rn(ai, w2));
+            if (MODE != 1 && ti != 0.0) {                                       // cyutils.pyx:163-164
+                if (k1) atomicAdd(&cell[r1].taint, __dmul_rn(ti, p));
+                if (k2) atomicAdd(&cell[r2].taint, __dmul_rn(ti, w2));
+            }
+        } else {
+            double a1 = 0.0, a2 = 0.0, u1 = 0.0, u2 = 0.0;
+            if (k1) a1 = atomicAdd(&cell[r1].area, __dmul_rn(ai, p));
+            if (k2) a2 = atomicAdd(&cell[r2].area, __dmul_rn(ai, w2));
+            if (MODE != 1 && ti != 0.0) {
+                if (k1) u1 = atomicAdd(&cell[r1].taint, __dmul_rn(ti, p));
+                if (k2) u2 = atomicAdd(&cell[r2].taint, __dmul_rn(ti, w2));
+            }
             const int NEVER = 0x7ff4dead;   // high word of a signalling NaN no sum produces
             one += (__double2hiint(a1) == NEVER) | (__double2hiint(a2) == NEVER) | (__double2hiint(u1) == NEVER) |
                    (__double2hiint(u2) == NEVER);
