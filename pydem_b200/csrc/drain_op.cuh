@@ -27,6 +27,24 @@ __device__ __forceinline__ uint32_t st_fetch_or(uint8_t *st, int32_t cell, uint3
 
 //   MODE 2: resumed full sweep of a shard: like MODE 0, but the seeds come from an explicit list
 //           (cells whose last upstream contribution arrived from a neighbouring rank).
+// Predicated atomics without branches.  Written as inline PTX so that the step below stays
+// straight-line code: with `if (k1) o1 = atomicSub(..); if (k2) o2 = atomicSub(..);` the compiler
+// wrapped each atomic in its own branch region and placed the test of the first result inside it,
+// i.e. the second decrement was only issued after the first had returned (seen in SASS: ATOMG, ISETP
+// on its result, then the next ATOMG) -- three dependent round trips per cell instead of two.
+__device__ __forceinline__ void red_add_f64_if(bool on, double *addr, double v)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t@q red.global.add.f64 [%1], %2;\n\t}"
+                 :: "r"((int)on), "l"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ int atom_add_s32_if(bool on, int32_t *addr, int v)
+{
+    int old = 0;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q atom.global.add.s32 %0, [%2], %3;\n\t}"
+                 : "+r"(old) : "r"((int)on), "l"(addr), "r"(v) : "memory");
+    return old;
+}
+
 template <int MODE>
 struct DrainOp {
     const uint8_t *link;   // SoA copy of the link bytes: only the seed scan reads it
@@ -97,19 +115,20 @@ struct DrainOp {
         // return values -- a comparison ptxas cannot fold -- for cross-checking: one more round
         // trip per cell.
         int one = 1;
+        int o1 = 0, o2 = 0;
         if (!strict) {
-            // results unused: nothing waits for the adds (they must not share code with the strict
-            // branch -- a returning add whose value is touched only under `if (strict)` still had
-            // its high word moved right behind it by the compiler, which made every step wait for
-            // the add before issuing the decrement: three round trips instead of two, seen in the
-            // ncu source view as a stall on the move, 1.03 -> 1.43 us per chain cell)
-            if (k1) atomicAdd(&cell[r1].area, __dmul_rn(ai, p));                // cyutils.pyx:161
-            if (k2) atomicAdd(&cell[r2].area, __dmul_rn(ai, w2));
-            if (MODE != 1 && ti != 0.0) {                                       // cyutils.pyx:163-164
-                if (k1) atomicAdd(&cell[r1].taint, __dmul_rn(ti, p));
-                if (k2) atomicAdd(&cell[r2].taint, __dmul_rn(ti, w2));
-            }
+            // straight-line: four adds without a result, then both decrements, then the tests
+            const bool tt = MODE != 1 && ti != 0.0;                                         // cyutils.pyx:163-164
+            red_add_f64_if(k1, &cell[r1].area, __dmul_rn(ai, p));                           // cyutils.pyx:161
+            red_add_f64_if(k2, &cell[r2].area, __dmul_rn(ai, w2));
+            red_add_f64_if(k1 && tt, &cell[r1].taint, __dmul_rn(ti, p));
+            red_add_f64_if(k2 && tt, &cell[r2].taint, __dmul_rn(ti, w2));
+            o1 = atom_add_s32_if(k1, &cell[r1].indeg, -1);
+            o2 = atom_add_s32_if(k2, &cell[r2].indeg, -1);
         } else {
+            // cross-check: every decrement waits for the adds' return values (a comparison ptxas
+            // cannot fold); kept apart from the normal path on purpose -- sharing the adds made the
+            // compiler touch their return values in the normal path as well
             double a1 = 0.0, a2 = 0.0, u1 = 0.0, u2 = 0.0;
             if (k1) a1 = atomicAdd(&cell[r1].area, __dmul_rn(ai, p));
             if (k2) a2 = atomicAdd(&cell[r2].area, __dmul_rn(ai, w2));
@@ -118,12 +137,11 @@ struct DrainOp {
                 if (k2) u2 = atomicAdd(&cell[r2].taint, __dmul_rn(ti, w2));
             }
             const int NEVER = 0x7ff4dead;   // high word of a signalling NaN no sum produces
-            one += (__double2hiint(a1) == NEVER) | (__double2hiint(a2) == NEVER) | (__double2hiint(u1) == NEVER) |
-                   (__double2hiint(u2) == NEVER);
+            const int one = 1 + ((__double2hiint(a1) == NEVER) | (__double2hiint(a2) == NEVER) | (__double2hiint(u1) == NEVER) |
+                                 (__double2hiint(u2) == NEVER));
+            if (k1) o1 = atomicSub(&cell[r1].indeg, one);
+            if (k2) o2 = atomicSub(&cell[r2].indeg, one);
         }
-        int o1 = 0, o2 = 0;
-        if (k1) o1 = atomicSub(&cell[r1].indeg, one);
-        if (k2) o2 = atomicSub(&cell[r2].indeg, one);
         const bool rdy1 = k1 && o1 == 1, rdy2 = k2 && o2 == 1;
         if (rdy1 && rdy2) {
             // follow the larger share, hand the other receiver to an idle lane
