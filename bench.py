@@ -404,7 +404,7 @@ def gpu_arm(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the sweep kernel, one launch (profiles/, per size)
-PROFILE_TRAFFIC = {4096: 1.333e9}   # profiles/r1_sweep_4096_conditioned_ncu_full.csv: 819 MB read + 514 MB written
+PROFILE_TRAFFIC = {4096: 1.345e9}   # profiles/r1_sweep_4096_conditioned_ncu_full.csv: 831 MB read + 514 MB written
 
 
 def main():

@@ -373,14 +373,15 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
 // (facets table dem_processing.py:173-182)
 __device__ __forceinline__ int32_t off_e1(int sec, int32_t C)
 {
-    const int r = (sec == 1 || sec == 2) ? -1 : ((sec == 5 || sec == 6) ? 1 : 0);
-    const int c = (sec == 0 || sec == 7) ? 1 : ((sec == 3 || sec == 4) ? -1 : 0);
+    // rows {0,-1,-1,0,0,1,1,0}, columns {1,0,0,-1,-1,0,0,1} as two packed 2-bit tables (value + 1)
+    const int r = ((0x6941 >> (2 * sec)) & 3) - 1;
+    const int c = ((0x9416 >> (2 * sec)) & 3) - 1;
     return r * C + c;
 }
 __device__ __forceinline__ int32_t off_e2(int sec, int32_t C)
 {
-    const int r = (sec < 4) ? -1 : 1;
-    const int c = (sec <= 1 || sec >= 6) ? 1 : -1;
+    const int r = ((sec >> 1) & 2) - 1;             // -1 for facets 0..3, +1 for 4..7
+    const int c = 1 - (((sec + 2) >> 1) & 2);       // +1 for facets 0,1,6,7, -1 for 2..5
     return r * C + c;
 }
 // host: tunables / diagnostics of a run (environment, read once)
