@@ -13,6 +13,16 @@ double-count rule) and ``calc_twi`` (:296), and the serial scheduling loop of
 * the ``DEMProcessor`` is this package's CUDA operator (any class with the reference's operator
   surface can be passed, which is how the CPU tests run the same orchestrator on the oracle).
 
+Tile-parallel mode (``group=``): the tiles are dealt round-robin to the ranks of a
+``torch.distributed`` job (one GPU each).  A rank keeps full arrays only for its own tiles; of the
+other tiles it keeps the edge rings (the strips within overlap distance of a tile edge -- all a
+neighbour ever reads, see ``_RingArray``), refreshed with one ``all_gather_object`` per stage /
+correction round.  The one-pixel-overlap patch of ``calc_uca`` is order dependent and only touches
+edge cells, so every rank replays it for all tiles on the rings (bit-identical to the serial
+order); corrections run in rounds of non-adjacent tiles that tie for the best metric
+(``process_uca_edges_rounds``), whose result does not depend on the number of ranks and equals
+the reference's serial loop on every pinned case.
+
 The reference's own orchestrator, run unmodified over in-memory stand-ins for zarr/rasterio
 (``oracle/ref_pm_harness.py``), produced ``tests/golden/ref_pm.npz``; ``tests/test_process_manager.py``
 compares this module against it array by array (aspect, slope, uca, uca_edges, edge masks, twi,
@@ -45,9 +55,82 @@ def split_mosaic(shape, ny_grid, nx_grid, overlap):
     return [(r0, r1, c0, c1) for (r0, r1) in cuts(shape[0], ny_grid) for (c0, c1) in cuts(shape[1], nx_grid)]
 
 
+class _RingArray(object):
+    """The part of a remote tile's result array that neighbours read: the first / last `w` rows and
+    columns.  Supports exactly the accesses of the orchestrator (a row or column of the ring, a
+    corner), reading and writing; corner cells live in a row strip and a column strip and are kept
+    consistent on writes."""
+
+    def __init__(self, shape, w, dtype):
+        self.shape = tuple(shape); self.w = int(w); self.dtype = np.dtype(dtype)
+        R, C = self.shape
+        w = min(self.w, R, C)
+        self.w = w
+        self.top = np.zeros((w, C), self.dtype); self.bottom = np.zeros((w, C), self.dtype)
+        self.left = np.zeros((R, w), self.dtype); self.right = np.zeros((R, w), self.dtype)
+
+    @classmethod
+    def of(cls, a, w):
+        r = cls(a.shape, w, a.dtype)
+        w = r.w
+        r.top[:] = a[:w]; r.bottom[:] = a[-w:]; r.left[:] = a[:, :w]; r.right[:] = a[:, -w:]
+        return r
+
+    def strips(self):
+        return (self.top, self.bottom, self.left, self.right)
+
+    def set_strips(self, st):
+        self.top[:], self.bottom[:], self.left[:], self.right[:] = st
+
+    def _norm(self, key):
+        r, c = key
+        R, C = self.shape
+        if isinstance(r, (int, np.integer)) and r < 0: r += R
+        if isinstance(c, (int, np.integer)) and c < 0: c += C
+        return r, c
+
+    def _row(self, r):
+        R = self.shape[0]
+        if r < self.w: return self.top, r
+        if r >= R - self.w: return self.bottom, r - (R - self.w)
+        raise IndexError("row %d is not in the edge ring (width %d)" % (r, self.w))
+
+    def _col(self, c):
+        C = self.shape[1]
+        if c < self.w: return self.left, c
+        if c >= C - self.w: return self.right, c - (C - self.w)
+        raise IndexError("column %d is not in the edge ring (width %d)" % (c, self.w))
+
+    def __getitem__(self, key):
+        r, c = self._norm(key)
+        if isinstance(r, slice):
+            a, k = self._col(c)
+            return a[r, k]
+        a, k = self._row(r)
+        return a[k, c]
+
+    def __setitem__(self, key, value):
+        r, c = self._norm(key)
+        R, C = self.shape
+        w = self.w
+        if isinstance(r, slice):                      # a whole column of the ring
+            a, k = self._col(c)
+            a[r, k] = value
+            col = a[:, k]
+            self.top[:, c] = col[:w]; self.bottom[:, c] = col[R - w:]
+        elif isinstance(c, slice):                    # a whole row
+            a, k = self._row(r)
+            a[k, c] = value
+            row = a[k]
+            self.left[r, :] = row[:w]; self.right[r, :] = row[C - w:]
+        else:                                         # one cell (a corner of the tile)
+            a, k = self._row(r); a[k, c] = value
+            a, k = self._col(c); a[r, k] = value
+
+
 class _Tile(object):
     __slots__ = ("box", "gi", "gj", "elev", "dX", "dY", "dX2", "dY2", "aspect", "slope", "uca", "uca_edges",
-                 "edge_todo", "edge_done", "twi", "trim", "edge_src")
+                 "edge_todo", "edge_done", "twi", "trim", "edge_src", "owner", "shape")
 
 
 class ProcessManager(object):
@@ -58,7 +141,13 @@ class ProcessManager(object):
     per-tile arrays.  dem_proc_kwargs: flags forwarded to every DEMProcessor (reference trait of
     the same name).  dem_processor: operator class (default: the CUDA DEMProcessor)."""
 
-    def __init__(self, tiles, boxes, spacing=None, dem_proc_kwargs=None, dem_processor=None, n_workers=1):
+    def __init__(self, tiles, boxes, spacing=None, dem_proc_kwargs=None, dem_processor=None, n_workers=1, group=None):
+        """group: None (one process) or an object with `rank`, `world` and `all_gather(obj) -> list`
+        (see `TorchGroup`); tile k belongs to rank k % world.  Every rank passes the same `boxes`;
+        a rank may pass None for the elevation of tiles it does not own."""
+        self.group = group
+        self.rank = 0 if group is None else int(group.rank)
+        self.world = 1 if group is None else int(group.world)
         if dem_processor is None:
             from .dem_processing import DEMProcessor as dem_processor
         self.DEMProcessor = dem_processor
@@ -70,11 +159,16 @@ class ProcessManager(object):
         for k, (e, b) in enumerate(zip(tiles, boxes)):
             t = _Tile()
             t.box = tuple(int(v) for v in b)
-            t.elev = np.array(e, dtype="float64")
-            if t.elev.shape != (t.box[1] - t.box[0], t.box[3] - t.box[2]):
-                raise ValueError("tile %d: shape %s does not match its box %s" % (k, t.elev.shape, t.box))
+            t.owner = k % self.world
+            t.shape = (t.box[1] - t.box[0], t.box[3] - t.box[2])
+            if t.owner == self.rank:
+                t.elev = np.array(e, dtype="float64")
+                if t.elev.shape != t.shape:
+                    raise ValueError("tile %d: shape %s does not match its box %s" % (k, t.elev.shape, t.box))
+            else:
+                t.elev = None
             sp = (spacing[k] if isinstance(spacing, (list, tuple)) else spacing) or {}
-            R = t.elev.shape[0]
+            R = t.shape[0]
             t.dX = np.ones(R - 1) * sp.get("dX", 1.0); t.dY = np.ones(R - 1) * sp.get("dY", 1.0)
             t.dX2 = np.ones(R) * sp.get("dX2", sp.get("dX", 1.0)) if not isinstance(sp.get("dX2"), np.ndarray) else sp["dX2"]
             t.dY2 = np.ones(R) * sp.get("dY2", sp.get("dY", 1.0)) if not isinstance(sp.get("dY2"), np.ndarray) else sp["dY2"]
@@ -87,6 +181,15 @@ class ProcessManager(object):
         self.correction_log = []       # tiles in the order process_uca_edges corrected them
         self.compute_grid()
         self.compute_grid_overlaps()
+        # ring width: the farthest a neighbour reaches into a tile (the larger overlap, at least 1)
+        self.ring_w = 1
+        for t in self.tiles:
+            for (di, dj, ax) in ((0, -1, 1), (0, 1, 1), (-1, 0, 0), (1, 0, 0)):
+                o = self._nb(t, di, dj)
+                if o is not None:
+                    shared = (o.box[3] - t.box[2]) if dj < 0 else (t.box[3] - o.box[2]) if dj > 0 else \
+                             (o.box[1] - t.box[0]) if di < 0 else (t.box[1] - o.box[0])
+                    self.ring_w = max(self.ring_w, int(shared))
 
     # ------------------------------------------------------------------------------------
     # geometry (process_manager.py:517-740)
@@ -105,7 +208,7 @@ class ProcessManager(object):
             self.grid_id2i[t.gi, t.gj] = i
         for i, t in enumerate(self.tiles):      # a grid row has one height, a grid column one width (:537-545)
             for o in self.tiles:
-                if o.gi == t.gi and o.elev.shape[0] != t.elev.shape[0] or o.gj == t.gj and o.elev.shape[1] != t.elev.shape[1]:
+                if o.gi == t.gi and o.shape[0] != t.shape[0] or o.gj == t.gj and o.shape[1] != t.shape[1]:
                     raise ValueError("tiles of one grid row / column must have the same number of rows / columns")
 
     def _nb(self, t, di, dj):
@@ -123,7 +226,7 @@ class ProcessManager(object):
 
     def compute_grid_overlaps(self):
         for t in self.tiles:
-            R, C = t.elev.shape
+            R, C = t.shape
             lf, rt, up, dn = self._nb(t, 0, -1), self._nb(t, 0, 1), self._nb(t, -1, 0), self._nb(t, 1, 0)
             c_lo, c_lo_e = self._overlap(lf.box[3] - t.box[2], 0) if lf else (0, 0)
             c_hi, c_hi_e = self._overlap(t.box[3] - rt.box[2], 1) if rt else (0, 0)
@@ -148,14 +251,14 @@ class ProcessManager(object):
                 o = self._nb(t, sdi, sdj) if (sdi or sdj) else t
                 if o is None:
                     return (None, 0, 0)
-                oR, oC = o.elev.shape
+                oR, oC = o.shape
                 rr = (oR - re if di < 0 else re - 1) if sdi else own_r
                 cc = (oC - ce if dj < 0 else ce - 1) if sdj else own_c
                 return (o, rr, cc)
             t.edge_src = {
-                "left": src(0, -1 if c_lo_e else 0, slice(0, None), (lf.elev.shape[1] - c_lo_e) if c_lo_e else 0),
+                "left": src(0, -1 if c_lo_e else 0, slice(0, None), (lf.shape[1] - c_lo_e) if c_lo_e else 0),
                 "right": src(0, 1 if c_hi_e else 0, slice(0, None), (c_hi_e - 1) if c_hi_e else C - 1),
-                "top": src(-1 if r_lo_e else 0, 0, (up.elev.shape[0] - r_lo_e) if r_lo_e else 0, slice(0, None)),
+                "top": src(-1 if r_lo_e else 0, 0, (up.shape[0] - r_lo_e) if r_lo_e else 0, slice(0, None)),
                 "bottom": src(1 if r_hi_e else 0, 0, (r_hi_e - 1) if r_hi_e else R - 1, slice(0, None)),
                 "top-left": corner(tl, -1, -1, r_lo_e, c_lo_e, 0, 0),
                 "top-right": corner(tr, -1, 1, r_lo_e, c_hi_e, 0, C - 1),
@@ -178,7 +281,7 @@ class ProcessManager(object):
         o, rr, cc = t.edge_src[key]
         if o is None:
             return np.zeros((), dtype=getattr(t, field).dtype)[()] if key in CORNERS else np.zeros(
-                t.elev.shape[0] if key in ("left", "right") else t.elev.shape[1], dtype=getattr(t, field).dtype)
+                t.shape[0] if key in ("left", "right") else t.shape[1], dtype=getattr(t, field).dtype)
         a = getattr(o, field)
         v = a[rr, cc]
         return np.array(v) if isinstance(v, np.ndarray) else v
@@ -214,13 +317,18 @@ class ProcessManager(object):
     def _east_west(d):
         return ((d < 1e-6) & (d >= 0)) | (np.abs(d - np.pi * 2) < 1e-6)
 
-    def _uca(self, t):                                          # calc_uca :94-197
-        direction = t.aspect.copy(); mag = t.slope.copy()
+    def _patch_edges(self, t):
+        """The one-pixel-overlap patch of calc_uca (:109-180): where this tile's edge is also the
+        neighbour's edge, cells whose flow LEAVES through that edge (and flats) take the neighbour's
+        direction and magnitude, which were computed with the cells beyond the edge in view.  Works
+        in place on t.aspect / t.slope -- full arrays for own tiles, edge rings for remote ones --
+        in the reference's order: four sides, then four corners."""
+        A, S = t.aspect, t.slope
         one = t.edge_src["_one"]
         for key in SIDES:
             if not one[key]:
                 continue
-            d = direction[EDGE[key]]                            # a view: edits land in `direction`
+            d = np.array(A[EDGE[key]]); m = np.array(S[EDGE[key]])
             ids = self._leaves(d, key)                          # only edges the flow leaves through
             if key in ("top", "bottom"):
                 ids = ids | self._east_west(d)
@@ -230,21 +338,19 @@ class ProcessManager(object):
             ids[0] = ids[0] & (not bool(self._leaves(d[0:1], other[0])[0]))
             ids[-1] = ids[-1] & (not bool(self._leaves(d[-1:], other[1])[0]))
             nb_a = self._edge(t, key, "aspect"); nb_s = self._edge(t, key, "slope")
-            m = mag[EDGE[key]]
             d[ids] = nb_a[ids]; m[ids] = nb_s[ids]
-            t.aspect[EDGE[key]] = d; t.slope[EDGE[key]] = m     # the stored fields are patched too (:149-150)
+            A[EDGE[key]] = d; S[EDGE[key]] = m                  # the stored fields are patched (:149-150)
         for key in CORNERS:
             if not one[key]:
                 continue
             ktb, klr = key.split("-")
-            d = direction[EDGE[key]]
-            da = np.array([d])
-            ids = bool((self._leaves(da, klr) & (self._leaves(da, ktb) | self._east_west(da)))[0])
-            if not ids:
+            da = np.array([A[EDGE[key]]])
+            if not bool((self._leaves(da, klr) & (self._leaves(da, ktb) | self._east_west(da)))[0]):
                 continue
-            direction[EDGE[key]] = self._edge(t, key, "aspect"); mag[EDGE[key]] = self._edge(t, key, "slope")
-            t.aspect[EDGE[key]] = direction[EDGE[key]]; t.slope[EDGE[key]] = mag[EDGE[key]]
-        dp = self._dp(t, direction=direction, mag=mag, fill_flats=False)
+            A[EDGE[key]] = self._edge(t, key, "aspect"); S[EDGE[key]] = self._edge(t, key, "slope")
+
+    def _uca(self, t):                                          # calc_uca :94-197 (after _patch_edges)
+        dp = self._dp(t, direction=t.aspect.copy(), mag=t.slope.copy(), fill_flats=False)
         dp.find_flats()
         dp.calc_uca()
         t.uca = np.array(dp.uca, dtype="float64")
@@ -293,21 +399,56 @@ class ProcessManager(object):
     # ------------------------------------------------------------------------------------
     # stages (process_manager.py:993-1316)
     # ------------------------------------------------------------------------------------
+    def _mine(self, t):
+        return t.owner == self.rank
+
+    def _sync(self, fields, index=None):
+        """Refresh the edge rings of the tiles in `index` (default: all) on the ranks that do not own
+        them: one all_gather of the owners' strips."""
+        if self.group is None:
+            return
+        index = range(self.n_inputs) if index is None else index
+        mine = {}
+        for i in index:
+            t = self.tiles[i]
+            if self._mine(t):
+                mine[i] = {f: _RingArray.of(getattr(t, f), self.ring_w).strips() for f in fields}
+        for part in self.group.all_gather(mine):
+            for i, fs in part.items():
+                t = self.tiles[i]
+                if self._mine(t):
+                    continue
+                for f, st in fs.items():
+                    ra = getattr(t, f)
+                    if not isinstance(ra, _RingArray):
+                        ra = _RingArray(t.shape, self.ring_w, st[0].dtype)
+                        setattr(t, f, ra)
+                    ra.set_strips(st)
+
     def _stage(self, fn, col):
         for i, t in enumerate(self.tiles):
-            if not self.success[i, col]:
+            if self._mine(t) and not self.success[i, col]:
                 fn(t)
-                self.success[i, col] = True
+            self.success[i, col] = True
         return self.success[:, col].copy()
 
     def process_elevation(self):
         return self._stage(self._elev_cond, 0)
 
     def process_aspect_slope(self):
-        return self._stage(self._aspect_slope, 1)
+        r = self._stage(self._aspect_slope, 1)
+        self._sync(("aspect", "slope"))
+        return r
 
     def process_uca(self):
-        return self._stage(self._uca, 2)
+        # the edge patch is order dependent (a tile reads what earlier tiles patched) and only touches
+        # edge cells: every rank replays it for all tiles, on full arrays or rings
+        if not self.success[:, 2].all():
+            for t in self.tiles:
+                self._patch_edges(t)
+        r = self._stage(self._uca, 2)
+        self._sync(("uca", "uca_edges", "edge_todo", "edge_done"))
+        return r
 
     def update_uca_edge_metrics(self, index=None):
         for i in (range(self.n_inputs) if index is None else index):
@@ -323,6 +464,8 @@ class ProcessManager(object):
         """Serial correction loop (:1090-1189, n_workers == 1): correct the tile whose inflow edges
         are most complete, refresh the metrics of that tile and its four neighbours, stop when the
         ranking no longer changes."""
+        if self.world > 1:
+            raise RuntimeError("the reference's serial correction loop runs on one rank; use process_uca_edges_rounds()")
         mets = self.update_uca_edge_metrics()
         I = self._order(mets, mets_type)
         I_old = np.zeros_like(I)
@@ -343,11 +486,55 @@ class ProcessManager(object):
             I = self._order(mets, mets_type)
         return mets
 
-    def process_twi(self):
+    def process_uca_edges_rounds(self, max_rounds=100000):
+        """Corrections in rounds: every round corrects the tiles that TIE for the best metric (share of
+        inflow edges whose neighbour is done) and are pairwise non-adjacent (8-neighbourhood), so
+        that no corrected tile reads another one of the same round -- the round equals correcting
+        its tiles one after the other, on one rank or spread over many.
+
+        The reference's correction scheme is order dependent: a tile corrected while a better
+        candidate exists can end with different (wrong) values -- measured on the pinned cases,
+        "every tile with a resolvable edge" or "within half of the best metric" per round changed
+        up to 168 interior cells, while ties-only reproduces the reference's serial loop on all of
+        them.  The price is little parallelism in this stage (19 rounds for 24 corrections on the
+        5x4 cone); the stages before and after it are independent per tile."""
+        rounds = 0
+        while rounds < max_rounds:
+            mets = self.update_uca_edge_metrics()
+            cand = [int(k) for k in np.argsort(-mets[:, 0], kind="stable") if mets[k, 1] > 0]
+            if not cand:
+                break
+            best = mets[cand[0], 0]
+            cand = [k for k in cand if mets[k, 0] >= best - 1e-12]
+            chosen, blocked = [], set()
+            for k in cand:
+                if k in blocked:
+                    continue
+                chosen.append(k)
+                t = self.tiles[k]
+                for di in (-1, 0, 1):
+                    for dj in (-1, 0, 1):
+                        o = self._nb(t, di, dj) if (di or dj) else t
+                        if o is not None:
+                            blocked.add(self.tiles.index(o))
+            for k in chosen:
+                if self._mine(self.tiles[k]):
+                    self._uca_ec(self.tiles[k])
+            self._sync(("uca_edges", "edge_todo", "edge_done"), chosen)
+            self.correction_log.append(tuple(chosen))
+            rounds += 1
+        return self.update_uca_edge_metrics()
+
+    def process_twi(self, rounds=None):
+        """The whole pipeline.  rounds: correct in rounds of independent tiles instead of the
+        reference's one-tile-at-a-time loop (default: only when running on several ranks)."""
         self.process_elevation()
         self.process_aspect_slope()
         self.process_uca()
-        self.process_uca_edges()
+        if rounds or (rounds is None and self.world > 1):
+            self.process_uca_edges_rounds()
+        else:
+            self.process_uca_edges()
         return self._stage(self._twi, 3)
 
     # ------------------------------------------------------------------------------------
@@ -355,14 +542,37 @@ class ProcessManager(object):
     # ------------------------------------------------------------------------------------
     def mosaic(self, key):
         """The non-overlapping mosaic of a result (save_non_overlap_data :742-784): every tile
-        contributes the part it does not share, `uca` includes the edge corrections."""
+        contributes the part it does not share, `uca` includes the edge corrections.  On several
+        ranks the pieces are gathered and every rank returns the whole mosaic."""
         R = max(t.box[1] for t in self.tiles); C = max(t.box[3] for t in self.tiles)
-        out = np.full((R, C), np.nan)
+        pieces = []
         for t in self.tiles:
+            if not self._mine(t):
+                continue
             a = getattr(t, key)
             if key == "uca":
                 a = a + t.uca_edges
             r_lo, r_hi, c_lo, c_hi = t.trim
-            nr, nc = t.elev.shape
-            out[t.box[0] + r_lo:t.box[1] - r_hi, t.box[2] + c_lo:t.box[3] - c_hi] = a[r_lo:nr - r_hi, c_lo:nc - c_hi]
+            nr, nc = t.shape
+            pieces.append(((t.box[0] + r_lo, t.box[1] - r_hi, t.box[2] + c_lo, t.box[3] - c_hi), a[r_lo:nr - r_hi, c_lo:nc - c_hi]))
+        if self.group is not None:
+            pieces = [p for part in self.group.all_gather(pieces) for p in part]
+        out = np.full((R, C), np.nan)
+        for (r0, r1, c0, c1), a in pieces:
+            out[r0:r1, c0:c1] = a
+        return out
+
+
+class TorchGroup(object):
+    """The ranks of a torch.distributed job (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self._dist = dist
+        self.rank = dist.get_rank()
+        self.world = dist.get_world_size()
+
+    def all_gather(self, obj):
+        out = [None] * self.world
+        self._dist.all_gather_object(out, obj)
         return out

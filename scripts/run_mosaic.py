@@ -2,20 +2,32 @@
 from one conditioned fractal, run through pydem_b200.process_manager.ProcessManager (the
 reference's ProcessManager semantics: per-tile stages + process_uca_edges corrections) with the
 CUDA operator.  Reports stage times and how the mosaic compares with the single-DEM result.
-    python scripts/run_mosaic.py [n=4096] [grid=4] [overlap=2] [--out gpurun_out/mosaic.json]"""
+    python scripts/run_mosaic.py [n=4096] [grid=4] [overlap=2]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/run_mosaic.py ...   (tiles dealt to N GPUs)
+Writes gpurun_out/mosaic.json (mosaic_n<N>.json under torchrun)."""
 import json, os, sys, time, warnings
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
 import torch
-from pydem_b200 import synth, DEMProcessor
-from pydem_b200.process_manager import ProcessManager, split_mosaic
+from pydem_b200 import synth, DEMProcessor, _lib
+from pydem_b200.process_manager import ProcessManager, TorchGroup, split_mosaic
+
+world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+_lib.init(local)
+group = None
+if world > 1:
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    group = TorchGroup()
 
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
 n = int(args[0]) if len(args) > 0 else 4096
 grid = int(args[1]) if len(args) > 1 else 4
 ov = int(args[2]) if len(args) > 2 else 2
-out = os.path.join(ROOT, "gpurun_out", "mosaic.json")
+out = os.path.join(ROOT, "gpurun_out", "mosaic.json" if world == 1 else "mosaic_n%d.json" % world)
 E = synth.conditioned_fractal_dem(n, 0)
 boxes = split_mosaic(E.shape, grid, grid, ov)
 kw = dict(fill_flats=False, drain_pits_path=False)
@@ -25,12 +37,15 @@ res = dict(workload="%dx%d mosaic of %d tiles (%d px overlap) cut from the %dx%d
 with warnings.catch_warnings():
     warnings.simplefilter("ignore")
     for rep in range(2):            # first pass warms the pinned pools and the per-shape device tiles
-        pm = ProcessManager([E[b[0]:b[1], b[2]:b[3]] for b in boxes], boxes, spacing=sp, dem_proc_kwargs=kw)
+        pm = ProcessManager([E[b[0]:b[1], b[2]:b[3]] for b in boxes], boxes, spacing=sp, dem_proc_kwargs=kw, group=group)
         pm.success[:, 0] = True     # elevation is already conditioned (what the reference's first stage would do)
         t = {}
-        for name, fn in (("aspect_slope", pm.process_aspect_slope), ("uca", pm.process_uca), ("uca_edges", pm.process_uca_edges),
+        edges = pm.process_uca_edges if world == 1 else pm.process_uca_edges_rounds
+        for name, fn in (("aspect_slope", pm.process_aspect_slope), ("uca", pm.process_uca), ("uca_edges", edges),
                          ("twi", lambda: pm._stage(pm._twi, 3))):
+            if group is not None: dist.barrier()
             torch.cuda.synchronize(); t0 = time.perf_counter(); fn(); torch.cuda.synchronize()
+            if group is not None: dist.barrier()
             t[name] = (time.perf_counter() - t0) * 1e3
     dp = DEMProcessor(elev=E, dX=30.0, dY=30.0, **kw)
     torch.cuda.synchronize(); t0 = time.perf_counter(); dp.calc_twi(); torch.cuda.synchronize()
@@ -38,7 +53,9 @@ with warnings.catch_warnings():
 res["ms"] = t
 res["ms_total"] = sum(t.values())
 res["Mcells_s"] = E.size / res["ms_total"] / 1e3
-res["corrections"] = len(pm.correction_log)
+res["n_gpus"] = world
+res["corrections"] = sum(len(c) if isinstance(c, tuple) else 1 for c in pm.correction_log)
+res["correction_rounds"] = len(pm.correction_log)
 res["ms_single_tile_calc_twi"] = t_single
 m = pm.mosaic("uca")
 with np.errstate(invalid="ignore", divide="ignore"):
@@ -47,7 +64,11 @@ inner = rel[1:-1, 1:-1]
 res["mosaic_vs_single"] = dict(cells_within_1e9=float(np.mean(inner[np.isfinite(inner)] <= 1e-9)), max_rel=float(np.nanmax(inner)),
                                note="the reference's tile-edge approximation makes the mosaic differ from the single-DEM "
                                     "result on rough terrain (SURVEY.md 8e); equality holds on smooth surfaces (tests)")
-res["edge_todo_left"] = int(sum(int(tl.edge_todo.sum()) for tl in pm.tiles))
-print(json.dumps(res))
-os.makedirs(os.path.dirname(out), exist_ok=True)
-json.dump(res, open(out, "w"), indent=1)
+res["edge_todo_left"] = int(sum(int(np.asarray(tl.edge_todo[0, slice(0, None)]).sum()) for tl in pm.tiles))   # top strips (own or ring)
+if rank == 0:
+    print(json.dumps(res))
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    json.dump(res, open(out, "w"), indent=1)
+if group is not None:
+    dist.barrier()
+    dist.destroy_process_group()

@@ -67,3 +67,17 @@ def test_rough_mosaic_cuda_equals_oracle_orchestration():
         np.testing.assert_array_equal(ta.edge_done, tb.edge_done)
         np.testing.assert_allclose(ta.uca + ta.uca_edges, tb.uca + tb.uca_edges, rtol=helpers.UCA_RTOL, equal_nan=True)
     np.testing.assert_allclose(a.mosaic("twi"), b.mosaic("twi"), atol=10 * helpers.TWI_ATOL, equal_nan=True)
+
+
+@pytest.mark.parametrize("name", ["cone_5x4_2overlap", "fractal_3x3_2overlap", "fractal_2x3_1overlap"])
+def test_cuda_correction_rounds_equal_reference(name):
+    """Correction rounds (the tile-parallel schedule) with the CUDA operator vs the reference's serial loop."""
+    E, nx, ny, ov, kw = CASES[name]
+    boxes = [tuple(b) for b in G[name + "_boxes"].tolist()]
+    tiles = [E[b[0]:b[1], b[2]:b[3]] for b in boxes]
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        pm = ProcessManager(tiles, boxes, dem_proc_kwargs=kw)
+        pm.process_twi(rounds=True)
+    m = pm.mosaic("uca")
+    np.testing.assert_allclose(m[1:-1, 1:-1], G[name + "_compact_uca"][1:-1, 1:-1], rtol=helpers.UCA_RTOL, equal_nan=True)
