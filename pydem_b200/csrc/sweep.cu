@@ -18,8 +18,10 @@
 //
 // For an acyclic graph this visits every cell exactly once and yields the reference's
 // sums up to fp64 re-association (the reference adds in (level, source index) order).
-// Cells on cycles never reach in-degree 0; they are counted (n_undone) and handled by
-// the level-synchronous restart path below, which follows cyutils.pyx literally.
+// Cells on cycles never reach in-degree 0; they are counted (n_undone) and reported.  The
+// reference's restart heuristic for such circular references (dem_processing.py:951-964,
+// "should never occur") is not replayed: the filter elev[j] <= elev[i] only admits cycles of
+// equal-elevation cells, whose mutual flow has weight 0 and is filtered.
 //
 // Traffic per cell (sweep): one 32-byte sector for the cell's own record and one per receiver
 // (fp64 atomic on .area + int atomic on .indeg of the same sector); the kernel is bound by

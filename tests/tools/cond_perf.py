@@ -1,8 +1,9 @@
 """Time the elevation-conditioning stages on the device (config-3 style input: quantised fractal
 with lakes) and the oracle restatement on a crop, and check them against each other on the crop.
-    python scripts/cond_perf.py [n] [crop]"""
+    python tests/tools/cond_perf.py [n] [crop]"""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
 import numpy as np
 from pydem_b200 import synth, tile as T
 from oracle import conditioning as oc

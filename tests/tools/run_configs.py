@@ -1,10 +1,11 @@
-"""BASELINE.json configs[0..2] on one B200 through the public operator (DEMProcessor): per-stage wall
+"""Test tooling (uses the oracle as the checker, hence under tests/).
+BASELINE.json configs[0..2] on one B200 through the public operator (DEMProcessor): per-stage wall
 times incl. host<->device copies, device-resident stage times, and a parity check of every config
 against the oracle (full size where the oracle finishes in seconds, cropped windows above).
-    python scripts/run_configs.py [--configs 1,2,3] [--size3 16384] [--out gpurun_out/configs.json]
+    python tests/tools/run_configs.py [--configs 1,2,3] [--size3 16384] [--out gpurun_out/configs.json]
 Each config runs in its own subprocess under a timeout so that one slow stage cannot eat the box."""
 import argparse, json, os, subprocess, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
