@@ -152,12 +152,14 @@ def register_tiles(E, nx_grid, ny_grid, overlap, tag, lat=(46.0, 45.0), lon=(-73
     return [names[k] for k in order], [boxes[k] for k in order]
 
 
-def run_reference_pm(E, nx_grid, ny_grid, overlap, tag, dem_processor=None, dem_proc_kwargs=None, debug_spacing=True):
+def run_reference_pm(E, nx_grid, ny_grid, overlap, tag, dem_processor=None, dem_proc_kwargs=None, debug_spacing=True,
+                     lat=(46.0, 45.0), lon=(-73.0, -72.0)):
     """ProcessManager.process_twi() + save_non_overlap_data() of the reference on in-memory tiles.
     dem_processor: class to put in place of ``pydem.process_manager.DEMProcessor`` (None = the
-    reference's own).  Returns a dict of the global arrays and the compact (non-overlapping) ones."""
+    reference's own).  debug_spacing=False keeps the spacing the reference derives from the rasters
+    (projected CRS: dX = pixel width, dY = pixel height, utils.py:132-137).  Returns a dict of the global arrays and the compact (non-overlapping) ones."""
     pm_mod = load_process_manager()
-    names, boxes = register_tiles(E, nx_grid, ny_grid, overlap, tag)
+    names, boxes = register_tiles(E, nx_grid, ny_grid, overlap, tag, lat=lat, lon=lon)
     out_path = "mem://%s/results.zarr" % tag
     for k in [k for k in _STORE if k.startswith(os.path.normpath("mem://%s" % tag))]:
         del _STORE[k]

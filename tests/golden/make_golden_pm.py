@@ -48,6 +48,18 @@ def main():
         for k in ("elev", "aspect", "slope", "uca", "uca_edges", "edge_todo", "edge_done", "twi", "compact_uca", "compact_twi"):
             out["%s_%s" % (name, k)] = r[k]
         print(name, "tiles", len(r["boxes"]), "corrections", len(r["correction_order"]))
+    # the spacing case: the reference keeps the spacing it derives from the rasters (no DEBUG override)
+    name = helpers.PM_SPACING_CASE
+    E = helpers.pm_cases()["fractal_3x3_2overlap"][0]
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        r = H.run_reference_pm(E, 3, 3, 2, name, debug_spacing=False, **helpers.PM_SPACING_GEO)
+    assert r["success"].all(), name
+    out[name + "_E"] = E
+    out[name + "_boxes"] = np.array(r["boxes"]); out[name + "_grid_slice"] = np.array(r["grid_slice"]); out[name + "_order"] = np.array(r["correction_order"])
+    for k in ("elev", "aspect", "slope", "uca", "uca_edges", "edge_todo", "edge_done", "twi", "compact_uca", "compact_twi"):
+        out["%s_%s" % (name, k)] = r[k]
+    print(name, "tiles", len(r["boxes"]), "corrections", len(r["correction_order"]))
     np.savez_compressed(os.path.join(HERE, "ref_pm.npz"), **out)
     print("wrote ref_pm.npz, %.0f kB" % (os.path.getsize(os.path.join(HERE, "ref_pm.npz")) / 1e3))
 

@@ -188,6 +188,26 @@ def pm_cases():
     return c
 
 
+# one more orchestrator case with the spacing the reference derives from the rasters instead of its
+# tests' dX = dY = 1: a 64x64 fractal spanning 1 degree of latitude and 1.5 of longitude
+PM_SPACING_CASE = "fractal_3x3_2overlap_spacing"
+PM_SPACING_GEO = dict(lat=(46.0, 45.0), lon=(-73.0, -71.5))
+
+
+def pm_spacing(shape, boxes):
+    """per-tile spacing of PM_SPACING_CASE, with the arithmetic of the reference's raster writer
+    (utils.mk_geotiff_obj :196-199 on the tile's own corner coordinates) and reader (utils.py:132-137):
+    dX = pixel width, dY = |pixel height| of each tile's raster"""
+    la = np.linspace(PM_SPACING_GEO["lat"][0], PM_SPACING_GEO["lat"][1], shape[0])
+    lo = np.linspace(PM_SPACING_GEO["lon"][0], PM_SPACING_GEO["lon"][1], shape[1])
+    out = []
+    for (te, be, le, re) in boxes:
+        ph = abs(la[te] - la[be - 1]) / ((be - te) - 1.0)
+        pw = abs(lo[le] - lo[re - 1]) / ((re - le) - 1.0)
+        out.append(dict(dX=pw, dY=ph, dX2=pw, dY2=ph))
+    return out
+
+
 def pm_compare(pm, G, name):
     """Our ProcessManager's per-tile arrays against the reference's side-by-side store (golden
     dict G).  Returns the worst deviation per field (bool fields: number of differing cells)."""

@@ -60,6 +60,23 @@ def test_orchestrator_equals_reference_process_manager(name):
     np.testing.assert_allclose(pm.mosaic("twi"), G[name + "_compact_twi"], atol=1e-8, equal_nan=True)
 
 
+def test_orchestrator_with_raster_derived_spacing():
+    """Non-unit, anisotropic spacing (what the reference derives from a projected raster) through the
+    whole orchestration: pixel 1.5/63 deg wide, 1/63 deg high."""
+    name = helpers.PM_SPACING_CASE
+    E = G[name + "_E"]
+    boxes = [tuple(b) for b in G[name + "_boxes"].tolist()]
+    tiles = [E[b[0]:b[1], b[2]:b[3]] for b in boxes]
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        pm = ProcessManager(tiles, boxes, spacing=helpers.pm_spacing(E.shape, boxes), dem_processor=oracle_factory)
+        pm.process_twi()
+    worst = helpers.pm_compare(pm, G, name)
+    for k, tol in TOL.items():
+        assert worst[k] <= tol, (name, worst)
+    assert pm.correction_log == G[name + "_order"].tolist()
+
+
 def test_reference_criterion_on_the_cone():
     """test_end_to_end.py:96: the mosaic's uca equals the single-tile uca away from the rim."""
     E, nx, ny, ov, kw = CASES["cone_5x4_2overlap"]
