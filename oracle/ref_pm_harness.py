@@ -29,14 +29,16 @@ import numpy as np
 from . import ref_harness
 
 _STORE = {}      # path -> ndarray          (the "zarr" store)
+_CHUNKS = {}     # path -> chunk shape given when the array was created
 _RASTERS = {}    # file name -> _Raster     (the "GeoTIFF" files)
 
 
 class _MemArray(object):
-    def __init__(self, a):
+    def __init__(self, a, chunks=None):
         self._a = a
+        self.chunks = list(chunks) if chunks is not None else list(a.shape)
 
-    shape = property(lambda self: self._a.shape)
+    shape = property(lambda self: list(self._a.shape))
     dtype = property(lambda self: self._a.dtype)
 
     def __getitem__(self, key):
@@ -55,7 +57,8 @@ class _MemGroup(object):
         self._p = path
 
     def __getitem__(self, name):
-        return _MemArray(_STORE[os.path.normpath(os.path.join(self._p, name))])
+        p = os.path.normpath(os.path.join(self._p, name))
+        return _MemArray(_STORE[p], _CHUNKS.get(p))
 
     def __contains__(self, name):
         return os.path.normpath(os.path.join(self._p, name)) in _STORE
@@ -65,8 +68,9 @@ def _zarr_open(path, mode="a", shape=None, chunks=None, dtype=None, fill_value=N
     p = os.path.normpath(path)
     if shape is not None and p not in _STORE:
         _STORE[p] = np.full(tuple(int(s) for s in shape), 0 if fill_value is None else fill_value, dtype=dtype or "float64")
+        _CHUNKS[p] = [int(c) for c in chunks] if chunks is not None else None
     if p in _STORE:
-        return _MemArray(_STORE[p])
+        return _MemArray(_STORE[p], _CHUNKS.get(p))
     return _MemGroup(p)
 
 
@@ -153,7 +157,7 @@ def register_tiles(E, nx_grid, ny_grid, overlap, tag, lat=(46.0, 45.0), lon=(-73
 
 
 def run_reference_pm(E, nx_grid, ny_grid, overlap, tag, dem_processor=None, dem_proc_kwargs=None, debug_spacing=True,
-                     lat=(46.0, 45.0), lon=(-73.0, -72.0)):
+                     lat=(46.0, 45.0), lon=(-73.0, -72.0), overviews=None):
     """ProcessManager.process_twi() + save_non_overlap_data() of the reference on in-memory tiles.
     dem_processor: class to put in place of ``pydem.process_manager.DEMProcessor`` (None = the
     reference's own).  debug_spacing=False keeps the spacing the reference derives from the rasters
@@ -180,6 +184,8 @@ def run_reference_pm(E, nx_grid, ny_grid, overlap, tag, dem_processor=None, dem_
                                        n_workers=1, dem_proc_kwargs=dict(dem_proc_kwargs or {}))
             pm.process_twi()
             pm.save_non_overlap_data()
+            if overviews:
+                pm.process_overviews(pm.out_path_noverlap, keys=["elev", "uca"], overviews=list(overviews))
     finally:
         pm_mod.DEMProcessor, pm_mod.DEBUG, pm_mod.calc_uca_ec = old_dp, old_dbg, old_ec
     res = {"correction_order": order}
@@ -189,6 +195,10 @@ def run_reference_pm(E, nx_grid, ny_grid, overlap, tag, dem_processor=None, dem_
     compact = os.path.normpath(pm.out_path_noverlap)
     for key in ("elev", "uca", "aspect", "slope", "twi"):
         res["compact_" + key] = np.array(_STORE[os.path.normpath(os.path.join(compact, key))])
+    for k in _STORE:
+        if k.startswith(compact + os.sep) and os.path.basename(k).split("_")[-1].isdigit():
+            res["overview_" + os.path.basename(k)] = np.array(_STORE[k])
+    res["compact_chunks"] = _CHUNKS.get(os.path.normpath(os.path.join(compact, "uca")))
     res["grid_slice"] = [(s[0].start, s[0].stop, s[1].start, s[1].stop) for s in pm.grid_slice]
     res["grid_slice_unique"] = [(s[0].start, s[0].stop, s[1].start, s[1].stop) for s in pm.grid_slice_unique]
     res["edge_data"] = pm.edge_data

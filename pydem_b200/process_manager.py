@@ -28,6 +28,8 @@ The reference's own orchestrator, run unmodified over in-memory stand-ins for za
 compares this module against it array by array (aspect, slope, uca, uca_edges, edge masks, twi,
 and the order in which tiles were corrected).
 """
+import warnings
+
 import numpy as np
 
 SIDES = ("left", "right", "top", "bottom")
@@ -561,6 +563,77 @@ class ProcessManager(object):
         for (r0, r1, c0, c1), a in pieces:
             out[r0:r1, c0:c1] = a
         return out
+
+    def process_overviews(self, keys=("elev", "uca", "aspect", "slope", "twi"), overviews=(3, 9, 27, 81, 243, 729, 2187)):
+        """Overview pyramids of the non-overlapping mosaics (process_overviews :933-941 applied to the
+        compact store, whose chunks are the mosaic size over the number of grid rows / columns,
+        save_non_overlap_data :746-748).  Returns {key: {ov: array}}."""
+        res = {}
+        for key in keys:
+            m = self.mosaic(key)
+            chunks = [m.shape[0] // self.grid_shape[0], m.shape[1] // self.grid_shape[1]]
+            res[key] = overview_pyramid(m, chunks, overviews)
+        return res
+
+
+def block_means(data, factor):
+    """One overview step of a chunk (process_manager.calc_overview :317-353): means over
+    factor x factor blocks; the columns / rows / corner left over at the end of the chunk are
+    averaged into one extra output column / row / cell.  None for an all-zero chunk (the reference
+    skips those)."""
+    data = np.asarray(data, dtype="float64")
+    if data.size == 0 or np.all(data == 0):
+        return None
+    R, C = data.shape
+    r, c = R // factor, C // factor
+    out = np.zeros((-(-R // factor), -(-C // factor)))
+    try:
+        with np.errstate(invalid="ignore"), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out[:r, :c] = data[:r * factor, :c * factor].reshape(r, factor, c, factor).transpose(0, 2, 1, 3).reshape(r, c, factor * factor).mean(axis=-1)
+            out[:r, c:] = data[:r * factor, c * factor:].reshape(r, -1).mean(axis=1)[:, None]
+            out[r:, :c] = data[r * factor:, :c * factor].reshape(-1, c).mean(axis=0)[None, :]
+            out[r:, c:] = data[r * factor:, c * factor:].mean()
+    except ValueError:
+        # a chunk narrower than the factor cannot be reshaped; the reference's worker fails on it too
+        # (its exception is swallowed, :349-350) and the chunk stays zero
+        return None
+    return out
+
+
+def overview_pyramid(base, chunks, overviews=(3, 9, 27, 81, 243, 729, 2187)):
+    """The reference's overview pyramid of one array (process_overviews / _calc_overview :933-991):
+    level `ov` is built from the previous level with factor ov // last_ov, chunk by chunk with the
+    reference's chunk arithmetic, until a level would be no larger than the factor.
+    Returns {ov: array}."""
+    out = {}
+    last, last_ov = np.asarray(base, dtype="float64"), 1
+    chunks = [int(c) for c in chunks]
+    for ov in overviews:
+        factor = ov // last_ov
+        shape = list(last.shape)
+        if any(c == 0 for c in chunks):
+            chunks = list(shape)
+        n_files = [np.ceil(s / c) for s, c in zip(shape, chunks)]
+        new_shape = [int(np.ceil(s / factor)) for s in shape]
+        new_chunks = [int(max(factor, np.ceil(ns / n))) for ns, n in zip(new_shape, n_files)]
+        if any(n <= factor for n in new_shape):
+            break
+        new = np.zeros(new_shape)
+        row = 0
+        while (row - 1) * new_chunks[0] < new_shape[0]:
+            col = 0
+            while (col - 1) * new_chunks[1] < new_shape[1]:
+                blk = block_means(last[row * new_chunks[0] * factor:(row + 1) * new_chunks[0] * factor,
+                                       col * new_chunks[1] * factor:(col + 1) * new_chunks[1] * factor], factor)
+                if blk is not None:
+                    tgt = new[row * new_chunks[0]:(row + 1) * new_chunks[0], col * new_chunks[1]:(col + 1) * new_chunks[1]]
+                    tgt[...] = blk[:tgt.shape[0], :tgt.shape[1]] if blk.shape != tgt.shape else blk
+                col += 1
+            row += 1
+        out[ov] = new
+        last, last_ov, chunks = new, ov, new_chunks
+    return out
 
 
 class TorchGroup(object):

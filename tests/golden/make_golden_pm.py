@@ -28,13 +28,16 @@ import helpers  # noqa: E402
 from oracle import ref_harness as rh, ref_pm_harness as H  # noqa: E402
 
 
+OVERVIEW_CASES = ("fractal_3x3_2overlap", "fractal_2x3_1overlap", "cone_5x4_3overlap")
+
+
 def main():
     out = {}
     ref = rh.load_reference()
     for name, (E, nx, ny, ov, kw) in helpers.pm_cases().items():
         with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            r = H.run_reference_pm(E, nx, ny, ov, name, dem_proc_kwargs=kw)
+            r = H.run_reference_pm(E, nx, ny, ov, name, dem_proc_kwargs=kw, overviews=[3, 9] if name in OVERVIEW_CASES else None)
             if name.startswith("cone") and ov >= 1:      # the reference's own tilings all overlap
                 dp = ref.DEMProcessor(elev=E.copy(), **kw)
                 dp.dX[:] = 1; dp.dY[:] = 1; dp.dX2[:] = 1; dp.dY2[:] = 1
@@ -47,6 +50,11 @@ def main():
         out[name + "_order"] = np.array(r["correction_order"])
         for k in ("elev", "aspect", "slope", "uca", "uca_edges", "edge_todo", "edge_done", "twi", "compact_uca", "compact_twi"):
             out["%s_%s" % (name, k)] = r[k]
+        if name in OVERVIEW_CASES:        # process_overviews(out_path_noverlap, keys=[elev, uca], overviews=[3, 9])
+            out[name + "_compact_elev"] = r["compact_elev"]
+            for k, v in r.items():
+                if k.startswith("overview_"):
+                    out["%s_%s" % (name, k)] = v
         print(name, "tiles", len(r["boxes"]), "corrections", len(r["correction_order"]))
     # the spacing case: the reference keeps the spacing it derives from the rasters (no DEBUG override)
     name = helpers.PM_SPACING_CASE

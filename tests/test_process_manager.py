@@ -77,6 +77,26 @@ def test_orchestrator_with_raster_derived_spacing():
     assert pm.correction_log == G[name + "_order"].tolist()
 
 
+@pytest.mark.parametrize("name", ["fractal_3x3_2overlap", "fractal_2x3_1overlap", "cone_5x4_3overlap"])
+def test_overview_pyramids_equal_reference(name):
+    """process_overviews (:933-991) on the compact mosaics: block means with the reference's chunk
+    arithmetic and end-of-chunk leftovers."""
+    from pydem_b200.process_manager import overview_pyramid
+    E, nx, ny, ov, kw = CASES[name]
+    chunks = [E.shape[0] // ny, E.shape[1] // nx]
+    # the arithmetic itself, on the reference's own mosaics: bit for bit
+    for key in ("elev", "uca"):
+        mine = overview_pyramid(G["%s_compact_%s" % (name, key)], chunks, (3, 9))
+        for o in (3, 9):
+            np.testing.assert_array_equal(mine[o], G["%s_overview_%s_%d" % (name, key, o)])
+    # and through the orchestrator
+    pm = run_pm(E, [tuple(b) for b in G[name + "_boxes"].tolist()], kw, oracle_factory)
+    res = pm.process_overviews(keys=("elev", "uca"), overviews=(3, 9))
+    for o in (3, 9):
+        np.testing.assert_array_equal(res["elev"][o], G["%s_overview_elev_%d" % (name, o)])
+        np.testing.assert_allclose(res["uca"][o], G["%s_overview_uca_%d" % (name, o)], rtol=1e-9, equal_nan=True)
+
+
 def test_reference_criterion_on_the_cone():
     """test_end_to_end.py:96: the mosaic's uca equals the single-tile uca away from the rim."""
     E, nx, ny, ov, kw = CASES["cone_5x4_2overlap"]
