@@ -132,12 +132,13 @@ def test_value_noise_is_shard_consistent():
     assert full.min() >= 1.0 and np.isfinite(full).all()
 
 
-def test_two_process_gloo_protocol():
+@pytest.mark.parametrize("world", [2, 3])     # 3: a middle rank talks to two neighbours
+def test_gloo_protocol(world):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in procs]
