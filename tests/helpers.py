@@ -227,3 +227,54 @@ def pm_compare(pm, G, name):
                 d = float(d.max())
             worst[key] = max(worst.get(key, 0.0), d)
     return worst
+
+
+def fuzz_case(seed):
+    """A small random DEM (plain / quantised / lakes / NaN holes / tilted plane + noise / integer
+    elevations) with random spacing and flags.  Returns (elev, kwargs, kind)."""
+    rng = np.random.default_rng(seed)
+    R = int(rng.integers(12, 56)); C = int(rng.integers(12, 56))
+    E = synth.fractal_dem(0, seed + 1000, shape=(R, C))
+    kind = rng.integers(0, 6)
+    if kind == 1:
+        E = np.round(E / rng.choice([5, 20, 50])) * rng.choice([5, 20, 50]) + 1
+    elif kind == 2:
+        yy, xx = np.mgrid[:R, :C]
+        for _ in range(int(rng.integers(1, 4))):
+            cy, cx, r = rng.integers(0, R), rng.integers(0, C), rng.integers(2, 8)
+            m = (yy - cy) ** 2 + (xx - cx) ** 2 <= r * r
+            E[m] = E[m].min()
+    elif kind == 3:
+        for _ in range(int(rng.integers(1, 4))):
+            i, j = rng.integers(0, R - 2), rng.integers(0, C - 2)
+            E[i:i + rng.integers(1, 3), j:j + rng.integers(1, 3)] = np.nan
+    elif kind == 4:
+        E = E * 0.01 + np.add.outer(np.arange(R) * rng.uniform(-2, 2), np.arange(C) * rng.uniform(-2, 2)) + 500
+    elif kind == 5:
+        E = np.round(E)  # integer elevations: many ties
+    kw = {}
+    if rng.random() < 0.5:
+        kw.update(dX=float(rng.uniform(5, 40)), dY=float(rng.uniform(5, 40)))
+    if rng.random() < 0.3:
+        kw.update(dX=np.linspace(20, 30, R - 1) * rng.uniform(0.5, 2), dY=np.full(R - 1, float(rng.uniform(10, 40))))
+        kw.update(dX2=np.linspace(20, 30, R), dY2=np.full(R, 27.0))
+    kw["drain_pits"] = bool(rng.random() < 0.7)
+    if rng.random() < 0.3: kw["drain_pits_min_border"] = True
+    if rng.random() < 0.3: kw.update(drain_pits_max_dist=int(rng.integers(2, 10)), drain_pits_max_iter=int(rng.integers(5, 40)))
+    if rng.random() < 0.3: kw.update(apply_uca_limit_edges=True, apply_twi_limits=True, apply_twi_limits_on_uca=True)
+    cond = rng.random() < 0.4 and kind != 3
+    kw["fill_flats"] = bool(cond); kw["drain_pits_path"] = bool(cond and rng.random() < 0.7)
+    return E, kw, kind
+
+
+def run_all(make, E, kw):
+    """Conditioning (per flags) + the three stages on a processor factory, every output incl. elev."""
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        dp = make(E.copy(), **kw)
+        mag, direction = dp.calc_slopes_directions()
+        out = dict(elev=np.array(dp.elev), mag0=np.array(mag), dir=np.array(direction), flats0=np.array(dp.flats))
+        out["uca"] = np.array(dp.calc_uca()); out["edge_todo"] = np.array(dp.edge_todo); out["edge_done"] = np.array(dp.edge_done)
+        out["mag"] = np.array(dp.mag); out["flats"] = np.array(dp.flats)
+        out["twi"] = np.array(dp.calc_twi()); out["twi10"] = np.array(dp.twi); out["twi_min_area"] = dp.twi_min_area
+    return out
