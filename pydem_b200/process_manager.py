@@ -19,9 +19,9 @@ other tiles it keeps the edge rings (the strips within overlap distance of a til
 neighbour ever reads, see ``_RingArray``), refreshed with one ``all_gather_object`` per stage /
 correction round.  The one-pixel-overlap patch of ``calc_uca`` is order dependent and only touches
 edge cells, so every rank replays it for all tiles on the rings (bit-identical to the serial
-order); corrections run in rounds of non-adjacent tiles that tie for the best metric
-(``process_uca_edges_rounds``), whose result does not depend on the number of ranks and equals
-the reference's serial loop on every pinned case.
+order); the correction loop takes the reference's serial decisions on every rank (the metrics
+only need rings) and the owner of the chosen tile executes it, so the result is the one-rank
+result by construction and only the stages around the corrections run in parallel.
 
 The reference's own orchestrator, run unmodified over in-memory stand-ins for zarr/rasterio
 (``oracle/ref_pm_harness.py``), produced ``tests/golden/ref_pm.npz``; ``tests/test_process_manager.py``
@@ -463,11 +463,12 @@ class ProcessManager(object):
         return np.argpartition(-mets[:, mets_type], min(self.n_workers * 2, mets.shape[0] - 1))
 
     def process_uca_edges(self, mets_type=0, max_count=100000):
-        """Serial correction loop (:1090-1189, n_workers == 1): correct the tile whose inflow edges
-        are most complete, refresh the metrics of that tile and its four neighbours, stop when the
-        ranking no longer changes."""
-        if self.world > 1:
-            raise RuntimeError("the reference's serial correction loop runs on one rank; use process_uca_edges_rounds()")
+        """The reference's correction loop (:1090-1189, n_workers == 1): correct the tile whose inflow
+        edges are most complete, refresh the metrics of that tile and its four neighbours, stop when
+        the ranking no longer changes.  On several ranks every rank takes the same decisions (the
+        metrics only need edge rings, which all ranks hold); the owner of the chosen tile corrects
+        it and its rings are refreshed -- the result is the serial loop's by construction.  (This
+        stage does not parallelise under the reference's semantics, see process_uca_edges_rounds.)"""
         mets = self.update_uca_edge_metrics()
         I = self._order(mets, mets_type)
         I_old = np.zeros_like(I)
@@ -475,7 +476,9 @@ class ProcessManager(object):
         while np.any(I_old != I) and count < max_count:
             count += 1
             k = int(I[0])
-            self._uca_ec(self.tiles[k])
+            if self._mine(self.tiles[k]):
+                self._uca_ec(self.tiles[k])
+            self._sync(("uca_edges", "edge_todo", "edge_done"), [k])
             self.correction_log.append(k)
             I_old = I.copy()
             t = self.tiles[k]
@@ -489,17 +492,19 @@ class ProcessManager(object):
         return mets
 
     def process_uca_edges_rounds(self, max_rounds=100000):
-        """Corrections in rounds: every round corrects the tiles that TIE for the best metric (share of
-        inflow edges whose neighbour is done) and are pairwise non-adjacent (8-neighbourhood), so
-        that no corrected tile reads another one of the same round -- the round equals correcting
-        its tiles one after the other, on one rank or spread over many.
+        """EXPERIMENTAL alternative to the reference's one-tile-at-a-time loop, not used by default:
+        every round corrects the tiles that TIE for the best metric (share of inflow edges whose
+        neighbour is done), have an edge a neighbour can resolve, and are pairwise non-adjacent
+        (8-neighbourhood), so that no corrected tile reads another one of the same round.
 
-        The reference's correction scheme is order dependent: a tile corrected while a better
-        candidate exists can end with different (wrong) values -- measured on the pinned cases,
-        "every tile with a resolvable edge" or "within half of the best metric" per round changed
-        up to 168 interior cells, while ties-only reproduces the reference's serial loop on all of
-        them.  The price is little parallelism in this stage (19 rounds for 24 corrections on the
-        5x4 cone); the stages before and after it are independent per tile."""
+        The reference's correction scheme is order dependent, and this schedule is NOT equivalent
+        to its loop in general: it reproduces the reference on the 11 pinned tilings, but on 200
+        random mosaics 35 differed -- mostly because the reference's loop also corrects a tile when
+        no neighbour edge is done yet (which flips todo flags and gets the iteration going), and
+        once through a genuine order effect.  Looser rounds ("every tile with a resolvable edge",
+        "within half of the best metric") changed up to 168 interior cells even on the pinned
+        cases.  Even where it is exact it saves little (19 rounds for 24 corrections on the 5x4
+        cone), so the tile-parallel mode keeps the serial loop and parallelises the stages around it."""
         rounds = 0
         while rounds < max_rounds:
             mets = self.update_uca_edge_metrics()
@@ -527,13 +532,13 @@ class ProcessManager(object):
             rounds += 1
         return self.update_uca_edge_metrics()
 
-    def process_twi(self, rounds=None):
-        """The whole pipeline.  rounds: correct in rounds of independent tiles instead of the
-        reference's one-tile-at-a-time loop (default: only when running on several ranks)."""
+    def process_twi(self, rounds=False):
+        """The whole pipeline (process_twi :1290-1316).  rounds=True swaps the reference's correction
+        loop for the experimental rounds schedule (process_uca_edges_rounds)."""
         self.process_elevation()
         self.process_aspect_slope()
         self.process_uca()
-        if rounds or (rounds is None and self.world > 1):
+        if rounds:
             self.process_uca_edges_rounds()
         else:
             self.process_uca_edges()

@@ -40,7 +40,7 @@ with warnings.catch_warnings():
         pm = ProcessManager([E[b[0]:b[1], b[2]:b[3]] for b in boxes], boxes, spacing=sp, dem_proc_kwargs=kw, group=group)
         pm.success[:, 0] = True     # elevation is already conditioned (what the reference's first stage would do)
         t = {}
-        edges = pm.process_uca_edges if world == 1 else pm.process_uca_edges_rounds
+        edges = pm.process_uca_edges          # the reference's serial decisions on every rank, the owner executes
         for name, fn in (("aspect_slope", pm.process_aspect_slope), ("uca", pm.process_uca), ("uca_edges", edges),
                          ("twi", lambda: pm._stage(pm._twi, 3))):
             if group is not None: dist.barrier()

@@ -1,9 +1,10 @@
 """Tile-parallel mode of the orchestrator (pydem_b200.process_manager with group=...) on the CPU:
-* correction rounds of independent tiles on ONE rank: the reference's own criterion on the cone
-  (mosaic uca == single-tile uca away from the rim) and the same mosaic as the reference
-  ProcessManager on the smooth cases;
-* two and three real processes over gloo (oracle operator): every rank ends with the same mosaic as
-  the one-rank run, bit for bit, and keeps full arrays only for its own tiles."""
+* the edge rings remote tiles are reduced to (_RingArray);
+* two and three real processes over gloo (oracle operator): every rank ends with the same mosaic and
+  the same order of corrections as the unmodified reference ProcessManager (golden fixture) and as
+  the one-rank run bit for bit, and keeps full arrays only for its own tiles;
+* the experimental correction rounds (not the default): equal to the reference on the pinned
+  tilings, never two adjacent tiles in a round."""
 import contextlib
 import io
 import os
@@ -27,12 +28,12 @@ def oracle_factory(**k):
     return OracleDEMProcessor(k.pop("elev"), **k)
 
 
-def run_rounds(E, boxes, kw, group=None):
+def run_rounds(E, boxes, kw, group=None, rounds=True):
     tiles = [E[b[0]:b[1], b[2]:b[3]] for b in boxes]
     with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
         warnings.simplefilter("ignore")
         pm = ProcessManager(tiles, boxes, dem_proc_kwargs=kw, dem_processor=oracle_factory, group=group)
-        pm.process_twi(rounds=True)
+        pm.process_twi(rounds=rounds)
     return pm
 
 
@@ -102,8 +103,8 @@ def _worker(rank, world, port, q, names):
         out = {}
         for name in names:
             E, nx, ny, ov, kw = CASES[name]
-            boxes = split_mosaic(E.shape, ny, nx, ov)
-            pm = run_rounds(E, boxes, kw, group=g)
+            boxes = [tuple(b) for b in G[name + "_boxes"].tolist()]
+            pm = run_rounds(E, boxes, kw, group=g, rounds=False)       # the default: the reference's serial decisions
             own_full = all(isinstance(t.uca, np.ndarray) == (t.owner == rank) for t in pm.tiles)
             out[name] = (pm.mosaic("uca"), pm.mosaic("twi"), pm.mosaic("aspect"), list(pm.correction_log), own_full)
         dist.barrier()
@@ -117,7 +118,7 @@ def _worker(rank, world, port, q, names):
 @pytest.mark.parametrize("world", [2, 3])
 def test_tile_parallel_over_gloo_equals_one_rank(world):
     import multiprocessing as mp
-    names = ["cone_3x3_1overlap", "fractal_3x3_2overlap", "fractal_2x3_1overlap"]
+    names = ["cone_3x3_1overlap", "fractal_3x3_2overlap", "fractal_2x3_1overlap", "cone_3x3_0overlap", "fractal_1x3_4overlap"]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -131,11 +132,12 @@ def test_tile_parallel_over_gloo_equals_one_rank(world):
         assert status == "ok", payload
     for name in names:
         E, nx, ny, ov, kw = CASES[name]
-        one = run_rounds(E, split_mosaic(E.shape, ny, nx, ov), kw)
+        one = run_rounds(E, [tuple(b) for b in G[name + "_boxes"].tolist()], kw, rounds=False)
         for rank, status, payload in res:
             uca, twi, aspect, log, own_full = payload[name]
-            np.testing.assert_array_equal(uca, one.mosaic("uca"))
+            np.testing.assert_array_equal(uca, one.mosaic("uca"))              # = one rank, bit for bit
             np.testing.assert_array_equal(twi, one.mosaic("twi"))
             np.testing.assert_array_equal(aspect, one.mosaic("aspect"))
-            assert log == list(one.correction_log)
+            assert log == list(one.correction_log) == G[name + "_order"].tolist()   # = the reference's scheduling
+            np.testing.assert_allclose(uca, G[name + "_compact_uca"], rtol=1e-9, equal_nan=True)
             assert own_full
