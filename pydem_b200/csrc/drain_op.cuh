@@ -169,9 +169,10 @@ struct DrainOp {
     // (3) reading both receivers' records with one 256-bit load each right behind the decrement and
     //     carrying the next cell's record in registers (one round trip per cell).  In isolation
     //     this halves the latency (scripts/ubench/chain.cu, cold synthetic river: 932 -> 485 ns per
-    //     cell); inside the sweep it moved the 4096^2 conditioned case by -14 % on one box and
-    //     +8 % on another (median of 15 sweeps each, builds alternated on the same GPU), and its
-    //     16 extra registers cost the bulk phase a resident block per SM (scan 0.98 -> 1.12 ms);
+    //     cell); inside the sweep the chain still took 1.08 us per cell (the ~100 instructions of a
+    //     step, executed by one lane with nothing to overlap them, weigh as much as a round trip)
+    //     and the 4096^2 conditioned sweep was slower, 5.4-5.9 against 5.0-5.2 ms (builds
+    //     alternated on one GPU): its 16 extra registers cost the bulk phase a resident block;
     // (4) the same for the lanes of a team (bounded chains): slower (6.5 -> 8.3 ms); draining a whole
     //     front of up to four ready cells per iteration from one lane (local-memory front): 12+ ms;
     // (5) keeping the receivers' link bytes in the record and prefetching the receivers' receivers
