@@ -278,3 +278,23 @@ def run_all(make, E, kw):
         out["mag"] = np.array(dp.mag); out["flats"] = np.array(dp.flats)
         out["twi"] = np.array(dp.calc_twi()); out["twi10"] = np.array(dp.twi); out["twi_min_area"] = dp.twi_min_area
     return out
+
+
+def update_call(make, E, kw, seed):
+    """full calc_uca, then calc_uca(uca_init, edge_init_data) with RANDOM neighbour strips (values,
+    done flags, a random subset of the tile's own todo edges): dem_processing.py:719-744, 778-862"""
+    R, C = E.shape
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        dp = make(E.copy(), **kw)
+        dp.calc_slopes_directions(); dp.calc_uca()
+        uca0 = np.array(dp.uca); todo0 = np.array(dp.edge_todo)
+        r2 = np.random.default_rng(88_000 + seed)
+        data = {"left": r2.uniform(1, 500, R), "right": r2.uniform(1, 500, R), "top": r2.uniform(1, 500, C), "bottom": r2.uniform(1, 500, C)}
+        done = {k: r2.random(v.size) < 0.6 for k, v in data.items()}
+        todo = {"left": todo0[:, 0] & (r2.random(R) < 0.9), "right": todo0[:, -1] & (r2.random(R) < 0.9),
+                "top": todo0[0] & (r2.random(C) < 0.9), "bottom": todo0[-1] & (r2.random(C) < 0.9)}
+        dp2 = make(E.copy(), direction=np.array(dp.direction), mag=np.array(dp.mag), **kw)
+        dp2.find_flats()
+        dp2.calc_uca(uca_init=uca0.copy(), edge_init_data=[data, done, todo])
+        return np.array(dp2.uca), np.array(dp2.edge_todo), np.array(dp2.edge_done)

@@ -46,34 +46,13 @@ def test_oracle_equals_reference_on_random_cases(block):
         assert r["mag_rel"] <= 1e-12 and r["dir_abs"] <= 1e-12 and r["uca_rel"] <= 1e-9 and r["twi_abs"] <= 1e-8, msg
 
 
-def _update_call(make, E, kw, seed):
-    """full calc_uca, then calc_uca(uca_init, edge_init_data) with RANDOM neighbour strips (values,
-    done flags, a random subset of the tile's own todo edges): dem_processing.py:719-744, 778-862"""
-    import contextlib, io, warnings
-    R, C = E.shape
-    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
-        warnings.simplefilter("ignore")
-        dp = make(E.copy(), **kw)
-        dp.calc_slopes_directions(); dp.calc_uca()
-        uca0 = np.array(dp.uca); todo0 = np.array(dp.edge_todo)
-        r2 = np.random.default_rng(88_000 + seed)
-        data = {"left": r2.uniform(1, 500, R), "right": r2.uniform(1, 500, R), "top": r2.uniform(1, 500, C), "bottom": r2.uniform(1, 500, C)}
-        done = {k: r2.random(v.size) < 0.6 for k, v in data.items()}
-        todo = {"left": todo0[:, 0] & (r2.random(R) < 0.9), "right": todo0[:, -1] & (r2.random(R) < 0.9),
-                "top": todo0[0] & (r2.random(C) < 0.9), "bottom": todo0[-1] & (r2.random(C) < 0.9)}
-        dp2 = make(E.copy(), direction=np.array(dp.direction), mag=np.array(dp.mag), **kw)
-        dp2.find_flats()
-        dp2.calc_uca(uca_init=uca0.copy(), edge_init_data=[data, done, todo])
-        return np.array(dp2.uca), np.array(dp2.edge_todo), np.array(dp2.edge_done)
-
-
 @pytest.mark.parametrize("block", range(3))
 def test_oracle_update_mode_equals_reference_on_random_edge_data(block):
     for seed in range(block * 10, block * 10 + 10):
         E, kw, kind = helpers.fuzz_case(seed)
         kw = dict(kw, fill_flats=False, drain_pits_path=False)
-        u1, t1, d1 = _update_call(lambda e, **k: ref_harness.ref_processor(e, **k), E, kw, seed)
-        u2, t2, d2 = _update_call(lambda e, **k: OracleDEMProcessor(e, **k), E, kw, seed)
+        u1, t1, d1 = helpers.update_call(lambda e, **k: ref_harness.ref_processor(e, **k), E, kw, seed)
+        u2, t2, d2 = helpers.update_call(lambda e, **k: OracleDEMProcessor(e, **k), E, kw, seed)
         msg = "seed %d kind %d shape %s" % (seed, kind, E.shape)
         assert np.array_equal(np.isnan(u1), np.isnan(u2)), msg
         np.testing.assert_allclose(u2, u1, rtol=1e-9, equal_nan=True, err_msg=msg)

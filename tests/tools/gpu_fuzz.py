@@ -24,5 +24,14 @@ for seed in range(s0, s0 + n):
     if not ok:
         bad += 1
         print("MISMATCH seed", seed, "kind", kind, E.shape, r)
+    # update mode with random neighbour strips
+    kwu = dict(kw, fill_flats=False, drain_pits_path=False)
+    u1, t1, d1 = helpers.update_call(lambda e, **k: OracleDEMProcessor(e, **k), E, kwu, seed)
+    u2, t2, d2 = helpers.update_call(lambda e, **k: DEMProcessor(elev=e, **k), E, kwu, seed)
+    with np.errstate(invalid="ignore"):
+        rel = float(np.nanmax(np.abs(u1 - u2) / np.abs(u1))) if np.isfinite(u1).any() else 0.0
+    if not (np.array_equal(np.isnan(u1), np.isnan(u2)) and rel <= 1e-9 and np.array_equal(t1, t2) and np.array_equal(d1, d2)):
+        bad += 1
+        print("UPDATE MISMATCH seed", seed, "kind", kind, E.shape, "rel", rel, int((t1 != t2).sum()), int((d1 != d2).sum()))
 print("cases", n, "mismatches", bad)
 sys.exit(1 if bad else 0)
