@@ -425,12 +425,7 @@ def _pack_edges(edge_init_data, R, C):
 
 
 def _raster_kwargs(fn):
-    """Elevation + per-row spacing from a raster file (reference utils.py:46-51).  Needs
-    rasterio/geopy, which are IO dependencies outside the hot path."""
-    try:
-        import rasterio  # noqa: F401
-    except ImportError as e:  # pragma: no cover
-        raise ImportError("reading %r needs rasterio (file IO is outside the accelerated hot path); "
-                          "pass elev=, dX=, dY= arrays instead" % fn) from e
-    from .raster_io import dem_processor_from_raster_kwargs  # pragma: no cover
-    return dem_processor_from_raster_kwargs(fn)  # pragma: no cover
+    """Elevation + per-row spacing from a raster file (reference utils.py:46-51), read by this
+    package's own baseline-GeoTIFF parser (pydem_b200/raster_io.py; rasterio / geopy are not needed)."""
+    from .raster_io import dem_processor_from_raster_kwargs
+    return dem_processor_from_raster_kwargs(fn)

@@ -1,0 +1,79 @@
+"""File side of DEMProcessor(elev_fn): the baseline-GeoTIFF reader and the spacing arithmetic of
+pydem_b200/raster_io.py (reference utils.py:46-51, 127-174)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ref_harness
+from pydem_b200 import raster_io as rio
+
+FIXTURE = os.path.join(ref_harness.REFERENCE_ROOT, "pydem", "test", "test_NN032_033_elev.tif")
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32", "int16", "uint8"])
+@pytest.mark.parametrize("tile", [None, 16])
+def test_write_read_round_trip(tmp_path, dtype, tile):
+    rng = np.random.default_rng(1)
+    a = (rng.random((37, 53)) * 200).astype(dtype)
+    tr = rio.Affine((0.25, 0.0, -73.0, 0.0, -0.5, 46.0))
+    fn = str(tmp_path / "t.tif")
+    rio.write_geotiff(fn, a, tr, projected=(tile is None), tile=tile)
+    r = rio.read_geotiff(fn)
+    np.testing.assert_array_equal(r["elev"], a)
+    assert r["elev"].dtype == np.dtype(dtype)
+    assert tuple(r["transform"]) == tuple(tr)
+    assert r["bounds"] == (-73.0, 46.0 - 37 * 0.5, -73.0 + 53 * 0.25, 46.0)
+    assert r["is_projected"] == (tile is None)
+
+
+def test_projected_spacing_is_the_pixel_size(tmp_path):
+    fn = str(tmp_path / "p.tif")
+    rio.write_geotiff(fn, np.ones((5, 4)), rio.Affine((30.0, 0.0, 5e5, 0.0, -25.0, 4e6)), projected=True)
+    kw = rio.dem_processor_from_raster_kwargs(fn)
+    np.testing.assert_array_equal(kw["dX"], np.full(4, 30.0)); np.testing.assert_array_equal(kw["dY"], np.full(4, 25.0))
+    np.testing.assert_array_equal(kw["dX2"], np.full(5, 30.0)); np.testing.assert_array_equal(kw["dY2"], np.full(5, 25.0))
+
+
+def test_vincenty_against_closed_forms():
+    a, rf = rio.ELLIPSOIDS["WGS-84"]
+    f = 1 / rf; e2 = f * (2 - f)
+    assert abs(rio.vincenty_km((0, 10), (0, 11)) - a * np.pi / 180) < 1e-9            # along the equator: a * dlon
+    phi = np.linspace(np.radians(45), np.radians(45.03), 200001)                      # meridian arc by quadrature
+    M = a * (1 - e2) / (1 - e2 * np.sin(phi) ** 2) ** 1.5
+    assert abs(rio.vincenty_km((45, -73), (45.03, -73)) - np.trapezoid(M, phi)) < 1e-9
+    N = a / np.sqrt(1 - e2 * np.sin(np.radians(45)) ** 2)                              # short east-west step: N cos(lat) dlon
+    assert abs(rio.vincenty_km((45, -73), (45, -73 + 1e-3)) - N * np.cos(np.radians(45)) * np.radians(1e-3)) < 1e-8
+    assert rio.vincenty_km((12.5, 7.0), (12.5, 7.0)) == 0.0
+
+
+def test_geographic_spacing_shapes_and_monotony(tmp_path):
+    fn = str(tmp_path / "g.tif")
+    rio.write_geotiff(fn, np.ones((6, 3)), rio.Affine((1 / 31.0, 0.0, -73.0, 0.0, -1 / 31.0, 46.0)), projected=False)
+    kw = rio.dem_processor_from_raster_kwargs(fn)
+    assert kw["dX"].shape == (5,) and kw["dY"].shape == (5,) and kw["dX2"].shape == (6,) and kw["dY2"].shape == (6,)
+    assert np.all(np.diff(kw["dX"]) > 0)             # rows go south from 46 N: parallels get longer
+    assert np.all(np.abs(kw["dY"] - 3585.5) < 1.0)   # ~1/31 degree of latitude in metres
+
+
+def test_rejects_what_it_cannot_read(tmp_path):
+    fn = str(tmp_path / "x.tif")
+    open(fn, "wb").write(b"not a tiff")
+    with pytest.raises(ValueError):
+        rio.read_geotiff(fn)
+
+
+@pytest.mark.skipif(not os.path.isfile(FIXTURE), reason="reference tree not present (GPU box)")
+def test_reads_the_reference_fixture():
+    """pydem/test/test_NN032_033_elev.tif is the 32x32 cone of utils_test_pydem.py:98-103, written by the
+    reference with the pixel-centred WGS84 layout of utils.mk_geotiff_obj (:178-206)."""
+    r = rio.read_geotiff(FIXTURE)
+    x, y = np.mgrid[-1:1:32j, -1:1:32j]
+    np.testing.assert_array_equal(r["elev"], 1 - np.sqrt(x ** 2 + y ** 2) / np.sqrt(2))
+    ph = pw = 1.0 / 31.0
+    np.testing.assert_allclose(r["transform"], (pw, 0, -73 - pw / 2, 0, -ph, 46 + ph / 2), rtol=0, atol=1e-12)
+    assert r["is_projected"] is False and r["ellipsoid"] == "WGS-84"
+    # and the operator accepts the file name, like the reference's DEMProcessor(elev_fn)
+    from pydem_b200 import DEMProcessor
+    dp = DEMProcessor(FIXTURE)
+    assert dp.elev.shape == (32, 32) and dp.dX.shape == (31,) and dp.dY2.shape == (32,)
