@@ -171,7 +171,7 @@ class ProcessManager(object):
                 t.elev = None
             sp = (spacing[k] if isinstance(spacing, (list, tuple)) else spacing) or {}
             R = t.shape[0]
-            t.dX = np.ones(R - 1) * sp.get("dX", 1.0); t.dY = np.ones(R - 1) * sp.get("dY", 1.0)
+            t.dX = np.ones(R - 1) * sp.get("dX", 1.0); t.dY = np.ones(R - 1) * sp.get("dY", 1.0)     # scalars or per-row arrays
             t.dX2 = np.ones(R) * sp.get("dX2", sp.get("dX", 1.0)) if not isinstance(sp.get("dX2"), np.ndarray) else sp["dX2"]
             t.dY2 = np.ones(R) * sp.get("dY2", sp.get("dY", 1.0)) if not isinstance(sp.get("dY2"), np.ndarray) else sp["dY2"]
             for nm in ("aspect", "slope", "uca", "uca_edges", "edge_todo", "edge_done", "twi"):
@@ -192,6 +192,41 @@ class ProcessManager(object):
                     shared = (o.box[3] - t.box[2]) if dj < 0 else (t.box[3] - o.box[2]) if dj > 0 else \
                              (o.box[1] - t.box[0]) if di < 0 else (t.box[1] - o.box[0])
                     self.ring_w = max(self.ring_w, int(shared))
+
+    INPUT_FILE_TYPES = ("tif", "tiff")      # of the reference's _INPUT_FILE_TYPES (:462-463), what raster_io reads
+
+    @classmethod
+    def from_directory(cls, in_path, unit_spacing=False, grid_round_decimals=2, **kwargs):
+        """The reference's entry point: a directory of elevation GeoTIFFs (ProcessManager(in_path=...),
+        :461-472, compute_index :484-509).  Files are taken in sorted order; a tile's pixel box in
+        the mosaic follows from its bounds and pixel size, its spacing from its georeferencing
+        (utils.mk_dx_dy_from_geotif_layer via pydem_b200.raster_io).  unit_spacing=True forces
+        dX = dY = 1 like the reference's DEBUG switch (process_manager.py:52, used by its tests)."""
+        import os
+        from . import raster_io
+        files = sorted(os.path.join(in_path, f) for f in os.listdir(in_path)
+                       if os.path.splitext(f)[-1].replace(".", "").lower() in cls.INPUT_FILE_TYPES)
+        if not files:
+            raise ValueError("no elevation rasters (%s) in %s" % (", ".join(cls.INPUT_FILE_TYPES), in_path))
+        rs = [raster_io.read_geotiff(f) for f in files]
+        a = rs[0]["transform"].a; e = rs[0]["transform"].e
+        for f, r in zip(files, rs):
+            if abs(r["transform"].a - a) > 1e-9 * abs(a) or abs(r["transform"].e - e) > 1e-9 * abs(e):
+                raise ValueError("%s: tiles of different resolution are not supported by the in-memory orchestrator" % f)
+        left = min(r["bounds"][0] for r in rs); top = max(r["bounds"][3] for r in rs)
+        tiles, boxes, spacing = [], [], []
+        for r in rs:
+            H, W = r["elev"].shape
+            c0 = int(round((r["bounds"][0] - left) / a)); r0 = int(round((top - r["bounds"][3]) / abs(e)))
+            tiles.append(np.asarray(r["elev"], dtype="float64")); boxes.append((r0, r0 + H, c0, c0 + W))
+            if unit_spacing:
+                spacing.append(dict(dX=1.0, dY=1.0, dX2=1.0, dY2=1.0))
+            else:
+                dX, dY, dX2, dY2 = raster_io.mk_dx_dy(r["transform"], H, r["is_projected"], r["ellipsoid"])
+                spacing.append(dict(dX=dX, dY=dY, dX2=dX2, dY2=dY2))
+        pm = cls(tiles, boxes, spacing=spacing, **kwargs)
+        pm.elev_source_files = files
+        return pm
 
     # ------------------------------------------------------------------------------------
     # geometry (process_manager.py:517-740)

@@ -77,3 +77,31 @@ def test_reads_the_reference_fixture():
     from pydem_b200 import DEMProcessor
     dp = DEMProcessor(FIXTURE)
     assert dp.elev.shape == (32, 32) and dp.dX.shape == (31,) and dp.dY2.shape == (32,)
+
+
+def test_orchestrator_from_a_directory_of_geotiffs(tmp_path):
+    """ProcessManager.from_directory on tiles written the way the reference's multi-file generator lays
+    them out (utils_test_pydem.mk_test_multifile :359-408: pixel-centred lat/lon per chunk) reproduces
+    the reference ProcessManager's result for the same tiling (golden fixture), scheduling included."""
+    import contextlib, io, warnings
+    import helpers
+    from oracle.oracle import OracleDEMProcessor
+    from pydem_b200.process_manager import ProcessManager
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_pm.npz"))
+    name = "cone_5x4_3overlap"
+    E = G[name + "_E"]
+    boxes = [tuple(b) for b in G[name + "_boxes"].tolist()]
+    la = np.linspace(46.0, 45.0, E.shape[0]); lo = np.linspace(-73.0, -72.0, E.shape[1])
+    for (te, be, le, re) in boxes:
+        ph = -abs(la[te] - la[be - 1]) / ((be - te) - 1.0); pw = abs(lo[le] - lo[re - 1]) / ((re - le) - 1.0)
+        tr = rio.Affine((pw, 0.0, lo[le] - pw / 2, 0.0, ph, la[te] - ph / 2))
+        rio.write_geotiff(str(tmp_path / ("tile_%04d_%04d.tif" % (te, le))), E[te:be, le:re], tr)
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        pm = ProcessManager.from_directory(str(tmp_path), unit_spacing=True,
+                                           dem_processor=lambda **k: OracleDEMProcessor(k.pop("elev"), **k))
+        assert [t.box for t in pm.tiles] == boxes
+        pm.process_twi()
+    worst = helpers.pm_compare(pm, G, name)
+    assert worst["elev"] == 0 and worst["edge_todo"] == 0 and worst["edge_done"] == 0 and worst["uca"] <= 1e-9, worst
+    assert pm.correction_log == G[name + "_order"].tolist()
