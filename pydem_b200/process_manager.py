@@ -181,6 +181,7 @@ class ProcessManager(object):
         self.uca_edge_metrics = np.zeros((self.n_inputs, 2))
         self.success = np.zeros((self.n_inputs, 4), bool)
         self.correction_log = []       # tiles in the order process_uca_edges corrected them
+        self.georef = None             # set by from_directory: extreme bounds of the inputs
         self.compute_grid()
         self.compute_grid_overlaps()
         # ring width: the farthest a neighbour reaches into a tile (the larger overlap, at least 1)
@@ -226,7 +227,27 @@ class ProcessManager(object):
                 spacing.append(dict(dX=dX, dY=dY, dX2=dX2, dY2=dY2))
         pm = cls(tiles, boxes, spacing=spacing, **kwargs)
         pm.elev_source_files = files
+        pm.georef = dict(left=left, top=top, right=max(r["bounds"][2] for r in rs), bottom=min(r["bounds"][1] for r in rs),
+                         projected=rs[0]["is_projected"])
         return pm
+
+    def save_geotiff(self, filename, key, dtype="float64", rescale=None):
+        """The non-overlapping mosaic of `key` as one GeoTIFF (save_geotiff :862-931: transform from the
+        extreme bounds of the inputs over the mosaic size, optional
+        (data - rescale[0]) / (rescale[1] - rescale[0]) * rescale[2]).  Uncompressed, 512 x 512 tiles
+        (the reference writes LZW through rasterio).  Needs a manager made by from_directory."""
+        from . import raster_io
+        if getattr(self, "georef", None) is None:
+            raise RuntimeError("save_geotiff needs the georeferencing of the inputs: build the manager with from_directory()")
+        m = self.mosaic(key)
+        g = self.georef
+        dlat = (g["bottom"] - g["top"]) / m.shape[0]; dlon = (g["right"] - g["left"]) / m.shape[1]
+        if rescale:
+            m = (m - rescale[0]) / (rescale[1] - rescale[0]) * rescale[2]
+        if self.rank == 0:
+            raster_io.write_geotiff(filename, m.astype(dtype), raster_io.Affine((dlon, 0.0, g["left"], 0.0, dlat, g["top"])),
+                                    projected=g["projected"], tile=512 if max(m.shape) > 512 else None)
+        return filename
 
     # ------------------------------------------------------------------------------------
     # geometry (process_manager.py:517-740)

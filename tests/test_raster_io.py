@@ -105,3 +105,11 @@ def test_orchestrator_from_a_directory_of_geotiffs(tmp_path):
     worst = helpers.pm_compare(pm, G, name)
     assert worst["elev"] == 0 and worst["edge_todo"] == 0 and worst["edge_done"] == 0 and worst["uca"] <= 1e-9, worst
     assert pm.correction_log == G[name + "_order"].tolist()
+    # and back to a file: the mosaic with the transform of save_geotiff (:889-895)
+    out = str(tmp_path / "uca_mosaic.tif")
+    pm.save_geotiff(out, "uca")
+    r = rio.read_geotiff(out)
+    np.testing.assert_array_equal(r["elev"], pm.mosaic("uca"))
+    pw = 1.0 / 31.0
+    np.testing.assert_allclose(r["transform"], ((-72 + pw / 2 - (-73 - pw / 2)) / 32, 0, -73 - pw / 2, 0, -((46 + pw / 2) - (45 - pw / 2)) / 32, 46 + pw / 2),
+                               rtol=0, atol=1e-12)
