@@ -113,3 +113,38 @@ def test_orchestrator_from_a_directory_of_geotiffs(tmp_path):
     pw = 1.0 / 31.0
     np.testing.assert_allclose(r["transform"], ((-72 + pw / 2 - (-73 - pw / 2)) / 32, 0, -73 - pw / 2, 0, -((46 + pw / 2) - (45 - pw / 2)) / 32, 46 + pw / 2),
                                rtol=0, atol=1e-12)
+
+
+def test_big_endian_multi_strip_tiff(tmp_path):
+    """A hand-built big-endian TIFF with 3-row strips and a ModelTransformation tag instead of
+    pixel scale + tiepoint: the reader's other code paths."""
+    import struct
+    H, W, rps = 7, 5, 3
+    a = (np.arange(H * W, dtype=">f4").reshape(H, W) * 1.5).astype(">f4")
+    strips = [a[i:i + rps].tobytes() for i in range(0, H, rps)]
+    n_tags = 10
+    ifd_off = 8
+    extra_off = ifd_off + 2 + 12 * n_tags + 4
+    offs_tbl = extra_off
+    cnts_tbl = offs_tbl + 4 * len(strips)
+    mt_off = cnts_tbl + 4 * len(strips)
+    data_off = mt_off + 16 * 8
+    soffs, pos = [], data_off
+    for st in strips:
+        soffs.append(pos); pos += len(st)
+    M = [2.0, 0, 0, 100.0, 0, -3.0, 0, 50.0, 0, 0, 0, 0, 0, 0, 0, 1]
+    def ent(tag, typ, cnt, val):
+        return struct.pack(">HHI", tag, typ, cnt) + val
+    body = b"MM" + struct.pack(">HI", 42, ifd_off) + struct.pack(">H", n_tags)
+    body += ent(256, 3, 1, struct.pack(">HH", W, 0)) + ent(257, 3, 1, struct.pack(">HH", H, 0)) + ent(258, 3, 1, struct.pack(">HH", 32, 0))
+    body += ent(259, 3, 1, struct.pack(">HH", 1, 0)) + ent(273, 4, len(strips), struct.pack(">I", offs_tbl)) + ent(277, 3, 1, struct.pack(">HH", 1, 0))
+    body += ent(278, 3, 1, struct.pack(">HH", rps, 0)) + ent(279, 4, len(strips), struct.pack(">I", cnts_tbl)) + ent(339, 3, 1, struct.pack(">HH", 3, 0))
+    body += ent(34264, 12, 16, struct.pack(">I", mt_off)) + struct.pack(">I", 0)
+    body += struct.pack(">%dI" % len(strips), *soffs) + struct.pack(">%dI" % len(strips), *[len(st) for st in strips])
+    body += struct.pack(">16d", *M) + b"".join(strips)
+    fn = str(tmp_path / "be.tif")
+    open(fn, "wb").write(body)
+    r = rio.read_geotiff(fn)
+    np.testing.assert_array_equal(r["elev"], a.astype("f4"))
+    assert tuple(r["transform"]) == (2.0, 0.0, 100.0, 0.0, -3.0, 50.0)
+    assert r["bounds"] == (100.0, 50.0 - 3.0 * H, 100.0 + 2.0 * W, 50.0)
