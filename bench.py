@@ -31,7 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "Mcells/s slope+aspect + UCA + TWI (D-infinity hot path, f64)"
+METRIC = "Mcells/s slope+aspect and UCA (one pass of the D-infinity hot path: slope+aspect -> UCA -> TWI, f64; per-stage values in per_stage)"
 SPACING = 30.0
 BYTES_PER_CELL = 24.0   # read elev 8 + direction 8, write uca 8 (also 24 for the stencil)
 
