@@ -148,3 +148,31 @@ def test_big_endian_multi_strip_tiff(tmp_path):
     np.testing.assert_array_equal(r["elev"], a.astype("f4"))
     assert tuple(r["transform"]) == (2.0, 0.0, 100.0, 0.0, -3.0, 50.0)
     assert r["bounds"] == (100.0, 50.0 - 3.0 * H, 100.0 + 2.0 * W, 50.0)
+
+
+def test_from_directory_keeps_the_rasters_spacing(tmp_path):
+    """Projected rasters, no unit-spacing override: every tile's dX / dY are its own pixel size
+    (utils.py:132-137) -- the golden run of the reference ProcessManager without its DEBUG switch."""
+    import contextlib, io, warnings
+    import helpers
+    from oracle.oracle import OracleDEMProcessor
+    from pydem_b200.process_manager import ProcessManager
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_pm.npz"))
+    name = helpers.PM_SPACING_CASE
+    E = G[name + "_E"]
+    boxes = [tuple(b) for b in G[name + "_boxes"].tolist()]
+    la = np.linspace(helpers.PM_SPACING_GEO["lat"][0], helpers.PM_SPACING_GEO["lat"][1], E.shape[0])
+    lo = np.linspace(helpers.PM_SPACING_GEO["lon"][0], helpers.PM_SPACING_GEO["lon"][1], E.shape[1])
+    for (te, be, le, re) in boxes:
+        ph = -abs(la[te] - la[be - 1]) / ((be - te) - 1.0); pw = abs(lo[le] - lo[re - 1]) / ((re - le) - 1.0)
+        rio.write_geotiff(str(tmp_path / ("tile_%04d_%04d.tif" % (te, le))), E[te:be, le:re],
+                          rio.Affine((pw, 0.0, lo[le] - pw / 2, 0.0, ph, la[te] - ph / 2)), projected=True)
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        pm = ProcessManager.from_directory(str(tmp_path), dem_processor=lambda **k: OracleDEMProcessor(k.pop("elev"), **k))
+        assert [t.box for t in pm.tiles] == boxes
+        pm.process_twi()
+    worst = helpers.pm_compare(pm, G, name)
+    assert worst["elev"] == 0 and worst["edge_todo"] == 0 and worst["edge_done"] == 0, worst
+    assert worst["slope"] <= 1e-13 * 1e6 and worst["aspect"] <= 1e-12 and worst["uca"] <= 1e-9, worst
+    assert pm.correction_log == G[name + "_order"].tolist()
