@@ -157,13 +157,15 @@ def register_tiles(E, nx_grid, ny_grid, overlap, tag, lat=(46.0, 45.0), lon=(-73
 
 
 def run_reference_pm(E, nx_grid, ny_grid, overlap, tag, dem_processor=None, dem_proc_kwargs=None, debug_spacing=True,
-                     lat=(46.0, 45.0), lon=(-73.0, -72.0), overviews=None):
+                     lat=(46.0, 45.0), lon=(-73.0, -72.0), overviews=None, drop=()):
     """ProcessManager.process_twi() + save_non_overlap_data() of the reference on in-memory tiles.
     dem_processor: class to put in place of ``pydem.process_manager.DEMProcessor`` (None = the
     reference's own).  debug_spacing=False keeps the spacing the reference derives from the rasters
     (projected CRS: dX = pixel width, dY = pixel height, utils.py:132-137).  Returns a dict of the global arrays and the compact (non-overlapping) ones."""
     pm_mod = load_process_manager()
     names, boxes = register_tiles(E, nx_grid, ny_grid, overlap, tag, lat=lat, lon=lon)
+    if drop:                                  # a mosaic with holes: the reference allows missing tiles (grid_id2i == -1)
+        names = [n for k, n in enumerate(names) if k not in drop]; boxes = [b for k, b in enumerate(boxes) if k not in drop]
     out_path = "mem://%s/results.zarr" % tag
     for k in [k for k in _STORE if k.startswith(os.path.normpath("mem://%s" % tag))]:
         del _STORE[k]
@@ -183,7 +185,8 @@ def run_reference_pm(E, nx_grid, ny_grid, overlap, tag, dem_processor=None, dem_
             pm = pm_mod.ProcessManager(in_path="mem://%s/chunks" % tag, out_path=out_path, elev_source_files=list(names),
                                        n_workers=1, dem_proc_kwargs=dict(dem_proc_kwargs or {}))
             pm.process_twi()
-            pm.save_non_overlap_data()
+            if not drop:                      # the reference's compact store cannot be laid out around a hole
+                pm.save_non_overlap_data()
             if overviews:
                 pm.process_overviews(pm.out_path_noverlap, keys=["elev", "uca"], overviews=list(overviews))
     finally:
@@ -192,9 +195,10 @@ def run_reference_pm(E, nx_grid, ny_grid, overlap, tag, dem_processor=None, dem_
     base = os.path.normpath(out_path)
     for key in ("elev", "aspect", "slope", "uca", "uca_edges", "edge_todo", "edge_done", "twi", "success"):
         res[key] = np.array(_STORE[os.path.normpath(os.path.join(base, key))])
-    compact = os.path.normpath(pm.out_path_noverlap)
+    compact = os.path.normpath(pm.out_path_noverlap) if not drop else "\0none"
     for key in ("elev", "uca", "aspect", "slope", "twi"):
-        res["compact_" + key] = np.array(_STORE[os.path.normpath(os.path.join(compact, key))])
+        if not drop:
+            res["compact_" + key] = np.array(_STORE[os.path.normpath(os.path.join(compact, key))])
     for k in _STORE:
         if k.startswith(compact + os.sep) and os.path.basename(k).split("_")[-1].isdigit():
             res["overview_" + os.path.basename(k)] = np.array(_STORE[k])

@@ -71,3 +71,23 @@ def test_orchestrator_equals_reference_on_random_mosaics(block):
         assert pm.correction_log == r["correction_order"], msg
         assert w["elev"] == 0 and w["edge_todo"] == 0 and w["edge_done"] == 0, msg
         assert w["slope"] <= 1e-12 and w["aspect"] <= 1e-12 and w["uca"] <= 1e-9 and w["uca_edges"] <= 1e-9 and w["twi"] <= 1e-7, msg
+
+
+@pytest.mark.parametrize("drop", [(4,), (0,), (8,), (5,), (1, 7)])
+def test_mosaics_with_missing_tiles(drop):
+    """The reference tolerates holes in the tile grid (grid_id2i == -1, process_manager.py:527, 613-655)."""
+    from oracle import ref_pm_harness as H
+    E = helpers.synth.fractal_dem(64, 3)
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        r = H.run_reference_pm(E, 3, 3, 2, "hole" + "_".join(map(str, drop)), drop=drop)
+        boxes = r["boxes"]
+        pm = ProcessManager([E[b[0]:b[1], b[2]:b[3]] for b in boxes], boxes,
+                            dem_processor=lambda **k: OracleDEMProcessor(k.pop("elev"), **k))
+        pm.process_twi()
+    assert r["success"].all() and len(boxes) == 9 - len(drop)
+    G = {"fz_" + k: v for k, v in r.items() if isinstance(v, np.ndarray)}
+    G["fz_grid_slice"] = np.array(r["grid_slice"])
+    w = helpers.pm_compare(pm, G, "fz")
+    assert pm.correction_log == r["correction_order"], w
+    assert w["elev"] == 0 and w["edge_todo"] == 0 and w["edge_done"] == 0 and w["uca"] <= 1e-9 and w["uca_edges"] <= 1e-9 and w["aspect"] <= 1e-12, w
