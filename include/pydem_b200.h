@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PDM_ABI_VERSION 1
+#define PDM_ABI_VERSION 2
 
 typedef enum {
     PDM_OK = 0,
@@ -56,7 +56,9 @@ typedef enum {
     /* 10: reserved */
     PDM_F_FLAT0 = 11,    /* [u8]   mag == -1 before the one-pixel extension (shard halo exchange) */
     PDM_F_LINK = 12,     /* [u8]   facet index + kept-receiver bits of each cell (shard halo exchange) */
-    PDM_F_COUNT_ = 13
+    PDM_F_TAINT = 13,    /* [f64]  sweep state: accumulated edge_todo weight (shard halo exchange) */
+    PDM_F_PROP = 14,     /* [f64]  share of the cardinal receiver (shard halo exchange; shares the TWI buffer) */
+    PDM_F_COUNT_ = 15
 } pdm_field;
 
 /* Flags of DEMProcessor that act on the hot path (dem_processing.py:105-154). */
@@ -216,7 +218,8 @@ int pdm_tile_pit_drain_paths(pdm_tile *t, const pdm_cond_params *p, pdm_cond_sta
  * driver fills halo rows (elev, then flat0, then link) from the neighbouring ranks -- NCCL
  * send/recv on the row views obtained with pdm_tile_device_ptr -- and calls the stages in this
  * order: slopes, ccl, {label_pack / label_unpack until no rank changed}, flats_extend, links,
- * indeg, {sweep, outbox_pack, inbox_begin, inbox_apply until no rank sent}, finalize.
+ * (LINK and PROP halo rows), indeg, {sweep, sweep_sent, UCA and TAINT halo rows until no rank sent},
+ * finalize.
  * Equivalent of pyDEM's cross-tile edge resolution (process_manager.py:1090-1249) with true
  * halo stencils, so the sharded result equals the single-tile result. */
 int pdm_tile_set_window(pdm_tile *t, int64_t row_off, int64_t R_global, int64_t own_lo, int64_t own_hi,
@@ -229,9 +232,7 @@ int pdm_shard_flats_extend(pdm_tile *t);
 int pdm_shard_links(pdm_tile *t, const pdm_uca_params *p);
 int pdm_shard_indeg(pdm_tile *t);
 int pdm_shard_sweep(pdm_tile *t, int first);
-int pdm_shard_outbox_pack(pdm_tile *t, int side, void *out_area, void *out_taint, void *out_count, void *nonzero);
-int pdm_shard_inbox_begin(pdm_tile *t);
-int pdm_shard_inbox_apply(pdm_tile *t, int side, const void *in_area, const void *in_taint, const void *in_count);
+int pdm_shard_sweep_sent(pdm_tile *t, void *sent);
 int pdm_shard_finalize(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *stats);
 
 /* ---- one-shot host-buffer calls ---------------------------------------------------------- */

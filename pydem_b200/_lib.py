@@ -14,10 +14,11 @@ LIB_PATH = os.environ.get("PYDEM_B200_LIB") or os.path.join(_HERE, "libpydem_b20
 
 # pdm_field
 (F_ELEV, F_MAG, F_DIR, F_FLATS, F_UCA, F_TWI, F_EDGE_TODO, F_EDGE_DONE, F_SECTION, F_TWI10, F_RESERVED, F_FLAT0,
- F_LINK) = range(13)
+ F_LINK, F_TAINT, F_PROP) = range(15)
 FIELD_DTYPE = {F_ELEV: np.float64, F_MAG: np.float64, F_DIR: np.float64, F_FLATS: np.uint8,
                F_UCA: np.float64, F_TWI: np.float64, F_EDGE_TODO: np.uint8, F_EDGE_DONE: np.uint8,
-               F_SECTION: np.int8, F_TWI10: np.float64, F_FLAT0: np.uint8, F_LINK: np.uint8}
+               F_SECTION: np.int8, F_TWI10: np.float64, F_FLAT0: np.uint8, F_LINK: np.uint8,
+               F_TAINT: np.float64, F_PROP: np.float64}
 
 
 class UcaParams(ct.Structure):
@@ -65,7 +66,7 @@ EXPORTS = [
     "pdm_tile_slopes_directions", "pdm_tile_find_flats", "pdm_tile_uca", "pdm_tile_pit_updates", "pdm_tile_uca_update",
     "pdm_tile_twi", "pdm_tile_set_window", "pdm_shard_slopes", "pdm_shard_ccl", "pdm_shard_label_pack",
     "pdm_shard_label_unpack", "pdm_shard_flats_extend", "pdm_shard_links", "pdm_shard_indeg", "pdm_shard_sweep",
-    "pdm_shard_outbox_pack", "pdm_shard_inbox_begin", "pdm_shard_inbox_apply", "pdm_shard_finalize",
+    "pdm_shard_sweep_sent", "pdm_shard_finalize",
     "pdm_slopes_directions", "pdm_uca", "pdm_uca_update", "pdm_twi",
     "pdm_default_cond_params", "pdm_tile_fill_pit_artifacts", "pdm_tile_fill_flats", "pdm_tile_pit_drain_paths",
 ]
@@ -118,14 +119,13 @@ def load():
     for nm in ("pdm_tile_fill_pit_artifacts", "pdm_tile_fill_flats", "pdm_tile_pit_drain_paths"):
         getattr(L, nm).argtypes = [_vp, ct.POINTER(CondParams), ct.POINTER(CondStats)]
     L.pdm_tile_set_window.argtypes = [_vp, _i64, _i64, _i64, _i64, _vp]
-    for nm in ("pdm_shard_slopes", "pdm_shard_ccl", "pdm_shard_flats_extend", "pdm_shard_indeg", "pdm_shard_inbox_begin"):
+    for nm in ("pdm_shard_slopes", "pdm_shard_ccl", "pdm_shard_flats_extend", "pdm_shard_indeg"):
         getattr(L, nm).argtypes = [_vp]
     L.pdm_shard_label_pack.argtypes = [_vp, _i64, _vp, _vp]
     L.pdm_shard_label_unpack.argtypes = [_vp, _i64, _vp, _vp, _vp]
     L.pdm_shard_links.argtypes = [_vp, ct.POINTER(UcaParams)]
     L.pdm_shard_sweep.argtypes = [_vp, ct.c_int]
-    L.pdm_shard_outbox_pack.argtypes = [_vp, ct.c_int, _vp, _vp, _vp, _vp]
-    L.pdm_shard_inbox_apply.argtypes = [_vp, ct.c_int, _vp, _vp, _vp]
+    L.pdm_shard_sweep_sent.argtypes = [_vp, _vp]
     L.pdm_shard_finalize.argtypes = [_vp, ct.POINTER(UcaParams), ct.POINTER(UcaStats)]
     L.pdm_slopes_directions.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
     L.pdm_uca.argtypes = [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
@@ -133,7 +133,7 @@ def load():
     L.pdm_uca_update.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
                                  ct.POINTER(UcaParams)] + [_vp] * 12 + [_vp, _vp]
     L.pdm_twi.argtypes = [_vp, _vp, _i64, ct.POINTER(TwiParams), _vp]
-    if L.pdm_abi_version() != 1:
+    if L.pdm_abi_version() != 2:
         raise RuntimeError("pydem_b200: ABI version mismatch (%d)" % L.pdm_abi_version())
     _lib = L
     return L

@@ -7,7 +7,7 @@
 
 #include <vector>
 
-#include "pdm_internal.cuh"
+#include "tsweep.cuh"
 
 static thread_local char g_err[512] = "";
 unsigned long long g_pdm_launches = 0;
@@ -50,6 +50,8 @@ static void *field_ptr(pdm_tile *t, int field)
         case PDM_F_TWI10: return t->twi10;
         case PDM_F_FLAT0: return t->flat0;
         case PDM_F_LINK: return t->link;
+        case PDM_F_TAINT: return pdm_taint(t);
+        case PDM_F_PROP: return t->twi;
         default: return nullptr;
     }
 }
@@ -173,9 +175,10 @@ int pdm_tile_destroy(pdm_tile *t)
                     t->edge_todo, t->edge_done, t->section, t->label, t->queue, t->dX, t->dY, t->dg,
                     t->thA, t->thB, t->th_row, t->row_area, t->d_counters, t->pit_cell, t->pit_beg, t->pit_end,
                     t->pit_dst, t->pit_w, t->pit_scratch_i, t->pit_scratch_d, t->edge_buf_d, t->edge_buf_b,
-                    t->glabel, t->glelev, t->twi10, t->rdX, t->rdY, t->rdg};
+                    t->glabel, t->glelev, t->twi10, t->rdX, t->rdY, t->rdg, t->ts_slots, t->ts_flag, t->ts_ctr, t->ts_seen};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (t->h_counters) cudaFreeHost(t->h_counters);
+    if (t->ts_hctr) cudaFreeHost(t->ts_hctr);
     for (int k = 0; k < 4; k++) if (t->ev[k]) cudaEventDestroy(t->ev[k]);
     if (t->copy_stream) { cudaStreamSynchronize(t->copy_stream); cudaStreamDestroy(t->copy_stream); }
     if (t->copy_ev) cudaEventDestroy(t->copy_ev);
@@ -357,6 +360,10 @@ int pdm_tile_uca(pdm_tile *t, const pdm_uca_params *p_in, pdm_uca_stats *stats)
     PDM_CUDA(cudaEventRecord(t->ev[2], t->stream));
     rc = read_counters(t);
     if (rc) return rc;
+    if (!t->legacy_graph) {
+        rc = pdm_ts_read_counters(t);
+        if (rc) return rc;
+    }
     if (t->h_counters[CT_WATCHDOG]) {
         pdm_set_error("pdm_tile_uca: work-list watchdog fired (QTAIL=%llu QHEAD=%llu QDONE=%llu PHASE1=%llu CHUNK=%llu DRAINED=%llu "
                       "SOURCES=%llu DEALT=%llu TAKEN=%llu EXITS=%llu)",
@@ -380,6 +387,17 @@ int pdm_tile_uca(pdm_tile *t, const pdm_uca_params *p_in, pdm_uca_stats *stats)
     st.n_pits_undrained = (int64_t)t->h_counters[CT_PITS_UNDRAINED];
     st.ms_sweep_scan = (float)((double)(t->h_counters[CT_T_SCAN] - t->h_counters[CT_T_START]) * 1e-6);
     st.ms_sweep_kernel = (float)((double)(t->h_counters[CT_T_END] - t->h_counters[CT_T_START]) * 1e-6);
+    if (!t->legacy_graph) {
+        const unsigned long long *h = t->ts_hctr;
+        st.n_sources = (int64_t)h[ts::TC_SOURCES];
+        st.n_drained = (int64_t)h[ts::TC_CELLS];
+        st.n_queue_items = (int64_t)h[ts::TC_VISITS];       // tile visits
+        st.ms_sweep_scan = 0.0f;
+        st.ms_sweep_kernel = (float)((double)(h[ts::TC_T_END] - h[ts::TC_T_START]) * 1e-6);
+        if (getenv("PYDEM_B200_TS_DEBUG"))
+            fprintf(stderr, "[ts] kernel %.3f ms | visits %llu (repeated in place %llu) | cells %llu | levels %llu | sources %llu\n",
+                    st.ms_sweep_kernel, h[ts::TC_VISITS], h[ts::TC_REQUEUE], h[ts::TC_CELLS], h[ts::TC_LEVELS], h[ts::TC_SOURCES]);
+    }
     if (getenv("PYDEM_B200_WL_DEBUG")) {
         const unsigned long long *h = t->h_counters;
         fprintf(stderr, "[wl] kernel %.3f ms scan %.3f ms | scan-phase cells %llu | chains: calls %llu cells %llu avg %.0f ns/cell | "

@@ -163,9 +163,12 @@ __device__ __forceinline__ bool sec_in(int sec, uint32_t mask) { return sec >= 0
 // inflow-border mask of _calc_uca_chunk 909-937 for the owned cells on the border of the global
 // grid.  Thread t < C: top-row candidate, t < 2C: bottom-row candidate, then two per owned row
 // (left / right column).  Also seeds taint (edge_todo as float, 944).
+// LEGACY: proportions / taint live in the Cell records of the work-list sweep; else the proportion
+// plane is read and only the mask is written (the tile sweep seeds taint from the mask).
+template <bool LEGACY>
 __global__ void __launch_bounds__(256)
 k_border_todo(const double *__restrict__ E, const uint8_t *__restrict__ link, Cell *__restrict__ cell,
-              Win w, const int32_t *__restrict__ pit_beg, const int32_t *__restrict__ pit_end, const double *__restrict__ pit_w,
+              const double *__restrict__ prop, Win w, const int32_t *__restrict__ pit_beg, const int32_t *__restrict__ pit_end, const double *__restrict__ pit_w,
               const int32_t *__restrict__ pit_dst, int64_t n_pit_edges,
               uint8_t *__restrict__ edge_todo, unsigned long long *counters)
 {
@@ -189,10 +192,10 @@ k_border_todo(const double *__restrict__ E, const uint8_t *__restrict__ link, Ce
     double outflow = 0.0;
     int sec = (lk & LK_NOSEC) ? -1 : (lk & LK_SEC_MASK);
     if (lk & LK_PIT) {
-        const int64_t slot = __double_as_longlong(cell[n].prop);
+        const int64_t slot = __double_as_longlong(LEGACY ? cell[n].prop : prop[n]);
         for (int32_t e = pit_beg[slot]; e < pit_end[slot]; e++) outflow += pit_w[e];
     } else {
-        const double p = cell[n].prop;
+        const double p = LEGACY ? cell[n].prop : prop[n];
         // scipy sums a column's entries in row-index order; two terms commute
         if (lk & LK_KEEP1) outflow += p;
         if (lk & LK_KEEP2) outflow += __dsub_rn(1.0, p);
@@ -214,8 +217,9 @@ k_border_todo(const double *__restrict__ E, const uint8_t *__restrict__ link, Ce
                 const uint8_t ml = link[mi * C + mj];
                 if (ml & (LK_NOSEC | LK_PIT)) continue;
                 const int ms = ml & LK_SEC_MASK;
-                if ((ml & LK_KEEP1) && g_e1r[ms] == -di && g_e1c[ms] == -dj) inflow += cell[mi * C + mj].prop;
-                if ((ml & LK_KEEP2) && g_e2r[ms] == -di && g_e2c[ms] == -dj) inflow += __dsub_rn(1.0, cell[mi * C + mj].prop);
+                const double mp = LEGACY ? cell[mi * C + mj].prop : prop[mi * C + mj];
+                if ((ml & LK_KEEP1) && g_e1r[ms] == -di && g_e1c[ms] == -dj) inflow += mp;
+                if ((ml & LK_KEEP2) && g_e2r[ms] == -di && g_e2c[ms] == -dj) inflow += __dsub_rn(1.0, mp);
             }
         for (int64_t e = 0; e < n_pit_edges; e++)
             if (pit_dst[e] == (int32_t)n) inflow += pit_w[e];
@@ -224,7 +228,7 @@ k_border_todo(const double *__restrict__ E, const uint8_t *__restrict__ link, Ce
     const double e0 = E[n];
     if (e0 != e0) todo = false;                                             // 935
     edge_todo[n] = todo ? 1 : 0;
-    if (todo) { cell[n].taint = 1.0; atomicAdd(&counters[CT_EDGE_TODO], 1ULL); }
+    if (todo) { if (LEGACY) cell[n].taint = 1.0; atomicAdd(&counters[CT_EDGE_TODO], 1ULL); }
 }
 
 }  // namespace
@@ -270,10 +274,26 @@ int pdm_launch_indeg_todo(pdm_tile *t)
                                            t->d_counters);
     PDM_LAUNCHED();
     const int64_t per = 2 * w.C + 2 * (w.hi - w.lo);
-    k_border_todo<<<(unsigned)((per + 255) / 256), 256, 0, t->stream>>>(
-        t->elev, t->link, t->cell, w, t->pit_beg, t->pit_end, t->pit_w, t->pit_dst, t->n_pit_edges,
+    k_border_todo<true><<<(unsigned)((per + 255) / 256), 256, 0, t->stream>>>(
+        t->elev, t->link, t->cell, t->twi, w, t->pit_beg, t->pit_end, t->pit_w, t->pit_dst, t->n_pit_edges,
         t->edge_todo, t->d_counters);
     PDM_LAUNCHED();
+    t->legacy_graph = true;
+    return PDM_OK;
+}
+
+// tile sweep: only the inflow-border mask is needed (in-degrees are counted per tile visit from the
+// neighbours' link bytes; the neighbours' link AND proportion halo rows must be in place on a shard)
+int pdm_launch_border_todo(pdm_tile *t)
+{
+    const Win &w = t->win;
+    PDM_CUDA(cudaMemsetAsync(t->edge_todo, 0, (size_t)t->N, t->stream));
+    const int64_t per = 2 * w.C + 2 * (w.hi - w.lo);
+    k_border_todo<false><<<(unsigned)((per + 255) / 256), 256, 0, t->stream>>>(
+        t->elev, t->link, nullptr, t->twi, w, t->pit_beg, t->pit_end, t->pit_w, t->pit_dst, t->n_pit_edges,
+        t->edge_todo, t->d_counters);
+    PDM_LAUNCHED();
+    t->legacy_graph = false;
     return PDM_OK;
 }
 
@@ -282,7 +302,7 @@ int pdm_launch_graph(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *st)
     (void)st;
     int rc = pdm_graph_links_pits(t, p);
     if (rc) return rc;
-    return pdm_launch_indeg_todo(t);
+    return pdm_sweep_legacy() ? pdm_launch_indeg_todo(t) : pdm_launch_border_todo(t);
 }
 
 int pdm_launch_section_export(pdm_tile *t)

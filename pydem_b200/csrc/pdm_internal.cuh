@@ -26,7 +26,12 @@
 #define LK_KEEP2 0x10      // edge to the diagonal receiver e2 survives the filter
 #define LK_PIT 0x20        // cell drains through a pit edge list (prop holds the slot)
 #define LK_NOSEC 0x40      // section outside 0..7 (flat / undefined): no receivers
-#define LK_SOURCE 0x80     // nobody drains into this cell (initial frontier)
+#define LK_SOURCE 0x80     // legacy work-list sweep: nobody drains into this cell (initial frontier)
+#define LK_PITIN 0x80      // tile sweep: the cell receives pit edges (same bit: the two sweeps never share a graph)
+
+// tile sweep: UCA / taint hold this signalling-NaN pattern until the cell's sum is final (no
+// arithmetic produces it: operations quiet a signalling NaN)
+#define TS_NOT_DONE 0x7ff4dead7ff4deadULL
 
 // Row window of a tile inside a (possibly larger, row-sharded) grid.  A stand-alone tile has
 // row_off = 0, Rg = R, lo = 0, hi = R.  A shard keeps halo rows around its owned rows [lo, hi);
@@ -91,7 +96,19 @@ struct pdm_tile {
     cudaEvent_t ev[4];
     cudaStream_t copy_stream;   // device->host copies that overlap the next stage (pdm_tile_download_async)
     cudaEvent_t copy_ev;
+    // tile sweep (tsweep.cu): ticket queue, per-tile state words, counters (+ pinned mirror), the
+    // "already seen" bytes of the two halo rows of a shard
+    int32_t *ts_slots;
+    uint32_t *ts_flag;
+    unsigned long long *ts_ctr, *ts_hctr;
+    uint8_t *ts_seen;
+    int64_t ts_cap, ts_ntiles_cap;
+    bool legacy_graph;          // the graph on the tile was built for the legacy work-list sweep
 };
+
+// tile sweep state carved out of the 32-byte-per-cell record array (the legacy sweep and the update
+// mode use it as Cell records; the tile sweep as three f64 planes: taint | pit acc area | pit acc taint)
+static inline double *pdm_taint(const pdm_tile *t) { return reinterpret_cast<double *>(t->cell); }
 
 void pdm_set_error(const char *fmt, ...);
 int pdm_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
@@ -127,6 +144,14 @@ int pdm_launch_selftest_div(unsigned long long seed, int blocks, long long per_t
 int pdm_restart_rounds(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *st);
 int pdm_graph_links_pits(pdm_tile *t, const pdm_uca_params *p);
 int pdm_launch_pits(pdm_tile *t, const pdm_uca_params *p);
+// tile sweep (tsweep.cu)
+int pdm_ts_reset_state(pdm_tile *t);
+int pdm_launch_tsweep(pdm_tile *t, int first);
+int pdm_ts_read_counters(pdm_tile *t);
+int pdm_launch_ts_finalize(pdm_tile *t, const pdm_uca_params *p);
+int pdm_launch_border_todo(pdm_tile *t);
+int pdm_launch_indeg_todo(pdm_tile *t);
+bool pdm_sweep_legacy();
 
 // counters slots.  The queue counters are hammered by every warp (fetch-and-add tickets,
 // pushes, completion counts, termination polls): each lives on its own 128-byte line so the

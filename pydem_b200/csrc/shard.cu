@@ -2,56 +2,26 @@
 // one big DEM plus one halo row per interior side.  The host driver (pydem_b200/sharded.py)
 // moves halo rows between neighbouring ranks with NCCL send/recv and calls the stages below.
 //
-// UCA across shards is the same dependency-ordered accumulation as on one tile.  A cell whose
-// receiver lives on the neighbouring rank pushes into the halo row, which acts as an out-box:
-// area and taint accumulate there and the in-degree counter counts the decrements (it goes
-// negative).  When the local work-list is quiescent the out-boxes are exchanged, added into the
-// neighbour's boundary row, and the cells whose in-degree reached zero seed the next local pass.
-// The loop ends when no rank sent anything: #rounds = 1 + the largest number of shard boundaries
-// any flow path crosses.  Because every owned cell sees its true 3x3 neighbourhood and "border"
-// means the border of the global grid, the result equals the single-tile result (this is the
-// gating-free form of pyDEM's cross-tile edge resolution, process_manager.py:1090-1249, where
-// tiles re-run calc_uca on edge deltas until nothing changes).
+// UCA across shards is the same tile-resident, pull-based accumulation as on one tile (tsweep.cu).
+// Tiles cover the owned rows; the halo rows are ring cells: a boundary cell pulls the contributions
+// of its donors on the neighbouring rank from the halo row once they are final there.  After a
+// local sweep has come to rest, every rank sends its boundary rows of UCA / taint (final values, or
+// the "not done" pattern) into the neighbours' halo rows and resumes the boundary tiles whose ring
+// received new donors.  The loop ends when no rank completed a boundary cell with a receiver across
+// the boundary: #rounds = 1 + the largest number of shard boundaries any flow path crosses.
+// Because every owned cell sees its true 3x3 neighbourhood and "border" means the border of the
+// global grid, the result equals the single-tile result -- bit for bit, since a cell's sum has a
+// fixed order (this is the gating-free form of pyDEM's cross-tile edge resolution,
+// process_manager.py:1090-1249, where tiles re-run calc_uca on edge deltas until nothing changes).
 #include <string.h>
 
 #include "pdm_internal.cuh"
 
+#include "tsweep.cuh"
+
 namespace {
 
-__global__ void __launch_bounds__(256)
-k_outbox_pack(Cell *cell, int64_t row, int64_t C,
-              double *__restrict__ out_a, double *__restrict__ out_t, int32_t *__restrict__ out_c, long long *nonzero)
-{
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool nz = false;
-    if (j < C) {
-        Cell &x = cell[row * C + j];
-        const int32_t c = -x.indeg;
-        out_a[j] = x.area; out_t[j] = x.taint; out_c[j] = c;
-        x.area = 0.0; x.taint = 0.0; x.indeg = 0;
-        nz = c != 0;
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, nz);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd((unsigned long long *)nonzero, (unsigned long long)__popc(m));
-}
-
-__global__ void __launch_bounds__(256)
-k_inbox_apply(Cell *cell, int64_t row, int64_t C,
-              const double *__restrict__ in_a, const double *__restrict__ in_t, const int32_t *__restrict__ in_c,
-              int32_t *__restrict__ seeds, unsigned long long *ctr)
-{
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= C) return;
-    const int32_t c = in_c[j];
-    if (c == 0) return;
-    const int64_t n = row * C + j;
-    Cell &x = cell[n];
-    x.area = __dadd_rn(x.area, in_a[j]);
-    x.taint = __dadd_rn(x.taint, in_t[j]);
-    const int32_t left = x.indeg - c;
-    x.indeg = left;
-    if (left == 0) seeds[atomicAdd(&ctr[CT_TMP1], 1ULL)] = (int32_t)n;
-}
+__global__ void k_add_sent(const unsigned long long *ctr, long long *out) { *out += (long long)ctr[ts::TC_SENT]; }
 
 }  // namespace
 
@@ -59,10 +29,6 @@ int pdm_launch_ccl(pdm_tile *t);
 int pdm_launch_flats_extend(pdm_tile *t);
 int pdm_launch_label_pack(pdm_tile *t, int64_t row, long long *out_l, double *out_e);
 int pdm_launch_label_unpack(pdm_tile *t, int64_t row, const long long *in_l, const double *in_e);
-int pdm_launch_indeg_todo(pdm_tile *t);
-int pdm_launch_sweep_first(pdm_tile *t);
-int pdm_launch_sweep_resume(pdm_tile *t);
-int pdm_launch_uca_finalize(pdm_tile *t, const pdm_uca_params *p);
 
 static int read_ctr(pdm_tile *t)
 {
@@ -149,52 +115,29 @@ int pdm_shard_links(pdm_tile *t, const pdm_uca_params *p_in)
     return pdm_graph_links_pits(t, &p);
 }
 
-// in-degree, sources, sweep state, inflow-border mask (link halo rows must be in place)
+// inflow-border mask + fresh sweep state (link AND proportion halo rows must be in place)
 int pdm_shard_indeg(pdm_tile *t)
 {
     if (!t) return PDM_ERR_ARG;
-    return pdm_launch_indeg_todo(t);
+    int rc = pdm_launch_border_todo(t);
+    if (rc) return rc;
+    return pdm_ts_reset_state(t);
 }
 
-// one local accumulation pass to quiescence; first != 0: seeds are the sources
+// one local accumulation pass until it comes to rest; first != 0: every tile, else the boundary
+// tiles whose halo row received new donors
 int pdm_shard_sweep(pdm_tile *t, int first)
 {
     if (!t) return PDM_ERR_ARG;
-    return first ? pdm_launch_sweep_first(t) : pdm_launch_sweep_resume(t);
+    return pdm_launch_tsweep(t, first);
 }
 
-// side 0: out-box toward the rank above (halo row lo-1), side 1: below (halo row hi).
-// nonzero (device int64) += number of cells with something to deliver.
-int pdm_shard_outbox_pack(pdm_tile *t, int side, void *out_area, void *out_taint, void *out_count, void *nonzero)
+// *sent (device int64) += boundary cells completed by the last pdm_shard_sweep whose receiver lives
+// on a neighbouring rank (0 on every rank = the sweep is over)
+int pdm_shard_sweep_sent(pdm_tile *t, void *sent)
 {
-    if (!t) return PDM_ERR_ARG;
-    const Win &w = t->win;
-    const int64_t row = side == 0 ? w.lo - 1 : w.hi;
-    if (row < 0 || row >= t->R) { pdm_set_error("pdm_shard_outbox_pack: no halo row on side %d", side); return PDM_ERR_ARG; }
-    k_outbox_pack<<<(unsigned)((t->C + 255) / 256), 256, 0, t->stream>>>(t->cell, row, t->C,
-                                                                         (double *)out_area, (double *)out_taint,
-                                                                         (int32_t *)out_count, (long long *)nonzero);
-    PDM_LAUNCHED();
-    return PDM_OK;
-}
-
-// reset the seed list before the in-boxes of a round are applied
-int pdm_shard_inbox_begin(pdm_tile *t)
-{
-    if (!t) return PDM_ERR_ARG;
-    PDM_CUDA(cudaMemsetAsync(t->d_counters + CT_TMP1, 0, sizeof(unsigned long long), t->stream));
-    return PDM_OK;
-}
-
-// side 0: what the rank above delivered to my first owned row, side 1: below -> last owned row
-int pdm_shard_inbox_apply(pdm_tile *t, int side, const void *in_area, const void *in_taint, const void *in_count)
-{
-    if (!t) return PDM_ERR_ARG;
-    const Win &w = t->win;
-    const int64_t row = side == 0 ? w.lo : w.hi - 1;
-    k_inbox_apply<<<(unsigned)((t->C + 255) / 256), 256, 0, t->stream>>>(t->cell, row, t->C,
-                                                                         (const double *)in_area, (const double *)in_taint,
-                                                                         (const int32_t *)in_count, t->label, t->d_counters);
+    if (!t || !sent || !t->ts_ctr) { pdm_set_error("pdm_shard_sweep_sent: bad argument / no sweep yet"); return PDM_ERR_ARG; }
+    k_add_sent<<<1, 1, 0, t->stream>>>(t->ts_ctr, (long long *)sent);
     PDM_LAUNCHED();
     return PDM_OK;
 }
@@ -204,22 +147,19 @@ int pdm_shard_finalize(pdm_tile *t, const pdm_uca_params *p_in, pdm_uca_stats *s
     if (!t) return PDM_ERR_ARG;
     pdm_uca_params p;
     if (p_in) p = *p_in; else pdm_default_uca_params(&p);
-    int rc = pdm_launch_uca_finalize(t, &p);
+    int rc = pdm_launch_ts_finalize(t, &p);
     if (rc) return rc;
     rc = read_ctr(t);
     if (rc) return rc;
-    if (t->h_counters[CT_WATCHDOG]) {
-        pdm_set_error("pdm_shard_finalize: work-list watchdog fired (QTAIL=%llu QHEAD=%llu QDONE=%llu PHASE1=%llu DRAINED=%llu)",
-                      t->h_counters[CT_QTAIL], t->h_counters[CT_QHEAD], t->h_counters[CT_QDONE], t->h_counters[CT_PHASE1],
-                      t->h_counters[CT_DRAINED]);
-        return PDM_ERR_STATE;
-    }
+    rc = pdm_ts_read_counters(t);
+    if (rc) return rc;
     t->have_uca = true; t->have_graph = true;
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         stats->n_cells = (t->win.hi - t->win.lo) * t->C;
-        stats->n_sources = (int64_t)t->h_counters[CT_SOURCES];
-        stats->n_drained = (int64_t)t->h_counters[CT_DRAINED];
+        stats->n_sources = (int64_t)t->ts_hctr[ts::TC_SOURCES];
+        stats->n_drained = (int64_t)t->ts_hctr[ts::TC_CELLS];
+        stats->n_queue_items = (int64_t)t->ts_hctr[ts::TC_VISITS];
         stats->n_undone = (int64_t)t->h_counters[CT_UNDONE];
         stats->n_edge_todo = (int64_t)t->h_counters[CT_EDGE_TODO];
         stats->min_area = t->min_area;

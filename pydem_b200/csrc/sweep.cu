@@ -74,7 +74,15 @@ k_twi(const double *__restrict__ uca, const double *__restrict__ mag, double *__
 
 }  // namespace
 
-static int g_sweep_blocks = 0, g_resume_blocks = 0;
+static int g_sweep_blocks = 0;
+
+// PYDEM_B200_SWEEP_LEGACY=1: the round-1 work-list sweep (L2 atomics) instead of the tile sweep (A/B runs)
+bool pdm_sweep_legacy()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("PYDEM_B200_SWEEP_LEGACY"); v = (e && atoi(e)) ? 1 : 0; }
+    return v != 0;
+}
 
 static int sweep_strict()
 {
@@ -100,22 +108,6 @@ int pdm_launch_sweep_first(pdm_tile *t)
     return PDM_OK;
 }
 
-// shard rounds: continue from the cells the in-box made ready (list in t->label, length in CT_TMP1)
-int pdm_launch_sweep_resume(pdm_tile *t)
-{
-    if (!g_resume_blocks) {
-        int rc = wl::grid_for(wl::k_worklist<DrainOp<2>, wl::DomainList>, &g_resume_blocks);
-        if (rc) return rc;
-    }
-    int rc = wl::reset_queue(t, 1);
-    if (rc) return rc;
-    DrainOp<2> op{t->link, t->cell, nullptr, (int32_t)t->C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w, sweep_strict()};
-    wl::k_worklist<<<g_resume_blocks, 256, 0, t->stream>>>(op, wl::DomainList{t->label, t->d_counters + CT_TMP1},
-                                                           wl::tuned(wl::Queue{t->queue, t->d_counters, (long long)t->N, t->d_counters + CT_TMP1}));
-    PDM_LAUNCHED();
-    return PDM_OK;
-}
-
 int pdm_launch_uca_finalize(pdm_tile *t, const pdm_uca_params *p)
 {
     const Win &w = t->win;
@@ -131,9 +123,16 @@ int pdm_launch_uca_finalize(pdm_tile *t, const pdm_uca_params *p)
 int pdm_launch_sweep_full(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *st)
 {
     (void)st;
-    int rc = pdm_launch_sweep_first(t);
+    if (t->legacy_graph) {
+        int rc = pdm_launch_sweep_first(t);
+        if (rc) return rc;
+        return pdm_launch_uca_finalize(t, p);
+    }
+    int rc = pdm_ts_reset_state(t);
     if (rc) return rc;
-    return pdm_launch_uca_finalize(t, p);
+    rc = pdm_launch_tsweep(t, 1);
+    if (rc) return rc;
+    return pdm_launch_ts_finalize(t, p);
 }
 
 int pdm_launch_twi(pdm_tile *t, const pdm_twi_params *p)

@@ -16,13 +16,19 @@ the reference; all arithmetic happens on the GPU.  There is no CPU fallback: a m
 library or device raises ``RuntimeError`` (the reference does the same when its Cython
 module is absent, dem_processing.py:714-715).
 
-Host<->device traffic: callers of the reference mutate the NumPy attributes between calls
-(``dp.dX[:] = 1`` in its tests, edge rows of ``direction`` in ``process_manager.calc_uca``),
-so every public ``calc_*`` call uploads its inputs from the attributes.  Stages that the
-reference chains internally (``calc_twi -> calc_uca -> calc_slopes_directions`` when the
-intermediate attribute is ``None``) stay resident in HBM and are downloaded once.
+Host<->device traffic: results stay in HBM and the array attributes (``mag direction flats uca
+edge_todo edge_done twi`` and a conditioned ``elev``) are *lazy*: the first read downloads the
+field (the object keeps its device tile alive until then), only the value a ``calc_*`` call
+returns is copied eagerly.  ``calc_twi()`` on a fresh object therefore moves the DEM in and the
+index out -- not the six intermediate fields nobody asked for.  Callers of the reference mutate
+the NumPy attributes between calls (``dp.dX[:] = 1`` in its tests, edge rows of ``direction`` in
+``process_manager.calc_uca``): once an attribute has been read (or assigned) the host array is
+the truth again and the next ``calc_*`` call uploads it, exactly as before.
+``PYDEM_B200_EAGER=1`` restores the eager behaviour (every output downloaded by the call that
+produced it).
 """
 import ctypes as ct
+import os
 import warnings
 
 import numpy as np
@@ -66,6 +72,9 @@ class DEMProcessor(object):
             kwargs["dY"] = np.ones(nrow - 1) * kwargs.get("dY", 1)
         for k, v in self._DEFAULTS.items():
             setattr(self, k, kwargs.pop(k, v))
+        self._host = {}          # lazy attributes: host copies (None = not on the host)
+        self._ondev = set()      # lazy attributes whose only valid copy lives on the device tile
+        self._eager = bool(int(os.environ.get("PYDEM_B200_EAGER", "0")))
         for k in self._ARRAYS:
             v = kwargs.pop(k, None)
             setattr(self, k, None if v is None else np.asarray(v))
@@ -78,8 +87,6 @@ class DEMProcessor(object):
         self.device = kwargs.pop("device", None)
         if kwargs:
             raise TypeError("DEMProcessor got unexpected keyword arguments %s" % sorted(kwargs))
-        self.edge_todo = None
-        self.edge_done = None
         self.section = None
         self.proportion = None
         self.A = None            # the reference's sparse matrix is never materialised here
@@ -88,6 +95,60 @@ class DEMProcessor(object):
         self._tile_shape = None
         self._chain = 0          # >0 while stages are chained inside one public call
         self._resident = set()   # fields valid in HBM during a chain
+
+    # ------------------------------------------------------------------------------------
+    # lazy array attributes
+    # ------------------------------------------------------------------------------------
+    _LAZY = {"elev": _lib.F_ELEV, "mag": _lib.F_MAG, "direction": _lib.F_DIR, "flats": _lib.F_FLATS, "uca": _lib.F_UCA,
+             "edge_todo": _lib.F_EDGE_TODO, "edge_done": _lib.F_EDGE_DONE}
+    _BOOL = ("flats", "edge_todo", "edge_done")
+
+    def _lazy_get(self, name):
+        v = self._host.get(name)
+        if v is None and name in self._ondev:
+            v = self._fetch(name)
+        return v
+
+    def _lazy_set(self, name, value):
+        self._host[name] = None if value is None else np.asarray(value)
+        self._ondev.discard(name)
+        if name == "elev" and value is not None:
+            self._shape = tuple(np.shape(value))
+
+    def _has(self, name):
+        return self._host.get(name) is not None or name in self._ondev
+
+    def _fetch(self, name):
+        """first read of a device-only attribute: download it.  From here on the host array is the
+        truth (the caller may mutate it), so the device copy is no longer trusted."""
+        out = _pinned.empty(self._tile_shape, _lib.FIELD_DTYPE[self._LAZY[name]])
+        _lib.check(_lib.load().pdm_tile_download(self._tile, self._LAZY[name], _lib.ptr(out)))
+        if name in self._BOOL:
+            out = out.view(np.bool_)
+        self._host[name] = out
+        self._ondev.discard(name)
+        return out
+
+    def _produced(self, *names):
+        """fields a stage has just written on the device"""
+        for n in names:
+            self._host[n] = None
+            self._ondev.add(n)
+        if self._eager:
+            for n in names:
+                self._fetch(n)
+
+    @property
+    def twi(self):
+        """10 * (un-scaled index), dem_processing.py:1674"""
+        if self._twi10 is None and self._twi_raw is not None:
+            self._twi10 = self._twi_raw * 10.0        # same IEEE product the device would form
+        return self._twi10
+
+    @twi.setter
+    def twi(self, value):
+        self._twi10 = None if value is None else np.asarray(value)
+        self._twi_raw = None
 
     # ------------------------------------------------------------------------------------
     # device plumbing
@@ -103,7 +164,7 @@ class DEMProcessor(object):
 
     def _get_tile(self):
         L = self._lib()
-        shape = tuple(self.elev.shape)
+        shape = tuple(self._shape)
         if self._tile is not None and self._tile_shape != shape:
             self._free_tile()
         if self._tile is None:
@@ -117,8 +178,14 @@ class DEMProcessor(object):
             self._tile, self._tile_shape = h, shape
         return self._tile
 
-    def _free_tile(self):
+    def _free_tile(self, keep_results=False):
+        """Park the device tile for the next DEMProcessor of this shape.  keep_results: download the
+        attributes that only live on the device first (otherwise they are dropped)."""
         if self._tile is not None:
+            if keep_results:
+                for n in list(self._ondev):
+                    self._fetch(n)
+            self._ondev = set()
             try:
                 key = (self._tile_shape, _lib._device)
                 if key not in DEMProcessor._TILE_CACHE:
@@ -143,11 +210,12 @@ class DEMProcessor(object):
     def __del__(self):
         self._free_tile()
 
-    def _up(self, field, arr):
-        """host -> HBM unless the field is already resident from a chained stage."""
-        if self._chain and field in self._resident:
+    def _up(self, field, name):
+        """host -> HBM unless the field is already resident from a chained stage or has never
+        left the device."""
+        if name in self._ondev or (self._chain and field in self._resident):
             return
-        a = np.asarray(arr)
+        a = np.asarray(self._host[name])
         if a.dtype == np.bool_ and _lib.FIELD_DTYPE[field] == np.uint8:
             a = a.view(np.uint8)                      # same bytes, no copy
         a = np.ascontiguousarray(a, dtype=_lib.FIELD_DTYPE[field])
@@ -174,7 +242,7 @@ class DEMProcessor(object):
         return a
 
     def _spacing(self):
-        R = self.elev.shape[0]
+        R = self._shape[0]
         dX = np.ascontiguousarray(self.dX, "float64"); dY = np.ascontiguousarray(self.dY, "float64")
         dX2 = np.ascontiguousarray(self.dX2, "float64"); dY2 = np.ascontiguousarray(self.dY2, "float64")
         if dX.shape != (R - 1,) or dY.shape != (R - 1,) or dX2.shape != (R,) or dY2.shape != (R,):
@@ -199,14 +267,6 @@ class DEMProcessor(object):
     # ------------------------------------------------------------------------------------
     # reference API
     # ------------------------------------------------------------------------------------
-    def _conditioning_flags(self):
-        """The flags the reference's conditioning routines read (for delegating them to the
-        reference implementation)."""
-        keys = ("fill_flats_below_sea", "fill_flats_source_tol", "fill_flats_peaks", "fill_flats_pits",
-                "fill_flats_max_iter", "drain_pits_max_iter", "drain_pits_max_dist", "drain_pits_max_dist_XY",
-                "maximum_pit_area")
-        return {k: getattr(self, k) for k in keys}
-
     def find_flats(self):
         """dem_processing.py:305-306"""
         self.flats = self.mag == FLAT_ID_INT
@@ -232,7 +292,7 @@ class DEMProcessor(object):
             L = self._lib()
             t = self._get_tile()
             self._spacing()
-            self._up(_lib.F_ELEV, np.asarray(self.elev, dtype="float64"))
+            self._up(_lib.F_ELEV, "elev")
             p = self._cond_params()
             stats = {}
             for name in stages:
@@ -240,7 +300,7 @@ class DEMProcessor(object):
                 _lib.check(getattr(L, "pdm_tile_" + name)(t, ct.byref(p), ct.byref(st)))
                 stats.update({k: getattr(st, k) for k, _ in st._fields_ if getattr(st, k)})
             self._resident = {_lib.F_ELEV}            # every derived field of the tile is stale now
-            self.elev = self._down(_lib.F_ELEV)
+            self._produced("elev")                    # the reference rebinds self.elev
             self.cond_stats = stats
             if stats.get("n_pits_undrained"):
                 warnings.warn("Warning %d pits had no place to drain to in this chunk" % stats["n_pits_undrained"])
@@ -275,15 +335,16 @@ class DEMProcessor(object):
             L = self._lib()
             t = self._get_tile()
             self._spacing()
-            self._up(_lib.F_ELEV, self.elev)
+            self._up(_lib.F_ELEV, "elev")
             _lib.check(L.pdm_tile_slopes_directions(t))
             self._resident.update((_lib.F_MAG, _lib.F_DIR, _lib.F_FLATS))
-            self.mag = self._down(_lib.F_MAG)
-            self.direction = self._down(_lib.F_DIR)
-            self.flats = self._down(_lib.F_FLATS).view(np.bool_)
+            self._produced("mag", "direction", "flats")
+            outer = self._chain == 1
         finally:
             self._end()
-        return self.mag, self.direction
+        if outer:
+            return self.mag, self.direction       # the call's return value: downloaded now
+        return None
 
     def _uca_params(self):
         p = _lib.UcaParams()
@@ -311,17 +372,17 @@ class DEMProcessor(object):
         left/right/top/bottom) and ``uca_init``."""
         self._begin()
         try:
-            if self.direction is None:
+            if not self._has("direction"):
                 self.calc_slopes_directions()
             L = self._lib()
             t = self._get_tile()
             self._spacing()
-            self._up(_lib.F_ELEV, self.elev)
-            self._up(_lib.F_DIR, self.direction)
-            self._up(_lib.F_MAG, self.mag)
-            if self.flats is None:
+            self._up(_lib.F_ELEV, "elev")
+            self._up(_lib.F_DIR, "direction")
+            self._up(_lib.F_MAG, "mag")
+            if not self._has("flats"):
                 raise ValueError("flats is not set: call calc_slopes_directions() or find_flats() first")
-            self._up(_lib.F_FLATS, self.flats)
+            self._up(_lib.F_FLATS, "flats")
             p = self._uca_params()
             st = _lib.UcaStats()
             if uca_init is None:
@@ -332,44 +393,49 @@ class DEMProcessor(object):
                 R, C = self._tile_shape
                 strips = _pack_edges(edge_init_data, R, C)
                 self._resident.discard(_lib.F_UCA)
-                self._up(_lib.F_UCA, np.asarray(uca_init).astype("float64"))       # 744
+                self.uca = np.asarray(uca_init).astype("float64")                   # 744
+                self._up(_lib.F_UCA, "uca")
                 args = [_lib.ptr(a) for a in strips]
                 _lib.check(L.pdm_tile_uca_update(t, ct.byref(p), *args, ct.byref(st)))
             self._resident.update((_lib.F_UCA, _lib.F_MAG, _lib.F_FLATS))
             self.uca_stats = st.as_dict()
-            self.uca = self._down(_lib.F_UCA)
-            self.edge_todo = self._down(_lib.F_EDGE_TODO).view(np.bool_)
-            self.edge_done = self._down(_lib.F_EDGE_DONE).view(np.bool_)
+            self._produced("uca", "edge_todo", "edge_done")
             if p.drain_pits and st.n_pits:
-                # _mk_connectivity_pits updates mag / flats of drained pits in place (1370-1371)
-                # _mk_connectivity_pits changes mag / flats only at the examined pits: patch the host
-                # arrays in place (like the reference) from a sparse readback
-                _lib.check(L.pdm_tile_sync(t))      # earlier mag / flats downloads must have landed before patching
-                npit = int(st.n_pits)
-                cells = np.empty(npit, np.int32); pmag = np.empty(npit, np.float64); pfl = np.empty(npit, np.uint8)
-                got = ct.c_int64(0)
-                _lib.check(L.pdm_tile_pit_updates(t, npit, _lib.ptr(cells), _lib.ptr(pmag), _lib.ptr(pfl), ct.byref(got)))
-                self.mag = self._patched(self.mag, cells, pmag, np.float64)
-                self.flats = self._patched(self.flats, cells, pfl.view(np.bool_), np.bool_)
+                # _mk_connectivity_pits updates mag / flats of drained pits in place (1370-1371).  It
+                # changes them only at the examined pits: host arrays the caller already holds are
+                # patched in place (like the reference) from a sparse readback; copies that only live
+                # on the device are already up to date
+                host_mag, host_fl = self._host.get("mag"), self._host.get("flats")
+                if host_mag is not None or host_fl is not None:
+                    _lib.check(L.pdm_tile_sync(t))
+                    npit = int(st.n_pits)
+                    cells = np.empty(npit, np.int32); pmag = np.empty(npit, np.float64); pfl = np.empty(npit, np.uint8)
+                    got = ct.c_int64(0)
+                    _lib.check(L.pdm_tile_pit_updates(t, npit, _lib.ptr(cells), _lib.ptr(pmag), _lib.ptr(pfl), ct.byref(got)))
+                    if host_mag is not None:
+                        self._host["mag"] = self._patched(host_mag, cells, pmag, np.float64)
+                    if host_fl is not None:
+                        self._host["flats"] = self._patched(host_fl, cells, pfl.view(np.bool_), np.bool_)
                 if st.n_pits_undrained:
                     warnings.warn("Warning %d pits had no place to drain to in this chunk" % st.n_pits_undrained)
             if st.n_undone:
                 warnings.warn("%d cells are on circular references and were not drained" % st.n_undone)
+            outer = self._chain == 1
         finally:
             self._end()
-        return self.uca
+        return self.uca if outer else None
 
     def calc_twi(self):
         """Topographic wetness index (dem_processing.py:1647-1677): returns the un-scaled
         index and stores ``self.twi = 10 * twi``."""
         self._begin()
         try:
-            if self.uca is None:
+            if not self._has("uca"):
                 self.calc_uca()
             L = self._lib()
             t = self._get_tile()
-            self._up(_lib.F_UCA, self.uca)
-            self._up(_lib.F_MAG, self.mag)
+            self._up(_lib.F_UCA, "uca")
+            self._up(_lib.F_MAG, "mag")
             p = _lib.TwiParams()
             L.pdm_default_twi_params(ct.byref(p))
             p.twi_min_slope = float(self.twi_min_slope)
@@ -379,7 +445,8 @@ class DEMProcessor(object):
             p.apply_twi_limits_on_uca = int(bool(self.apply_twi_limits_on_uca))
             _lib.check(L.pdm_tile_twi(t, ct.byref(p)))
             twi = self._down(_lib.F_TWI)
-            self.twi = self._down(_lib.F_TWI10)                             # 1674: 10 * twi, scaled on the GPU
+            self._twi10 = None                                              # 1674: self.twi = 10 * twi, formed on first read
+            self._twi_raw = twi
         finally:
             self._end()
         return twi
@@ -393,14 +460,23 @@ class DEMProcessor(object):
             L = self._lib()
             t = self._get_tile()
             self._spacing()
-            self._up(_lib.F_ELEV, self.elev)
-            self._up(_lib.F_DIR, self.direction)
-            self._up(_lib.F_MAG, self.mag)
-            self._up(_lib.F_FLATS, self.flats)
+            self._up(_lib.F_ELEV, "elev")
+            self._up(_lib.F_DIR, "direction")
+            self._up(_lib.F_MAG, "mag")
+            self._up(_lib.F_FLATS, "flats")
             self.section = self._down(_lib.F_SECTION)    # (synchronous: computed on demand)
         finally:
             self._end()
         return self.section
+
+
+def _install_lazy():
+    for _name in DEMProcessor._LAZY:
+        setattr(DEMProcessor, _name, property(lambda self, _n=_name: self._lazy_get(_n),
+                                              lambda self, v, _n=_name: self._lazy_set(_n, v)))
+
+
+_install_lazy()
 
 
 def _pack_edges(edge_init_data, R, C):

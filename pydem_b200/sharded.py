@@ -6,16 +6,17 @@ travel between neighbouring ranks with NCCL send/recv (``Group.exchange``), ever
 local CUDA work through the ``pdm_shard_*`` C ABI (csrc/shard.cu):
 
     elev halo -> slope/aspect (a1) -> flat0 halo -> region labels (+ label rounds) -> flats (a2)
-    -> links (a3/a4) -> link halo -> in-degree / inflow mask
-    -> { local sweep to quiescence ; exchange out-boxes ; apply in-boxes } until nobody sent
+    -> links (a3/a4) -> link + proportion halo -> inflow mask, fresh sweep state
+    -> { local sweep until it rests ; exchange boundary rows of UCA / taint } until nobody sent
     -> finalize -> TWI
 
 This is pyDEM's cross-tile UCA edge resolution (reference process_manager.py:1090-1249:
 tiles exchange edge strips and re-run calc_uca on the deltas until nothing changes) in its
-gating-free form: contributions that cross a shard boundary are accumulated in the halo row
-(out-box) together with the number of in-degree decrements they stand for.  Because every
-owned cell is computed from its true 3x3 neighbourhood and "border" means the border of the
-whole DEM, the sharded result equals the single-tile result.
+gating-free form: a boundary cell pulls the contributions of its donors on the neighbouring
+rank from the halo row once they are final there ("not done" travels as a NaN bit pattern).
+Because every owned cell is computed from its true 3x3 neighbourhood, in a fixed summation
+order, and "border" means the border of the whole DEM, the sharded result equals the
+single-tile result bit for bit.
 
 ``Group`` hides where the ranks live: ``DistGroup`` = this process is one rank of a
 torch.distributed job; ``LocalGroup`` = all ranks live in this process (tests on one GPU, and
@@ -146,9 +147,8 @@ class ShardEngine(object):
         dev = torch.device("cuda", torch.cuda.current_device())
         C = s.C
         mk = lambda dt: torch.zeros(C, dtype=dt, device=dev)
-        # packed exchange buffers: labels (int64 + f64) and out-boxes (f64 area, f64 taint, int32 count)
+        # packed exchange buffers of the region labels (int64 + f64)
         self.lab = {k: (mk(torch.int64), mk(torch.float64)) for k in ("send_up", "send_down", "recv_up", "recv_down")}
-        self.box = {k: torch.zeros(C * 5, dtype=torch.int32, device=dev) for k in ("send_up", "send_down", "recv_up", "recv_down")}
         self.flag = torch.zeros(1, dtype=torch.int64, device=dev)
         self.views = {}
 
@@ -183,32 +183,11 @@ class ShardEngine(object):
                                   self.flag.data_ptr())
         return self.flag
 
-    def _box_ptrs(self, key):
-        b, C = self.box[key], self.spec.C
-        p = b.data_ptr()
-        return p, p + 8 * C, p + 16 * C   # area f64[C] | taint f64[C] | count i32[C]
-
-    def outbox_pack(self):
-        s = self.spec
+    def sweep_sent(self):
+        """device int64: boundary cells the last sweep completed whose receiver lives on a neighbour"""
         self.flag.zero_()
-        if s.halo_top:
-            self.tile.shard_stage("outbox_pack", 0, *self._box_ptrs("send_up"), self.flag.data_ptr())
-        if s.halo_bot:
-            self.tile.shard_stage("outbox_pack", 1, *self._box_ptrs("send_down"), self.flag.data_ptr())
+        self.tile.shard_stage("sweep_sent", self.flag.data_ptr())
         return self.flag
-
-    def inbox_apply(self):
-        s = self.spec
-        self.tile.shard_stage("inbox_begin")
-        if s.halo_top:
-            self.tile.shard_stage("inbox_apply", 0, *self._box_ptrs("recv_up"))
-        if s.halo_bot:
-            self.tile.shard_stage("inbox_apply", 1, *self._box_ptrs("recv_down"))
-
-    def box_bufs(self):
-        s = self.spec
-        return dict(send_up=self.box["send_up"] if s.halo_top else None, recv_up=self.box["recv_up"] if s.halo_top else None,
-                    send_down=self.box["send_down"] if s.halo_bot else None, recv_down=self.box["recv_down"] if s.halo_bot else None)
 
     def lab_bufs(self, which):
         s = self.spec
@@ -275,10 +254,11 @@ def run_hot_path(engines, group, twi=True, profile=False, **uca_flags):
     for e in engines:
         e.tile.shard_links(**uca_flags)
     group.exchange([e.halo_bufs(T.F_LINK) for e in engines])
+    group.exchange([e.halo_bufs(T.F_PROP) for e in engines])
     for e in engines:
         e.tile.shard_stage("indeg")
     tm.mark("ms_graph")
-    # a6/a7: local sweeps + out-box rounds
+    # a6/a7: local sweeps + exchanges of the boundary rows
     rounds, first = 0, 1
     while True:
         for e in engines:
@@ -288,13 +268,12 @@ def run_hot_path(engines, group, twi=True, profile=False, **uca_flags):
         rounds += 1
         if group.world == 1:
             break
-        sent = group.allreduce_sum([e.outbox_pack() for e in engines])[0]
+        sent = group.allreduce_sum([e.sweep_sent() for e in engines])[0]
         if sent == 0:
             tm.mark("ms_exchange")
             break
-        group.exchange([e.box_bufs() for e in engines])
-        for e in engines:
-            e.inbox_apply()
+        group.exchange([e.halo_bufs(T.F_UCA) for e in engines])
+        group.exchange([e.halo_bufs(T.F_TAINT) for e in engines])
         tm.mark("ms_exchange")
     stats = []
     for e in engines:

@@ -7,7 +7,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (F_DIR, F_EDGE_DONE, F_EDGE_TODO, F_ELEV, F_FLAT0, F_FLATS, F_LINK, F_MAG,  # noqa: F401
-                   F_SECTION, F_TWI, F_UCA)
+                   F_PROP, F_SECTION, F_TAINT, F_TWI, F_UCA)
 
 
 class DeviceTile(object):

@@ -27,7 +27,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
         u = dt.download(T.F_UCA)
         np.save("/tmp/ab_uca_%s_%s.npy" % (kind, os.environ["AB_TAG"].replace("/", "_")), u)
         print(json.dumps(dict(cfg=os.environ["AB_TAG"], kind=kind, n=n, ms_graph=round(best["ms_graph"], 3),
-                              ms_sweep=round(best["ms_sweep"], 3), ms_sweep_median=round(float(np.median(allms)), 3), ms_sweep_scan=round(best.get("ms_sweep_scan", 0), 3),
+                              ms_sweep=round(best["ms_sweep"], 3), ms_sweep_kernel=round(best.get("ms_sweep_kernel", 0), 3), ms_sweep_median=round(float(np.median(allms)), 3), ms_sweep_scan=round(best.get("ms_sweep_scan", 0), 3),
                               n_queue_items=best.get("n_queue_items"))), flush=True)
         dt.close()
     sys.exit(0)
@@ -35,7 +35,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
 from pydem_b200 import synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 opts = sys.argv[2:] or ["strict=0", "strict=1"]
-KEYS = {"lib": "PYDEM_B200_LIB", "strict": "PYDEM_B200_SWEEP_STRICT", "backoff": "PYDEM_B200_WL_BACKOFF", "occ": "PYDEM_B200_WL_OCC", "dbg": "PYDEM_B200_WL_DEBUG"}
+KEYS = {"tile": "PYDEM_B200_TS_TILE", "legacy": "PYDEM_B200_SWEEP_LEGACY", "tocc": "PYDEM_B200_TS_OCC", "tdbg": "PYDEM_B200_TS_DEBUG",
+        "lib": "PYDEM_B200_LIB", "strict": "PYDEM_B200_SWEEP_STRICT", "backoff": "PYDEM_B200_WL_BACKOFF", "occ": "PYDEM_B200_WL_OCC", "dbg": "PYDEM_B200_WL_DEBUG"}
 np.save("/tmp/ab_cond_%d.npy" % n, synth.conditioned_fractal_dem(n, 0))
 np.save("/tmp/ab_raw_%d.npy" % n, synth.fractal_dem(n, 0))
 for o in opts:

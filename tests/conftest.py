@@ -17,8 +17,7 @@ def pytest_configure(config):
 def cuda_lib():
     """Build (if stale) and load the CUDA library; GPU tests fail loudly without it."""
     from pydem_b200 import build, _lib
-    if not os.path.exists(_lib.LIB_PATH):
-        build.build()
+    build.build()      # no-op when the library is newer than its sources
     _lib.load()
     _lib.init(0)
     return _lib

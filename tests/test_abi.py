@@ -27,7 +27,7 @@ def test_library_exports_header_symbols(lib):
     missing = [s for s in sorted(declared) if not hasattr(L, s)]
     assert not missing, missing
     assert declared == set(lib.EXPORTS)
-    assert L.pdm_abi_version() == 1
+    assert L.pdm_abi_version() == 2
 
 
 def test_struct_layouts_match_defaults(lib):

@@ -1,9 +1,10 @@
 """CPU suite for the N>1 path: two real processes over gloo.
 
 * the neighbour-exchange / all-reduce plumbing of pydem_b200.sharded.DistGroup,
-* the out-box protocol itself (accumulate cross-boundary pushes + in-degree decrements in a halo
-  row, exchange, resume from the cells that became ready, stop when nobody sent): simulated in
-  NumPy on the oracle's drainage graph, it must reproduce the single-tile oracle UCA."""
+* the boundary-row protocol itself (a cell pulls its donors' final values; "not done" travels as
+  NaN in the boundary rows that neighbours exchange after every local sweep; stop when no rank
+  completed a cell whose receiver lives across a boundary): simulated in NumPy on the oracle's
+  drainage graph, it must reproduce the single-tile oracle UCA."""
 import os
 import socket
 import sys
@@ -41,7 +42,7 @@ def _worker(rank, world, port, q):
         if rank < world - 1:
             assert float(b["recv_down"][0]) == 10.0 * (rank + 1) + 1
         assert g.allreduce_sum([torch.tensor([rank + 1])])[0] == world * (world + 1) // 2
-        # --- out-box protocol on the oracle's graph
+        # --- boundary-row protocol on the oracle's graph
         E = synth.fractal_dem(0, 5, shape=(60, 40)) * 0.05 + synth.cone_dem(60)[:, :40] * 200 + 1
         R, Cc = E.shape
         dp = OracleDEMProcessor(E, fill_flats=False, drain_pits_path=False, drain_pits=False)
@@ -49,43 +50,41 @@ def _worker(rank, world, port, q):
         dp2 = OracleDEMProcessor(E, fill_flats=False, drain_pits_path=False, drain_pits=False)
         dp2.calc_slopes_directions(); gr, sec = dp2._graph()
         cptr, cidx, cdat, rptr, ridx = gr.export()
+        wgt = {}
+        for i in range(R * Cc):
+            for e in range(cptr[i], cptr[i + 1]):
+                wgt[(i, int(cidx[e]))] = cdat[e]
         r0, r1 = sharded.row_blocks(R, world)[rank]
         own = np.zeros(R * Cc, bool); own[r0 * Cc:r1 * Cc] = True
-        indeg = (rptr[1:] - rptr[:-1]).astype(np.int64)
-        area = np.ones(R * Cc)
-        outbox_a = np.zeros(R * Cc); outbox_c = np.zeros(R * Cc, np.int64)
-        ready = [int(i) for i in np.nonzero(own & (indeg == 0))[0]]
+        area = np.full(R * Cc, np.nan)          # NaN = not done (the device uses a signalling-NaN pattern)
+        todo = set(int(i) for i in np.nonzero(own)[0])
         rounds = 0
         while True:
-            while ready:                       # local sweep to quiescence
-                i = ready.pop()
-                for e in range(cptr[i], cptr[i + 1]):
-                    r, w = int(cidx[e]), cdat[e]
-                    if own[r]:
-                        area[r] += area[i] * w; indeg[r] -= 1
-                        if indeg[r] == 0:
-                            ready.append(r)
-                    else:
-                        outbox_a[r] += area[i] * w; outbox_c[r] += 1
+            sent = 0
+            progress = True
+            while progress:                    # local sweep until it rests
+                progress = False
+                for r in sorted(todo):
+                    srcs = [int(x) for x in ridx[rptr[r]:rptr[r + 1]]]
+                    if all(not np.isnan(area[x]) for x in srcs):
+                        area[r] = 1.0 + sum(area[x] * wgt[(x, r)] for x in srcs)
+                        todo.discard(r); progress = True
+                        sent += sum(1 for e in range(cptr[r], cptr[r + 1]) if not own[cidx[e]])
             rounds += 1
-            up = slice((r0 - 1) * Cc, r0 * Cc); down = slice(r1 * Cc, (r1 + 1) * Cc)
-            bufs = dict(send_up=torch.from_numpy(np.concatenate([outbox_a[up], outbox_c[up].astype(float)])) if rank > 0 else None,
-                        recv_up=torch.zeros(2 * Cc, dtype=torch.float64) if rank > 0 else None,
-                        send_down=torch.from_numpy(np.concatenate([outbox_a[down], outbox_c[down].astype(float)])) if rank < world - 1 else None,
-                        recv_down=torch.zeros(2 * Cc, dtype=torch.float64) if rank < world - 1 else None)
-            sent = int(outbox_c.sum())
             if g.allreduce_sum([torch.tensor([sent])])[0] == 0:
                 break
+            A2 = area.reshape(R, Cc)
+            bufs = dict(send_up=torch.from_numpy(A2[r0].copy()) if rank > 0 else None,
+                        recv_up=torch.zeros(Cc, dtype=torch.float64) if rank > 0 else None,
+                        send_down=torch.from_numpy(A2[r1 - 1].copy()) if rank < world - 1 else None,
+                        recv_down=torch.zeros(Cc, dtype=torch.float64) if rank < world - 1 else None)
             g.exchange([bufs])
-            outbox_a[:] = 0; outbox_c[:] = 0
-            for key, row in (("recv_up", r0), ("recv_down", r1 - 1)):
-                if bufs[key] is None:
-                    continue
-                a = bufs[key].numpy()
-                sl = slice(row * Cc, (row + 1) * Cc)
-                cnt = a[Cc:].astype(np.int64)
-                area[sl] += a[:Cc]; indeg[sl] -= cnt
-                ready += [int(row * Cc + j) for j in np.nonzero((cnt > 0) & (indeg[sl] == 0))[0]]
+            if rank > 0:
+                A2[r0 - 1] = bufs["recv_up"].numpy()
+            if rank < world - 1:
+                A2[r1] = bufs["recv_down"].numpy()
+        indeg = np.zeros(R * Cc, np.int64)
+        indeg[list(todo)] = 1
         mine = area.reshape(R, Cc)[r0:r1]
         refm = ref[r0:r1]
         ok = np.allclose(np.where(np.isnan(refm), 0, mine), np.nan_to_num(refm), rtol=1e-12) and (indeg[own] == 0).all()
