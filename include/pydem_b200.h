@@ -56,9 +56,8 @@ typedef enum {
     /* 10: reserved */
     PDM_F_FLAT0 = 11,    /* [u8]   mag == -1 before the one-pixel extension (shard halo exchange) */
     PDM_F_LINK = 12,     /* [u8]   facet index + kept-receiver bits of each cell (shard halo exchange) */
-    PDM_F_TAINT = 13,    /* [f64]  sweep state: accumulated edge_todo weight (shard halo exchange) */
-    PDM_F_PROP = 14,     /* [f64]  share of the cardinal receiver (shard halo exchange; shares the TWI buffer) */
-    PDM_F_COUNT_ = 15
+    PDM_F_CELL = 13,     /* [32 B] sweep record of a cell: area, taint, proportion, link, donor mask (shard halo exchange) */
+    PDM_F_COUNT_ = 14
 } pdm_field;
 
 /* Flags of DEMProcessor that act on the hot path (dem_processing.py:105-154). */
@@ -218,7 +217,7 @@ int pdm_tile_pit_drain_paths(pdm_tile *t, const pdm_cond_params *p, pdm_cond_sta
  * driver fills halo rows (elev, then flat0, then link) from the neighbouring ranks -- NCCL
  * send/recv on the row views obtained with pdm_tile_device_ptr -- and calls the stages in this
  * order: slopes, ccl, {label_pack / label_unpack until no rank changed}, flats_extend, links,
- * (LINK and PROP halo rows), indeg, {sweep, sweep_sent, UCA and TAINT halo rows until no rank sent},
+ * (LINK halo rows), indeg, (CELL halo rows), {sweep, sweep_sent, CELL halo rows until no rank sent},
  * finalize.
  * Equivalent of pyDEM's cross-tile edge resolution (process_manager.py:1090-1249) with true
  * halo stencils, so the sharded result equals the single-tile result. */

@@ -14,11 +14,11 @@ LIB_PATH = os.environ.get("PYDEM_B200_LIB") or os.path.join(_HERE, "libpydem_b20
 
 # pdm_field
 (F_ELEV, F_MAG, F_DIR, F_FLATS, F_UCA, F_TWI, F_EDGE_TODO, F_EDGE_DONE, F_SECTION, F_TWI10, F_RESERVED, F_FLAT0,
- F_LINK, F_TAINT, F_PROP) = range(15)
+ F_LINK, F_CELL) = range(14)
 FIELD_DTYPE = {F_ELEV: np.float64, F_MAG: np.float64, F_DIR: np.float64, F_FLATS: np.uint8,
                F_UCA: np.float64, F_TWI: np.float64, F_EDGE_TODO: np.uint8, F_EDGE_DONE: np.uint8,
                F_SECTION: np.int8, F_TWI10: np.float64, F_FLAT0: np.uint8, F_LINK: np.uint8,
-               F_TAINT: np.float64, F_PROP: np.float64}
+               F_CELL: np.dtype((np.void, 32))}
 
 
 class UcaParams(ct.Structure):

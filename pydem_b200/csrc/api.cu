@@ -31,6 +31,7 @@ static size_t field_elem_size(int field)
     switch (field) {
         case PDM_F_FLATS: case PDM_F_EDGE_TODO: case PDM_F_EDGE_DONE: case PDM_F_SECTION:
         case PDM_F_FLAT0: case PDM_F_LINK: return 1;
+        case PDM_F_CELL: return 32;
         default: return 8;
     }
 }
@@ -50,8 +51,7 @@ static void *field_ptr(pdm_tile *t, int field)
         case PDM_F_TWI10: return t->twi10;
         case PDM_F_FLAT0: return t->flat0;
         case PDM_F_LINK: return t->link;
-        case PDM_F_TAINT: return pdm_taint(t);
-        case PDM_F_PROP: return t->twi;
+        case PDM_F_CELL: return t->cell;
         default: return nullptr;
     }
 }
@@ -395,8 +395,19 @@ int pdm_tile_uca(pdm_tile *t, const pdm_uca_params *p_in, pdm_uca_stats *stats)
         st.ms_sweep_scan = 0.0f;
         st.ms_sweep_kernel = (float)((double)(h[ts::TC_T_END] - h[ts::TC_T_START]) * 1e-6);
         if (getenv("PYDEM_B200_TS_DEBUG"))
-            fprintf(stderr, "[ts] kernel %.3f ms | visits %llu (repeated in place %llu) | cells %llu | levels %llu | sources %llu\n",
-                    st.ms_sweep_kernel, h[ts::TC_VISITS], h[ts::TC_REQUEUE], h[ts::TC_CELLS], h[ts::TC_LEVELS], h[ts::TC_SOURCES]);
+            fprintf(stderr, "[ts] kernel %.3f ms | visits %llu (repeated in place %llu, deferred %llu) | cells %llu | levels %llu | sources %llu\n",
+                    st.ms_sweep_kernel, h[ts::TC_VISITS], h[ts::TC_REQUEUE], h[ts::TC_DEFER], h[ts::TC_CELLS], h[ts::TC_LEVELS], h[ts::TC_SOURCES]);
+        if (getenv("PYDEM_B200_TS_DEBUG") && atoi(getenv("PYDEM_B200_TS_DEBUG")) > 1) {
+            fprintf(stderr, "[ts] CTA-time per phase, ms summed over CTAs: claim %.2f load %.2f count %.2f levels %.2f store %.2f schedule %.2f\n",
+                    h[ts::TC_PHASE] * 1e-6, h[ts::TC_PHASE + 1] * 1e-6, h[ts::TC_PHASE + 2] * 1e-6, h[ts::TC_PHASE + 3] * 1e-6,
+                    h[ts::TC_PHASE + 4] * 1e-6, h[ts::TC_PHASE + 5] * 1e-6);
+            fprintf(stderr, "[ts] passes: %llu, %.0f cycles per pass\n", h[ts::TC_PHASE + 7],
+                    h[ts::TC_PHASE + 7] ? (double)h[ts::TC_PHASE + 6] / (double)h[ts::TC_PHASE + 7] : 0.0);
+            fprintf(stderr, "[ts] timeline (100 us buckets) visits/kcells:");
+            for (int b = 0; b < 64; b++)
+                if (h[ts::TC_HIST + 2 * b]) fprintf(stderr, " %d:%llu/%llu", b, h[ts::TC_HIST + 2 * b], h[ts::TC_HIST + 2 * b + 1] / 1000);
+            fprintf(stderr, "\n");
+        }
     }
     if (getenv("PYDEM_B200_WL_DEBUG")) {
         const unsigned long long *h = t->h_counters;

@@ -106,9 +106,19 @@ struct pdm_tile {
     bool legacy_graph;          // the graph on the tile was built for the legacy work-list sweep
 };
 
-// tile sweep state carved out of the 32-byte-per-cell record array (the legacy sweep and the update
-// mode use it as Cell records; the tile sweep as three f64 planes: taint | pit acc area | pit acc taint)
-static inline double *pdm_taint(const pdm_tile *t) { return reinterpret_cast<double *>(t->cell); }
+// sweep state of one cell in the tile sweep (tsweep.cu): exactly one 32-byte DRAM sector, in the
+// same array the legacy sweep and the update mode use for their Cell records
+struct __align__(32) TRec {
+    double area;      // accumulated upstream area (cyutils.pyx:161); TS_NOT_DONE until final
+    double taint;     // accumulated edge_todo weight (cyutils.pyx:163); TS_NOT_DONE until final
+    double prop;      // share of the cardinal receiver; for pit cells: slot of the pit edge list
+    uint8_t link;     // LK_* byte
+    uint8_t dmask;    // which of the 8 neighbours (W E N S NW NE SW SE) drain into this cell
+    uint8_t flags;    // TR_*
+    uint8_t pad[5];
+};
+#define TR_TODO 0x01   // inflow-border cell: its taint starts at 1 (dem_processing.py:909-944)
+static inline TRec *pdm_trec(const pdm_tile *t) { return reinterpret_cast<TRec *>(t->cell); }
 
 void pdm_set_error(const char *fmt, ...);
 int pdm_cuda_fail(cudaError_t e, const char *what, const char *file, int line);

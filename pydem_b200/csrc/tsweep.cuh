@@ -19,15 +19,14 @@ enum {
     TC_T_START = 70,    // globaltimer ns: first CTA in / last CTA out
     TC_T_END = 71,
     TC_QUEUED = 72,     // tiles queued by the set-up of this launch
-    TC_N = 96
+    TC_DEFER = 73,      // visits deferred to the back of the queue (neighbour published, queue busy)
+    TC_PHASE = 80,      // debug: ns summed over CTAs per phase {claim, load, count, levels, store, schedule}
+    TC_HIST = 96,       // PYDEM_B200_TS_DEBUG timeline: per 100 us bucket {visits, cells completed} x 64
+    TC_N = 96 + 128
 };
 
 struct Args {
-    const uint8_t *link;
-    const double *prop;
-    double *area;             // = UCA: TS_NOT_DONE until the cell's sum is final
-    double *taint;            // same convention
-    const uint8_t *edge_todo;
+    TRec *rec;                // sweep records (pdm_internal.cuh)
     const double *row_area;
     const int32_t *pit_beg, *pit_end, *pit_dst;
     const double *pit_w;
@@ -39,6 +38,8 @@ struct Args {
     uint32_t cap_mask;
     uint32_t *flag;
     unsigned long long *ctr;
+    int32_t dbg;
+    int32_t has_pits;         // the graph has pit edges: pit receivers are gated on their pit counters
 };
 
 }  // namespace ts

@@ -6,8 +6,8 @@ travel between neighbouring ranks with NCCL send/recv (``Group.exchange``), ever
 local CUDA work through the ``pdm_shard_*`` C ABI (csrc/shard.cu):
 
     elev halo -> slope/aspect (a1) -> flat0 halo -> region labels (+ label rounds) -> flats (a2)
-    -> links (a3/a4) -> link + proportion halo -> inflow mask, fresh sweep state
-    -> { local sweep until it rests ; exchange boundary rows of UCA / taint } until nobody sent
+    -> links (a3/a4) -> link halo -> inflow mask, sweep records -> record halo
+    -> { local sweep until it rests ; exchange boundary rows of sweep records } until nobody sent
     -> finalize -> TWI
 
 This is pyDEM's cross-tile UCA edge resolution (reference process_manager.py:1090-1249:
@@ -254,9 +254,9 @@ def run_hot_path(engines, group, twi=True, profile=False, **uca_flags):
     for e in engines:
         e.tile.shard_links(**uca_flags)
     group.exchange([e.halo_bufs(T.F_LINK) for e in engines])
-    group.exchange([e.halo_bufs(T.F_PROP) for e in engines])
     for e in engines:
         e.tile.shard_stage("indeg")
+    group.exchange([e.halo_bufs(T.F_CELL) for e in engines])      # the neighbours' boundary records (static part + "not done")
     tm.mark("ms_graph")
     # a6/a7: local sweeps + exchanges of the boundary rows
     rounds, first = 0, 1
@@ -272,8 +272,7 @@ def run_hot_path(engines, group, twi=True, profile=False, **uca_flags):
         if sent == 0:
             tm.mark("ms_exchange")
             break
-        group.exchange([e.halo_bufs(T.F_UCA) for e in engines])
-        group.exchange([e.halo_bufs(T.F_TAINT) for e in engines])
+        group.exchange([e.halo_bufs(T.F_CELL) for e in engines])
         tm.mark("ms_exchange")
     stats = []
     for e in engines:

@@ -6,8 +6,8 @@ import ctypes as ct
 import numpy as np
 
 from . import _lib
-from ._lib import (F_DIR, F_EDGE_DONE, F_EDGE_TODO, F_ELEV, F_FLAT0, F_FLATS, F_LINK, F_MAG,  # noqa: F401
-                   F_PROP, F_SECTION, F_TAINT, F_TWI, F_UCA)
+from ._lib import (F_CELL, F_DIR, F_EDGE_DONE, F_EDGE_TODO, F_ELEV, F_FLAT0, F_FLATS, F_LINK, F_MAG,  # noqa: F401
+                   F_SECTION, F_TWI, F_UCA)
 
 
 class DeviceTile(object):
@@ -63,7 +63,10 @@ class DeviceTile(object):
             pass
         o = _CAI()
         dt = np.dtype(_lib.FIELD_DTYPE[field])
-        o.__cuda_array_interface__ = dict(shape=self.shape, typestr=dt.str, data=(self.device_ptr(field), False),
+        shape, typestr = self.shape, dt.str
+        if dt.kind == "V":                       # 32-byte sweep records: rows of raw bytes
+            shape, typestr = (self.R, self.C * dt.itemsize), "|u1"
+        o.__cuda_array_interface__ = dict(shape=shape, typestr=typestr, data=(self.device_ptr(field), False),
                                           version=2, strides=None)
         return torch.as_tensor(o, device="cuda")
 
