@@ -107,10 +107,11 @@ class ClockSampler(object):
 # ----------------------------------------------------------------------------------------------
 # CPU legs (oracle = checker; only this file's cpu_baseline / --impl reference legs may time it)
 # ----------------------------------------------------------------------------------------------
-def _cpu_hot_path(E, use_ref_sweep, drain_pits=False):
+def _cpu_hot_path(E, use_ref_sweep, drain_pits=True, keep=False):
     """One pass of the hot path on one host core.  use_ref_sweep: run the accumulation with the
     reference's own compiled Cython kernel (oracle/_ref/cyutils*.so, built from
-    /root/reference/pydem/cyfuncs/cyutils.pyx) instead of the oracle's restatement of it."""
+    /root/reference/pydem/cyfuncs/cyutils.pyx) instead of the oracle's restatement of it.
+    keep: return the output arrays (the parity check of the GPU arm) instead of the cell count."""
     from oracle import oracle as orc
     dp = orc.OracleDEMProcessor(E, dX=SPACING, dY=SPACING, fill_flats=False, drain_pits_path=False, drain_pits=drain_pits)
     dp.calc_slopes_directions()
@@ -132,41 +133,103 @@ def _cpu_hot_path(E, use_ref_sweep, drain_pits=False):
         area[dp.flats.ravel()] = np.nan
         dp.uca = area.reshape(R, C)
         dp.twi_min_area = SPACING * SPACING
-    dp.calc_twi()
+    twi = dp.calc_twi()
+    if keep:
+        return dict(mag=np.asarray(dp.mag), direction=np.asarray(dp.direction), flats=np.asarray(dp.flats),
+                    uca=np.asarray(dp.uca), edge_todo=np.asarray(dp.edge_todo), edge_done=np.asarray(dp.edge_done),
+                    twi=np.asarray(twi))
     return E.size
 
 
+# the reference arm's unit of work: the benchmark DEM cut 4 x 4 into tiles with a one-pixel overlap, one
+# tile per process -- how the reference's ProcessManager spreads a DEM over cores
+# (process_manager.py:1251-1288, tiles from compute_grid with overlap, :560-600)
+REF_GRID = 4
+
+
+def _ref_tiles(n):
+    t = n // REF_GRID
+    out = []
+    for a in range(REF_GRID):
+        for b in range(REF_GRID):
+            out.append((max(a * t - 1, 0), min((a + 1) * t + 1, n), max(b * t - 1, 0), min((b + 1) * t + 1, n)))
+    return out
+
+
+_REF_DEM = {}
+
+
+def _ref_dem(n, variant):
+    key = (n, variant)
+    if key not in _REF_DEM:
+        from pydem_b200 import synth
+        _REF_DEM[key] = (synth.conditioned_fractal_dem(n, 0, wrap_rows=True) if variant == "conditioned"
+                         else synth.fractal_dem(n, 0))
+    return _REF_DEM[key]
+
+
 def _ref_worker(args):
-    seed, n, use_ref, variant = args
-    from pydem_b200 import synth
-    E = synth.conditioned_fractal_dem(n, seed) if variant == "conditioned" else synth.fractal_dem(n, seed)
+    box, n, use_ref, variant = args
+    E = np.ascontiguousarray(_ref_dem(n, variant)[box[0]:box[1], box[2]:box[3]])     # inherited from the parent (fork)
     t = time.perf_counter()
-    cells = _cpu_hot_path(E, use_ref)
+    cells = _cpu_hot_path(E, use_ref, drain_pits=(variant == "conditioned"))
     return cells, time.perf_counter() - t
 
 
-def cpu_baseline_leg(E_full, window=4096, drain_pits=False):
+def cpu_baseline_leg(E_full, window=4096, drain_pits=True):
     """Oracle port, one core, on the benchmark DEM itself (top-left window when the DEM is larger than
-    `window`): ~10-20 s of CPU work at 4096 x 4096."""
+    `window`): ~10-20 s of CPU work at 4096 x 4096.  Returns (baseline dict, oracle arrays or None)."""
     w = min(window, E_full.shape[0], E_full.shape[1])
     E = np.ascontiguousarray(E_full[:w, :w])
     _cpu_hot_path(E[:256, :256].copy(), False, drain_pits)   # builds/loads the oracle library
     t = time.perf_counter()
-    cells = _cpu_hot_path(E, False, drain_pits)
+    arrays = _cpu_hot_path(E, False, drain_pits, keep=True)
     dt = time.perf_counter() - t
-    what = "the whole benchmark DEM" if w == E_full.shape[0] == E_full.shape[1] else "the %dx%d top-left window of the benchmark DEM" % (w, w)
-    return {"value": cells / dt / 1e6, "unit": "Mcells/s", "cores": 1, "kind": "port",
-            "sample": "oracle/pdm_oracle.c (C restatement, 1 core) on %s (%dx%d), slope+aspect + UCA + TWI, drain_pits=%s, %.1f s"
-                      % (what, w, w, bool(drain_pits), dt)}
+    whole = w == E_full.shape[0] == E_full.shape[1]
+    what = "the whole benchmark DEM" if whole else "the %dx%d top-left window of the benchmark DEM" % (w, w)
+    return ({"value": E.size / dt / 1e6, "unit": "Mcells/s", "cores": 1, "kind": "port",
+             "sample": "oracle/pdm_oracle.c (C restatement, 1 core) on %s (%dx%d), slope+aspect + UCA + TWI, drain_pits=%s, %.1f s"
+                       % (what, w, w, bool(drain_pits), dt)}, arrays if whole else None)
+
+
+# parity bar of tests/helpers.py (north_star: stated float tolerance, integer / bool outputs bit-exact)
+PARITY_BAR = {"mag_rel": 1e-12, "direction_abs": 1e-12, "uca_rel": 1e-9, "twi_abs": 1e-9}
+
+
+def parity_block(ref, got):
+    """Error measures of the GPU arm's outputs against the oracle's on the same DEM, and the verdict."""
+    out = {}
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for k in ("mag", "direction", "uca", "twi"):
+            a, b = np.asarray(ref[k], float), np.asarray(got[k], float)
+            d = np.abs(a - b)
+            fin = np.isfinite(d)
+            out[k + "_nan_mismatch"] = int((np.isnan(a) != np.isnan(b)).sum())
+            out[k + "_abs"] = float(d[fin].max()) if fin.any() else 0.0
+            rel = d / np.abs(a)
+            fin = np.isfinite(rel)
+            out[k + "_rel"] = float(rel[fin].max()) if fin.any() else 0.0
+        for k in ("flats", "edge_todo", "edge_done"):
+            out[k + "_mismatch_bits"] = int((np.asarray(ref[k], bool) != np.asarray(got[k], bool)).sum())
+    ok = all(out[k + "_mismatch_bits"] == 0 for k in ("flats", "edge_todo", "edge_done"))
+    ok = ok and all(out[k + "_nan_mismatch"] == 0 for k in ("mag", "direction", "uca", "twi"))
+    ok = ok and out["mag_rel"] <= PARITY_BAR["mag_rel"] and out["direction_abs"] <= PARITY_BAR["direction_abs"]
+    ok = ok and out["uca_rel"] <= PARITY_BAR["uca_rel"] and out["twi_abs"] <= PARITY_BAR["twi_abs"]
+    out["bar"] = PARITY_BAR
+    out["ok"] = bool(ok)
+    return out
 
 
 def reference_arm(args):
-    """Reference CPU path on all host cores.  The reference has no intra-tile threading; its
-    ProcessManager runs one tile per process (process_manager.py:1251-1288).  The same here: every
-    core gets its own 1024x1024 window per step.  Only the reference's native piece can travel to
-    the GPU box (oracle/_ref: cyutils.pyx compiled with the reference's flags) -- it does the UCA
-    sweep, ~90% of the reference's time; the NumPy layers around it run as the oracle's C port
-    (faster than the reference's NumPy, i.e. optimistic for the reference)."""
+    """Reference CPU path on all host cores, like for like with the GPU arm: the SAME seed-0 benchmark
+    DEM with the same flags, cut 4 x 4 into tiles with a one-pixel overlap, one tile per process -- the
+    reference has no intra-tile threading, its ProcessManager runs one tile per process
+    (process_manager.py:1251-1288).  A step = the 16 tiles of the DEM.  Only the reference's native piece
+    can travel to the GPU box (oracle/_ref: cyutils.pyx compiled with the reference's flags): it does the
+    UCA sweep, ~90% of the reference's time; the NumPy layers around it run as the oracle's C port
+    (faster than the reference's NumPy, i.e. optimistic for the reference) -- hence kind "port+ref-sweep".
+    A second stated baseline: the reference's compiled sweep on the WHOLE DEM as one tile on one core
+    (one timed run, what a user without the tiling gets)."""
     import multiprocessing as mp
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -175,34 +238,58 @@ def reference_arm(args):
     orc.build()
     use_ref = ref_harness.load_ref_cyutils() is not None
     cores = os.cpu_count() or 1
-    win = 1024 if args.steps <= 8 else 512      # bounded sample: the whole run stays within a few minutes
+    n = args.size
+    variant = args.variant
+    pits = variant == "conditioned"
+    E = _ref_dem(n, variant)
+    tiles = _ref_tiles(n)
+    procs = min(cores, len(tiles))
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
-        for _ in range(max(args.warmup, 0) and 1):
-            pool.map(_ref_worker, [(1000 + c, 256, use_ref, args.variant) for c in range(cores)])
+    whole = None
+    with ctx.Pool(procs) as pool:
+        jobs = [(box, n, use_ref, variant) for box in tiles]
+        if args.warmup > 0:
+            pool.map(_ref_worker, [((0, 258, 0, 258), n, use_ref, variant)] * procs)
+        # second baseline, concurrently on one more process: the whole DEM as ONE tile on one core
+        if not args.no_whole_dem:
+            whole_pool = ctx.Pool(1)
+            whole_job = whole_pool.apply_async(_ref_worker, (((0, n, 0, n), n, use_ref, variant),))
         t0 = time.perf_counter()
         cells = 0
         for s in range(args.steps):
-            res = pool.map(_ref_worker, [(s * cores + c, win, use_ref, args.variant) for c in range(cores)])
-            cells += sum(r[0] for r in res)
+            res = pool.map(_ref_worker, jobs, chunksize=1)
+            cells += n * n          # the DEM's cells (overlap pixels are computed twice, counted once)
         dt = time.perf_counter() - t0
+        if not args.no_whole_dem:
+            c_w, t_w = whole_job.get()
+            whole_pool.close()
+            whole = {"value": c_w / t_w / 1e6, "unit": "Mcells/s", "cores": 1, "seconds": t_w,
+                     "sample": "the whole %dx%d benchmark DEM as one tile, one core, one run (ran beside the tiled steps)" % (n, n)}
     val = cells / dt / 1e6
+    kind = "port+ref-sweep" if use_ref else "port"
+    flags_txt = "fill_flats=False, drain_pits_path=False, drain_pits=%s" % pits
     line = {"metric": METRIC, "value": val, "unit": "Mcells/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "%s fractal DEM, dX=dY=30 m, slope+aspect + UCA + TWI, fill_flats=False, "
-                                   "drain_pits_path=False, pit drains off in the CPU sweep; bounded sample: %d windows of "
-                                   "%dx%d per step (one per host core)"
-                                   % ("priority-flood conditioned" if args.variant == "conditioned" else "raw", cores, win, win)},
-            "cpu_baseline": {"value": val, "unit": "Mcells/s", "cores": cores,
-                             "kind": "reference" if use_ref else "port",
+            "config": {"workload": _workload_text(n, variant, flags_txt),
+                       "parallelism": "%d processes, the DEM cut %dx%d into %dx%d tiles (+1 pixel overlap), one tile per "
+                                      "process (reference ProcessManager style)" % (procs, REF_GRID, REF_GRID, n // REF_GRID, n // REF_GRID)},
+            "cpu_baseline": {"value": val, "unit": "Mcells/s", "cores": procs, "kind": kind,
                              "sample": ("UCA sweep = the reference's compiled cyutils.drain_area (oracle/_ref); " if use_ref
                                         else "UCA sweep = oracle restatement; ") +
-                                       "stencil/flats/graph/TWI = oracle C port; %d processes x %dx%d windows x %d steps"
-                                       % (cores, win, win, args.steps)},
+                                       "stencil/flats/graph/pit drains/TWI = oracle C port; %d steps x 16 tiles of the same "
+                                       "seed-0 DEM the GPU arm runs" % args.steps,
+                             "whole_dem_one_core": whole},
             "e2e": {"value": val, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def _workload_text(n, variant, flags_txt):
+    return ("%dx%d fractal DEM (spectral synthesis, seed 0, H=0.8, 1..1001 m%s), dX=dY=30 m, "
+            "slope+aspect + UCA + TWI, %s (BASELINE.json configs[1], %s variant)"
+            % (n, n, ", priority-flood+eps conditioned" if variant == "conditioned" else "", flags_txt,
+               "primary" if variant == "conditioned" else "'sinks'"))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -277,10 +364,7 @@ def gpu_arm(args):
                 stage_ms["uca"].append(sev[1].elapsed_time(sev[2]))
                 stage_ms["twi"].append(sev[2].elapsed_time(sev[3]))
         cells_per_step = n * n
-        workload = ("%dx%d fractal DEM (spectral synthesis, seed 0, H=0.8, 1..1001 m%s), dX=dY=30 m, "
-                    "slope+aspect + UCA + TWI, %s (BASELINE.json configs[1], %s variant)"
-                    % (n, n, ", priority-flood+eps conditioned" if variant == "conditioned" else "", flags_txt,
-                       "primary" if variant == "conditioned" else "'sinks'"))
+        workload = _workload_text(n, variant, flags_txt)
         parallelism = "1 GPU, single tile"
     else:
         from pydem_b200 import sharded
@@ -299,6 +383,9 @@ def gpu_arm(args):
                        world, n, flags_txt))
         parallelism = "row-block x%d" % world
 
+    shard_parity = None
+    if world > 1 and not args.no_parity:
+        shard_parity = sharded_check(sh, E, world, rank, pits_flag)
     sampler = ClockSampler(local) if rank == 0 else None
     _note("setup done")
     for _ in range(args.warmup):
@@ -341,6 +428,11 @@ def gpu_arm(args):
             chk = float(twi[n // 2, n // 2])   # the step's result is read on the host
             dp._free_tile()
             return chk
+        gpu_out = None
+        if rank == 0 and not args.no_parity:
+            gpu_out = dict(mag=dt.download(T.F_MAG), direction=dt.download(T.F_DIR), flats=dt.download(T.F_FLATS),
+                           uca=dt.download(T.F_UCA), edge_todo=dt.download(T.F_EDGE_TODO), edge_done=dt.download(T.F_EDGE_DONE),
+                           twi=dt.download(T.F_TWI))
         dt.close()
         for _ in range(max(1, min(args.warmup, 2))):
             e2e_step()
@@ -401,8 +493,52 @@ def gpu_arm(args):
                     "frac_of_hbm_peak": cells_per_step * 32.0 / (ms_t * 1e-3) / 1e9 / peak_gbs,
                     "note": "32 B/cell: read uca 8 + mag 8, write twi 8 + 10*twi 8"},
         }
-        line["cpu_baseline"] = cpu_baseline_leg(E, drain_pits=bool(pits_flag))
+        line["cpu_baseline"], oracle_out = cpu_baseline_leg(E, drain_pits=bool(pits_flag))
+        if gpu_out is not None and oracle_out is not None:
+            # the oracle has just computed the whole benchmark DEM for the baseline: check the GPU arm against it
+            line["parity"] = parity_block(oracle_out, gpu_out)
+            line["parity"]["against"] = "oracle (oracle/pdm_oracle.c) on the whole benchmark DEM, same flags"
+    else:
+        line["parity"] = shard_parity
     print(json.dumps(line), flush=True)
+    if line.get("parity") and not line["parity"].get("ok", True):
+        print("bench.py: PARITY FAILURE: %s" % json.dumps(line["parity"]), file=sys.stderr, flush=True)
+        sys.exit(3)
+
+
+def sharded_check(sh, block, world, rank, pits_flag):
+    """One-off check before the timed loop: the NCCL-sharded result of this rank's rows against the
+    single-tile result of the whole (stacked) DEM computed on this rank's own GPU; all ranks must agree."""
+    import torch
+    import torch.distributed as dist
+    from pydem_b200 import DEMProcessor, tile as T
+    sh.step()
+    s = sh.spec
+    full = np.concatenate([block] * world, axis=0)
+    dp = DEMProcessor(elev=full, dX=SPACING, dY=SPACING, fill_flats=False, drain_pits_path=False, drain_pits=bool(pits_flag))
+    dp.calc_twi()
+    out = {}
+    ok = True
+    for name, f, exact in (("mag", T.F_MAG, True), ("direction", T.F_DIR, True), ("flats", T.F_FLATS, True),
+                           ("edge_todo", T.F_EDGE_TODO, True), ("edge_done", T.F_EDGE_DONE, True), ("uca", T.F_UCA, False)):
+        a = sh.engine.tile.download(f)[s.lo:s.hi]
+        b = np.asarray(getattr(dp, name))[s.r0:s.r1]
+        if exact:
+            bad = int((a.astype(bool) != b).sum()) if a.dtype.kind != "f" else int(((a != b) & ~(np.isnan(a) & np.isnan(b))).sum())
+        else:
+            with np.errstate(invalid="ignore", divide="ignore"):
+                rel = np.abs(a - b) / np.abs(b)
+            bad = int((rel[np.isfinite(rel)] > PARITY_BAR["uca_rel"]).sum()) + int((np.isnan(a) != np.isnan(b)).sum())
+        out[name + "_mismatches"] = bad
+        ok = ok and bad == 0
+    dp._free_tile()
+    tot = torch.tensor([out[k] for k in sorted(out)], device="cuda", dtype=torch.int64)
+    dist.all_reduce(tot)
+    res = {k: int(v) for k, v in zip(sorted(out), tot.tolist())}
+    res["ok"] = all(v == 0 for v in res.values())
+    res["against"] = ("single-tile run of the whole %dx%d DEM on every rank's own GPU (uca rtol %g, everything else bit-exact), "
+                      "summed over %d ranks" % (full.shape[0], full.shape[1], PARITY_BAR["uca_rel"], world))
+    return res
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the sweep kernel, one launch (profiles/, per size)
@@ -419,6 +555,8 @@ def main():
     ap.add_argument("--variant", default="conditioned", choices=["conditioned", "sinks"],
                     help="conditioned: priority-flood conditioned fractal, default flags (BASELINE.md primary); "
                          "sinks: raw fractal with drain_pits=False")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle / single-tile check of the GPU arm's outputs")
+    ap.add_argument("--no-whole-dem", action="store_true", help="reference arm: skip the one-core whole-DEM run")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

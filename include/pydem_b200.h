@@ -132,6 +132,16 @@ int         pdm_init(int device);
 int         pdm_device_count(int *count);
 /* number of CUDA kernels this library has launched in this process (bench accounting) */
 unsigned long long pdm_launch_count(void);
+
+/* Engine of the UCA accumulation (a7) on stand-alone tiles, process-wide.
+ *   mode 0: work-list sweep (L2 atomics, fastest on one tile; default), 1: tile sweep (pull-based,
+ *   tile-resident, bit-reproducible; always used by the pdm_shard_* path), -1: take it from the
+ *   environment (PYDEM_B200_SWEEP=worklist|tile).
+ *   strict 1: the work-list holds every count-off back until the adds it publishes have returned
+ *   (cross-check of its ordering assumption), 0: off, -1: PYDEM_B200_SWEEP_STRICT.
+ * Replaces nothing in the reference (cyutils.drain_area, cyutils.pyx:78-187, has one engine). */
+int pdm_set_sweep_mode(int mode, int strict);
+int pdm_get_sweep_mode(void);
 /* page-locked host buffers for the host-buffer entry points (full-rate PCIe copies) */
 int         pdm_host_alloc(size_t bytes, void **out);
 int         pdm_host_free(void *p);
@@ -232,6 +242,15 @@ int pdm_shard_links(pdm_tile *t, const pdm_uca_params *p);
 int pdm_shard_indeg(pdm_tile *t);
 int pdm_shard_sweep(pdm_tile *t, int first);
 int pdm_shard_sweep_sent(pdm_tile *t, void *sent);
+/* One sweep across the GPUs of the row shards instead of exchange rounds: every rank exports CUDA IPC
+ * handles of its sweep records and of its tile queue (pdm_shard_p2p_export: *size in = room at buf, out =
+ * bytes written; buf NULL asks for the size), the host driver hands each rank the blobs of the ranks above /
+ * below and of rank 0 (NULL where there is none / on rank 0), and from then on pdm_shard_sweep(t, 1) on
+ * every rank is the whole accumulation: boundary tiles read the neighbour's boundary row and wake its
+ * tiles over NVLink peer memory, one in-flight counter on rank 0 ends all kernels together.
+ * Semantics as pyDEM's process_uca_edges (process_manager.py:1090-1249) without its rounds. */
+int pdm_shard_p2p_export(pdm_tile *t, void *buf, int64_t *size);
+int pdm_shard_p2p_connect(pdm_tile *t, const void *up, const void *down, const void *root, int world, int rank);
 int pdm_shard_finalize(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *stats);
 
 /* ---- one-shot host-buffer calls ---------------------------------------------------------- */

@@ -9,3 +9,4 @@ surface (reference pydem/dem_processing.py:98-258, 587, 682, 1647), so it can st
 __version__ = "0.1.0"
 
 from .dem_processing import DEMProcessor  # noqa: F401
+from ._lib import set_sweep, get_sweep  # noqa: F401,E402

@@ -61,7 +61,7 @@ class CondStats(ct.Structure):
 # every symbol include/pydem_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "pdm_abi_version", "pdm_last_error", "pdm_init", "pdm_device_count", "pdm_default_uca_params",
-    "pdm_default_twi_params", "pdm_launch_count", "pdm_host_alloc", "pdm_host_free", "pdm_tile_create", "pdm_tile_destroy", "pdm_tile_set_spacing",
+    "pdm_default_twi_params", "pdm_launch_count", "pdm_shard_p2p_export", "pdm_shard_p2p_connect", "pdm_set_sweep_mode", "pdm_get_sweep_mode", "pdm_host_alloc", "pdm_host_free", "pdm_tile_create", "pdm_tile_destroy", "pdm_tile_set_spacing",
     "pdm_tile_upload", "pdm_tile_download", "pdm_tile_download_async", "pdm_tile_device_ptr", "pdm_tile_mark_resident", "pdm_tile_set_stencil_parity", "pdm_tile_sync", "pdm_selftest_division",
     "pdm_tile_slopes_directions", "pdm_tile_find_flats", "pdm_tile_uca", "pdm_tile_pit_updates", "pdm_tile_uca_update",
     "pdm_tile_twi", "pdm_tile_set_window", "pdm_shard_slopes", "pdm_shard_ccl", "pdm_shard_label_pack",
@@ -91,6 +91,7 @@ def load():
     L.pdm_init.argtypes = [ct.c_int]
     L.pdm_device_count.argtypes = [ct.POINTER(ct.c_int)]
     L.pdm_launch_count.restype = ct.c_ulonglong
+    L.pdm_set_sweep_mode.argtypes = [ct.c_int, ct.c_int]
     L.pdm_host_alloc.argtypes = [ct.c_size_t, ct.POINTER(_vp)]
     L.pdm_host_free.argtypes = [_vp]
     L.pdm_default_uca_params.argtypes = [ct.POINTER(UcaParams)]
@@ -125,6 +126,8 @@ def load():
     L.pdm_shard_label_unpack.argtypes = [_vp, _i64, _vp, _vp, _vp]
     L.pdm_shard_links.argtypes = [_vp, ct.POINTER(UcaParams)]
     L.pdm_shard_sweep.argtypes = [_vp, ct.c_int]
+    L.pdm_shard_p2p_export.argtypes = [_vp, _vp, ct.POINTER(_i64)]
+    L.pdm_shard_p2p_connect.argtypes = [_vp, _vp, _vp, _vp, ct.c_int, ct.c_int]
     L.pdm_shard_sweep_sent.argtypes = [_vp, _vp]
     L.pdm_shard_finalize.argtypes = [_vp, ct.POINTER(UcaParams), ct.POINTER(UcaStats)]
     L.pdm_slopes_directions.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
@@ -171,3 +174,18 @@ def init(device=None):
 
 def ptr(a):
     return None if a is None else ct.c_void_p(a.ctypes.data)
+
+
+SWEEP_MODES = {"worklist": 0, "tile": 1, "env": -1}
+
+
+def set_sweep(mode="env", strict=None):
+    """Engine of the UCA accumulation on stand-alone tiles: "worklist" (default, fastest), "tile"
+    (pull-based, bit-reproducible; the row-sharded path always uses it) or "env"
+    (PYDEM_B200_SWEEP).  strict=True makes the work-list hold every count-off back until its
+    adds have returned (cross-check)."""
+    check(load().pdm_set_sweep_mode(SWEEP_MODES[mode], -1 if strict is None else int(bool(strict))))
+
+
+def get_sweep():
+    return "worklist" if load().pdm_get_sweep_mode() == 0 else "tile"

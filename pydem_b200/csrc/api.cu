@@ -175,7 +175,8 @@ int pdm_tile_destroy(pdm_tile *t)
                     t->edge_todo, t->edge_done, t->section, t->label, t->queue, t->dX, t->dY, t->dg,
                     t->thA, t->thB, t->th_row, t->row_area, t->d_counters, t->pit_cell, t->pit_beg, t->pit_end,
                     t->pit_dst, t->pit_w, t->pit_scratch_i, t->pit_scratch_d, t->edge_buf_d, t->edge_buf_b,
-                    t->glabel, t->glelev, t->twi10, t->rdX, t->rdY, t->rdg, t->ts_slots, t->ts_flag, t->ts_ctr, t->ts_seen};
+                    t->glabel, t->glelev, t->twi10, t->rdX, t->rdY, t->rdg, t->ts_ctl, t->ts_seen};
+    pdm_ts_p2p_close(t);
     for (void *p : ptrs) if (p) cudaFree(p);
     if (t->h_counters) cudaFreeHost(t->h_counters);
     if (t->ts_hctr) cudaFreeHost(t->ts_hctr);
@@ -403,6 +404,10 @@ int pdm_tile_uca(pdm_tile *t, const pdm_uca_params *p_in, pdm_uca_stats *stats)
                     h[ts::TC_PHASE + 4] * 1e-6, h[ts::TC_PHASE + 5] * 1e-6);
             fprintf(stderr, "[ts] passes: %llu, %.0f cycles per pass\n", h[ts::TC_PHASE + 7],
                     h[ts::TC_PHASE + 7] ? (double)h[ts::TC_PHASE + 6] / (double)h[ts::TC_PHASE + 7] : 0.0);
+            fprintf(stderr, "[ts] late visits: %llu visits, %llu cells; us per visit: claim %.2f load %.2f count %.2f flow %.2f (store) %.2f schedule+wait %.2f\n",
+                    h[ts::TC_LATE + 6], h[ts::TC_LATE + 7], h[ts::TC_LATE] * 1e-3 / (double)(h[ts::TC_LATE + 6] + 1), h[ts::TC_LATE + 1] * 1e-3 / (double)(h[ts::TC_LATE + 6] + 1),
+                    h[ts::TC_LATE + 2] * 1e-3 / (double)(h[ts::TC_LATE + 6] + 1), h[ts::TC_LATE + 3] * 1e-3 / (double)(h[ts::TC_LATE + 6] + 1),
+                    h[ts::TC_LATE + 4] * 1e-3 / (double)(h[ts::TC_LATE + 6] + 1), h[ts::TC_LATE + 5] * 1e-3 / (double)(h[ts::TC_LATE + 6] + 1));
             fprintf(stderr, "[ts] timeline (100 us buckets) visits/kcells:");
             for (int b = 0; b < 64; b++)
                 if (h[ts::TC_HIST + 2 * b]) fprintf(stderr, " %d:%llu/%llu", b, h[ts::TC_HIST + 2 * b], h[ts::TC_HIST + 2 * b + 1] / 1000);

@@ -98,11 +98,22 @@ struct pdm_tile {
     cudaEvent_t copy_ev;
     // tile sweep (tsweep.cu): ticket queue, per-tile state words, counters (+ pinned mirror), the
     // "already seen" bytes of the two halo rows of a shard
+    void *ts_ctl;               // one allocation: [counters | tile flags | queue slots] (shared with peer GPUs through CUDA IPC)
     int32_t *ts_slots;
     uint32_t *ts_flag;
     unsigned long long *ts_ctr, *ts_hctr;
     uint8_t *ts_seen;
     int64_t ts_cap, ts_ntiles_cap;
+    // one sweep across GPUs (shard.cu, pdm_shard_p2p_*): mapped peer memory of the row neighbours and of rank 0
+    struct P2P {
+        int on, world, rank;
+        unsigned long long launches;       // start barrier target = world * launches
+        void *map_rec[2], *map_ctl[2], *map_root;     // what cudaIpcOpenMemHandle returned (to close)
+        const void *rec[2]; void *ctl[2]; void *root_ctl;
+        long long off_flag[2], off_slots[2], lo[2], hi[2];
+        int nty[2];
+        unsigned cap_mask[2];
+    } p2p;
     bool legacy_graph;          // the graph on the tile was built for the legacy work-list sweep
 };
 
@@ -159,6 +170,7 @@ int pdm_ts_reset_state(pdm_tile *t);
 int pdm_launch_tsweep(pdm_tile *t, int first);
 int pdm_ts_read_counters(pdm_tile *t);
 int pdm_launch_ts_finalize(pdm_tile *t, const pdm_uca_params *p);
+void pdm_ts_p2p_close(pdm_tile *t);
 int pdm_launch_border_todo(pdm_tile *t);
 int pdm_launch_indeg_todo(pdm_tile *t);
 bool pdm_sweep_legacy();

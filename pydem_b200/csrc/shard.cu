@@ -29,6 +29,8 @@ int pdm_launch_ccl(pdm_tile *t);
 int pdm_launch_flats_extend(pdm_tile *t);
 int pdm_launch_label_pack(pdm_tile *t, int64_t row, long long *out_l, double *out_e);
 int pdm_launch_label_unpack(pdm_tile *t, int64_t row, const long long *in_l, const double *in_e);
+int pdm_ts_p2p_export(pdm_tile *t, ts::P2PExport *e);
+int pdm_ts_p2p_connect(pdm_tile *t, const ts::P2PExport *up, const ts::P2PExport *down, const ts::P2PExport *root, int world, int rank);
 
 static int read_ctr(pdm_tile *t)
 {
@@ -140,6 +142,31 @@ int pdm_shard_sweep_sent(pdm_tile *t, void *sent)
     k_add_sent<<<1, 1, 0, t->stream>>>(t->ts_ctr, (long long *)sent);
     PDM_LAUNCHED();
     return PDM_OK;
+}
+
+// ---- one sweep across GPUs: the row neighbours' boundary records, tile state words and queues as mapped
+//      peer memory (CUDA IPC over NVLink), the termination counter on rank 0.
+// *size: in: room at buf, out: bytes of the export blob (send it to the ranks above / below and, from rank 0,
+// to every rank -- e.g. with an all-gather)
+int pdm_shard_p2p_export(pdm_tile *t, void *buf, int64_t *size)
+{
+    if (!t || !size) { pdm_set_error("pdm_shard_p2p_export: NULL argument"); return PDM_ERR_ARG; }
+    const int64_t need = (int64_t)sizeof(ts::P2PExport);
+    if (!buf || *size < need) { *size = need; if (!buf) return PDM_OK; pdm_set_error("pdm_shard_p2p_export: need %lld bytes", (long long)need); return PDM_ERR_ARG; }
+    *size = need;
+    return pdm_ts_p2p_export(t, reinterpret_cast<ts::P2PExport *>(buf));
+}
+
+int pdm_shard_p2p_connect(pdm_tile *t, const void *up, const void *down, const void *root, int world, int rank)
+{
+    if (!t || world < 1 || rank < 0 || rank >= world) { pdm_set_error("pdm_shard_p2p_connect: bad argument"); return PDM_ERR_ARG; }
+    if ((t->win.lo > 0) != (up != nullptr) || (t->win.hi < t->R) != (down != nullptr) || (rank == 0) != (root == nullptr)) {
+        pdm_set_error("pdm_shard_p2p_connect: need the export of the rank above iff the tile has a halo row above, the one below "
+                      "iff it has one below, and rank 0's export on every other rank");
+        return PDM_ERR_ARG;
+    }
+    return pdm_ts_p2p_connect(t, reinterpret_cast<const ts::P2PExport *>(up), reinterpret_cast<const ts::P2PExport *>(down),
+                              reinterpret_cast<const ts::P2PExport *>(root), world, rank);
 }
 
 int pdm_shard_finalize(pdm_tile *t, const pdm_uca_params *p_in, pdm_uca_stats *stats)

@@ -76,20 +76,44 @@ k_twi(const double *__restrict__ uca, const double *__restrict__ mag, double *__
 
 static int g_sweep_blocks = 0;
 
-// PYDEM_B200_SWEEP_LEGACY=1: the round-1 work-list sweep (L2 atomics) instead of the tile sweep (A/B runs)
+// Which engine runs the accumulation on a stand-alone tile (pdm_set_sweep_mode; default from the
+// environment: PYDEM_B200_SWEEP=worklist|tile, default worklist):
+//   0 work-list (worklist.cuh / drain_op.cuh): flow paths followed cell by cell through L2 atomics --
+//     the fastest on one tile; sums in arrival order (fp64 atomics: equal up to re-association from
+//     run to run), ordering of a receiver's adds against its count-off rests on same-sector program
+//     order at L2 (drain_op.cuh; `strict` removes that assumption at the price of a round trip per cell);
+//   1 tile sweep (tsweep.cu): pull-based, tile-resident, no floating-point atomics, ordered by the PTX
+//     memory model only, bit-reproducible -- the engine of the row-sharded path and the cross-check
+//     of the work-list in the GPU tests.
+static int g_sweep_mode = -1, g_sweep_strict = -1;
+
 bool pdm_sweep_legacy()
 {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("PYDEM_B200_SWEEP_LEGACY"); v = (e && atoi(e)) ? 1 : 0; }
-    return v != 0;
+    if (g_sweep_mode < 0) {
+        const char *e = getenv("PYDEM_B200_SWEEP"), *l = getenv("PYDEM_B200_SWEEP_LEGACY");
+        int v = 0;
+        if (e) v = (e[0] == 't' || e[0] == 'T' || e[0] == '1') ? 1 : 0;
+        else if (l) v = atoi(l) ? 0 : 1;
+        g_sweep_mode = v;
+    }
+    return g_sweep_mode == 0;
 }
 
 static int sweep_strict()
 {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("PYDEM_B200_SWEEP_STRICT"); v = (e && atoi(e)) ? 1 : 0; }
-    return v;
+    if (g_sweep_strict < 0) { const char *e = getenv("PYDEM_B200_SWEEP_STRICT"); g_sweep_strict = (e && atoi(e)) ? 1 : 0; }
+    return g_sweep_strict;
 }
+
+extern "C" int pdm_set_sweep_mode(int mode, int strict)
+{
+    if (mode < -1 || mode > 1) { pdm_set_error("pdm_set_sweep_mode: mode must be -1 (environment), 0 (work-list) or 1 (tile sweep)"); return PDM_ERR_ARG; }
+    g_sweep_mode = mode;
+    g_sweep_strict = strict < 0 ? -1 : (strict ? 1 : 0);
+    return PDM_OK;
+}
+
+extern "C" int pdm_get_sweep_mode(void) { return pdm_sweep_legacy() ? 0 : 1; }
 
 // first pass: every owned cell nobody drains into is a seed
 int pdm_launch_sweep_first(pdm_tile *t)

@@ -48,6 +48,8 @@
 // the boundary rows of records and resumes the tiles whose ring received new donors, until no rank
 // completed such a cell (sharded.py).
 #include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
 
 #include "tsweep.cuh"
 
@@ -111,68 +113,85 @@ __device__ __forceinline__ void off_e2(int sec, int &dr, int &dc)
     dc = 1 - (((sec + 2) >> 1) & 2);
 }
 
-// Shared memory of one tile = one warp.  The records stay in their 32-byte global layout: rows of the
+// Shared memory of one CTA = one tile.  The records stay in their 32-byte global layout: rows of the
 // tile + ring arrive as bulk asynchronous copies (TMA, cp.async.bulk) signalled through an mbarrier.
 template <int TW_, int TH_>
 struct Smem {
     static constexpr int TW = TW_, TH = TH_, HW = TW_ + 2, HH = TH_ + 2, HN = HW * HH, TN = TW_ * TH_;
-    static constexpr int CPR = TW_ / 32;          // cells per lane and row
-    static constexpr int CPL = CPR * TH_;         // cells per lane: one bit each in the lane's masks
     TRec rec[HN];
     unsigned long long mbar;                      // mbarrier of the bulk copies
     double rowa[TH_];                             // cell area of the tile's rows (dX2 * dY2, dem_processing.py:885)
-    uint32_t cand[32][2];                         // per lane: own cells to re-examine in the next pass (bit = owner_bit)
-    uint32_t claim[TN / 32];                      // per own cell: a chain has taken it
+    uint32_t cnt[(HN + 3) / 4];                   // one byte per staged cell: own cells: donors that are not final yet; ring cells: 0x80
+    uint16_t fr[TN];                              // the cells in the order they became ready (a topological order of this visit)
+    int n_fr;                                     // entries of fr = cells that became ready (tickets of the producers)
+    int head;                                     // tickets of the consumers
+    int live;                                     // ready cells not finished yet (queued or held by a lane); 0 = the visit is over
+    int completed;                                // cells completed in this visit
+    int undone;                                   // own cells not final when the tile was staged
+    int nsrc;                                     // of those: cells nobody drains into (first visit)
+    unsigned notify;                              // neighbour tiles that got a new donor (bit = 3 * dy + dx; 9: the neighbouring rank)
+    int late;                                     // a pit of this tile released a receiver inside this tile: run again
+    int next_tile, next_mode, next_first;
     unsigned long long x_ph[8], x_t;              // debug: ns per phase
+    unsigned long long x_late[8];                 // the same for visits that start after dbg x 100 us (dbg >= 10)
+    int x_is_late;
 };
-
-// Which lane owns cell (y, x) of the tile, and which bit of that lane's masks.  A lane owns CPR cells of
-// every row; consecutive rows are rotated by 5 columns so that rows, columns and most diagonal runs of
-// a river spread over different lanes.
-#define TS_ROT 5
-template <class S> __device__ __forceinline__ int owner_lane(int y, int x) { return ((x & 31) + TS_ROT * y) & 31; }
-template <class S> __device__ __forceinline__ int owner_bit(int y, int x) { return y * S::CPR + (x >> 5); }
-template <class S> __device__ __forceinline__ void cell_of(int lane, int bit, int &y, int &x)
-{
-    y = bit / S::CPR;
-    x = ((lane - TS_ROT * y) & 31) + 32 * (bit - y * S::CPR);
-}
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void queue_push(const Args &a, int32_t tile)
+// Tile state words, queue slots and the in-flight counter are also written by the neighbouring GPUs when one
+// sweep spans several row shards (a.p2p): every access to them is then a system-scope atomic.
+__device__ __forceinline__ unsigned long long add_u64(const Args &a, unsigned long long *p, unsigned long long v)
 {
-    const unsigned long long t = atomicAdd(&a.ctr[TC_TAIL], 1ULL);
-    const int32_t old = atomicExch(a.slots + (t & a.cap_mask), tile);
+    return a.p2p ? atomicAdd_system(p, v) : atomicAdd(p, v);
+}
+__device__ __forceinline__ uint32_t or_u32(const Args &a, uint32_t *p, uint32_t v) { return a.p2p ? atomicOr_system(p, v) : atomicOr(p, v); }
+__device__ __forceinline__ uint32_t exch_u32(const Args &a, uint32_t *p, uint32_t v) { return a.p2p ? atomicExch_system(p, v) : atomicExch(p, v); }
+__device__ __forceinline__ int32_t exch_i32(const Args &a, int32_t *p, int32_t v) { return a.p2p ? atomicExch_system(p, v) : atomicExch(p, v); }
+__device__ __forceinline__ uint32_t cas_u32(const Args &a, uint32_t *p, uint32_t c, uint32_t v) { return a.p2p ? atomicCAS_system(p, c, v) : atomicCAS(p, c, v); }
+// release / acquire fence of a visit: device scope, system scope when peers read this GPU's records
+__device__ __forceinline__ void fence_visit(const Args &a)
+{
+    if (a.p2p) asm volatile("fence.acq_rel.sys;" ::: "memory");
+    else fence_acq_rel_gpu();
+}
+
+// push into a queue given by its counters / slots (this rank's or a peer's)
+__device__ __forceinline__ void queue_push_to(const Args &a, unsigned long long *ctr, int32_t *slots, uint32_t cap_mask, int32_t tile)
+{
+    const unsigned long long t = add_u64(a, &ctr[TC_TAIL], 1ULL);
+    const int32_t old = exch_i32(a, slots + (t & cap_mask), tile);
     if (old >= 0) atomicExch(&a.ctr[TC_ABORT], 2ULL);   // ring overrun: cannot happen (cap >= 4 x tiles), reported if it does
 }
+__device__ __forceinline__ void queue_push(const Args &a, int32_t tile) { queue_push_to(a, a.ctr, a.slots, a.cap_mask, tile); }
 
 // "tile Y has a new donor": make it pending; whoever finds it idle owns the duty to schedule it
 __device__ __forceinline__ bool notify_tile(const Args &a, int32_t y)
 {
-    const uint32_t old = atomicOr(&a.flag[y], TF_PENDING);
+    const uint32_t old = or_u32(a, &a.flag[y], TF_PENDING);
     if ((old & (TF_PENDING | TF_RUNNING | TF_COMPLETE)) == 0) {
-        atomicAdd(&a.ctr[TC_INFLIGHT], 1ULL);
+        add_u64(a, a.inflight, 1ULL);
         return true;
     }
     return false;
 }
 
-// lane 0: wait for a queue item (ticket = fetch-and-add, never retries).  -1: the sweep is over.
+// one thread: wait for a queue item (ticket = fetch-and-add, never retries).  -1: the sweep is over.
 __device__ int32_t acquire_tile(const Args &a)
 {
     const unsigned long long h = atomicAdd(&a.ctr[TC_HEAD], 1ULL);
     int32_t *slot = a.slots + (h & a.cap_mask);
     unsigned ns = 32, polls = 0;
     unsigned long long t_last = 0, v_last = 0;
+    const unsigned every = a.p2p ? 31u : 7u;      // the counter of a multi-GPU sweep lives on rank 0: poll it over NVLink less often
     for (;;) {
         // only the holder of this ticket consumes this slot in this lap: take it with one exchange
-        const int32_t v = atomicExch(slot, -1);
+        const int32_t v = exch_i32(a, slot, -1);
         if (v >= 0) return v;
-        if ((++polls & 7u) == 0) {
+        if ((++polls & every) == 0) {
             // in-flight tiles only reach 0 when everything is done (a tile is counted from the moment
             // it is made pending until its run has ended and scheduled its successors)
-            if (ld_volatile_u64(&a.ctr[TC_INFLIGHT]) == 0ULL) return -1;
+            if (ld_volatile_u64(a.inflight) == 0ULL) return -1;
             if (ld_volatile_u64(&a.ctr[TC_ABORT])) return -1;
             if ((polls & 1023u) == 0) {
                 // watchdog (never fires in a correct run): no tile visit anywhere for 4 s
@@ -186,42 +205,10 @@ __device__ int32_t acquire_tile(const Args &a)
     }
 }
 
-template <class S> __device__ __forceinline__ void mark_candidate(S &s, int y, int x)
-{
-    const int b = owner_bit<S>(y, x);
-    atomicOr(&s.cand[owner_lane<S>(y, x)][b >> 5], 1u << (b & 31));
-}
-
-// both words of a staged record final?  (cells completed during this visit are written by other lanes
-// with one 16-byte store; testing both words makes the test independent of how that store is performed)
-template <class S> __device__ __forceinline__ bool cell_done(const S &s, int k)
-{
-    const double2 v = *reinterpret_cast<const double2 *>(&s.rec[k].area);
-    return is_done(v.x) && is_done(v.y);
-}
-
-// all donors of ring cell k done (and, for a receiver of pit edges, its pit counter at zero)?
+// drained pit: push along its long-range edges (rare; plain fence ordering).  A receiver released inside
+// this tile makes the tile run again (s.late); one in another tile makes that tile pending.
 template <class S>
-__device__ __forceinline__ bool cell_ready(const S &s, const Args &a, int k, int64_t n)
-{
-    const unsigned long long w = *reinterpret_cast<const unsigned long long *>(&s.rec[k].link);
-    unsigned dm = (unsigned)(w >> 8) & 0xffu;
-    while (dm) {
-        const int q = __ffs(dm) - 1;
-        dm &= dm - 1;
-        if (!cell_done(s, k + nbr_off<S::HW>(q))) return false;
-    }
-    if ((w & LK_PITIN) && a.has_pits) {
-        if (ld_volatile_i32(a.pit_cnt + n) != 0) return false;
-        fence_acq_rel_gpu();       // counter seen at zero: the pit accumulators of this cell are final
-    }
-    return true;
-}
-
-// drained pit: push along its long-range edges (rare; plain fence ordering)
-template <class S>
-__device__ __forceinline__ void pit_push(S &s, const Args &a, double slot_bits, double ar, double tt, int rows_valid, int cols_valid,
-                                         int64_t r0, int64_t c0, int my_tile)
+__device__ __noinline__ void pit_push(S &s, const Args &a, double slot_bits, double ar, double tt, int my_tile)
 {
     const int64_t slot = __double_as_longlong(slot_bits);
     const int32_t e0 = a.pit_beg[slot], e1 = a.pit_end[slot];
@@ -240,91 +227,194 @@ __device__ __forceinline__ void pit_push(S &s, const Args &a, double slot_bits, 
         if (ri < a.w.lo || ri >= a.w.hi) continue;       // (pit edges never cross a shard: refused at graph build)
         const int y = (int)((ri - a.w.lo) / S::TH) * a.ntx + (int)(rj / S::TW);
         if (y == my_tile) {
-            const int ry = (int)(ri - r0), rx = (int)(rj - c0);
-            if (ry >= 0 && ry < rows_valid && rx >= 0 && rx < cols_valid) mark_candidate(s, ry, rx);
+            s.late = 1;
         } else if (notify_tile(a, y)) {
             queue_push(a, y);
         }
     }
 }
 
-#define TS_MARK(idx) if (a.dbg && lane == 0) { const unsigned long long now = globaltimer_ns(); s.x_ph[idx] += now - s.x_t; s.x_t = now; }
+#define TS_MARK(idx) if (a.dbg && tid == 0) { const unsigned long long now = globaltimer_ns(); s.x_ph[idx] += now - s.x_t; if (s.x_is_late) s.x_late[idx] += now - s.x_t; s.x_t = now; }
 
-// One warp = one tile at a time.
+__device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+__device__ __forceinline__ int ld_volatile_shared_i32(const int *p)
+{
+    int v;
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ double2 ld_volatile_shared_f64x2(const double *p)
+{
+    double2 v;
+    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_shared_f64x2(double *p, double x, double y)
+{
+    asm volatile("st.volatile.shared.v2.f64 [%0], {%1, %2};" ::"r"(smem_u32(p)), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ unsigned ld_volatile_shared_u16(const uint16_t *p)
+{
+    unsigned short v;
+    asm volatile("ld.volatile.shared.u16 %0, [%1];" : "=h"(v) : "r"(smem_u32(p)) : "memory");
+    return (unsigned)v;
+}
+
+// One ready cell: PULL its sums (cyutils.pyx:161-163 seen from the receiver) over its donors in ascending
+// neighbour order (W, E, N, S, NW, NE, SW, SE) -- a fixed order, so a cell's value does not depend on the
+// schedule, the tile size or the sharding -- publish them in shared and global memory, and count the
+// cell off at its receivers.  r1 / r2: in-tile receivers that became ready (ring index) or -1.
+template <class S>
+__device__ __forceinline__ void drain_cell(S &s, const Args &a, int k, int rows_valid, int cols_valid, int64_t r0, int64_t c0,
+                                           int tile, unsigned &notify, int &r1, int &r2)
+{
+    constexpr int HW = S::HW;
+    const int hy = k / HW, hx = k - hy * HW;        // ring coordinates: own cells 1..TH, 1..TW
+    const unsigned long long w = *reinterpret_cast<const unsigned long long *>(&s.rec[k].link);
+    unsigned dm = (unsigned)(w >> 8) & 0xffu;
+    const unsigned lk = (unsigned)w & 0xffu;
+    double ar = s.rowa[hy - 1];                                                  // dem_processing.py:885, 901
+    double tt = ((w >> 16) & TR_TODO) ? 1.0 : 0.0;                               // 944
+    while (dm) {
+        const int q = __ffs(dm) - 1;
+        dm &= dm - 1;
+        const TRec &d = s.rec[k + nbr_off<HW>(q)];
+        const double2 v = *reinterpret_cast<const double2 *>(&d.area);
+        const double p = d.prop;
+        const double wgt = q < 4 ? p : __dsub_rn(1.0, p);                        // dem_processing.py:1082
+        ar = __dadd_rn(ar, __dmul_rn(v.x, wgt));                                 // cyutils.pyx:161
+        tt = __dadd_rn(tt, __dmul_rn(v.y, wgt));                                 // cyutils.pyx:163
+    }
+    const int64_t n = (r0 + hy - 1) * a.w.C + (c0 + hx - 1);
+    if ((lk & LK_PITIN) && a.has_pits) {
+        ar = __dadd_rn(ar, __ldcg(a.pit_acc_a + n));
+        tt = __dadd_rn(tt, __ldcg(a.pit_acc_t + n));
+    }
+    *reinterpret_cast<double2 *>(&s.rec[k].area) = make_double2(ar, tt);
+    fence_cta();                                   // the sums are visible in the CTA before the cell is counted off
+    atomicOr(&s.cnt[k >> 2], 0x40u << (8 * (k & 3)));      // completed in this visit: written to global memory when the visit ends
+    r1 = -1; r2 = -1;
+    if (!(lk & (LK_NOSEC | LK_PIT))) {
+        const int sec = lk & LK_SEC_MASK;
+        int dr1, dc1, dr2, dc2;
+        off_e1(sec, dr1, dc1); off_e2(sec, dr2, dc2);
+        const int k1 = k + dr1 * HW + dc1, k2 = k + dr2 * HW + dc2;
+        const bool v1 = (lk & LK_KEEP1) != 0, v2 = (lk & LK_KEEP2) != 0;
+        uint32_t o1 = 0, o2 = 0;
+        if (v1) o1 = atomicSub(&s.cnt[k1 >> 2], 1u << (8 * (k1 & 3))) >> (8 * (k1 & 3));
+        if (v2) o2 = atomicSub(&s.cnt[k2 >> 2], 1u << (8 * (k2 & 3))) >> (8 * (k2 & 3));
+        o1 &= 0xffu; o2 &= 0xffu;
+        if (o1 == 1u) r1 = k1;
+        if (o2 == 1u) r2 = k2;
+        if (r1 >= 0 || r2 >= 0) fence_cta();       // the last decrement has observed the others: their sums are visible
+        if ((o1 | o2) & 0xc0u) {
+            // a receiver in the ring: another tile (or the neighbouring rank) has a new donor
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                if (!((e ? o2 : o1) & 0xc0u)) continue;
+                const int ry = hy + (e ? dr2 : dr1), rx = hx + (e ? dc2 : dc1);
+                const int64_t gr = r0 + ry - 1;
+                if (gr < a.w.lo || gr >= a.w.hi)     // receiver on the neighbouring rank: bit 9 + the peer's tile (10..12 above, 13..15 below)
+                    notify |= (1u << 9) | (1u << ((gr < a.w.lo ? 10 : 13) + (rx < 1 ? 0 : (rx > cols_valid ? 2 : 1))));
+                else notify |= 1u << ((ry < 1 ? 0 : (ry > rows_valid ? 2 : 1)) * 3 + (rx < 1 ? 0 : (rx > cols_valid ? 2 : 1)));
+            }
+        }
+    } else if ((lk & LK_PIT) && a.has_pits) {
+        pit_push(s, a, s.rec[k].prop, ar, tt, tile);
+    }
+}
+
+// One CTA = one tile at a time.
 //
-// A visit: claim the tile, stage it (TMA), then PASSES until nothing moves: in a pass every lane looks at
-// its own undone cells that got a new done donor ("candidates"; all undone cells in the first pass) and
-// tests whether all donors are done (phase 1); after a warp barrier the ready cells pull their sums in
-// ascending neighbour order, are written to shared and global memory, and nominate their in-tile
-// receivers as candidates of the next pass (phase 2).  A pass is one dependency level inside the tile;
-// its critical path is two shared-memory loads and the fp64 adds -- no lists, no counters, no atomics
-// with a result.  Both phases read only what was written before the previous barrier: no races.
-template <int TW, int TH>
-__global__ void __launch_bounds__(32) k_tsweep(const Args a)
+// A visit: claim the tile, stage it and its ring (TMA), count for every own cell that is not final the
+// donors that are not final (ring cells included), and queue the cells at zero.  Then every lane of the
+// CTA follows flow paths: it takes a ready cell (ticket queue in shared memory), pulls its sums, writes
+// them to shared and global memory, counts the cell off at its in-tile receivers and continues with a
+// receiver that reached zero (a second one goes to the queue).  No level barrier: hill slopes are worked
+// by all lanes at once, a river crossing the tile advances on one lane at shared-memory latency.
+template <int TW, int TH, int NT>
+__global__ void __launch_bounds__(NT, 1) k_tsweep(const Args a)
 {
     typedef Smem<TW, TH> S;
-    constexpr int HW = S::HW, CPL = S::CPL;
-    static_assert(CPL <= 64, "a lane's cells must fit one 64-bit mask");
+    constexpr int HW = S::HW, TN = S::TN;
+    static_assert(TW % 4 == 0, "own cells are counted four to a word");
     extern __shared__ __align__(128) unsigned char ts_raw[];
     S &s = *reinterpret_cast<S *>(ts_raw);
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t C = a.w.C;
     const unsigned FULL = 0xffffffffu;
     const uint32_t mbar = smem_u32(&s.mbar);
-    unsigned long long x_cells = 0, x_levels = 0, x_sources = 0, x_rerun = 0, x_defer = 0, x_sent = 0, x_pass_cyc = 0;
-    s.cand[lane][0] = 0; s.cand[lane][1] = 0;
-    if (lane == 0) {
-        for (int q = 0; q < 8; q++) s.x_ph[q] = 0;
+    unsigned long long x_cells = 0, x_levels = 0, x_sources = 0, x_rerun = 0, x_defer = 0, x_sent = 0;
+    if (tid == 0) {
+        for (int q = 0; q < 8; q++) { s.x_ph[q] = 0; s.x_late[q] = 0; }
+        s.x_is_late = 0;
         s.x_t = globaltimer_ns();
         atomicMin(&a.ctr[TC_T_START], s.x_t);
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (a.p2p) {
+            // one sweep over several GPUs: nobody starts before every rank has queued its tiles and
+            // counted them in (else the global in-flight counter could touch zero too early)
+            const unsigned long long t0 = globaltimer_ns();
+            unsigned polls = 0;
+            while (ld_volatile_u64(a.arrived) < a.start_target) {
+                __nanosleep(200);
+                if ((++polls & 255u) == 0 && globaltimer_ns() - t0 > 4000000000ULL) { atomicExch(&a.ctr[TC_ABORT], 3ULL); break; }
+            }
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
+        }
+        s.next_tile = ld_volatile_u64(&a.ctr[TC_ABORT]) ? -1 : acquire_tile(a); s.next_mode = 0; s.next_first = 0;
     }
-    __syncwarp();
+    __syncthreads();
     uint32_t mphase = 0;
-    int tile = 0;
-    if (lane == 0) tile = acquire_tile(a);
-    tile = __shfl_sync(FULL, tile, 0);
+    int tile = s.next_tile;
     // mode 0: tile came from the queue (pending -> claim it); 1: handed over by the previous tile of
-    // this warp (already claimed); 2: same tile again in place (ring reload only)
+    // this CTA (already claimed); 2: same tile again in place (ring reload only)
     int mode = 0, first = 0;
     while (tile >= 0) {
-        if (lane == 0) {
+        if (tid == 0) {
             if (mode == 0) {
                 // claim: pending -> running.  Everything published before the notification that made
-                // the tile pending is visible after this atomic + fence + warp barrier.
-                const uint32_t old = atomicExch(&a.flag[tile], TF_RUNNING | TF_VISITED);
-                first = (old & TF_VISITED) ? 0 : 1;
+                // the tile pending is visible after this atomic + fence + CTA barrier.
+                const uint32_t old = exch_u32(a, &a.flag[tile], TF_RUNNING | TF_VISITED);
+                s.next_first = (old & TF_VISITED) ? 0 : 1;
             }
-            fence_acq_rel_gpu();
+            fence_visit(a);
+            s.n_fr = 0; s.undone = 0; s.nsrc = 0; s.notify = 0; s.late = 0;
+            if (a.dbg >= 10) s.x_is_late = (globaltimer_ns() - ld_volatile_u64(&a.ctr[TC_T_START])) > (unsigned long long)a.dbg * 100000ULL;
         }
-        first = __shfl_sync(FULL, first, 0);
         TS_MARK(0)
         const int ty = tile / a.ntx, tx = tile - ty * a.ntx;
         const int64_t r0 = a.w.lo + (int64_t)ty * TH, c0 = (int64_t)tx * TW;
         const int rows_valid = (int)min((int64_t)TH, a.w.hi - r0), cols_valid = (int)min((int64_t)TW, C - c0);
         const int64_t j0 = max(c0 - 1, (int64_t)0), j1 = min(c0 + cols_valid + 1, C);      // columns of the ring that exist
         const int64_t i0 = max(r0 - 1, (int64_t)0), i1 = min(r0 + rows_valid + 1, a.w.R);  // rows of the ring that exist
+        const int nring = 2 * (cols_valid + 2) + 2 * rows_valid;
         // ---- stage the tile
         if (mode != 2) {
             // shared memory was read / written through the generic proxy during the previous visit
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) {
+            __syncthreads();
+            if (tid == 0) {
                 const uint32_t bytes = (uint32_t)((i1 - i0) * (j1 - j0) * (int64_t)sizeof(TRec));
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
             }
-            __syncwarp();
-            for (int64_t gi = i0 + lane; gi < i1; gi += 32) {
+            for (int64_t gi = i0 + tid; gi < i1; gi += NT) {
                 const int hy = (int)(gi - (r0 - 1));
                 const uint32_t dst = smem_u32(&s.rec[hy * HW + (int)(j0 - (c0 - 1))]);
                 const uint32_t bytes = (uint32_t)((j1 - j0) * (int64_t)sizeof(TRec));
+                // a halo row of a multi-GPU sweep is read where it lives: the neighbour's boundary row, over NVLink
+                const TRec *src = a.rec + gi * C + j0;
+                if (a.p2p) {
+                    if (gi < a.w.lo && (a.p2p & 1)) src = a.halo_src[0] + j0;
+                    else if (gi >= a.w.hi && (a.p2p & 2)) src = a.halo_src[1] + j0;
+                }
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(dst), "l"(a.rec + gi * C + j0), "r"(bytes), "r"(mbar) : "memory");
+                             ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
             }
-            for (int y = lane; y < rows_valid; y += 32) s.rowa[y] = __ldg(a.row_area + r0 + y);
+            for (int y = tid; y < rows_valid; y += NT) s.rowa[y] = __ldg(a.row_area + r0 + y);
             // ring cells outside the grid: done, no receivers (nothing else ever reads beyond the ring)
-            for (int idx = lane; idx < 2 * (cols_valid + 2) + 2 * rows_valid; idx += 32) {
+            for (int idx = tid; idx < nring; idx += NT) {
                 int hy, hx;
                 if (idx < cols_valid + 2) { hy = 0; hx = idx; }
                 else if (idx < 2 * (cols_valid + 2)) { hy = rows_valid + 1; hx = idx - (cols_valid + 2); }
@@ -344,10 +434,14 @@ __global__ void __launch_bounds__(32) k_tsweep(const Args a)
                 }
                 mphase ^= 1u;
             }
-            __syncwarp();
+        } else {
+            __syncthreads();           // thread 0 has reset the visit's counters
         }
+        first = s.next_first;
+        for (int i = tid; i < TN / 2; i += NT) reinterpret_cast<uint32_t *>(s.fr)[i] = 0xffffffffu;      // empty queue slots
+        for (int i = tid; i < (S::HN + 3) / 4; i += NT) s.cnt[i] = 0x80808080u;                            // ring cells never become ready
         // ring cells: (re)load in place for a repeated visit; a cell counts as done only when both words are final
-        for (int idx = lane; idx < 2 * (cols_valid + 2) + 2 * rows_valid; idx += 32) {
+        for (int idx = tid; idx < nring; idx += NT) {
             int hy, hx;
             if (idx < cols_valid + 2) { hy = 0; hx = idx; }
             else if (idx < 2 * (cols_valid + 2)) { hy = rows_valid + 1; hx = idx - (cols_valid + 2); }
@@ -356,168 +450,132 @@ __global__ void __launch_bounds__(32) k_tsweep(const Args a)
             if (gi < 0 || gi >= a.w.R || gj < 0 || gj >= C) continue;
             TRec &rr = s.rec[hy * HW + hx];
             double2 v;
-            if (mode == 2) v = __ldcg(reinterpret_cast<const double2 *>(&a.rec[gi * C + gj].area));
+            if (mode == 2) {
+                const TRec *src = a.rec + gi * C + gj;
+                if (a.p2p && gi < a.w.lo && (a.p2p & 1)) src = a.halo_src[0] + gj;
+                else if (a.p2p && gi >= a.w.hi && (a.p2p & 2)) src = a.halo_src[1] + gj;
+                v.x = __longlong_as_double((long long)ld_volatile_u64(reinterpret_cast<const unsigned long long *>(&src->area)));
+                v.y = __longlong_as_double((long long)ld_volatile_u64(reinterpret_cast<const unsigned long long *>(&src->taint)));
+            }
             else v = *reinterpret_cast<const double2 *>(&rr.area);
             if (!is_done(v.x) || !is_done(v.y)) { v.x = __longlong_as_double((long long)TS_NOT_DONE); v.y = 0.0; }
             *reinterpret_cast<double2 *>(&rr.area) = v;
         }
+        __syncthreads();
         TS_MARK(1)
-        // ---- this lane's undone cells: the candidates of the first pass
-        uint32_t cand0 = 0, cand1 = 0;
-        int nsrc = 0, undone_at_load = 0;
-        for (int i = lane; i < S::TN / 32; i += 32) s.claim[i] = 0;
-#pragma unroll 8
-        for (int b = 0; b < CPL; b++) {
-            int y, x;
-            cell_of<S>(lane, b, y, x);
-            if (y < rows_valid && x < cols_valid) {
-                const TRec &rr = s.rec[(y + 1) * HW + x + 1];
-                if (!is_done(rr.area)) {
-                    if (b < 32) cand0 |= 1u << b; else cand1 |= 1u << (b - 32);
-                    undone_at_load++;
-                    if (first && rr.dmask == 0 && !(rr.link & LK_PITIN)) nsrc++;
-                }
-            }
-        }
-        __syncwarp();
-        TS_MARK(2)
-        // ---- passes.  Phase 1: every lane tests its candidate cells (own cells that may have become
-        //      ready).  Phase 2: a ready cell pulls its sum and the lane FOLLOWS THE FLOW PATH: it tests
-        //      the cell's receivers (any lane's cells) and continues with one that is ready and that it
-        //      can claim -- a river crosses the tile on one lane, one cell after the other, with no
-        //      warp-wide step in between.  A receiver that is not ready yet is left as a candidate for
-        //      its owner: whoever completes its last donor finds it ready, and should two lanes
-        //      complete the last two donors at the same moment and both see the other's cell
-        //      unfinished, the owner's next pass picks it up.
-        unsigned notify = 0;
-        int lvl = 0, completed = 0;
-        const long long c_in = a.dbg ? clock64() : 0;
-        for (;;) {
-            uint32_t ready0 = 0, ready1 = 0;
+        // ---- count: per own cell that is not final, its donors that are not final; cells at zero are ready
+        {
+            int undone_here = 0, nsrc_here = 0;
+            for (int g = tid; g < TN / 4; g += NT) {
+                const int y = g / (TW / 4), x4 = (g - y * (TW / 4)) * 4;
+                if (y < rows_valid) {
 #pragma unroll
-            for (int h = 0; h < (CPL > 32 ? 2 : 1); h++) {
-                for (uint32_t mm = h ? cand1 : cand0; mm; mm &= mm - 1) {
-                    const int b = __ffs(mm) - 1 + 32 * h;
-                    int y, x;
-                    cell_of<S>(lane, b, y, x);
-                    const int k = (y + 1) * HW + x + 1;
-                    if (is_done(s.rec[k].area)) continue;
-                    if (cell_ready(s, a, k, (r0 + y) * C + (c0 + x))) { if (h) ready1 |= 1u << (b - 32); else ready0 |= 1u << b; }
-                }
-            }
-            if (!__any_sync(FULL, (ready0 | ready1) != 0)) break;
-            __syncwarp();
-#pragma unroll
-            for (int h = 0; h < (CPL > 32 ? 2 : 1); h++) {
-                for (uint32_t mm = h ? ready1 : ready0; mm; mm &= mm - 1) {
-                    const int b = __ffs(mm) - 1 + 32 * h;
-                    int y, x;
-                    cell_of<S>(lane, b, y, x);
-                    int spare = -1;          // a second receiver that became ready at a fork
-                    for (;;) {
-                        // ---- pull (cyutils.pyx:161-163 seen from the receiver), ascending neighbour order
+                    for (int u = 0; u < 4; u++) {
+                        const int x = x4 + u;
+                        if (x >= cols_valid) continue;
                         const int k = (y + 1) * HW + x + 1;
-                        const unsigned long long w = *reinterpret_cast<const unsigned long long *>(&s.rec[k].link);
-                        const uint8_t lk = (uint8_t)w;
-                        double ar = s.rowa[y];                                                   // dem_processing.py:885, 901
-                        double tt = ((w >> 16) & TR_TODO) ? 1.0 : 0.0;                           // 944
-                        unsigned dm = (unsigned)(w >> 8) & 0xffu;
-                        while (dm) {
-                            const int q = __ffs(dm) - 1;
-                            dm &= dm - 1;
-                            const TRec &d = s.rec[k + nbr_off<HW>(q)];
-                            const double p = d.prop;
-                            const double wgt = q < 4 ? p : __dsub_rn(1.0, p);                    // dem_processing.py:1082
-                            ar = __dadd_rn(ar, __dmul_rn(d.area, wgt));                          // cyutils.pyx:161
-                            tt = __dadd_rn(tt, __dmul_rn(d.taint, wgt));                         // cyutils.pyx:163
-                        }
-                        const int64_t n = (r0 + y) * C + (c0 + x);
-                        if ((lk & LK_PITIN) && a.has_pits) {
-                            ar = __dadd_rn(ar, __ldcg(a.pit_acc_a + n));
-                            tt = __dadd_rn(tt, __ldcg(a.pit_acc_t + n));
-                        }
-                        *reinterpret_cast<double2 *>(&s.rec[k].area) = make_double2(ar, tt);
-                        *reinterpret_cast<double2 *>(&a.rec[n].area) = make_double2(ar, tt);
-                        completed++;
-                        // ---- the receivers
-                        int ny = -1, nx = -1;
-                        if (lk & LK_PIT) {
-                            pit_push(s, a, s.rec[k].prop, ar, tt, rows_valid, cols_valid, r0, c0, tile);
-                        } else if (!(lk & LK_NOSEC)) {
-                            const int sec = lk & LK_SEC_MASK;
-#pragma unroll
-                            for (int e = 0; e < 2; e++) {
-                                if (!(lk & (e == 0 ? LK_KEEP1 : LK_KEEP2))) continue;
-                                int dr, dc;
-                                if (e == 0) off_e1(sec, dr, dc); else off_e2(sec, dr, dc);
-                                const int ry = y + dr, rx = x + dc;
-                                if (ry >= 0 && ry < rows_valid && rx >= 0 && rx < cols_valid) {
-                                    const int rk = (ry + 1) * HW + rx + 1;
-                                    bool mine = false;
-                                    if (cell_ready(s, a, rk, (r0 + ry) * C + (c0 + rx))) {
-                                        const int ro = ry * TW + rx;
-                                        mine = !(atomicOr(&s.claim[ro >> 5], 1u << (ro & 31)) & (1u << (ro & 31)));
-                                    } else {
-                                        mark_candidate(s, ry, rx);
-                                    }
-                                    if (mine) {
-                                        if (ny < 0) { ny = ry; nx = rx; }
-                                        else if (spare < 0) spare = ry * TW + rx;
-                                        else mark_candidate(s, ry, rx);      // claimed but parked: its owner takes it in the next pass
-                                    }
-                                } else {
-                                    const int64_t gr = r0 + ry;
-                                    if (gr < a.w.lo || gr >= a.w.hi) notify |= 1u << 9;           // receiver on the neighbouring rank
-                                    else notify |= 1u << ((ry < 0 ? 0 : (ry >= rows_valid ? 2 : 1)) * 3 + (rx < 0 ? 0 : (rx >= cols_valid ? 2 : 1)));
-                                }
+                        unsigned c = 0;
+                        if (!is_done(s.rec[k].area)) {
+                            undone_here++;
+                            const unsigned long long w = *reinterpret_cast<const unsigned long long *>(&s.rec[k].link);
+                            unsigned dm = (unsigned)(w >> 8) & 0xffu;
+                            if (first && dm == 0 && !(w & LK_PITIN)) nsrc_here++;
+                            while (dm) {
+                                const int q = __ffs(dm) - 1;
+                                dm &= dm - 1;
+                                c += is_done(s.rec[k + nbr_off<HW>(q)].area) ? 0u : 1u;
                             }
+                            if ((w & LK_PITIN) && a.has_pits) {
+                                if (ld_volatile_i32(a.pit_cnt + (r0 + y) * C + (c0 + x)) != 0) c += 1;       // pit edges still to arrive: not in this visit
+                                else fence_acq_rel_gpu();       // counter seen at zero: the pit accumulators of this cell are final
+                            }
+                            if (c == 0) s.fr[atomicAdd(&s.n_fr, 1)] = (uint16_t)k;      // (published by the CTA barrier below)
                         }
-                        if (ny < 0 && spare >= 0) { ny = spare / TW; nx = spare - ny * TW; spare = -1; }
-                        if (ny < 0) break;
-                        y = ny; x = nx;
+                        reinterpret_cast<uint8_t *>(s.cnt)[k] = (uint8_t)c;
                     }
                 }
             }
-            __syncwarp();
-            cand0 = s.cand[lane][0];
-            if (cand0) s.cand[lane][0] = 0;
-            if (CPL > 32) { cand1 = s.cand[lane][1]; if (cand1) s.cand[lane][1] = 0; }
-            lvl++;
+            if (undone_here) atomicAdd(&s.undone, undone_here);
+            if (nsrc_here) atomicAdd(&s.nsrc, nsrc_here);
         }
-        if (a.dbg) x_pass_cyc += (unsigned long long)(clock64() - c_in);
-        TS_MARK(3)
-        // ---- totals of the visit
-        int completed_all = completed, undone_all = undone_at_load, nsrc_all = nsrc;
-        for (int d = 16; d > 0; d >>= 1) {
-            completed_all += __shfl_xor_sync(FULL, completed_all, d);
-            undone_all += __shfl_xor_sync(FULL, undone_all, d);
-            nsrc_all += __shfl_xor_sync(FULL, nsrc_all, d);
-            notify |= __shfl_xor_sync(FULL, notify, d);
-        }
-        // ---- schedule.  The global stores of all lanes are ordered before the fence of lane 0 by the warp
-        //      barrier; the notifying atomics follow the fence.  Lane b < 9 looks after neighbour tile b of
-        //      the 3x3 block, lane 9 after this tile's own state word: one round trip for all of them.
-        __syncwarp();
-        if (lane == 0) fence_acq_rel_gpu();
-        __syncwarp();
+        __syncthreads();
+        TS_MARK(2)
+        // ---- flow paths
+        unsigned notify = 0;
+        if (tid == 0) { s.live = s.n_fr; s.head = 0; s.completed = 0; }
+        __syncthreads();
         {
-            const unsigned nm = notify;
+            int k = -1, ticket = -1, mine = 0;
+            for (int it = 0;; it++) {
+                if (it && __all_sync(__activemask(), k < 0)) __nanosleep(100);       // a warp without work leaves the issue slots to the others
+                if (k < 0) {
+                    if (ticket < 0) ticket = atomicAdd(&s.head, 1);
+                    if (ticket < TN) {
+                        const unsigned v = ld_volatile_shared_u16(&s.fr[ticket]);
+                        if (v != 0xffffu) { k = (int)v; ticket = -1; fence_cta(); }
+                    }
+                    if (k < 0 && ld_volatile_shared_i32(&s.live) == 0) break;
+                }
+                if (k >= 0) {
+                    int r1, r2;
+                    drain_cell(s, a, k, rows_valid, cols_valid, r0, c0, tile, notify, r1, r2);
+                    mine++;
+                    if (r1 >= 0 && r2 >= 0) {
+                        atomicAdd(&s.live, 1);
+                        *reinterpret_cast<volatile uint16_t *>(&s.fr[atomicAdd(&s.n_fr, 1)]) = (uint16_t)r2;
+                        k = r1;
+                    } else if (r1 >= 0) k = r1;
+                    else if (r2 >= 0) k = r2;
+                    else { k = -1; atomicSub(&s.live, 1); }
+                }
+            }
+            if (mine) atomicAdd(&s.completed, mine);
+        }
+        __syncthreads();
+        // ---- write the cells completed in this visit to global memory (the only global stores of a visit;
+        //      none is in flight while the lanes synchronise through shared memory above)
+        for (int g = tid; g < TN; g += NT) {
+            const int y = g / TW, x = g - y * TW;
+            const int k = (y + 1) * HW + x + 1;
+            if (reinterpret_cast<const uint8_t *>(s.cnt)[k] & 0x40u)
+                *reinterpret_cast<double2 *>(&a.rec[(r0 + y) * C + (c0 + x)].area) = *reinterpret_cast<const double2 *>(&s.rec[k].area);
+        }
+        TS_MARK(3)
+        // ---- schedule.  The global stores of all threads are ordered before the fence of thread 0 by the CTA
+        //      barrier; the notifying atomics follow the fence.  Lane b < 9 of warp 0 looks after neighbour
+        //      tile b of the 3x3 block, lane 9 after this tile's own state word: one round trip for all.
+        if (notify) atomicOr(&s.notify, notify);
+        __syncthreads();
+        if (warp == 0) {
+            if (lane == 0) fence_visit(a);
+            __syncwarp();
+            const unsigned nm = s.notify;
+            const int completed_all = s.completed, undone_all = s.undone;
+            // lanes 0..8: the 3x3 block of this rank's tiles; lanes 10..12 / 13..15: the three tiles of the
+            // neighbouring rank above / below (one sweep across GPUs: their state words are peer memory)
             const int y2 = ty + lane / 3 - 1, x2 = tx + lane % 3 - 1;
-            const bool mine = lane < 9 && lane != 4 && ((nm >> lane) & 1u) && y2 >= 0 && y2 < a.nty && x2 >= 0 && x2 < a.ntx;
-            const int32_t nb = y2 * a.ntx + x2;
+            const bool mine_local = lane < 9 && lane != 4 && ((nm >> lane) & 1u) && y2 >= 0 && y2 < a.nty && x2 >= 0 && x2 < a.ntx;
+            const int side = lane >= 13 ? 1 : 0, x3 = tx + (lane - 10) % 3 - 1;
+            const bool mine_peer = lane >= 10 && lane < 16 && ((nm >> lane) & 1u) && ((a.p2p >> side) & 1) && x3 >= 0 && x3 < a.ntx;
+            const bool mine = mine_local || mine_peer;
+            const int32_t nb = mine_peer ? a.peer_tile0[side] + x3 : y2 * a.ntx + x2;
             uint32_t old = TF_PENDING;
-            if (mine) old = atomicOr(&a.flag[nb], TF_PENDING);
+            if (mine_local) old = or_u32(a, &a.flag[nb], TF_PENDING);
+            if (mine_peer) old = atomicOr_system(&a.peer_flag[side][nb], TF_PENDING);
             const bool complete = completed_all == undone_all;
             uint32_t own_old = 0;
-            if (lane == 9) own_old = atomicCAS(&a.flag[tile], TF_RUNNING | TF_VISITED, TF_VISITED | (complete ? TF_COMPLETE : 0u));
+            if (lane == 9) {
+                if (s.late) or_u32(a, &a.flag[tile], TF_PENDING);       // a pit released a receiver in this tile: not released
+                own_old = cas_u32(a, &a.flag[tile], TF_RUNNING | TF_VISITED, TF_VISITED | (complete ? TF_COMPLETE : 0u));
+            }
             own_old = __shfl_sync(FULL, own_old, 9);
             const bool released = own_old == (TF_RUNNING | TF_VISITED);
             const bool idle = mine && (old & (TF_PENDING | TF_RUNNING | TF_COMPLETE)) == 0;   // I made it pending: I schedule it
             const unsigned im = __ballot_sync(FULL, idle);
             const int n_idle = __popc(im);
-            // a released warp continues with its first idle successor itself (no queue round trip on the
-            // critical path of a river); everything else goes to the queue
-            const int take_lane = (released && im) ? __ffs(im) - 1 : -1;
+            // a released CTA continues with its first idle successor on this rank itself (no queue round trip
+            // on the critical path of a river); everything else goes to the queue (a peer's tile: the peer's)
+            const int take_lane = (released && (im & 0x1ffu)) ? __ffs(im & 0x1ffu) - 1 : -1;
             // in-flight accounting: +1 per tile made pending, -1 for this tile if released.  The handed-over
             // tile inherits this tile's count, so a river moves on without touching the counter.  Increments
             // are performed before the tiles become visible in the queue, the decrement comes last.
@@ -533,27 +591,30 @@ __global__ void __launch_bounds__(32) k_tsweep(const Args a)
                 }
                 requeue_self = __shfl_sync(FULL, requeue_self, 0);
             }
-            if (lane == 0 && n_push > 0) (void)atomicAdd(&a.ctr[TC_INFLIGHT], (unsigned long long)n_push);
-            if (n_push > 0) { if (lane == 0) fence_acq_rel_gpu(); __syncwarp(); }
-            if (idle && lane != take_lane) queue_push(a, nb);
+            if (lane == 0 && n_push > 0) (void)add_u64(a, a.inflight, (unsigned long long)n_push);
+            if (n_push > 0) { if (lane == 0) fence_visit(a); __syncwarp(); }
+            if (idle && lane != take_lane) {
+                if (mine_peer) queue_push_to(a, a.peer_ctr[side], a.peer_slots[side], a.peer_cap_mask[side], nb);
+                else queue_push(a, nb);
+            }
             int next_tile = -1, next_mode = 0, next_first = 0;
             if (released) {
                 if (take_lane >= 0) {
                     next_tile = __shfl_sync(FULL, nb, take_lane);
                     next_first = (__shfl_sync(FULL, old, take_lane) & TF_VISITED) ? 0 : 1;
                     next_mode = 1;
-                    if (lane == take_lane) atomicExch(&a.flag[nb], TF_RUNNING | TF_VISITED);     // claim (lane 0 fences at the top of the visit)
+                    if (lane == take_lane) exch_u32(a, &a.flag[nb], TF_RUNNING | TF_VISITED);     // claim (thread 0 fences at the top of the visit)
                 } else if (lane == 0) {
-                    atomicAdd(&a.ctr[TC_INFLIGHT], ~0ULL);   // -1
+                    add_u64(a, a.inflight, ~0ULL);   // -1
                 }
             } else if (requeue_self) {
                 if (lane == 0) {
-                    atomicExch(&a.flag[tile], TF_PENDING | TF_VISITED);     // still counted in flight
+                    exch_u32(a, &a.flag[tile], TF_PENDING | TF_VISITED);     // still counted in flight
                     queue_push(a, tile);
                     x_defer++;
                 }
             } else {
-                if (lane == 0) { atomicExch(&a.flag[tile], TF_RUNNING | TF_VISITED); x_rerun++; }
+                if (lane == 0) { exch_u32(a, &a.flag[tile], TF_RUNNING | TF_VISITED); x_rerun++; }
                 next_tile = tile; next_mode = 2;
             }
             if (lane == 0) {
@@ -564,17 +625,19 @@ __global__ void __launch_bounds__(32) k_tsweep(const Args a)
                     atomicAdd(&a.ctr[TC_HIST + 2 * b], 1ULL);
                     atomicAdd(&a.ctr[TC_HIST + 2 * b + 1], (unsigned long long)completed_all);
                 }
-                x_cells += (unsigned long long)completed_all; x_levels += (unsigned long long)lvl;
-                x_sources += (unsigned long long)nsrc_all; x_sent += (unsigned long long)((nm >> 9) & 1u);
+                if (a.dbg && s.x_is_late) { s.x_late[6] += 1; s.x_late[7] += (unsigned long long)completed_all; }
+                x_cells += (unsigned long long)completed_all; 
+                x_sources += (unsigned long long)s.nsrc; x_sent += (unsigned long long)((nm >> 9) & 1u);
                 if (next_tile < 0) { next_tile = acquire_tile(a); next_mode = 0; }
+                s.next_tile = next_tile; s.next_mode = next_mode;
+                if (next_mode == 1) s.next_first = next_first; else if (next_mode == 2) s.next_first = 0;
             }
-            tile = __shfl_sync(FULL, next_tile, 0);
-            mode = __shfl_sync(FULL, next_mode, 0);
-            first = next_mode == 1 ? next_first : 0;
         }
+        __syncthreads();
+        tile = s.next_tile; mode = s.next_mode;
         TS_MARK(5)
     }
-    if (lane == 0) {
+    if (tid == 0) {
         if (x_cells) atomicAdd(&a.ctr[TC_CELLS], x_cells);
         if (x_levels) atomicAdd(&a.ctr[TC_LEVELS], x_levels);
         if (x_sources) atomicAdd(&a.ctr[TC_SOURCES], x_sources);
@@ -584,7 +647,7 @@ __global__ void __launch_bounds__(32) k_tsweep(const Args a)
         atomicMax(&a.ctr[TC_T_END], globaltimer_ns());
         if (a.dbg) {
             for (int q = 0; q < 6; q++) atomicAdd(&a.ctr[TC_PHASE + q], s.x_ph[q]);
-            atomicAdd(&a.ctr[TC_PHASE + 6], x_pass_cyc);
+            for (int q = 0; q < 8; q++) atomicAdd(&a.ctr[TC_LATE + q], s.x_late[q]);
             atomicAdd(&a.ctr[TC_PHASE + 7], x_levels);
         }
     }
@@ -641,13 +704,23 @@ k_ts_setup(Args a, int mode, int TW, uint8_t *seen)
     }
     __syncthreads();
     if (tid == 0) {
-        a.ctr[TC_HEAD] = 0; a.ctr[TC_TAIL] = (unsigned long long)s_count; a.ctr[TC_INFLIGHT] = (unsigned long long)s_count;
+        a.ctr[TC_HEAD] = 0; a.ctr[TC_TAIL] = (unsigned long long)s_count;
         a.ctr[TC_ABORT] = 0; a.ctr[TC_SENT] = 0;
         a.ctr[TC_T_START] = ~0ULL; a.ctr[TC_T_END] = 0;
         if (mode == 0) { a.ctr[TC_VISITS] = 0; a.ctr[TC_CELLS] = 0; a.ctr[TC_SOURCES] = 0; a.ctr[TC_LEVELS] = 0; a.ctr[TC_REQUEUE] = 0; a.ctr[TC_DEFER] = 0; }
         a.ctr[TC_QUEUED] = (unsigned long long)s_count;
         for (int b = 0; b < 128; b++) a.ctr[TC_HIST + b] = 0;
-        for (int q = 0; q < 8; q++) a.ctr[TC_PHASE + q] = 0;
+        for (int q = 0; q < 8; q++) { a.ctr[TC_PHASE + q] = 0; a.ctr[TC_LATE + q] = 0; }
+        if (a.p2p) {
+            // one sweep across GPUs: count this rank's tiles into the global counter (it is back at zero when a
+            // sweep ends; rank 0 must add, not set: other ranks may already have counted in), make the queue and
+            // the records written by the kernels before this one visible to the peers, then arrive at the start barrier
+            atomicAdd_system(a.inflight, (unsigned long long)s_count);
+            __threadfence_system();
+            atomicAdd_system(a.arrived, 1ULL);
+        } else {
+            *a.inflight = (unsigned long long)s_count;
+        }
     }
 }
 
@@ -733,9 +806,10 @@ k_pit_mark(const int32_t *__restrict__ pit_dst, int64_t n_edges, uint8_t *link)
 
 struct Variant { int tw, th, nt; size_t smem; void (*kernel)(const Args); int blocks; };
 
-#define TS_VARIANT(tw, th) {tw, th, 32, sizeof(Smem<tw, th>), k_tsweep<tw, th>, 0}
+#define TS_VARIANT(tw, th, nt) {tw, th, nt, sizeof(Smem<tw, th>), k_tsweep<tw, th, nt>, 0}
 static Variant g_variants[] = {
-    TS_VARIANT(32, 32), TS_VARIANT(32, 16), TS_VARIANT(64, 16), TS_VARIANT(64, 32), TS_VARIANT(32, 64), TS_VARIANT(32, 8),
+    TS_VARIANT(32, 32, 64), TS_VARIANT(32, 32, 128), TS_VARIANT(64, 32, 128), TS_VARIANT(64, 32, 256), TS_VARIANT(64, 64, 256),
+    TS_VARIANT(64, 16, 64), TS_VARIANT(32, 16, 64), TS_VARIANT(32, 32, 32),
 };
 
 static int pick_variant()
@@ -773,17 +847,21 @@ static int ts_prepare(pdm_tile *t, Variant **out)
     int64_t cap = 1024;
     while (cap < 4 * ntiles) cap <<= 1;
     if (t->ts_cap < cap || t->ts_ntiles_cap < ntiles) {
-        if (t->ts_slots) { cudaFree(t->ts_slots); t->ts_slots = nullptr; }
-        if (t->ts_flag) { cudaFree(t->ts_flag); t->ts_flag = nullptr; }
-        PDM_CUDA(cudaMalloc(&t->ts_slots, (size_t)cap * 4));
-        PDM_CUDA(cudaMalloc(&t->ts_flag, (size_t)ntiles * 4));
+        if (t->p2p.on) { pdm_set_error("tile sweep: the control block is shared with peer GPUs and cannot grow; connect after the first sweep geometry is known"); return PDM_ERR_STATE; }
+        if (t->ts_ctl) { cudaFree(t->ts_ctl); t->ts_ctl = nullptr; }
+        // one allocation [counters | tile flags | queue slots], at least 4 MiB so that it is a cudaMalloc
+        // allocation of its own (CUDA IPC shares whole allocations)
+        const size_t off_flag = (size_t)TC_N * 8, off_slots = (off_flag + (size_t)ntiles * 4 + 255) & ~(size_t)255;
+        size_t bytes = off_slots + (size_t)cap * 4;
+        if (bytes < ((size_t)4 << 20)) bytes = (size_t)4 << 20;
+        PDM_CUDA(cudaMalloc(&t->ts_ctl, bytes));
+        PDM_CUDA(cudaMemsetAsync(t->ts_ctl, 0, bytes, t->stream));
+        t->ts_ctr = reinterpret_cast<unsigned long long *>(t->ts_ctl);
+        t->ts_flag = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(t->ts_ctl) + off_flag);
+        t->ts_slots = reinterpret_cast<int32_t *>(reinterpret_cast<char *>(t->ts_ctl) + off_slots);
         t->ts_cap = cap; t->ts_ntiles_cap = ntiles;
     }
-    if (!t->ts_ctr) {
-        PDM_CUDA(cudaMalloc(&t->ts_ctr, TC_N * sizeof(unsigned long long)));
-        PDM_CUDA(cudaMallocHost((void **)&t->ts_hctr, TC_N * sizeof(unsigned long long)));
-        PDM_CUDA(cudaMemsetAsync(t->ts_ctr, 0, TC_N * sizeof(unsigned long long), t->stream));
-    }
+    if (!t->ts_hctr) PDM_CUDA(cudaMallocHost((void **)&t->ts_hctr, TC_N * sizeof(unsigned long long)));
     if (!t->ts_seen) PDM_CUDA(cudaMalloc(&t->ts_seen, (size_t)2 * w.C));
     *out = &v;
     return PDM_OK;
@@ -793,6 +871,7 @@ static Args ts_args(pdm_tile *t, const Variant &v)
 {
     const Win &w = t->win;
     Args a;
+    memset(&a, 0, sizeof(a));
     a.rec = pdm_trec(t);
     a.row_area = t->row_area;
     a.pit_beg = t->pit_beg; a.pit_end = t->pit_end; a.pit_dst = t->pit_dst; a.pit_w = t->pit_w;
@@ -807,7 +886,132 @@ static Args ts_args(pdm_tile *t, const Variant &v)
     if (dbg < 0) { const char *e = getenv("PYDEM_B200_TS_DEBUG"); dbg = e ? atoi(e) : 0; }
     a.dbg = dbg;
     a.has_pits = t->n_pit_edges > 0 ? 1 : 0;
+    a.inflight = t->ts_ctr + TC_INFLIGHT;
+    a.arrived = t->ts_ctr + TC_ARRIVED;
     return a;
+}
+
+// Args of one sweep across the GPUs of the row shards: the neighbours' boundary rows, tile state words and
+// queues are mapped peer memory, the in-flight counter and the start barrier live on rank 0
+static void ts_args_p2p(pdm_tile *t, const Variant &v, Args &a)
+{
+    const pdm_tile::P2P &q = t->p2p;
+    a.p2p = 0;
+    for (int side = 0; side < 2; side++) {
+        if (!q.rec[side]) continue;
+        a.p2p |= 1 << side;
+        // above: the peer's last owned row; below: its first owned row
+        const long long prow = side == 0 ? q.hi[0] - 1 : q.lo[1];
+        a.halo_src[side] = reinterpret_cast<const TRec *>(q.rec[side]) + prow * t->win.C;
+        char *ctl = reinterpret_cast<char *>(q.ctl[side]);
+        a.peer_ctr[side] = reinterpret_cast<unsigned long long *>(ctl);
+        a.peer_flag[side] = reinterpret_cast<uint32_t *>(ctl + q.off_flag[side]);
+        a.peer_slots[side] = reinterpret_cast<int32_t *>(ctl + q.off_slots[side]);
+        a.peer_cap_mask[side] = q.cap_mask[side];
+        a.peer_tile0[side] = side == 0 ? (q.nty[0] - 1) * a.ntx : 0;
+    }
+    unsigned long long *root = reinterpret_cast<unsigned long long *>(q.root_ctl ? q.root_ctl : t->ts_ctl);
+    a.inflight = root + TC_INFLIGHT;
+    a.arrived = root + TC_ARRIVED;
+    a.start_target = (unsigned long long)q.world * q.launches;
+    if (!a.p2p) a.p2p = 4;      // a single rank of a p2p group still uses the system-scope protocol
+    (void)v;
+}
+
+// ---- CUDA IPC plumbing of the multi-GPU sweep (called through pdm_shard_p2p_* in shard.cu)
+static int alloc_offset(const void *p, long long *off)
+{
+    // offset of p inside its cudaMalloc allocation (IPC handles name whole allocations); the driver entry
+    // point is fetched through the runtime, the library does not link libcuda
+    typedef int (*fn_t)(unsigned long long *, size_t *, unsigned long long);
+    static fn_t fn = nullptr;
+    if (!fn) {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        PDM_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &qr));
+        if (!f) { pdm_set_error("cuMemGetAddressRange not available"); return PDM_ERR_CUDA; }
+        fn = (fn_t)f;
+    }
+    unsigned long long base = 0; size_t size = 0;
+    if (fn(&base, &size, (unsigned long long)(uintptr_t)p) != 0) { pdm_set_error("cuMemGetAddressRange failed"); return PDM_ERR_CUDA; }
+    *off = (long long)((unsigned long long)(uintptr_t)p - base);
+    return PDM_OK;
+}
+
+int pdm_ts_p2p_export(pdm_tile *t, P2PExport *e)
+{
+    Variant *v = nullptr;
+    int rc = ts_prepare(t, &v);
+    if (rc) return rc;
+    memset(e, 0, sizeof(*e));
+    PDM_CUDA(cudaStreamSynchronize(t->stream));
+    PDM_CUDA(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(e->h_rec), t->cell));
+    PDM_CUDA(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(e->h_ctl), t->ts_ctl));
+    if ((rc = alloc_offset(t->cell, &e->off_rec)) || (rc = alloc_offset(t->ts_ctl, &e->off_ctl))) return rc;
+    e->off_flag = (long long)(reinterpret_cast<char *>(t->ts_flag) - reinterpret_cast<char *>(t->ts_ctl));
+    e->off_slots = (long long)(reinterpret_cast<char *>(t->ts_slots) - reinterpret_cast<char *>(t->ts_ctl));
+    e->lo = t->win.lo; e->hi = t->win.hi; e->C = t->win.C;
+    e->ntx = (int)((t->win.C + v->tw - 1) / v->tw); e->nty = (int)((t->win.hi - t->win.lo + v->th - 1) / v->th);
+    e->cap_mask = (unsigned)(t->ts_cap - 1);
+    e->device = t->device;
+    e->proc_tag = (long long)getpid();
+    e->raw_rec = t->cell; e->raw_ctl = t->ts_ctl;
+    return PDM_OK;
+}
+
+static int open_peer(const unsigned char *handle, long long off, void **map, void **ptr)
+{
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    PDM_CUDA(cudaIpcOpenMemHandle(map, h, cudaIpcMemLazyEnablePeerAccess));
+    *ptr = reinterpret_cast<char *>(*map) + off;
+    return PDM_OK;
+}
+
+// up / down: the exports of the ranks holding the rows above / below (nullptr at the ends of the grid);
+// root: rank 0's export (nullptr on rank 0 itself)
+int pdm_ts_p2p_connect(pdm_tile *t, const P2PExport *up, const P2PExport *down, const P2PExport *root, int world, int rank)
+{
+    pdm_tile::P2P &q = t->p2p;
+    if (q.on) { pdm_set_error("pdm_shard_p2p_connect: already connected"); return PDM_ERR_STATE; }
+    Variant *v = nullptr;
+    int rc = ts_prepare(t, &v);
+    if (rc) return rc;
+    memset(&q, 0, sizeof(q));
+    const P2PExport *nb[2] = {up, down};
+    const long long me = (long long)getpid();
+    for (int side = 0; side < 2; side++) {
+        const P2PExport *e = nb[side];
+        if (!e) continue;
+        if (e->C != t->win.C) { pdm_set_error("pdm_shard_p2p_connect: the neighbour has %lld columns, this tile %lld", e->C, (long long)t->win.C); return PDM_ERR_ARG; }
+        if (e->proc_tag == me) { q.rec[side] = e->raw_rec; q.ctl[side] = e->raw_ctl; }
+        else {
+            void *p = nullptr;
+            if ((rc = open_peer(e->h_rec, e->off_rec, &q.map_rec[side], &p))) return rc;
+            q.rec[side] = p;
+            if ((rc = open_peer(e->h_ctl, e->off_ctl, &q.map_ctl[side], &q.ctl[side]))) return rc;
+        }
+        q.off_flag[side] = e->off_flag; q.off_slots[side] = e->off_slots;
+        q.lo[side] = e->lo; q.hi[side] = e->hi; q.nty[side] = e->nty; q.cap_mask[side] = e->cap_mask;
+    }
+    if (root) {
+        if (root->proc_tag == me) q.root_ctl = root->raw_ctl;
+        else if (up && root->device == up->device && !memcmp(root->h_ctl, up->h_ctl, 64)) q.root_ctl = q.ctl[0];   // rank 1: rank 0 is the upper neighbour (an allocation is opened once)
+        else if ((rc = open_peer(root->h_ctl, root->off_ctl, &q.map_root, &q.root_ctl))) return rc;
+    }
+    q.world = world; q.rank = rank; q.launches = 0; q.on = 1;
+    return PDM_OK;
+}
+
+void pdm_ts_p2p_close(pdm_tile *t)
+{
+    pdm_tile::P2P &q = t->p2p;
+    for (int side = 0; side < 2; side++) {
+        if (q.map_rec[side]) cudaIpcCloseMemHandle(q.map_rec[side]);
+        if (q.map_ctl[side]) cudaIpcCloseMemHandle(q.map_ctl[side]);
+    }
+    if (q.map_root) cudaIpcCloseMemHandle(q.map_root);
+    memset(&q, 0, sizeof(q));
 }
 
 // the sweep state of a fresh graph: records of the owned rows (link halo rows in place on a shard),
@@ -830,13 +1034,20 @@ int pdm_ts_reset_state(pdm_tile *t)
     return PDM_OK;
 }
 
-// first != 0: every tile is pending; else (shard resume) the boundary tiles that received donors
+// first != 0: every tile is pending; else (shard resume) the boundary tiles that received donors.
+// On a tile connected to its row neighbours (pdm_shard_p2p_connect) the one launch with first != 0 is the
+// whole multi-GPU sweep: every rank launches it once, the kernels run until the global counter is at zero.
 int pdm_launch_tsweep(pdm_tile *t, int first)
 {
     Variant *v = nullptr;
     int rc = ts_prepare(t, &v);
     if (rc) return rc;
-    const Args a = ts_args(t, *v);
+    Args a = ts_args(t, *v);
+    if (t->p2p.on) {
+        if (!first) { pdm_set_error("tile sweep: a multi-GPU sweep has no resume rounds"); return PDM_ERR_STATE; }
+        t->p2p.launches++;
+        ts_args_p2p(t, *v, a);
+    }
     {
         int64_t nfill = (int64_t)a.cap_mask + 1;
         if (first && 2 * a.w.C > nfill) nfill = 2 * a.w.C;

@@ -20,9 +20,11 @@ enum {
     TC_T_END = 71,
     TC_QUEUED = 72,     // tiles queued by the set-up of this launch
     TC_DEFER = 73,      // visits deferred to the back of the queue (neighbour published, queue busy)
+    TC_ARRIVED = 76,    // multi-GPU sweep, on rank 0: ranks whose queues are set up, summed over all sweeps so far (never reset)
     TC_PHASE = 80,      // debug: ns summed over CTAs per phase {claim, load, count, levels, store, schedule}
     TC_HIST = 96,       // PYDEM_B200_TS_DEBUG timeline: per 100 us bucket {visits, cells completed} x 64
-    TC_N = 96 + 128
+    TC_LATE = 96 + 128, // debug: phases {claim, load, count, flow, store, schedule} ns, visits, cells of the visits after dbg x 100 us
+    TC_N = 96 + 128 + 8
 };
 
 struct Args {
@@ -40,6 +42,31 @@ struct Args {
     unsigned long long *ctr;
     int32_t dbg;
     int32_t has_pits;         // the graph has pit edges: pit receivers are gated on their pit counters
+    // ---- one sweep across the row shards of several GPUs (peer memory over NVLink; shard.cu):
+    unsigned long long *inflight;   // tiles pending or running, all ranks together (rank 0's counter; = ctr + TC_INFLIGHT on one GPU)
+    unsigned long long *arrived;    // start barrier: ranks whose queues are set up (rank 0's counter, monotonic)
+    unsigned long long start_target;
+    int32_t p2p;                    // bit 0: the rows above [lo] live on a peer, bit 1: the rows below [hi)
+    const TRec *halo_src[2];        // the peer's boundary row of records (its last / first owned row), column 0
+    uint32_t *peer_flag[2];         // the peer's tile state words, queue and counters
+    int32_t *peer_slots[2];
+    unsigned long long *peer_ctr[2];
+    uint32_t peer_cap_mask[2];
+    int32_t peer_tile0[2];          // first tile of the peer's boundary tile row
+};
+
+// what a rank publishes to its neighbours (pdm_shard_p2p_export): CUDA IPC handles of the record array and of
+// the control block [counters | tile flags | queue slots], offsets of the pointers inside their allocations
+struct P2PExport {
+    unsigned char h_rec[64], h_ctl[64];
+    long long off_rec, off_ctl;
+    long long off_flag, off_slots;      // relative to the control block
+    long long lo, hi, C;                // owned local rows, columns
+    int ntx, nty;
+    unsigned cap_mask;
+    int device;
+    long long proc_tag;                 // same process: pointers are used as they are (tests on one GPU)
+    void *raw_rec, *raw_ctl;
 };
 
 }  // namespace ts

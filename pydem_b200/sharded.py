@@ -126,6 +126,21 @@ class DistGroup(object):
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return [int(t.item())]
 
+    def connect_p2p(self, engine):
+        """Map the row neighbours' sweep records and tile queues (CUDA IPC over NVLink) so that the UCA
+        accumulation is ONE sweep across all ranks instead of exchange rounds (csrc/shard.cu,
+        pdm_shard_p2p_*).  Collective: every rank calls it once after its tile window is set."""
+        import torch
+        blob = engine.p2p_export()
+        mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8).cuda()
+        allb = [torch.empty_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(allb, mine)
+        blobs = [bytes(b.cpu().numpy().tobytes()) for b in allb]
+        engine.p2p_connect(blobs[self.rank - 1] if self.rank > 0 else None,
+                           blobs[self.rank + 1] if self.rank < self.world - 1 else None,
+                           blobs[0] if self.rank > 0 else None, self.world, self.rank)
+        self.dist.barrier()
+
 
 # ----------------------------------------------------------------------------------------------
 # GPU engine of one rank
@@ -151,6 +166,23 @@ class ShardEngine(object):
         self.lab = {k: (mk(torch.int64), mk(torch.float64)) for k in ("send_up", "send_down", "recv_up", "recv_down")}
         self.flag = torch.zeros(1, dtype=torch.int64, device=dev)
         self.views = {}
+        self.p2p = False
+
+    # ---- one sweep across GPUs (pdm_shard_p2p_*)
+    def p2p_export(self):
+        import ctypes as ct
+        L, h = self.tile.L, self.tile.h
+        size = ct.c_int64(0)
+        self.T._lib.check(L.pdm_shard_p2p_export(h, None, ct.byref(size)))
+        buf = (ct.c_ubyte * size.value)()
+        self.T._lib.check(L.pdm_shard_p2p_export(h, buf, ct.byref(size)))
+        return bytes(buf)
+
+    def p2p_connect(self, up, down, root, world, rank):
+        import ctypes as ct
+        keep = [ct.create_string_buffer(b, len(b)) if b is not None else None for b in (up, down, root)]
+        self.T._lib.check(self.tile.L.pdm_shard_p2p_connect(self.tile.h, *keep, int(world), int(rank)))
+        self.p2p = True
 
     def rows(self, field):
         if field not in self.views:
@@ -256,11 +288,20 @@ def run_hot_path(engines, group, twi=True, profile=False, **uca_flags):
     group.exchange([e.halo_bufs(T.F_LINK) for e in engines])
     for e in engines:
         e.tile.shard_stage("indeg")
-    group.exchange([e.halo_bufs(T.F_CELL) for e in engines])      # the neighbours' boundary records (static part + "not done")
+    p2p = all(e.p2p for e in engines)
+    if not p2p:
+        group.exchange([e.halo_bufs(T.F_CELL) for e in engines])      # the neighbours' boundary records (static part + "not done")
     tm.mark("ms_graph")
-    # a6/a7: local sweeps + exchanges of the boundary rows
+    # a6/a7: local sweeps + exchanges of the boundary rows -- or, with the neighbours' records mapped as peer
+    # memory, ONE sweep across all ranks: no rounds, no host synchronisation
     rounds, first = 0, 1
     while True:
+        if p2p:
+            for e in engines:
+                e.tile.shard_stage("sweep", 1)
+            tm.mark("ms_sweep_first")
+            rounds = 1
+            break
         for e in engines:
             e.tile.shard_stage("sweep", first)
         tm.mark("ms_sweep_first" if first else "ms_sweep_resume")
@@ -341,6 +382,9 @@ class ShardedDEM(object):
         s = self.spec
         d = np.full(R - 1, float(spacing)); d2 = np.full(R, float(spacing))
         self.engine = ShardEngine(s, d, d, d2, d2, stream=torch.cuda.current_stream().cuda_stream)
+        import os
+        if w > 1 and os.environ.get("PYDEM_B200_SHARD_P2P", "1") != "0":
+            self.group.connect_p2p(self.engine)
         loc = np.full((s.Rl, cols), np.nan)
         # every rank holds the same periodic block (spectral synthesis, conditioned with wrapping
         # rows): stacked vertically the blocks join seamlessly, so per-GPU work is identical (weak

@@ -1,0 +1,3 @@
+cd $GRAFT_REPO_ROOT
+timeout 300 python tests/tools/gpu_check.py > gpurun_out/r2_check12.log 2>&1; grep -c "^OK" gpurun_out/r2_check12.log; grep -v "^OK" gpurun_out/r2_check12.log | tail -8
+PYDEM_B200_TS_DEBUG=2 timeout 900 python scripts/sweep_ab.py 4096 legacy=1 tile=0 tile=1 tile=2 tile=3 tile=4 tile=5 tile=6 tile=7 > gpurun_out/r2_ab12.log 2>&1; grep -E '^\{|^cond|^raw|rror' gpurun_out/r2_ab12.log; grep "CTA-time\|passes\|\[ts\] kernel" gpurun_out/r2_ab12.log | awk 'NR%48==4 || NR%48==5 || NR%48==6'

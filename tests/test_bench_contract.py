@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_the_contract_line():
     env = dict(os.environ, RANK="0", WORLD_SIZE="1")
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--size", "1024"],
                        capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
@@ -19,9 +19,10 @@ def test_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["unit"] == "Mcells/s" and d["higher_is_better"] is True
     assert d["metric"].startswith("Mcells/s") and d["dtype"] == "f64" and d["data"] == "synthetic"
     assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1 and d["gpu_launches"] == 0
-    assert "workload" in d["config"]
+    assert "workload" in d["config"] and "seed 0" in d["config"]["workload"] and "drain_pits=True" in d["config"]["workload"]
+    assert d["cpu_baseline"]["whole_dem_one_core"]["cores"] == 1
     cb = d["cpu_baseline"]
-    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert cb["kind"] in ("port+ref-sweep", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
