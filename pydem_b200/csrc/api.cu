@@ -404,10 +404,12 @@ int pdm_tile_uca(pdm_tile *t, const pdm_uca_params *p_in, pdm_uca_stats *stats)
                     h[ts::TC_PHASE + 4] * 1e-6, h[ts::TC_PHASE + 5] * 1e-6);
             fprintf(stderr, "[ts] passes: %llu, %.0f cycles per pass\n", h[ts::TC_PHASE + 7],
                     h[ts::TC_PHASE + 7] ? (double)h[ts::TC_PHASE + 6] / (double)h[ts::TC_PHASE + 7] : 0.0);
-            fprintf(stderr, "[ts] late visits: %llu visits, %llu cells; us per visit: claim %.2f load %.2f count %.2f flow %.2f (store) %.2f schedule+wait %.2f\n",
+            fprintf(stderr, "[ts] late visits: %llu visits, %llu cells; us per visit: claim %.2f load %.2f count %.2f flow %.2f busy turns of the busiest warp %.1f schedule+wait %.2f\n",
                     h[ts::TC_LATE + 6], h[ts::TC_LATE + 7], h[ts::TC_LATE] * 1e-3 / (double)(h[ts::TC_LATE + 6] + 1), h[ts::TC_LATE + 1] * 1e-3 / (double)(h[ts::TC_LATE + 6] + 1),
                     h[ts::TC_LATE + 2] * 1e-3 / (double)(h[ts::TC_LATE + 6] + 1), h[ts::TC_LATE + 3] * 1e-3 / (double)(h[ts::TC_LATE + 6] + 1),
-                    h[ts::TC_LATE + 4] * 1e-3 / (double)(h[ts::TC_LATE + 6] + 1), h[ts::TC_LATE + 5] * 1e-3 / (double)(h[ts::TC_LATE + 6] + 1));
+                    h[ts::TC_LATE + 4] * 1.0 / (double)(h[ts::TC_LATE + 6] + 1), h[ts::TC_LATE + 5] * 1e-3 / (double)(h[ts::TC_LATE + 6] + 1));
+            fprintf(stderr, "[ts] late visits, all warps' busy turns: cycles total %llu in drain step %llu hand-over %llu | busy turns summed over warps %llu\n",
+                    h[ts::TC_DBG2], h[ts::TC_DBG2 + 1], h[ts::TC_DBG2 + 2], h[ts::TC_DBG2 + 3]);
             fprintf(stderr, "[ts] timeline (100 us buckets) visits/kcells:");
             for (int b = 0; b < 64; b++)
                 if (h[ts::TC_HIST + 2 * b]) fprintf(stderr, " %d:%llu/%llu", b, h[ts::TC_HIST + 2 * b], h[ts::TC_HIST + 2 * b + 1] / 1000);

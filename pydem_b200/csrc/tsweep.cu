@@ -62,6 +62,7 @@ namespace ts {
 #define TF_COMPLETE 4u
 #define TF_VISITED 8u
 
+#define TS_MARK_DONE 0x40000000u   // counter word of a cell completed in this visit (written to global memory when the visit ends)
 #define RD_NONE 0xFFFFu    // receiver descriptor: no receiver in that slot
 #define RD_OUT 0x8000u     // receiver outside the tile: low bits = bit of the notify mask (9 = other rank)
 
@@ -121,7 +122,8 @@ struct Smem {
     TRec rec[HN];
     unsigned long long mbar;                      // mbarrier of the bulk copies
     double rowa[TH_];                             // cell area of the tile's rows (dX2 * dY2, dem_processing.py:885)
-    uint32_t cnt[(HN + 3) / 4];                   // one byte per staged cell: own cells: donors that are not final yet; ring cells: 0x80
+    uint32_t cnt[HN];                             // per staged cell: own cells: donors that are not final yet (TS_MARK_DONE once completed in this visit); ring cells: bit 31
+    uint32_t rcv[HN];                             // own cells that are not final: ring indices of the two receivers (low / high half, 0xffff = none)
     uint16_t fr[TN];                              // the cells in the order they became ready (a topological order of this visit)
     int n_fr;                                     // entries of fr = cells that became ready (tickets of the producers)
     int head;                                     // tickets of the consumers
@@ -135,6 +137,8 @@ struct Smem {
     unsigned long long x_ph[8], x_t;              // debug: ns per phase
     unsigned long long x_late[8];                 // the same for visits that start after dbg x 100 us (dbg >= 10)
     int x_is_late;
+    unsigned long long x_dbg2[4];
+    int x_busy_it;                                // debug: iterations in which the busiest warp held a cell
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -236,7 +240,11 @@ __device__ __noinline__ void pit_push(S &s, const Args &a, double slot_bits, dou
 
 #define TS_MARK(idx) if (a.dbg && tid == 0) { const unsigned long long now = globaltimer_ns(); s.x_ph[idx] += now - s.x_t; if (s.x_is_late) s.x_late[idx] += now - s.x_t; s.x_t = now; }
 
+#ifdef TS_NO_CTA_FENCE
+__device__ __forceinline__ void fence_cta() { asm volatile("" ::: "memory"); }
+#else
 __device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+#endif
 __device__ __forceinline__ int ld_volatile_shared_i32(const int *p)
 {
     int v;
@@ -260,68 +268,76 @@ __device__ __forceinline__ unsigned ld_volatile_shared_u16(const uint16_t *p)
     return (unsigned)v;
 }
 
-// One ready cell: PULL its sums (cyutils.pyx:161-163 seen from the receiver) over its donors in ascending
-// neighbour order (W, E, N, S, NW, NE, SW, SE) -- a fixed order, so a cell's value does not depend on the
-// schedule, the tile size or the sharding -- publish them in shared and global memory, and count the
-// cell off at its receivers.  r1 / r2: in-tile receivers that became ready (ring index) or -1.
+// One ready cell: PULL its sums (cyutils.pyx:161-163 seen from the receiver) over its donors, publish
+// them in shared and global memory, and count the cell off at its receivers.  The sum has a fixed shape
+// -- own area + (((W + E) + (N + S)) + ((NW + NE) + (SW + SE))) with exact zeros for neighbours that are
+// not donors -- so a cell's value does not depend on the schedule, the tile shape or the sharding.
+// Written for the dependent path of a river (one lane, nothing to overlap with): all eight neighbours are
+// staged, so their loads are unconditional and in flight together with the cell's own word (~30 cycles);
+// the sums are a depth-4 tree (~8 cycles a level); the two count-offs are in flight together; measured
+// ~150 cycles a cell in isolation (scripts/ubench/smem_lat.cu).  r1 / r2: in-tile receivers that became
+// ready (ring index) or -1.
 template <class S>
 __device__ __forceinline__ void drain_cell(S &s, const Args &a, int k, int rows_valid, int cols_valid, int64_t r0, int64_t c0,
                                            int tile, unsigned &notify, int &r1, int &r2)
 {
     constexpr int HW = S::HW;
-    const int hy = k / HW, hx = k - hy * HW;        // ring coordinates: own cells 1..TH, 1..TW
-    const unsigned long long w = *reinterpret_cast<const unsigned long long *>(&s.rec[k].link);
-    unsigned dm = (unsigned)(w >> 8) & 0xffu;
-    const unsigned lk = (unsigned)w & 0xffu;
-    double ar = s.rowa[hy - 1];                                                  // dem_processing.py:885, 901
-    double tt = ((w >> 16) & TR_TODO) ? 1.0 : 0.0;                               // 944
-    while (dm) {
-        const int q = __ffs(dm) - 1;
-        dm &= dm - 1;
-        const TRec &d = s.rec[k + nbr_off<HW>(q)];
-        const double2 v = *reinterpret_cast<const double2 *>(&d.area);
-        const double p = d.prop;
-        const double wgt = q < 4 ? p : __dsub_rn(1.0, p);                        // dem_processing.py:1082
-        ar = __dadd_rn(ar, __dmul_rn(v.x, wgt));                                 // cyutils.pyx:161
-        tt = __dadd_rn(tt, __dmul_rn(v.y, wgt));                                 // cyutils.pyx:163
+    const TRec *rk = &s.rec[k];
+    const unsigned long long w = *reinterpret_cast<const unsigned long long *>(&rk->link);
+    double2 v[8];
+    double p[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const TRec *d = rk + nbr_off<HW>(q);
+        v[q] = *reinterpret_cast<const double2 *>(&d->area);
+        p[q] = d->prop;
     }
-    const int64_t n = (r0 + hy - 1) * a.w.C + (c0 + hx - 1);
+    const uint32_t rv = s.rcv[k];
+    const int hy = k / HW;                          // ring row: own cells 1..TH
+    const double base = s.rowa[hy - 1];                                          // dem_processing.py:885, 901
+    const unsigned dm = (unsigned)(w >> 8) & 0xffu;
+    const unsigned lk = (unsigned)w & 0xffu;
+    double ca[8], ct[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const double wgt = q < 4 ? p[q] : __dsub_rn(1.0, p[q]);                  // dem_processing.py:1082
+        const bool on = (dm >> q) & 1u;
+        ca[q] = on ? __dmul_rn(v[q].x, wgt) : 0.0;                               // cyutils.pyx:161
+        ct[q] = on ? __dmul_rn(v[q].y, wgt) : 0.0;                               // cyutils.pyx:163
+    }
+    double ar = __dadd_rn(__dadd_rn(__dadd_rn(ca[0], ca[1]), __dadd_rn(ca[2], ca[3])), __dadd_rn(__dadd_rn(ca[4], ca[5]), __dadd_rn(ca[6], ca[7])));
+    double tt = __dadd_rn(__dadd_rn(__dadd_rn(ct[0], ct[1]), __dadd_rn(ct[2], ct[3])), __dadd_rn(__dadd_rn(ct[4], ct[5]), __dadd_rn(ct[6], ct[7])));
+    ar = __dadd_rn(base, ar);
+    tt = __dadd_rn(((w >> 16) & TR_TODO) ? 1.0 : 0.0, tt);                       // 944
     if ((lk & LK_PITIN) && a.has_pits) {
+        const int64_t n = (r0 + hy - 1) * a.w.C + (c0 + (k - hy * HW) - 1);
         ar = __dadd_rn(ar, __ldcg(a.pit_acc_a + n));
         tt = __dadd_rn(tt, __ldcg(a.pit_acc_t + n));
     }
     *reinterpret_cast<double2 *>(&s.rec[k].area) = make_double2(ar, tt);
+    s.cnt[k] = TS_MARK_DONE;                       // (nobody counts a completed cell off any more)
     fence_cta();                                   // the sums are visible in the CTA before the cell is counted off
-    atomicOr(&s.cnt[k >> 2], 0x40u << (8 * (k & 3)));      // completed in this visit: written to global memory when the visit ends
-    r1 = -1; r2 = -1;
-    if (!(lk & (LK_NOSEC | LK_PIT))) {
-        const int sec = lk & LK_SEC_MASK;
-        int dr1, dc1, dr2, dc2;
-        off_e1(sec, dr1, dc1); off_e2(sec, dr2, dc2);
-        const int k1 = k + dr1 * HW + dc1, k2 = k + dr2 * HW + dc2;
-        const bool v1 = (lk & LK_KEEP1) != 0, v2 = (lk & LK_KEEP2) != 0;
-        uint32_t o1 = 0, o2 = 0;
-        if (v1) o1 = atomicSub(&s.cnt[k1 >> 2], 1u << (8 * (k1 & 3))) >> (8 * (k1 & 3));
-        if (v2) o2 = atomicSub(&s.cnt[k2 >> 2], 1u << (8 * (k2 & 3))) >> (8 * (k2 & 3));
-        o1 &= 0xffu; o2 &= 0xffu;
-        if (o1 == 1u) r1 = k1;
-        if (o2 == 1u) r2 = k2;
-        if (r1 >= 0 || r2 >= 0) fence_cta();       // the last decrement has observed the others: their sums are visible
-        if ((o1 | o2) & 0xc0u) {
-            // a receiver in the ring: another tile (or the neighbouring rank) has a new donor
+    const int k1 = (int)(rv & 0xffffu), k2 = (int)(rv >> 16);
+    uint32_t o1 = 0, o2 = 0;
+    if (k1 != 0xffff) o1 = atomicSub(&s.cnt[k1], 1u);
+    if (k2 != 0xffff) o2 = atomicSub(&s.cnt[k2], 1u);
+    r1 = o1 == 1u ? k1 : -1;
+    r2 = o2 == 1u ? k2 : -1;
+    if (r1 >= 0 || r2 >= 0) fence_cta();           // the last count-off has observed the others: their sums are visible
+    if ((o1 | o2) & 0x80000000u) {
+        // a receiver in the ring: another tile (or the neighbouring rank) has a new donor
 #pragma unroll
-            for (int e = 0; e < 2; e++) {
-                if (!((e ? o2 : o1) & 0xc0u)) continue;
-                const int ry = hy + (e ? dr2 : dr1), rx = hx + (e ? dc2 : dc1);
-                const int64_t gr = r0 + ry - 1;
-                if (gr < a.w.lo || gr >= a.w.hi)     // receiver on the neighbouring rank: bit 9 + the peer's tile (10..12 above, 13..15 below)
-                    notify |= (1u << 9) | (1u << ((gr < a.w.lo ? 10 : 13) + (rx < 1 ? 0 : (rx > cols_valid ? 2 : 1))));
-                else notify |= 1u << ((ry < 1 ? 0 : (ry > rows_valid ? 2 : 1)) * 3 + (rx < 1 ? 0 : (rx > cols_valid ? 2 : 1)));
-            }
+        for (int e = 0; e < 2; e++) {
+            if (!((e ? o2 : o1) & 0x80000000u)) continue;
+            const int kk = e ? k2 : k1;
+            const int ry = kk / HW, rx = kk - ry * HW;
+            const int64_t gr = r0 + ry - 1;
+            if (gr < a.w.lo || gr >= a.w.hi)     // receiver on the neighbouring rank: bit 9 + the peer's tile (10..12 above, 13..15 below)
+                notify |= (1u << 9) | (1u << ((gr < a.w.lo ? 10 : 13) + (rx < 1 ? 0 : (rx > cols_valid ? 2 : 1))));
+            else notify |= 1u << ((ry < 1 ? 0 : (ry > rows_valid ? 2 : 1)) * 3 + (rx < 1 ? 0 : (rx > cols_valid ? 2 : 1)));
         }
-    } else if ((lk & LK_PIT) && a.has_pits) {
-        pit_push(s, a, s.rec[k].prop, ar, tt, tile);
     }
+    if ((lk & LK_PIT) && a.has_pits) pit_push(s, a, s.rec[k].prop, ar, tt, tile);
 }
 
 // One CTA = one tile at a time.
@@ -333,7 +349,7 @@ __device__ __forceinline__ void drain_cell(S &s, const Args &a, int k, int rows_
 // receiver that reached zero (a second one goes to the queue).  No level barrier: hill slopes are worked
 // by all lanes at once, a river crossing the tile advances on one lane at shared-memory latency.
 template <int TW, int TH, int NT>
-__global__ void __launch_bounds__(NT, 1) k_tsweep(const Args a)
+__global__ void __launch_bounds__(NT, 1) k_tsweep(const __grid_constant__ Args a)
 {
     typedef Smem<TW, TH> S;
     constexpr int HW = S::HW, TN = S::TN;
@@ -347,6 +363,7 @@ __global__ void __launch_bounds__(NT, 1) k_tsweep(const Args a)
     unsigned long long x_cells = 0, x_levels = 0, x_sources = 0, x_rerun = 0, x_defer = 0, x_sent = 0;
     if (tid == 0) {
         for (int q = 0; q < 8; q++) { s.x_ph[q] = 0; s.x_late[q] = 0; }
+        for (int q = 0; q < 4; q++) s.x_dbg2[q] = 0;
         s.x_is_late = 0;
         s.x_t = globaltimer_ns();
         atomicMin(&a.ctr[TC_T_START], s.x_t);
@@ -381,7 +398,7 @@ __global__ void __launch_bounds__(NT, 1) k_tsweep(const Args a)
             }
             fence_visit(a);
             s.n_fr = 0; s.undone = 0; s.nsrc = 0; s.notify = 0; s.late = 0;
-            if (a.dbg >= 10) s.x_is_late = (globaltimer_ns() - ld_volatile_u64(&a.ctr[TC_T_START])) > (unsigned long long)a.dbg * 100000ULL;
+            if (a.dbg >= 10) s.x_is_late = (globaltimer_ns() - ld_volatile_u64(&a.ctr[TC_T_START])) > (unsigned long long)(a.dbg % 1000) * 100000ULL;
         }
         TS_MARK(0)
         const int ty = tile / a.ntx, tx = tile - ty * a.ntx;
@@ -439,7 +456,7 @@ __global__ void __launch_bounds__(NT, 1) k_tsweep(const Args a)
         }
         first = s.next_first;
         for (int i = tid; i < TN / 2; i += NT) reinterpret_cast<uint32_t *>(s.fr)[i] = 0xffffffffu;      // empty queue slots
-        for (int i = tid; i < (S::HN + 3) / 4; i += NT) s.cnt[i] = 0x80808080u;                            // ring cells never become ready
+        for (int i = tid; i < S::HN; i += NT) s.cnt[i] = 0x80000000u;                                      // ring cells never become ready (bit 31 survives their few count-offs)
         // ring cells: (re)load in place for a repeated visit; a cell counts as done only when both words are final
         for (int idx = tid; idx < nring; idx += NT) {
             int hy, hx;
@@ -490,8 +507,21 @@ __global__ void __launch_bounds__(NT, 1) k_tsweep(const Args a)
                                 else fence_acq_rel_gpu();       // counter seen at zero: the pit accumulators of this cell are final
                             }
                             if (c == 0) s.fr[atomicAdd(&s.n_fr, 1)] = (uint16_t)k;      // (published by the CTA barrier below)
+                            // the two receivers as ring indices (facets table dem_processing.py:173-182; a receiver in the
+                            // ring belongs to another tile: its counter word only tells that)
+                            const unsigned lk = (unsigned)w & 0xffu;
+                            uint32_t rv = 0xffffffffu;
+                            if (!(lk & (LK_NOSEC | LK_PIT))) {
+                                const int sec = lk & LK_SEC_MASK;
+                                int dr1, dc1, dr2, dc2;
+                                off_e1(sec, dr1, dc1); off_e2(sec, dr2, dc2);
+                                const uint32_t k1 = (lk & LK_KEEP1) ? (uint32_t)(k + dr1 * HW + dc1) : 0xffffu;
+                                const uint32_t k2 = (lk & LK_KEEP2) ? (uint32_t)(k + dr2 * HW + dc2) : 0xffffu;
+                                rv = k1 | (k2 << 16);
+                            }
+                            s.rcv[k] = rv;
                         }
-                        reinterpret_cast<uint8_t *>(s.cnt)[k] = (uint8_t)c;
+                        s.cnt[k] = c;
                     }
                 }
             }
@@ -502,42 +532,82 @@ __global__ void __launch_bounds__(NT, 1) k_tsweep(const Args a)
         TS_MARK(2)
         // ---- flow paths
         unsigned notify = 0;
-        if (tid == 0) { s.live = s.n_fr; s.head = 0; s.completed = 0; }
+        if (tid == 0) { s.live = s.n_fr; s.head = 0; s.completed = 0; s.x_busy_it = 0; }
         __syncthreads();
         {
-            int k = -1, ticket = -1, mine = 0;
+            // Every lane follows flow paths.  A warp runs in lock step: lanes holding a cell drain it, lanes
+            // without one look for work in the queue -- only every fourth turn while a lane of the warp is on
+            // a path (the look costs ~60 cycles on that lane's dependent chain).  A warp leaves, all lanes
+            // together, when nothing is queued or held anywhere in the CTA.
+            int k = -1, ticket = -1, mine = 0, busy_it = 0;
+            long long c_turn = 0, c_drain = 0, c_hand = 0, c_look = 0, c0t = 0;
             for (int it = 0;; it++) {
-                if (it && __all_sync(__activemask(), k < 0)) __nanosleep(100);       // a warp without work leaves the issue slots to the others
-                if (k < 0) {
-                    if (ticket < 0) ticket = atomicAdd(&s.head, 1);
-                    if (ticket < TN) {
-                        const unsigned v = ld_volatile_shared_u16(&s.fr[ticket]);
-                        if (v != 0xffffu) { k = (int)v; ticket = -1; fence_cta(); }
+                const bool any_busy = __any_sync(FULL, k >= 0);
+                busy_it += any_busy ? 1 : 0;
+                if (a.dbg) c0t = clock64();
+                if (!any_busy || (it & 3) == 0) {
+                    if (k < 0) {
+                        if (ticket < 0) ticket = atomicAdd(&s.head, 1);
+                        if (ticket < TN) {
+                            const unsigned v = ld_volatile_shared_u16(&s.fr[ticket]);
+                            if (v != 0xffffu) { k = (int)v; ticket = -1; fence_cta(); }
+                        }
                     }
-                    if (k < 0 && ld_volatile_shared_i32(&s.live) == 0) break;
+                    if (!any_busy) {
+                        const int live = ld_volatile_shared_i32(&s.live);
+                        if (__all_sync(FULL, k < 0)) {
+                            if (live == 0) break;
+                            __nanosleep(100);      // a warp without work leaves the issue slots to the others
+                        }
+                    }
                 }
+                long long c1t = 0, c2t = 0;
+                if (a.dbg) c1t = clock64();
+                int spare = -1;
                 if (k >= 0) {
                     int r1, r2;
                     drain_cell(s, a, k, rows_valid, cols_valid, r0, c0, tile, notify, r1, r2);
                     mine++;
-                    if (r1 >= 0 && r2 >= 0) {
-                        atomicAdd(&s.live, 1);
-                        *reinterpret_cast<volatile uint16_t *>(&s.fr[atomicAdd(&s.n_fr, 1)]) = (uint16_t)r2;
-                        k = r1;
-                    } else if (r1 >= 0) k = r1;
+                    if (r1 >= 0 && r2 >= 0) { k = r1; spare = r2; }
+                    else if (r1 >= 0) k = r1;
                     else if (r2 >= 0) k = r2;
                     else { k = -1; atomicSub(&s.live, 1); }
                 }
+                // forks stay in the warp: a D-infinity flow path is a band two or three cells wide whose cells
+                // fork and join again on every level; handing the second branch to the queue would make it wait
+                // for a lane to look there (hundreds of cycles, on every level of a river).  The j-th forking
+                // lane gives its second receiver to the j-th lane without a cell; the queue takes the rest.
+                if (a.dbg) c2t = clock64();
+                unsigned fm = __ballot_sync(FULL, spare >= 0);
+                if (fm) {
+                    unsigned im = __ballot_sync(FULL, k < 0);
+                    while (fm) {
+                        const int src = __ffs(fm) - 1;
+                        fm &= fm - 1;
+                        const int val = __shfl_sync(FULL, spare, src);
+                        if (im) {
+                            const int dst = __ffs(im) - 1;
+                            im &= im - 1;
+                            if (lane == dst) k = val;      // (a ticket it may hold stays valid: it looks there again when this path has ended)
+                            if (lane == src) atomicAdd(&s.live, 1);
+                        } else if (lane == src) {
+                            atomicAdd(&s.live, 1);
+                            *reinterpret_cast<volatile uint16_t *>(&s.fr[atomicAdd(&s.n_fr, 1)]) = (uint16_t)val;
+                        }
+                    }
+                    __syncwarp();      // the receiving lanes read what the handing lanes have observed
+                }
+                if (a.dbg && any_busy) { const long long c3t = clock64(); c_turn += c3t - c0t; c_drain += c2t - c1t; c_hand += c3t - c2t; c_look += c1t - c0t; }
             }
             if (mine) atomicAdd(&s.completed, mine);
+            if (a.dbg && lane == 0) { atomicMax(&s.x_busy_it, busy_it); atomicAdd(&s.x_dbg2[0], (unsigned long long)c_turn); atomicAdd(&s.x_dbg2[1], (unsigned long long)c_drain); atomicAdd(&s.x_dbg2[2], (unsigned long long)c_hand); atomicAdd(&s.x_dbg2[3], (unsigned long long)busy_it); }
         }
         __syncthreads();
-        // ---- write the cells completed in this visit to global memory (the only global stores of a visit;
-        //      none is in flight while the lanes synchronise through shared memory above)
+        // ---- write the cells completed in this visit to global memory
         for (int g = tid; g < TN; g += NT) {
             const int y = g / TW, x = g - y * TW;
             const int k = (y + 1) * HW + x + 1;
-            if (reinterpret_cast<const uint8_t *>(s.cnt)[k] & 0x40u)
+            if (s.cnt[k] == TS_MARK_DONE)
                 *reinterpret_cast<double2 *>(&a.rec[(r0 + y) * C + (c0 + x)].area) = *reinterpret_cast<const double2 *>(&s.rec[k].area);
         }
         TS_MARK(3)
@@ -625,7 +695,8 @@ __global__ void __launch_bounds__(NT, 1) k_tsweep(const Args a)
                     atomicAdd(&a.ctr[TC_HIST + 2 * b], 1ULL);
                     atomicAdd(&a.ctr[TC_HIST + 2 * b + 1], (unsigned long long)completed_all);
                 }
-                if (a.dbg && s.x_is_late) { s.x_late[6] += 1; s.x_late[7] += (unsigned long long)completed_all; }
+                if (a.dbg && s.x_is_late) { s.x_late[6] += 1; s.x_late[7] += (unsigned long long)completed_all; s.x_late[4] += (unsigned long long)s.x_busy_it; }
+                if (a.dbg && !s.x_is_late) { for (int q = 0; q < 4; q++) s.x_dbg2[q] = 0; }
                 x_cells += (unsigned long long)completed_all; 
                 x_sources += (unsigned long long)s.nsrc; x_sent += (unsigned long long)((nm >> 9) & 1u);
                 if (next_tile < 0) { next_tile = acquire_tile(a); next_mode = 0; }
@@ -648,6 +719,7 @@ __global__ void __launch_bounds__(NT, 1) k_tsweep(const Args a)
         if (a.dbg) {
             for (int q = 0; q < 6; q++) atomicAdd(&a.ctr[TC_PHASE + q], s.x_ph[q]);
             for (int q = 0; q < 8; q++) atomicAdd(&a.ctr[TC_LATE + q], s.x_late[q]);
+            for (int q = 0; q < 4; q++) atomicAdd(&a.ctr[TC_DBG2 + q], s.x_dbg2[q]);
             atomicAdd(&a.ctr[TC_PHASE + 7], x_levels);
         }
     }
@@ -710,7 +782,7 @@ k_ts_setup(Args a, int mode, int TW, uint8_t *seen)
         if (mode == 0) { a.ctr[TC_VISITS] = 0; a.ctr[TC_CELLS] = 0; a.ctr[TC_SOURCES] = 0; a.ctr[TC_LEVELS] = 0; a.ctr[TC_REQUEUE] = 0; a.ctr[TC_DEFER] = 0; }
         a.ctr[TC_QUEUED] = (unsigned long long)s_count;
         for (int b = 0; b < 128; b++) a.ctr[TC_HIST + b] = 0;
-        for (int q = 0; q < 8; q++) { a.ctr[TC_PHASE + q] = 0; a.ctr[TC_LATE + q] = 0; }
+        for (int q = 0; q < 8; q++) { a.ctr[TC_PHASE + q] = 0; a.ctr[TC_LATE + q] = 0; a.ctr[TC_DBG2 + q] = 0; }
         if (a.p2p) {
             // one sweep across GPUs: count this rank's tiles into the global counter (it is back at zero when a
             // sweep ends; rank 0 must add, not set: other ranks may already have counted in), make the queue and

@@ -24,7 +24,8 @@ enum {
     TC_PHASE = 80,      // debug: ns summed over CTAs per phase {claim, load, count, levels, store, schedule}
     TC_HIST = 96,       // PYDEM_B200_TS_DEBUG timeline: per 100 us bucket {visits, cells completed} x 64
     TC_LATE = 96 + 128, // debug: phases {claim, load, count, flow, store, schedule} ns, visits, cells of the visits after dbg x 100 us
-    TC_N = 96 + 128 + 8
+    TC_DBG2 = 96 + 128 + 8, // debug: cycles {busy turns total, inside the drain step, in the hand-over, looking for work} of the busiest-warp turns of late visits
+    TC_N = 96 + 128 + 16
 };
 
 struct Args {

@@ -21,6 +21,8 @@ E[R // 2 - 3:R // 2 + 3, 100:400] = E[R // 2 - 3:R // 2 + 3, 100:400].min()     
 spec = sharded.ShardSpec(R, C, g.rank, g.world)
 d = np.full(R - 1, 30.0); d2 = np.full(R, 30.0)
 eng = sharded.ShardEngine(spec, d, d, d2, d2, stream=torch.cuda.current_stream().cuda_stream)
+if g.world > 1 and os.environ.get("PYDEM_B200_SHARD_P2P", "1") != "0":
+    g.connect_p2p(eng)      # one sweep across the GPUs (peer memory) instead of exchange rounds
 loc = np.full((spec.Rl, C), np.nan); loc[spec.lo:spec.hi] = E[spec.r0:spec.r1]
 eng.tile.upload(T.F_ELEV, loc)
 st = sharded.run_hot_path([eng], g)[0]

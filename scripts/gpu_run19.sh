@@ -1,0 +1,16 @@
+cd $GRAFT_REPO_ROOT
+cat > /tmp/exp.py <<'PY'
+import sys, os
+sys.path.insert(0, os.environ["GRAFT_REPO_ROOT"])
+import numpy as np, torch
+from pydem_b200 import synth, tile as T
+n = 4096
+E = synth.conditioned_fractal_dem(n, 0)
+dt = T.DeviceTile(n, n, stream=torch.cuda.current_stream().cuda_stream)
+dt.set_spacing(30.0, 30.0); dt.upload(T.F_ELEV, E)
+for rep in range(3):
+    dt.slopes_directions()
+    st = dt.uca(drain_pits=1)
+    print(st["ms_sweep"], st["ms_sweep_kernel"], st["n_drained"], st["n_undone"])
+PY
+
