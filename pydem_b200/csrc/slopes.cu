@@ -210,6 +210,232 @@ __device__ __forceinline__ bool cell_fast(const double *__restrict__ E, const Wi
     return true;
 }
 
+// ------------------------------------------------------------------------------------------
+// Tiled kernel (default).  A block stages the elevation tile + halo in shared memory with bulk
+// asynchronous copies (TMA, one cp.async.bulk per row, mbarrier completion) and the per-fence geometry of
+// its rows once; a thread then computes FOUR consecutive cells of a row from registers (3 x 6 window read
+// with 16-byte shared loads, outputs written with 16-byte stores).  Against the one-cell-per-thread kernel
+// (9 elevation + 22 geometry loads per cell through L1) that is 18 shared loads per four cells, and the
+// facet bookkeeping keeps only (m2, facet code, s1, s2) per candidate instead of seven doubles: the
+// stencil is bound by the fp64 pipe, and every integer / select instruction saved frees an issue slot for it.
+// Same arithmetic as cell_fast, bit for bit (tests/test_gpu_parity.py::test_fast_stencil_*).
+// ------------------------------------------------------------------------------------------
+struct FenceGeom {          // geometry of one fence (between two rows), shared memory
+    double dX, dY, dg, thA, thB, rdX, rdY, rdg, x2, y2;
+    int ok, pad;
+};
+
+// one facet on values; best = (m2, code, s1, s2) with code = facet | lazy << 3 | clamped-to-diagonal << 4
+__device__ __forceinline__ bool facet_lean(int k, double n1, double n2, double nd, double d1, double d2, double dg,
+                                           double r1, double r2, double rg, double d1sq, double d2sq,
+                                           double &m2, int &code, double &bs1, double &bs2)
+{
+    const bool p1 = n1 > 0.0, p2 = n2 > 0.0;
+    const double u = __dmul_rn(n2, d1sq), v = __dmul_rn(n1, d2sq);
+    const bool A = p1 && p2;
+    const bool band = A && !(fabs(u - v) > 1e-8 * v);
+    const bool over = u > v;
+    const bool a_under = A && !over;
+    const bool use_s1 = a_under || (p1 && !p2);
+    const bool use_sd = (A && over) || (!p1 && p2 && nd > 0.0);
+    const double q1 = mdiv(use_s1 ? n1 : nd, use_s1 ? d1 : dg, use_s1 ? r1 : rg);
+    const double q2 = mdiv(n2, d2, r2);
+    double rad2 = __dmul_rn(q1, q1);
+    if (a_under) rad2 = __dadd_rn(rad2, __dmul_rn(q2, q2));
+    if ((use_s1 || use_sd) && rad2 > m2) {
+        m2 = rad2;
+        code = k | (a_under ? 8 : 0) | (use_sd ? 16 : 0);
+        bs1 = q1; bs2 = q2;
+    }
+    return !band;
+}
+
+// returns false when the cell must take the parity path.  u / l: the fences above / below the cell's row.
+__device__ __forceinline__ bool cell_lean(double c, double eE, double eW, double eN, double eNE, double eNW,
+                                          double eS, double eSE, double eSW, const FenceGeom &u, const FenceGeom &l,
+                                          double &m2_out, double &dr_out)
+{
+    bool ok = true;
+    {
+        const double ev[9] = {c, eE, eW, eN, eNE, eNW, eS, eSE, eSW};
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            const unsigned hi32 = (unsigned)__double2hiint(ev[k]) & 0x7fffffffu;
+            const bool zero = (hi32 | (unsigned)__double2loint(ev[k])) == 0u;
+            ok = ok && (zero || (hi32 >= 0x25000000u && hi32 <= 0x5D000000u));   // 2^-431 .. 2^465 (see cell_fast)
+        }
+    }
+    if (!ok) return false;
+    const double cE = __dsub_rn(c, eE), cN = __dsub_rn(c, eN), cW = __dsub_rn(c, eW), cS = __dsub_rn(c, eS);
+    const double cNE = __dsub_rn(c, eNE), cNW = __dsub_rn(c, eNW), cSW = __dsub_rn(c, eSW), cSE = __dsub_rn(c, eSE);
+    double m2 = -1.0, bs1 = 0.0, bs2 = 0.0;
+    int code = -1;
+    bool sure = true;
+    sure &= facet_lean(0, cE, __dsub_rn(eE, eNE), cNE, u.dX, u.dY, u.dg, u.rdX, u.rdY, u.rdg, u.x2, u.y2, m2, code, bs1, bs2);
+    sure &= facet_lean(1, cN, __dsub_rn(eN, eNE), cNE, u.dY, u.dX, u.dg, u.rdY, u.rdX, u.rdg, u.y2, u.x2, m2, code, bs1, bs2);
+    sure &= facet_lean(2, cN, __dsub_rn(eN, eNW), cNW, u.dY, u.dX, u.dg, u.rdY, u.rdX, u.rdg, u.y2, u.x2, m2, code, bs1, bs2);
+    sure &= facet_lean(3, cW, __dsub_rn(eW, eNW), cNW, u.dX, u.dY, u.dg, u.rdX, u.rdY, u.rdg, u.x2, u.y2, m2, code, bs1, bs2);
+    sure &= facet_lean(4, cW, __dsub_rn(eW, eSW), cSW, l.dX, l.dY, l.dg, l.rdX, l.rdY, l.rdg, l.x2, l.y2, m2, code, bs1, bs2);
+    sure &= facet_lean(5, cS, __dsub_rn(eS, eSW), cSW, l.dY, l.dX, l.dg, l.rdY, l.rdX, l.rdg, l.y2, l.x2, m2, code, bs1, bs2);
+    sure &= facet_lean(6, cS, __dsub_rn(eS, eSE), cSE, l.dY, l.dX, l.dg, l.rdY, l.rdX, l.rdg, l.y2, l.x2, m2, code, bs1, bs2);
+    sure &= facet_lean(7, cE, __dsub_rn(eE, eSE), cSE, l.dX, l.dY, l.dg, l.rdX, l.rdY, l.rdg, l.x2, l.y2, m2, code, bs1, bs2);
+    if (!sure) return false;
+    m2_out = m2;
+    if (code < 0) { dr_out = -1.0; return true; }
+    // direction of the winning facet: r * a + q * pi/2 (tables dem_processing.py:185-193)
+    const int k = code & 7;
+    const double a = (k & 1) ? -1.0 : 1.0;
+    const double qpi2 = __dmul_rn((double)((k + 1) >> 1), PDM_PI / 2);
+    const bool typeA = (0x99 >> k) & 1;                      // facets 0, 3, 4, 7
+    const FenceGeom &f = k < 4 ? u : l;
+    const double th = typeA ? f.thA : f.thB;
+    const double r = (code & 8) ? atan2(bs2, bs1) : ((code & 16) ? th : 0.0);
+    dr_out = __dadd_rn(__dmul_rn(r, a), qpi2);
+    return true;
+}
+
+#define ST_TX 32            // threads along x
+#define ST_TY 8             // rows of a block
+
+// ST_CPT cells per thread along x; ST_W columns per block; staged columns: 2 left + 2 right (keeps every row
+// copy 16-byte aligned)
+template <int ST_CPT, int MINB>
+__global__ void __launch_bounds__(ST_TX * ST_TY, MINB)
+k_slopes_tiled(const double *__restrict__ E, Win w, Geom g, int use_tma,
+               double *__restrict__ mag, double *__restrict__ dir, uint8_t *__restrict__ flat0,
+               int32_t *__restrict__ label)
+{
+    constexpr int ST_W = ST_TX * ST_CPT, ST_SW = ST_W + 4;
+    __shared__ __align__(128) double tile[(ST_TY + 2) * ST_SW];
+    __shared__ FenceGeom fg[ST_TY + 1];
+    __shared__ __align__(8) unsigned long long mbar;
+    const int64_t C = w.C;
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * ST_TX + tx;
+    const int64_t c0 = (int64_t)blockIdx.x * ST_W, r0 = w.lo + (int64_t)blockIdx.y * ST_TY;
+    // staged rows r0-1 .. r0+ST_TY, columns c0-2 .. c0+ST_W+1, clipped to the local array
+    const int64_t ia = max(r0 - 1, (int64_t)0), ib = min(r0 + ST_TY + 1, w.R);
+    const int64_t ja = max(c0 - 2, (int64_t)0), jb = min(c0 + ST_W + 2, C);
+    const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&mbar);
+    if (use_tma) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(1) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)((ib - ia) * (jb - ja) * 8);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+        }
+        if (tid < (int)(ib - ia)) {
+            const int64_t gi = ia + tid;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tile[(gi - (r0 - 1)) * ST_SW + (ja - (c0 - 2))]);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(E + gi * C + ja), "r"((uint32_t)((jb - ja) * 8)), "r"(mb) : "memory");
+        }
+    } else {
+        for (int idx = tid; idx < (int)((ib - ia) * (jb - ja)); idx += ST_TX * ST_TY) {
+            const int64_t gi = ia + idx / (int)(jb - ja), gj = ja + idx % (int)(jb - ja);
+            tile[(gi - (r0 - 1)) * ST_SW + (gj - (c0 - 2))] = __ldg(E + gi * C + gj);
+        }
+    }
+    // geometry of the fences r0-1 .. r0+ST_TY-1 (fence f lies between local rows f and f+1)
+    if (tid < ST_TY + 1) {
+        const int64_t f = r0 - 1 + tid;
+        FenceGeom q;
+        q.ok = 0; q.pad = 0;
+        q.dX = q.dY = q.dg = q.thA = q.thB = q.rdX = q.rdY = q.rdg = q.x2 = q.y2 = 0.0;
+        if (f >= 0 && f < w.R - 1) {
+            q.dX = __ldg(g.dX + f); q.dY = __ldg(g.dY + f); q.dg = __ldg(g.dg + f);
+            q.thA = __ldg(g.thA + f); q.thB = __ldg(g.thB + f);
+            q.rdX = __ldg(g.rdX + f); q.rdY = __ldg(g.rdY + f); q.rdg = __ldg(g.rdg + f);
+            q.x2 = __dmul_rn(q.dX, q.dX); q.y2 = __dmul_rn(q.dY, q.dY);
+            const double lo = 1e-5, hi = PDM_PI / 2 - 1e-5;     // spacing sanity of the fast path (see cell_fast)
+            q.ok = q.dX > 1e-150 && q.dY > 1e-150 && q.dg < 1e150 && q.thA > lo && q.thA < hi && q.thB > lo && q.thB < hi;
+        }
+        fg[tid] = q;
+    }
+    if (use_tma) {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(mb), "r"(0) : "memory");
+        }
+    }
+    __syncthreads();
+    const int64_t i = r0 + ty, j0 = c0 + (int64_t)tx * ST_CPT;
+    if (i >= w.hi || j0 >= C) return;
+    const bool top = w.top(i), bot = w.bottom(i);
+    const FenceGeom &gu = fg[ty], &gl = fg[ty + 1];
+    const bool row_fast = !top && !bot && gu.ok && gl.ok;
+    // 3 x (CPT+2) window of this thread's cells: columns j0-1 .. j0+CPT = staged columns CPT*tx+1 .. CPT*tx+CPT+2
+    double win[3][ST_CPT + 2];
+    if (row_fast) {
+#pragma unroll
+        for (int rr = 0; rr < 3; rr++) {
+            const double *src = &tile[(ty + rr) * ST_SW + ST_CPT * tx + 1];
+#pragma unroll
+            for (int q = 0; q < ST_CPT + 2; q++) win[rr][q] = src[q];
+        }
+    }
+    double om[ST_CPT], od[ST_CPT];
+    unsigned flats = 0;
+#pragma unroll
+    for (int u = 0; u < ST_CPT; u++) {
+        const int64_t j = j0 + u;
+        double m2 = -1.0, dr = -1.0;
+        if (j < C) {
+            const bool border = top | bot | (j == 0) | (j == C - 1);
+            if (!border) {
+                bool done = false;
+                if (row_fast)
+                    done = cell_lean(win[1][u + 1], win[1][u + 2], win[1][u], win[0][u + 1], win[0][u + 2], win[0][u],
+                                     win[2][u + 1], win[2][u + 2], win[2][u], gu, gl, m2, dr);
+                if (!done) {
+                    m2 = -1.0; dr = -1.0;
+                    cell_facets<true>(E, w, i, j, g, m2, dr);
+                }
+            } else {
+                // copy-from-interior passes 1782-1795, resolved per border cell (see k_slopes)
+                const double hp = PDM_PI / 2, thp = 3 * PDM_PI / 2, tp = 2 * PDM_PI;
+                const int64_t si = top ? i + 1 : (bot ? i - 1 : i);
+                const int64_t sj = (j == 0) ? 1 : (j == C - 1 ? C - 2 : j);
+                double sm = -1.0, sd_ = -1.0;
+                cell_facets<true>(E, w, si, sj, g, sm, sd_);
+                bool take = true;
+                if (j == 0) take = take && (sd_ > hp && sd_ < thp);
+                if (j == C - 1) take = take && (sd_ < hp || sd_ > thp);
+                if (top) take = take && (sd_ > 0.0 && sd_ < PDM_PI);
+                if (bot) take = take && (sd_ > PDM_PI && sd_ < tp);
+                if (take) { m2 = sm; dr = sd_; }
+                cell_facets<false>(E, w, i, j, g, m2, dr);
+            }
+        }
+        const bool fl = (m2 == -1.0);
+        om[u] = (m2 > 0.0) ? sqrt(m2) : m2;                                  // 1901
+        od[u] = dr;
+        flats |= (fl ? 1u : 0u) << (8 * u);
+    }
+    const int64_t n = i * C + j0;
+    if (ST_CPT == 4 && j0 + ST_CPT <= C && (C & 3) == 0) {
+        *reinterpret_cast<double2 *>(mag + n) = make_double2(om[0], om[1]);
+        *reinterpret_cast<double2 *>(mag + n + 2) = make_double2(om[2 % ST_CPT], om[3 % ST_CPT]);
+        *reinterpret_cast<double2 *>(dir + n) = make_double2(od[0], od[1]);
+        *reinterpret_cast<double2 *>(dir + n + 2) = make_double2(od[2 % ST_CPT], od[3 % ST_CPT]);
+        *reinterpret_cast<uint32_t *>(flat0 + n) = flats;
+    } else if (ST_CPT == 2 && j0 + ST_CPT <= C && (C & 1) == 0) {
+        *reinterpret_cast<double2 *>(mag + n) = make_double2(om[0], om[1 % ST_CPT]);
+        *reinterpret_cast<double2 *>(dir + n) = make_double2(od[0], od[1 % ST_CPT]);
+        *reinterpret_cast<uint16_t *>(flat0 + n) = (uint16_t)((flats & 1u) | ((flats >> 8) & 1u) << 8);
+    } else {
+#pragma unroll
+        for (int u = 0; u < ST_CPT; u++)
+            if (j0 + u < C) { mag[n + u] = om[u]; dir[n + u] = od[u]; flat0[n + u] = (uint8_t)((flats >> (8 * u)) & 1u); }
+    }
+#pragma unroll
+    for (int u = 0; u < ST_CPT; u++)
+        if (j0 + u < C && ((flats >> (8 * u)) & 1u)) label[n + u] = (int32_t)(n + u);   // union-find root of the flat-region labelling (flats.cu)
+}
+
 // 3 blocks per SM (80 registers, 136 B of spills) beats the unconstrained 114 registers / 2 blocks:
 // 0.92 -> 0.84 ms at 4096^2 (scripts/stencil_ab.py), same bits
 __global__ void __launch_bounds__(256, 3)
@@ -310,8 +536,35 @@ int pdm_launch_slopes(pdm_tile *t)
     dim3 grid((unsigned)((w.C + 31) / 32), (unsigned)((w.hi - w.lo + 7) / 8));
     // PYDEM_B200_STENCIL=parity runs the literal 8 x (3 div + atan2) formulation everywhere (tests
     // compare both bit for bit)
+    // PYDEM_B200_STENCIL=v1: the one-cell-per-thread fast kernel of round 1 (A/B runs)
     static int fast = -1;
-    if (fast < 0) { const char *e = getenv("PYDEM_B200_STENCIL"); fast = (e && !strcmp(e, "parity")) ? 0 : 1; }
+    if (fast < 0) { const char *e = getenv("PYDEM_B200_STENCIL"); fast = (e && !strcmp(e, "parity")) ? 0 : ((e && !strcmp(e, "v1")) ? 1 : ((e && !strncmp(e, "tiled", 5) && e[5]) ? atoi(e + 5) : 2)); }
+    if (fast >= 2 && !t->stencil_parity) {
+        dim3 b2(ST_TX, ST_TY);
+        // bulk copies need 16-byte aligned rows: an even number of columns (the arrays are 256-byte aligned)
+        const int use_tma = (w.C % 2 == 0) ? 1 : 0;
+        const unsigned gy = (unsigned)((w.hi - w.lo + ST_TY - 1) / ST_TY);
+#define ST_LAUNCH(CPT, MINB) k_slopes_tiled<CPT, MINB><<<dim3((unsigned)((w.C + ST_TX * CPT - 1) / (ST_TX * CPT)), gy), b2, 0, t->stream>>>( \
+            t->elev, w, g, use_tma, t->mag, t->dir, t->flat0, t->label)
+        switch (fast) {
+            case 3: ST_LAUNCH(4, 3); break;
+            case 4: ST_LAUNCH(2, 2); break;
+            case 5: ST_LAUNCH(2, 3); break;
+            case 6: ST_LAUNCH(1, 3); break;
+            case 7: ST_LAUNCH(1, 2); break;
+            case 8: ST_LAUNCH(1, 4); break;
+            case 9: ST_LAUNCH(2, 4); break;
+            case 10: ST_LAUNCH(2, 5); break;
+            case 11: ST_LAUNCH(2, 6); break;
+            case 12: ST_LAUNCH(1, 5); break;
+            case 13: ST_LAUNCH(1, 6); break;
+            case 14: ST_LAUNCH(4, 4); break;
+            case 15: ST_LAUNCH(4, 2); break;
+            default: ST_LAUNCH(2, 4); break;      // best of the A/B on B200 (scripts/stencil_ab.py): 64 registers, 4 blocks / SM
+        }
+        PDM_LAUNCHED();
+        return PDM_OK;
+    }
     k_slopes<<<grid, block, 0, t->stream>>>(t->elev, w, g, t->stencil_parity ? 0 : fast, t->mag, t->dir, t->flat0, t->label);
     PDM_LAUNCHED();
     return PDM_OK;

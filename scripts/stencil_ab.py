@@ -19,7 +19,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
         if rep >= 3: ms.append(ev[0].elapsed_time(ev[1]))
     out = {f: dt.download(getattr(T, "F_" + f)) for f in ("MAG", "DIR", "FLATS")}
     np.savez("/tmp/sab_out_%s.npz" % tag, **out)
-    print(json.dumps(dict(lib=os.environ.get("PYDEM_B200_LIB", "default"), n=n, ms_best=round(min(ms), 4), ms_median=round(float(np.median(ms)), 4))), flush=True)
+    print(json.dumps(dict(lib=os.environ.get("PYDEM_B200_LIB", "default"), stencil=os.environ.get("PYDEM_B200_STENCIL", "tiled"), n=n, ms_best=round(min(ms), 4), ms_median=round(float(np.median(ms)), 4))), flush=True)
     sys.exit(0)
 from pydem_b200 import synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
@@ -28,7 +28,8 @@ np.save("/tmp/sab_%d.npy" % n, synth.conditioned_fractal_dem(n, 0))
 for rnd in range(2):
     for k, lib in enumerate(libs):
         env = dict(os.environ)
-        if lib != "default": env["PYDEM_B200_LIB"] = os.path.abspath(lib)
+        if lib.startswith("stencil="): env["PYDEM_B200_STENCIL"] = lib.split("=")[1]      # stencil=v1 | parity | tiled
+        elif lib != "default": env["PYDEM_B200_LIB"] = os.path.abspath(lib)
         subprocess.run([sys.executable, os.path.abspath(__file__), "--child", str(n), str(k)], env=env, check=False)
 ref = np.load("/tmp/sab_out_0.npz")
 for k in range(1, len(libs)):
