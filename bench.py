@@ -422,10 +422,13 @@ def gpu_arm(args):
         Eh = _pinned.pinned_copy(E)
         kw = dict(dX=SPACING, dY=SPACING, fill_flats=False, drain_pits_path=False, drain_pits=bool(pits_flag))
 
-        def e2e_step():
+        def e2e_step(all_outputs=False):
             dp = DEMProcessor(elev=Eh, **kw)
-            twi = dp.calc_twi()
+            twi = dp.calc_twi()                # what the reference call returns (dem_processing.py:1647-1677)
             chk = float(twi[n // 2, n // 2])   # the step's result is read on the host
+            if all_outputs:                    # every array attribute the reference object carries after the call
+                for name in ("mag", "direction", "uca", "flats", "edge_todo", "edge_done"):
+                    chk += float(getattr(dp, name)[n // 2, n // 2])
             dp._free_tile()
             return chk
         gpu_out = None
@@ -434,21 +437,37 @@ def gpu_arm(args):
                            uca=dt.download(T.F_UCA), edge_todo=dt.download(T.F_EDGE_TODO), edge_done=dt.download(T.F_EDGE_DONE),
                            twi=dt.download(T.F_TWI))
         dt.close()
-        for _ in range(max(1, min(args.warmup, 2))):
-            e2e_step()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        t_e2e = (time.perf_counter() - t0) / args.steps
+
+        def time_e2e(all_outputs):
+            for _ in range(max(1, min(args.warmup, 2))):
+                e2e_step(all_outputs)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                e2e_step(all_outputs)
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / args.steps
+        t_e2e = time_e2e(False)
+        t_all = time_e2e(True)
+        # result-only: DEMProcessor(elev=<pinned host>).calc_twi() returns twi; the other arrays stay on the device
+        # until somebody reads them (lazy attributes).  all_outputs: mag, direction, uca, twi + 3 masks are read too.
         e2e = {"value": cells_per_step / t_e2e / 1e6, "unit": "Mcells/s", "ms_per_step": t_e2e * 1e3,
                "h2d_bytes_per_step": int(n * n * 8 + 4 * n * 8),
-               "d2h_bytes_per_step": int(n * n * (8 * 5 + 3))}   # mag, direction, uca, twi, 10*twi + 3 masks
+               "d2h_bytes_per_step": int(n * n * 8),
+               "what": "DEMProcessor(elev=<pinned host array>).calc_twi() -> twi on the host",
+               "all_outputs": {"value": cells_per_step / t_all / 1e6, "unit": "Mcells/s", "ms_per_step": t_all * 1e3,
+                               "h2d_bytes_per_step": int(n * n * 8 + 4 * n * 8),
+                               "d2h_bytes_per_step": int(n * n * (8 * 4 + 3)),
+                               "what": "the same call + reading mag, direction, uca, flats, edge_todo, edge_done on the host"}}
     else:
         e2e = sh.e2e(args.steps)
     _note("e2e done")
 
+    config4 = None
+    if world > 1 and not args.no_config4:
+        sh.close()
+        config4 = config4_leg(args, world, rank)
+        _note("config 4 done")
     if rank != 0:
         return
     ms_sweep = float(np.mean(sweep_kernel_ms)) if sweep_kernel_ms and sweep_kernel_ms[0] else float(np.mean(sweep_ms))
@@ -500,10 +519,79 @@ def gpu_arm(args):
             line["parity"]["against"] = "oracle (oracle/pdm_oracle.c) on the whole benchmark DEM, same flags"
     else:
         line["parity"] = shard_parity
+        if config4 is not None:
+            line["config4"] = config4
     print(json.dumps(line), flush=True)
     if line.get("parity") and not line["parity"].get("ok", True):
         print("bench.py: PARITY FAILURE: %s" % json.dumps(line["parity"]), file=sys.stderr, flush=True)
         sys.exit(3)
+
+
+def config4_leg(args, world, rank):
+    """BASELINE.json configs[3] at its own shape: ONE non-periodic fractal (value-noise) DEM of
+    (8192 * N) x 65536 cells, 8192 x 65536 per GPU (N = 8: 65536 x 65536), row-sharded, UCA as one sweep across
+    the GPUs.  Device-resident timing of a few steps + checks that need no second implementation at that size:
+    a 1024 x 1024 window of every rank's rows against the oracle (stencil outputs are local: mag bit-exact,
+    direction to 1e-12; flats exact away from the window edge), every cell drained, NaN exactly on flats,
+    min(uca) = one cell.  The reference cannot run this size at all (32-bit indices, cyutils.pyx:27)."""
+    import torch
+    import torch.distributed as dist
+    from pydem_b200 import sharded, tile as T
+    rows, cols = args.config4_rows, args.config4_cols
+    t0 = time.perf_counter()
+    sh = sharded.ShardedDEM(rows_per_rank=rows, cols=cols, spacing=SPACING, seed=11, profile=True, noise=True)
+    t_gen = time.perf_counter() - t0
+    stats = {}
+    for _ in range(1):
+        stats.update(sh.step())
+    dist.barrier(); torch.cuda.synchronize()
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    steps = args.config4_steps
+    ev0.record()
+    for _ in range(steps):
+        stats.update(sh.step())
+    ev1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    tms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item()) / steps
+    # ---- checks
+    s = sh.spec
+    tile = sh.engine.tile
+    uca = sh.engine.rows(T.F_UCA)[s.lo:s.hi]
+    fl = sh.engine.rows(T.F_FLATS)[s.lo:s.hi]
+    bad = torch.zeros(4, dtype=torch.int64, device="cuda")
+    bad[0] = int(stats.get("n_undone", 0))
+    bad[1] = int((torch.isnan(uca) != (fl != 0)).sum().item())
+    bad[2] = int((uca[~torch.isnan(uca)] < SPACING * SPACING).sum().item())
+    wn = min(1024, s.r1 - s.r0 - 2, cols)
+    wi, wj = s.lo + (s.r1 - s.r0 - wn) // 2, (cols - wn) // 2
+    Ew = sh.engine.rows(T.F_ELEV)[wi:wi + wn, wj:wj + wn].cpu().numpy()
+    from oracle import oracle as orc
+    dp = orc.OracleDEMProcessor(np.ascontiguousarray(Ew), dX=SPACING, dY=SPACING, fill_flats=False, drain_pits_path=False, drain_pits=False)
+    dp.calc_slopes_directions()
+    mg = sh.engine.rows(T.F_MAG)[wi:wi + wn, wj:wj + wn].cpu().numpy()[2:-2, 2:-2]
+    dr = sh.engine.rows(T.F_DIR)[wi:wi + wn, wj:wj + wn].cpu().numpy()[2:-2, 2:-2]
+    # interior of the window only; pits the oracle would drain are excluded by comparing where both are defined
+    om, od = np.asarray(dp.mag)[2:-2, 2:-2], np.asarray(dp.direction)[2:-2, 2:-2]
+    both = (om > 0) & (mg > 0)
+    with np.errstate(invalid="ignore"):
+        bad[3] = int((np.abs(mg[both] - om[both]) > 1e-12 * np.abs(om[both])).sum() + (np.abs(dr[both] - od[both]) > 1e-12).sum())
+    frac_checked = float(both.mean())
+    dist.all_reduce(bad)
+    cells = rows * cols * world
+    out = {"workload": "one %dx%d value-noise DEM (8 octaves, seed 11, non-periodic, generated on the device), %d rows x %d columns per GPU, "
+                       "dX=dY=30 m, slope+aspect + UCA + TWI, fill_flats=False, drain_pits_path=False, drain_pits=False"
+                       % (rows * world, cols, rows, cols),
+           "value": cells / (ms * 1e-3) / 1e6, "unit": "Mcells/s", "ms_per_step": ms, "steps": steps, "n_gpus": world,
+           "cells": cells, "bytes_resident_per_gpu": int(93 * rows * cols), "seconds_setup": t_gen,
+           "stages": {k: stats.get(k) for k in ("ms_slopes", "ms_flats", "ms_graph", "ms_sweep_first", "ms_finalize_twi", "sweep_rounds",
+                                                 "label_rounds", "n_sources", "n_queue_items") if k in stats},
+           "checks": {"undone_cells": int(bad[0]), "nan_pattern_vs_flats_mismatches": int(bad[1]), "uca_below_one_cell": int(bad[2]),
+                      "window_1024_vs_oracle_stencil_mismatches": int(bad[3]), "window_fraction_compared": frac_checked,
+                      "ok": bool(int(bad.sum()) == 0)}}
+    sh.close()
+    return out
 
 
 def sharded_check(sh, block, world, rank, pits_flag):
@@ -556,6 +644,10 @@ def main():
                     help="conditioned: priority-flood conditioned fractal, default flags (BASELINE.md primary); "
                          "sinks: raw fractal with drain_pits=False")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle / single-tile check of the GPU arm's outputs")
+    ap.add_argument("--no-config4", action="store_true", help="N > 1: skip the extra run of BASELINE configs[3] at its own shape")
+    ap.add_argument("--config4-rows", type=int, default=8192, help="rows per GPU of the config-4 run")
+    ap.add_argument("--config4-cols", type=int, default=65536)
+    ap.add_argument("--config4-steps", type=int, default=3)
     ap.add_argument("--no-whole-dem", action="store_true", help="reference arm: skip the one-core whole-DEM run")
     args = ap.parse_args()
     if args.impl == "reference":

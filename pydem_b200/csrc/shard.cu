@@ -169,6 +169,15 @@ int pdm_shard_p2p_connect(pdm_tile *t, const void *up, const void *down, const v
                               reinterpret_cast<const ts::P2PExport *>(root), world, rank);
 }
 
+// unmap the peers' memory (collective use: every rank disconnects, barrier, then tiles may be destroyed)
+int pdm_shard_p2p_disconnect(pdm_tile *t)
+{
+    if (!t) { pdm_set_error("NULL tile"); return PDM_ERR_ARG; }
+    PDM_CUDA(cudaStreamSynchronize(t->stream));
+    pdm_ts_p2p_close(t);
+    return PDM_OK;
+}
+
 int pdm_shard_finalize(pdm_tile *t, const pdm_uca_params *p_in, pdm_uca_stats *stats)
 {
     if (!t) return PDM_ERR_ARG;

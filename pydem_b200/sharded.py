@@ -371,7 +371,10 @@ class ShardedDEM(object):
     """bench.py's N>1 workload: a value-noise DEM of (rows_per_rank * world) x cols, one row block
     per rank of the torch.distributed job; ``step()`` runs the whole hot path once."""
 
-    def __init__(self, rows_per_rank, cols, spacing=30.0, seed=0, profile=False, block=None):
+    def __init__(self, rows_per_rank, cols, spacing=30.0, seed=0, profile=False, block=None, noise=False):
+        """block: the rows every rank holds (periodic block, weak scaling with identical work per GPU);
+        noise=True: rank r holds rows [r * rows_per_rank, ...) of ONE non-periodic value-noise DEM,
+        generated on the device (BASELINE.json configs[3]: 65536 x 65536 over 8 GPUs = 8192 x 65536 each)."""
         import torch
         from . import tile as T
         self.T, self.torch = T, torch
@@ -385,6 +388,16 @@ class ShardedDEM(object):
         import os
         if w > 1 and os.environ.get("PYDEM_B200_SHARD_P2P", "1") != "0":
             self.group.connect_p2p(self.engine)
+        self.profile = profile
+        self.cells = (s.r1 - s.r0) * cols
+        if noise:
+            view = self.engine.rows(T.F_ELEV)                     # zero-copy torch view of the tile's elevation field
+            view.fill_(float("nan"))                              # halo rows arrive through the exchange
+            synth.value_noise_dem_torch(view[s.lo:s.hi], s.r0, seed=seed)
+            self.engine.tile.mark_resident(T.F_ELEV)
+            self.host_elev = None
+            torch.cuda.synchronize()
+            return
         loc = np.full((s.Rl, cols), np.nan)
         # every rank holds the same periodic block (spectral synthesis, conditioned with wrapping
         # rows): stacked vertically the blocks join seamlessly, so per-GPU work is identical (weak
@@ -392,10 +405,17 @@ class ShardedDEM(object):
         if block is None:
             block = synth.conditioned_fractal_dem(rows_per_rank, seed, shape=(rows_per_rank, cols), wrap_rows=True)
         loc[s.lo:s.hi] = block
-        self.profile = profile
         self.host_elev = loc
         self.engine.tile.upload(T.F_ELEV, loc)
-        self.cells = (s.r1 - s.r0) * cols
+
+    def close(self):
+        """collective: unmap the peers' memory on every rank before any rank frees its tile"""
+        if self.engine.p2p:
+            self.T._lib.check(self.engine.tile.L.pdm_shard_p2p_disconnect(self.engine.tile.h))
+            self.engine.p2p = False
+            self.torch.cuda.synchronize()
+            self.group.dist.barrier()
+        self.engine.tile.close()
 
     def step(self):
         return run_hot_path([self.engine], self.group, profile=self.profile)[0]

@@ -67,6 +67,44 @@ def value_noise_dem(row0, nrows, ncols, seed=2, octaves=8, base=1024, lo=1.0, hi
     return lo + (hi - lo) * out
 
 
+def value_noise_dem_torch(out, row0, seed=2, octaves=8, base=1024, lo=1.0, hi=1001.0, chunk=256):
+    """``value_noise_dem`` evaluated on the device, row chunk by row chunk, straight into ``out`` (a
+    float64 torch tensor of shape (nrows, ncols), e.g. a view of a tile's elevation field): the same
+    IEEE operations and the same 64-bit integer hash as the NumPy version, so both give identical
+    bits (tests/test_sharded_gloo.py).  A 8192 x 65536 shard (config 4) takes about a second."""
+    import torch
+    nrows, ncols = out.shape
+    dev = out.device
+    jj = torch.arange(ncols, dtype=torch.float64, device=dev)[None, :]
+    for a in range(0, nrows, chunk):
+        b = min(a + chunk, nrows)
+        ii = torch.arange(row0 + a, row0 + b, dtype=torch.float64, device=dev)[:, None]
+        acc = torch.zeros((b - a, ncols), dtype=torch.float64, device=dev)
+        amp, norm = 1.0, 0.0
+        for o in range(octaves):
+            cell = max(base >> o, 1)
+            y = ii / cell
+            x = jj / cell
+            y0 = torch.floor(y); x0 = torch.floor(x)
+            fy = y - y0; fx = x - x0
+            sy = fy * fy * (3 - 2 * fy); sx = fx * fx * (3 - 2 * fx)
+            salt = (seed * 83492791 + o * 2654435761)
+
+            def lat(p, q):
+                h = (p.to(torch.int64) * 73856093) ^ (q.to(torch.int64) * 19349663) ^ salt
+                h = (h ^ (h >> 13)) * 1274126177
+                h = h ^ (h >> 16)
+                return (h & 0xFFFFFF).to(torch.float64) / float(0xFFFFFF)
+
+            v00 = lat(y0, x0); v01 = lat(y0, x0 + 1); v10 = lat(y0 + 1, x0); v11 = lat(y0 + 1, x0 + 1)
+            acc += amp * ((v00 * (1 - sx) + v01 * sx) * (1 - sy) + (v10 * (1 - sx) + v11 * sx) * sy)
+            norm += amp
+            amp *= 0.55
+        acc /= norm
+        out[a:b] = lo + (hi - lo) * acc
+    return out
+
+
 def _host_lib():
     src = os.path.join(_HERE, "csrc_host", "priority_flood.c")
     so = os.path.join(_HERE, "libpdm_synth.so")

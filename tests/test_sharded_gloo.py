@@ -146,3 +146,13 @@ def test_gloo_protocol(world):
     for rank, ok, info in res:
         assert ok, "rank %d: %s" % (rank, info)
     assert all(r[2] >= 2 for r in res)
+
+
+def test_value_noise_generators_agree():
+    """The device-side generator of the config-4 DEM (torch, row chunks) and the NumPy one give identical bits."""
+    import torch
+    from pydem_b200 import synth
+    a = synth.value_noise_dem(4000, 130, 517, seed=11)
+    out = torch.empty((130, 517), dtype=torch.float64)
+    synth.value_noise_dem_torch(out, 4000, seed=11, chunk=48)
+    assert np.array_equal(a, out.numpy())
