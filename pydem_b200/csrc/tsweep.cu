@@ -286,6 +286,11 @@ __device__ __forceinline__ void drain_cell(S &s, const Args &a, int k, int rows_
     constexpr int HW = S::HW;
     const TRec *rk = &s.rec[k];
     const unsigned long long w = *reinterpret_cast<const unsigned long long *>(&rk->link);
+    const uint32_t rv = s.rcv[k];
+    const int hy = k / HW;                          // ring row: own cells 1..TH
+    unsigned dm = (unsigned)(w >> 8) & 0xffu;
+    const unsigned lk = (unsigned)w & 0xffu;
+#ifndef TS_DRAIN_LOOP
     double2 v[8];
     double p[8];
 #pragma unroll
@@ -294,11 +299,7 @@ __device__ __forceinline__ void drain_cell(S &s, const Args &a, int k, int rows_
         v[q] = *reinterpret_cast<const double2 *>(&d->area);
         p[q] = d->prop;
     }
-    const uint32_t rv = s.rcv[k];
-    const int hy = k / HW;                          // ring row: own cells 1..TH
     const double base = s.rowa[hy - 1];                                          // dem_processing.py:885, 901
-    const unsigned dm = (unsigned)(w >> 8) & 0xffu;
-    const unsigned lk = (unsigned)w & 0xffu;
     double ca[8], ct[8];
 #pragma unroll
     for (int q = 0; q < 8; q++) {
@@ -311,6 +312,22 @@ __device__ __forceinline__ void drain_cell(S &s, const Args &a, int k, int rows_
     double tt = __dadd_rn(__dadd_rn(__dadd_rn(ct[0], ct[1]), __dadd_rn(ct[2], ct[3])), __dadd_rn(__dadd_rn(ct[4], ct[5]), __dadd_rn(ct[6], ct[7])));
     ar = __dadd_rn(base, ar);
     tt = __dadd_rn(((w >> 16) & TR_TODO) ? 1.0 : 0.0, tt);                       // 944
+#else
+    // donors in ascending neighbour order (W, E, N, S, NW, NE, SW, SE), a few instructions each: a cell has
+    // two or three donors, and a single lane on a river pays for every instruction of the step
+    double ar = s.rowa[hy - 1];                                                  // dem_processing.py:885, 901
+    double tt = ((w >> 16) & TR_TODO) ? 1.0 : 0.0;                               // 944
+    while (dm) {
+        const int q = __ffs(dm) - 1;
+        dm &= dm - 1;
+        const TRec *d = rk + nbr_off<HW>(q);
+        const double2 v = *reinterpret_cast<const double2 *>(&d->area);
+        const double p = d->prop;
+        const double wgt = q < 4 ? p : __dsub_rn(1.0, p);                        // dem_processing.py:1082
+        ar = __dadd_rn(ar, __dmul_rn(v.x, wgt));                                 // cyutils.pyx:161
+        tt = __dadd_rn(tt, __dmul_rn(v.y, wgt));                                 // cyutils.pyx:163
+    }
+#endif
     if ((lk & LK_PITIN) && a.has_pits) {
         const int64_t n = (r0 + hy - 1) * a.w.C + (c0 + (k - hy * HW) - 1);
         ar = __dadd_rn(ar, __ldcg(a.pit_acc_a + n));
