@@ -205,6 +205,11 @@ int pdm_tile_uca_update(pdm_tile *t, const pdm_uca_params *p,
                         const uint8_t *todo_left, const uint8_t *todo_right,
                         const uint8_t *todo_top, const uint8_t *todo_bottom,
                         pdm_uca_stats *stats);
+/* on != 0: pdm_tile_uca_update reuses the graph (receivers, proportions, pit drains) built by the tile's last
+ * pdm_tile_uca instead of rebuilding it on every call like the reference does (dem_processing.py:787-793) --
+ * for tiles that stay in HBM between the edge corrections of a mosaic (process_manager.py:224-284), whose
+ * direction / magnitude do not change in between.  The caller must not upload DIR / MAG / FLATS in between. */
+int pdm_tile_set_keep_graph(pdm_tile *t, int on);
 /* a9: calc_twi (1647-1677).  In: UCA, MAG.  Out: TWI (un-scaled, the return value) and TWI10
  * (= 10 * twi, the attribute). */
 int pdm_tile_twi(pdm_tile *t, const pdm_twi_params *p);

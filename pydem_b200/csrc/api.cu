@@ -284,6 +284,15 @@ int pdm_tile_mark_resident(pdm_tile *t, int field)
     return PDM_OK;
 }
 
+// Device-resident mosaic tiles: keep the drainage graph (link bytes, proportions, pit edge lists) of the last
+// pdm_tile_uca for the following pdm_tile_uca_update calls instead of rebuilding it per call.
+int pdm_tile_set_keep_graph(pdm_tile *t, int on)
+{
+    if (!t) { pdm_set_error("NULL tile"); return PDM_ERR_ARG; }
+    t->keep_graph = on != 0;
+    return PDM_OK;
+}
+
 int pdm_selftest_division(unsigned long long seed, long long n_pairs, unsigned long long *mismatches)
 {
     if (!mismatches || n_pairs <= 0) { pdm_set_error("pdm_selftest_division: bad argument"); return PDM_ERR_ARG; }

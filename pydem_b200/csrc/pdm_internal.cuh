@@ -78,6 +78,7 @@ struct pdm_tile {
     bool have_spacing, have_elev, have_slopes, have_flats, have_graph, have_uca;
     bool stencil_parity; // run the literal (slow) stencil formulation on this tile (tests)
     bool queue_ready;    // queue slots are all -1 except those the last work-list run used
+    bool keep_graph;     // update mode reuses the graph of the last full sweep (device-resident mosaic tiles)
     // pit edge lists (device)
     int32_t *pit_cell;     // [pit_cap] cells examined by the pit search (flats & elev > 0)
     int32_t *pit_beg;      // [pit_cap] first / one-past-last edge of each pit in pit_dst/pit_w

@@ -153,9 +153,12 @@ int pdm_launch_update(pdm_tile *t, const pdm_uca_params *p, const double *const 
         if ((rc = wl::grid_for(wl::k_worklist<FloodOp<1>, wl::DomainBorder>, &g_blocks_flood1))) return rc;
         if ((rc = wl::grid_for(wl::k_worklist<DrainOp<1>, wl::DomainBorder>, &g_blocks_drain1))) return rc;
     }
-    // the reference rebuilds section/proportion and the matrix on every call (787-793)
+    // the reference rebuilds section/proportion and the matrix on every call (787-793).  A tile that stays
+    // resident between the corrections of a mosaic (pdm_tile_set_keep_graph) keeps the graph of its full sweep:
+    // link bytes, proportions and pit edge lists are not touched by an update, and the pits must NOT be searched
+    // again -- their drains have already patched mag / flats in place (1370-1371)
     PDM_CUDA(cudaEventRecord(t->ev[0], t->stream));
-    if ((rc = pdm_graph_links_pits(t, p))) return rc;
+    if (!(t->keep_graph && t->have_graph && t->legacy_graph) && (rc = pdm_graph_links_pits(t, p))) return rc;   // (the tile sweep recycles the proportion plane)
     PDM_CUDA(cudaEventRecord(t->ev[1], t->stream));
     // stage the strips
     if (!t->edge_buf_d) {

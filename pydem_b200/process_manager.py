@@ -710,3 +710,188 @@ class TorchGroup(object):
         out = [None] * self.world
         self._dist.all_gather_object(out, obj)
         return out
+
+
+class ResidentProcessManager(ProcessManager):
+    """The same orchestrator with the tiles RESIDENT on the GPU (BASELINE.json
+    configs[4]): a tile's elevation goes to HBM once, slope / aspect / flats / UCA / edge masks stay there
+    through all stages, and only the edge rings -- the strips a neighbour can read, `_RingArray` -- live on
+    the host, where the reference's scheduling decisions, its one-pixel-overlap patch and its corner rules
+    are taken exactly as in the base class.  An edge correction (calc_uca_ec, process_manager.py:224-284)
+    then moves four strips of (value, done, todo) to the device, runs the update sweep on the resident UCA
+    with the graph of the tile's full sweep (pdm_tile_set_keep_graph; the reference rebuilds it per call,
+    dem_processing.py:787-793) and reads the three rings back -- instead of uploading elevation, direction
+    and magnitude and downloading every array per call like the host-side manager above.
+
+    Needs the CUDA operator (it drives `pydem_b200.tile.DeviceTile` directly) and a torch CUDA build for the
+    zero-copy views of the tile fields.  Elevation conditioning (stage 0) runs through the base class."""
+
+    UCA_FLAGS = ("drain_pits", "drain_pits_min_border", "drain_pits_max_iter", "drain_pits_max_dist",
+                 "apply_uca_limit_edges", "uca_saturation_limit", "circular_ref_maxcount")
+
+    def __init__(self, *a, **kw):
+        if kw.get("dem_processor") is not None:
+            raise ValueError("ResidentProcessManager drives the CUDA tiles directly; dem_processor cannot be replaced")
+        ProcessManager.__init__(self, *a, **kw)
+        import torch
+        from . import tile as T
+        self._T, self._torch = T, torch
+        self._dev = {}
+        self._mag0 = {}
+        flags = {}
+        for k in self.UCA_FLAGS:
+            if k in self.dem_proc_kwargs and self.dem_proc_kwargs[k] is not None:
+                flags[k] = self.dem_proc_kwargs[k]
+        if "drain_pits_max_dist_XY" in self.dem_proc_kwargs and self.dem_proc_kwargs["drain_pits_max_dist_XY"]:
+            flags["drain_pits_max_dist_xy"] = float(self.dem_proc_kwargs["drain_pits_max_dist_XY"])
+        self._uca_flags = {k: (int(v) if isinstance(v, (bool, np.bool_)) else v) for k, v in flags.items()}
+        self.bytes_moved = dict(h2d=0, d2h=0)
+
+    # ---- device tiles and rings
+    def _tile(self, t):
+        k = id(t)
+        if k not in self._dev:
+            T = self._T
+            dt = T.DeviceTile(t.shape[0], t.shape[1], stream=self._torch.cuda.current_stream().cuda_stream)
+            dt.set_spacing(t.dX, t.dY, t.dX2, t.dY2)
+            dt.upload(T.F_ELEV, t.elev)
+            dt.set_keep_graph(True)
+            self.bytes_moved["h2d"] += t.elev.nbytes
+            self._dev[k] = dt
+        return self._dev[k]
+
+    def _ring_down(self, t, field, as_bool=False):
+        """edge ring of a resident field -> host `_RingArray`"""
+        v = self._tile(t).as_torch(field)
+        w = min(self.ring_w, t.shape[0], t.shape[1])
+        st = [v[:w], v[-w:], v[:, :w], v[:, -w:]]
+        st = [x.contiguous().cpu().numpy() for x in st]
+        if as_bool:
+            st = [x.astype(bool) for x in st]
+        ra = _RingArray(t.shape, self.ring_w, st[0].dtype)
+        ra.set_strips(st)
+        self.bytes_moved["d2h"] += sum(x.nbytes for x in st)
+        return ra
+
+    def _ring_up(self, t, field, ra):
+        """host ring -> the resident field's edge strips"""
+        v = self._tile(t).as_torch(field)
+        w = ra.w
+        dev = v.device
+        for dst, src in ((v[:w], ra.top), (v[-w:], ra.bottom), (v[:, :w], ra.left), (v[:, -w:], ra.right)):
+            dst.copy_(self._torch.from_numpy(np.ascontiguousarray(src)).to(dev))
+            self.bytes_moved["h2d"] += src.nbytes
+
+    def full(self, t, key):
+        """a whole result array of an own tile, read back from the device"""
+        T = self._T
+        f = {"aspect": T.F_DIR, "slope": T.F_MAG, "uca": T.F_UCA, "twi": T.F_TWI, "edge_todo": T.F_EDGE_TODO,
+             "edge_done": T.F_EDGE_DONE, "elev": T.F_ELEV}[key]
+        a = self._tile(t).download(f)
+        self.bytes_moved["d2h"] += a.nbytes
+        if key == "twi":
+            a = a * 10.0                        # DEMProcessor.twi stores 10 * twi (dem_processing.py:1674)
+        return a.astype(bool) if key in ("edge_todo", "edge_done") else a
+
+    # ---- workers on resident tiles
+    def _aspect_slope(self, t):
+        T = self._T
+        dt = self._tile(t)
+        dt.slopes_directions()
+        t.aspect = self._ring_down(t, T.F_DIR); t.slope = self._ring_down(t, T.F_MAG)
+
+    def _uca(self, t):
+        T = self._T
+        dt = self._tile(t)
+        self._ring_up(t, T.F_DIR, t.aspect); self._ring_up(t, T.F_MAG, t.slope)      # the one-pixel-overlap patch
+        dt.mark_resident(T.F_DIR); dt.mark_resident(T.F_MAG)
+        # the pit drains of calc_uca patch mag in place (dem_processing.py:1370-1371), but the reference's TWI stage
+        # reads the slope as stored BEFORE calc_uca (process_manager.py:296-315): keep that copy on the device
+        self._mag0[id(t)] = dt.as_torch(T.F_MAG).clone()
+        dt.find_flats()
+        st = dt.uca(**self._uca_flags)
+        if st.get("n_pits_undrained"):
+            warnings.warn("Warning %d pits had no place to drain to in this chunk" % st["n_pits_undrained"])
+        t.uca = self._ring_down(t, T.F_UCA)
+        t.edge_todo = self._ring_down(t, T.F_EDGE_TODO, True); t.edge_done = self._ring_down(t, T.F_EDGE_DONE, True)
+        t.uca_edges = _RingArray(t.shape, self.ring_w, np.float64)
+
+    def _uca_ec(self, t):
+        from .dem_processing import _pack_edges
+        T = self._T
+        data = {k: self._edge(t, k, "uca") + self._edge(t, k, "uca_edges") for k in SIDES}
+        done = {k: self._edge(t, k, "edge_done") for k in SIDES}
+        todo = {k: np.array(t.edge_todo[EDGE[k]]) for k in SIDES}
+        todo_nb = {k: self._edge(t, k, "edge_todo") for k in SIDES}
+        for key in ("top-left", "bottom-right", "top-right", "bottom-left"):        # the corner rule (:257-270), as in the base class
+            ktb, klr = key.split("-")
+            ir, ic = EDGE[key]
+            if done[ktb][ic] & done[klr][ir]:
+                done[ktb][ic] = False
+                if t.edge_src["_one"][key] and self._edge(t, key, "edge_done"):
+                    v = self._edge(t, key, "uca") + self._edge(t, key, "uca_edges")
+                    data[klr][ir] = v; data[ktb][ic] = v
+        todo = {k: v & (todo_nb[k] == False) for k, v in todo.items()}  # noqa: E712 (:274)
+        strips = _pack_edges([data, done, todo], t.shape[0], t.shape[1])
+        self.bytes_moved["h2d"] += sum(a.nbytes for a in strips)
+        self._tile(t).uca_update(strips, **self._uca_flags)        # the resident UCA is uca + uca_edges = uca_init of the call
+        total = self._ring_down(t, T.F_UCA)
+        edges = _RingArray(t.shape, self.ring_w, np.float64)
+        edges.set_strips([a - b for a, b in zip(total.strips(), t.uca.strips())])
+        t.uca_edges = edges
+        t.edge_todo = self._ring_down(t, T.F_EDGE_TODO, True); t.edge_done = self._ring_down(t, T.F_EDGE_DONE, True)
+
+    def _twi(self, t):
+        kw = {k: self.dem_proc_kwargs[k] for k in ("twi_min_slope", "uca_saturation_limit", "apply_twi_limits", "apply_twi_limits_on_uca")
+              if k in self.dem_proc_kwargs}
+        kw = {k: (int(v) if isinstance(v, (bool, np.bool_)) else v) for k, v in kw.items()}
+        # a fresh DEMProcessor(uca=...) of the base class carries twi_min_area = inf unless the caller set it
+        dt = self._tile(t)
+        if id(t) in self._mag0:
+            dt.as_torch(self._T.F_MAG).copy_(self._mag0.pop(id(t)))
+        dt.twi(twi_min_area=float(self.dem_proc_kwargs.get("twi_min_area", np.inf)), **kw)
+        t.twi = True                                # resident; read with full(t, "twi")
+
+    def _sync(self, fields, index=None):
+        """rings of own tiles are rings already"""
+        if self.group is None:
+            return
+        index = range(self.n_inputs) if index is None else index
+        mine = {}
+        for i in index:
+            t = self.tiles[i]
+            if self._mine(t):
+                mine[i] = {f: getattr(t, f).strips() for f in fields}
+        for part in self.group.all_gather(mine):
+            for i, fs in part.items():
+                t = self.tiles[i]
+                if self._mine(t):
+                    continue
+                for f, st in fs.items():
+                    ra = getattr(t, f)
+                    if not isinstance(ra, _RingArray):
+                        ra = _RingArray(t.shape, self.ring_w, st[0].dtype)
+                        setattr(t, f, ra)
+                    ra.set_strips(st)
+
+    def mosaic(self, key):
+        R = max(t.box[1] for t in self.tiles); C = max(t.box[3] for t in self.tiles)
+        pieces = []
+        for t in self.tiles:
+            if not self._mine(t):
+                continue
+            a = self.full(t, key)                   # the resident UCA already includes the edge corrections
+            r_lo, r_hi, c_lo, c_hi = t.trim
+            nr, nc = t.shape
+            pieces.append(((t.box[0] + r_lo, t.box[1] - r_hi, t.box[2] + c_lo, t.box[3] - c_hi), a[r_lo:nr - r_hi, c_lo:nc - c_hi]))
+        if self.group is not None:
+            pieces = [p for part in self.group.all_gather(pieces) for p in part]
+        out = np.full((R, C), np.nan)
+        for (r0, r1, c0, c1), a in pieces:
+            out[r0:r1, c0:c1] = a
+        return out
+
+    def close(self):
+        for dt in self._dev.values():
+            dt.close()
+        self._dev = {}

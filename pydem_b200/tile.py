@@ -128,6 +128,20 @@ class DeviceTile(object):
         _lib.check(self.L.pdm_tile_uca(self.h, ct.byref(p), ct.byref(st)))
         return st.as_dict()
 
+    def uca_update(self, strips, **flags):
+        """Edge-update mode on the resident UCA (= uca_init): strips = the 12 arrays of
+        dem_processing._pack_edges (data x4, done x4, todo x4; left, right, top, bottom)."""
+        p = _lib.UcaParams()
+        self.L.pdm_default_uca_params(ct.byref(p))
+        for k, v in flags.items():
+            setattr(p, k, v)
+        st = _lib.UcaStats()
+        _lib.check(self.L.pdm_tile_uca_update(self.h, ct.byref(p), *[_lib.ptr(a) for a in strips], ct.byref(st)))
+        return st.as_dict()
+
+    def set_keep_graph(self, on=True):
+        _lib.check(self.L.pdm_tile_set_keep_graph(self.h, int(bool(on))))
+
     def twi(self, twi_min_area=None, **flags):
         p = _lib.TwiParams()
         self.L.pdm_default_twi_params(ct.byref(p))
