@@ -377,7 +377,7 @@ def gpu_arm(args):
             return st
         cells_per_step = n * n * world
         workload = ("%dx%d DEM = the %dx%d block of the 1-GPU run (%s) repeated %d times vertically (periodic, "
-                    "seamless), row-sharded over %d GPUs (%d rows each, halo rows over NCCL send/recv), dX=dY=30 m, "
+                    "seamless), row-sharded over %d GPUs (%d rows each, halo rows over NCCL send/recv, UCA as one work-list sweep across the GPUs over NVLink peer memory), dX=dY=30 m, "
                     "slope+aspect + UCA + TWI, %s (pit drains are not available on shards)"
                     % (n * world, n, n, n, "conditioned fractal" if variant == "conditioned" else "raw fractal", world,
                        world, n, flags_txt))
@@ -483,7 +483,9 @@ def gpu_arm(args):
         "e2e": e2e,
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "wl::k_worklist<DrainOp<0>> (UCA accumulation sweep)", "bound": "hbm",
+        "roofline": {"kernel": ("wl::k_worklist<DrainOp<0>> (UCA accumulation sweep)" if world == 1 else
+                                "wl::k_worklist<DrainOp<3>> (UCA accumulation sweep, one sweep across the GPUs over NVLink peer memory)"),
+                     "bound": "hbm",
                      "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": (achieved / peak_gbs) if achieved else None,
                      "traffic": PROFILE_TRAFFIC.get(n), "peak_source": peak_src,

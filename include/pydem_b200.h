@@ -256,6 +256,9 @@ int pdm_shard_sweep_sent(pdm_tile *t, void *sent);
  * Semantics as pyDEM's process_uca_edges (process_manager.py:1090-1249) without its rounds. */
 int pdm_shard_p2p_export(pdm_tile *t, void *buf, int64_t *size);
 int pdm_shard_p2p_connect(pdm_tile *t, const void *up, const void *down, const void *root, int world, int rank);
+/* the same with every rank's export (world blobs back to back in rank order, e.g. from an all-gather): the
+ * accumulation then runs on the work-list engine as one sweep across the GPUs */
+int pdm_shard_p2p_connect_all(pdm_tile *t, const void *blobs, int world, int rank);
 int pdm_shard_p2p_disconnect(pdm_tile *t);   /* unmap the peers' memory: all ranks, then a barrier, before any tile is destroyed */
 int pdm_shard_finalize(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *stats);
 

@@ -27,6 +27,10 @@ __device__ __forceinline__ uint32_t st_fetch_or(uint8_t *st, int32_t cell, uint3
 
 //   MODE 2: resumed full sweep of a shard: like MODE 0, but the seeds come from an explicit list
 //           (cells whose last upstream contribution arrived from a neighbouring rank).
+//   MODE 3: full sweep of a row shard as part of ONE sweep across several GPUs: like MODE 0, but a
+//           receiver in a halo row is the neighbouring rank's boundary cell -- the push goes into that
+//           rank's record over NVLink (push_peer) and a cell it makes ready into that rank's in-box
+//           (worklist.cuh, p2p_service).
 // Predicated atomics without branches.  Written as inline PTX so that the step below stays
 // straight-line code: with `if (k1) o1 = atomicSub(..); if (k2) o2 = atomicSub(..);` the compiler
 // wrapped each atomic in its own branch region and placed the test of the first result inside it,
@@ -47,6 +51,7 @@ __device__ __forceinline__ int atom_add_s32_if(bool on, int32_t *addr, int v)
 
 template <int MODE>
 struct DrainOp {
+    static constexpr bool P2P = MODE == 3;
     const uint8_t *link;   // SoA copy of the link bytes: only the seed scan reads it
     Cell *cell;            // 32-byte sweep records
     const uint8_t *st;
@@ -56,10 +61,33 @@ struct DrainOp {
     const int32_t *pit_dst;
     const double *pit_w;
     int32_t strict;        // hold the decrements back until the adds have returned (see process())
+    // MODE 3 only
+    int32_t own_lo, own_hi;              // owned cells [own_lo, own_hi); the rows next to them are halo rows
+    Cell *peer_cell[2];                  // the neighbour's record behind column 0 of the halo row above / below
+    unsigned long long *peer_ctr[2];     // its counters and in-box
+    int32_t *peer_inbox[2];
+    int32_t peer_cell0[2];               // the neighbour's own index of that record
 
     __device__ __forceinline__ bool is_seed(int32_t c) const
     {
-        return MODE == 0 ? (link[c] & LK_SOURCE) != 0 : (MODE == 2 ? true : (st[c] & ST_START) != 0);
+        return (MODE == 0 || MODE == 3) ? (link[c] & LK_SOURCE) != 0 : (MODE == 2 ? true : (st[c] & ST_START) != 0);
+    }
+    // MODE 3: receiver r lives on the neighbouring GPU.  The adds must be part of the record before the
+    // decrement that may publish it: over NVLink that order is enforced with a system-scope fence (rare: only
+    // cells of a boundary row come here).  The decrement's return value is back before the chain goes on,
+    // so the in-box push below is counted before this chain can be counted as finished.
+    __device__ __forceinline__ void push_peer(int32_t r, double da, double dt, bool tt) const
+    {
+        const int side = r < own_lo ? 0 : 1;
+        const int32_t col = r - (side == 0 ? own_lo - C : own_hi);
+        Cell *P = peer_cell[side] + col;
+        atomicAdd_system(&P->area, da);
+        if (tt) atomicAdd_system(&P->taint, dt);
+        __threadfence_system();
+        if (atomicAdd_system(&P->indeg, -1) == 1) {
+            const unsigned long long s = atomicAdd_system(peer_ctr[side] + CT_INBOX_TAIL, 1ULL);
+            wl::st_volatile_i32(peer_inbox[side] + s, peer_cell0[side] + col);
+        }
     }
     __device__ __forceinline__ bool skip(int32_t r) const { return MODE == 1 && (st[r] & ST_START); }
 
@@ -105,6 +133,15 @@ struct DrainOp {
             if (!(k1 || k2)) return -1;
         }
         const double w2 = __dsub_rn(1.0, p);                                    // dem_processing.py:1082
+        if (MODE == 3) {
+            const bool x1 = k1 && (r1 < own_lo || r1 >= own_hi), x2 = k2 && (r2 < own_lo || r2 >= own_hi);
+            if (x1 || x2) {
+                if (x1) push_peer(r1, __dmul_rn(ai, p), __dmul_rn(ti, p), ti != 0.0);
+                if (x2) push_peer(r2, __dmul_rn(ai, w2), __dmul_rn(ti, w2), ti != 0.0);
+                k1 = k1 && !x1; k2 = k2 && !x2;
+                if (!(k1 || k2)) return -1;
+            }
+        }
         // Ordering: a receiver's area must contain this contribution before the decrement that may
         // publish it.  The adds and the decrement of one receiver go to the SAME 32-byte sector and
         // are issued in program order by one thread, so they travel the same SM -> L2-slice path

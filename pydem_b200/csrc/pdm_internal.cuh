@@ -18,6 +18,7 @@
 #include "../../include/pydem_b200.h"
 
 #define PDM_PI 3.141592653589793
+#define PDM_MAX_WORLD 16   // ranks of one multi-GPU sweep (one box)
 
 // link byte written by the graph kernel (reference: section of
 // _calc_uca_section_proportion + the keep filter of _mk_adjacency_matrix 1136-1137)
@@ -78,6 +79,7 @@ struct pdm_tile {
     bool have_spacing, have_elev, have_slopes, have_flats, have_graph, have_uca;
     bool stencil_parity; // run the literal (slow) stencil formulation on this tile (tests)
     bool queue_ready;    // queue slots are all -1 except those the last work-list run used
+    const unsigned long long *queue_dirty_ctr;   // the counters whose CT_QTAIL counts those slots (d_counters, or the shared block of a multi-GPU sweep)
     bool keep_graph;     // update mode reuses the graph of the last full sweep (device-resident mosaic tiles)
     // pit edge lists (device)
     int32_t *pit_cell;     // [pit_cap] cells examined by the pit search (flats & elev > 0)
@@ -110,6 +112,8 @@ struct pdm_tile {
         int on, world, rank;
         unsigned long long launches;       // start barrier target = world * launches
         void *map_rec[2], *map_ctl[2], *map_root;     // what cudaIpcOpenMemHandle returned (to close)
+        void *map_all[PDM_MAX_WORLD];                 // control blocks of the ranks that are neither neighbours nor rank 0
+        void *all_ctl[PDM_MAX_WORLD];                 // every rank's control block (own included); all set = the work-list sweep may span the GPUs
         const void *rec[2]; void *ctl[2]; void *root_ctl;
         long long off_flag[2], off_slots[2], lo[2], hi[2];
         int nty[2];
@@ -175,6 +179,10 @@ void pdm_ts_p2p_close(pdm_tile *t);
 int pdm_launch_border_todo(pdm_tile *t);
 int pdm_launch_indeg_todo(pdm_tile *t);
 bool pdm_sweep_legacy();
+bool pdm_shard_worklist_p2p(const pdm_tile *t);
+int pdm_launch_sweep_p2p(pdm_tile *t);
+int pdm_launch_sweep_first(pdm_tile *t);
+int pdm_launch_uca_finalize(pdm_tile *t, const pdm_uca_params *p);
 
 // counters slots.  The queue counters are hammered by every warp (fetch-and-add tickets,
 // pushes, completion counts, termination polls): each lives on its own 128-byte line so the
@@ -209,6 +217,11 @@ enum {
     CT_X_CHAIN_CALLS = 116, CT_X_CHAIN_CELLS = 117, CT_X_CHAIN_NS = 118, CT_X_TEAM_LANES = 119, CT_X_TEAM_NS = 120,
     CT_X_POLLS = 121, CT_X_SCAN_CELLS = 122,
     CT_X_LAST = 122,
-    CT_N = 128
+    // one work-list sweep across the row shards of several GPUs (drain_op.cuh MODE 3): the counters then live in the
+    // control block the peers have mapped (tsweep.cuh, TC_WLC)
+    CT_INBOX_TAIL = 128,  // cells made ready by a peer GPU (it pushes them into this rank's in-box)
+    CT_INBOX_HEAD = 144,  // in-box tickets handed out
+    CT_GTERM = 160,       // number of the last multi-GPU sweep known to be over everywhere (monotonic, never reset)
+    CT_N = 176
 };
 

@@ -31,6 +31,7 @@ int pdm_launch_label_pack(pdm_tile *t, int64_t row, long long *out_l, double *ou
 int pdm_launch_label_unpack(pdm_tile *t, int64_t row, const long long *in_l, const double *in_e);
 int pdm_ts_p2p_export(pdm_tile *t, ts::P2PExport *e);
 int pdm_ts_p2p_connect(pdm_tile *t, const ts::P2PExport *up, const ts::P2PExport *down, const ts::P2PExport *root, int world, int rank);
+int pdm_ts_p2p_connect_ranks(pdm_tile *t, const ts::P2PExport *const *ex, int world, int rank);
 
 static int read_ctr(pdm_tile *t)
 {
@@ -121,6 +122,7 @@ int pdm_shard_links(pdm_tile *t, const pdm_uca_params *p_in)
 int pdm_shard_indeg(pdm_tile *t)
 {
     if (!t) return PDM_ERR_ARG;
+    if (pdm_shard_worklist_p2p(t)) return pdm_launch_indeg_todo(t);    // Cell records of the work-list sweep
     int rc = pdm_launch_border_todo(t);
     if (rc) return rc;
     return pdm_ts_reset_state(t);
@@ -131,6 +133,10 @@ int pdm_shard_indeg(pdm_tile *t)
 int pdm_shard_sweep(pdm_tile *t, int first)
 {
     if (!t) return PDM_ERR_ARG;
+    if (t->legacy_graph && pdm_shard_worklist_p2p(t)) {
+        if (!first) { pdm_set_error("pdm_shard_sweep: a multi-GPU sweep has no resume rounds"); return PDM_ERR_STATE; }
+        return pdm_launch_sweep_p2p(t);
+    }
     return pdm_launch_tsweep(t, first);
 }
 
@@ -169,6 +175,22 @@ int pdm_shard_p2p_connect(pdm_tile *t, const void *up, const void *down, const v
                               reinterpret_cast<const ts::P2PExport *>(root), world, rank);
 }
 
+// every rank's export, world blobs of pdm_shard_p2p_export's size back to back in rank order (e.g. the result of
+// an all-gather): maps the row neighbours' records and every rank's control block.  With all ranks known the
+// accumulation runs on the work-list engine as ONE sweep across the GPUs (PYDEM_B200_SHARD_SWEEP=tile keeps
+// the tile sweep).
+int pdm_shard_p2p_connect_all(pdm_tile *t, const void *blobs, int world, int rank)
+{
+    if (!t || !blobs || world < 1 || world > PDM_MAX_WORLD || rank < 0 || rank >= world) { pdm_set_error("pdm_shard_p2p_connect_all: bad argument"); return PDM_ERR_ARG; }
+    if ((t->win.lo > 0) != (rank > 0) || (t->win.hi < t->R) != (rank + 1 < world)) {
+        pdm_set_error("pdm_shard_p2p_connect_all: the tile's halo rows do not match rank %d of %d", rank, world);
+        return PDM_ERR_ARG;
+    }
+    const ts::P2PExport *ex[PDM_MAX_WORLD];
+    for (int r = 0; r < world; r++) ex[r] = reinterpret_cast<const ts::P2PExport *>(blobs) + r;
+    return pdm_ts_p2p_connect_ranks(t, ex, world, rank);
+}
+
 // unmap the peers' memory (collective use: every rank disconnects, barrier, then tiles may be destroyed)
 int pdm_shard_p2p_disconnect(pdm_tile *t)
 {
@@ -183,19 +205,28 @@ int pdm_shard_finalize(pdm_tile *t, const pdm_uca_params *p_in, pdm_uca_stats *s
     if (!t) return PDM_ERR_ARG;
     pdm_uca_params p;
     if (p_in) p = *p_in; else pdm_default_uca_params(&p);
-    int rc = pdm_launch_ts_finalize(t, &p);
+    const bool wl = t->legacy_graph;     // the work-list engine ran (one sweep across the GPUs)
+    int rc = wl ? pdm_launch_uca_finalize(t, &p) : pdm_launch_ts_finalize(t, &p);
     if (rc) return rc;
     rc = read_ctr(t);
     if (rc) return rc;
     rc = pdm_ts_read_counters(t);
     if (rc) return rc;
+    const unsigned long long *wlc = t->ts_hctr + ts::TC_WLC;
+    if (wl && wlc[CT_WATCHDOG]) {
+        pdm_set_error("pdm_shard_finalize: multi-GPU work-list sweep gave up (code %llu: 1 = no progress, 2 = in-box overrun, 3 = lost in-box slot; "
+                      "QTAIL=%llu QHEAD=%llu QDONE=%llu INBOX=%llu DRAINED=%llu)", wlc[CT_WATCHDOG], wlc[CT_QTAIL], wlc[CT_QHEAD],
+                      wlc[CT_QDONE], wlc[CT_INBOX_TAIL], wlc[CT_DRAINED]);
+        return PDM_ERR_STATE;
+    }
     t->have_uca = true; t->have_graph = true;
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         stats->n_cells = (t->win.hi - t->win.lo) * t->C;
-        stats->n_sources = (int64_t)t->ts_hctr[ts::TC_SOURCES];
-        stats->n_drained = (int64_t)t->ts_hctr[ts::TC_CELLS];
-        stats->n_queue_items = (int64_t)t->ts_hctr[ts::TC_VISITS];
+        stats->n_sources = wl ? (int64_t)t->h_counters[CT_SOURCES] : (int64_t)t->ts_hctr[ts::TC_SOURCES];
+        stats->n_drained = wl ? (int64_t)wlc[CT_DRAINED] : (int64_t)t->ts_hctr[ts::TC_CELLS];
+        stats->n_queue_items = wl ? (int64_t)wlc[CT_QTAIL] : (int64_t)t->ts_hctr[ts::TC_VISITS];
+        if (wl) stats->ms_sweep_kernel = (float)((double)(wlc[CT_T_END] - wlc[CT_T_START]) * 1e-6);
         stats->n_undone = (int64_t)t->h_counters[CT_UNDONE];
         stats->n_edge_todo = (int64_t)t->h_counters[CT_EDGE_TODO];
         stats->min_area = t->min_area;

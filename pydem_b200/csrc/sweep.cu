@@ -29,8 +29,20 @@
 #include <stdlib.h>
 
 #include "drain_op.cuh"
+#include "tsweep.cuh"
 
 namespace {
+
+// multi-GPU work-list sweep, set-up: the seed count goes where the peers can read it, then this rank
+// arrives at the start barrier on rank 0 (everything queued before this kernel -- records, queue and
+// in-box resets -- is complete and, after the fence, visible to the peers)
+__global__ void k_wl_p2p_arrive(unsigned long long *wlc, const unsigned long long *nseeds, unsigned long long *arrived)
+{
+    wlc[CT_SOURCES] = *nseeds;
+    wlc[CT_INBOX_TAIL] = 0; wlc[CT_INBOX_HEAD] = 0; wlc[CT_WATCHDOG] = 0;
+    __threadfence_system();
+    atomicAdd_system(arrived, 1ULL);
+}
 
 // a6 epilogue: dem_processing.py:966-980 (owned cells [n0, n1)): sweep records -> uca, edge_done
 __global__ void __launch_bounds__(256)
@@ -128,6 +140,71 @@ int pdm_launch_sweep_first(pdm_tile *t)
     DrainOp<0> op{t->link, t->cell, nullptr, (int32_t)t->C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w, sweep_strict()};
     wl::k_worklist<<<g_sweep_blocks, 256, 0, t->stream>>>(op, wl::DomainRange{w.lo * w.C, (w.hi - w.lo) * w.C},
                                                           wl::tuned(wl::Queue{t->queue, t->d_counters, (long long)t->N, t->d_counters + CT_SOURCES}));
+    PDM_LAUNCHED();
+    return PDM_OK;
+}
+
+// Can the work-list sweep of this row shard run as one sweep across the GPUs?  (every rank's control block
+// mapped: pdm_shard_p2p_connect_all; PYDEM_B200_SHARD_SWEEP=tile keeps the tile sweep)
+bool pdm_shard_worklist_p2p(const pdm_tile *t)
+{
+    static int want = -1;
+    if (want < 0) { const char *e = getenv("PYDEM_B200_SHARD_SWEEP"); want = (e && (e[0] == 't' || e[0] == 'T')) ? 0 : 1; }
+    if (!want || !t->p2p.on || t->p2p.world < 2 || t->p2p.world > PDM_MAX_WORLD) return false;
+    for (int r = 0; r < t->p2p.world; r++) if (!t->p2p.all_ctl[r]) return false;
+    return true;
+}
+
+// ONE work-list sweep across the row shards of all GPUs (every rank launches it once per step): seeds =
+// this rank's sources, pushes across a shard boundary go straight into the neighbour's records and in-box
+// over NVLink, the end is detected on the counters of all ranks (worklist.cuh, p2p_service).
+static int g_sweep_blocks_p2p = 0;
+int pdm_launch_sweep_p2p(pdm_tile *t)
+{
+    if (!pdm_shard_worklist_p2p(t)) { pdm_set_error("pdm_launch_sweep_p2p: the tile is not connected to every rank"); return PDM_ERR_STATE; }
+    if (!g_sweep_blocks_p2p) {
+        int rc = wl::grid_for(wl::k_worklist<DrainOp<3>, wl::DomainRange>, &g_sweep_blocks_p2p);
+        if (rc) return rc;
+    }
+    pdm_tile::P2P &pp = t->p2p;
+    const Win &w = t->win;
+    unsigned long long *wlc = t->ts_ctr + ts::TC_WLC;
+    // queue slots the previous run used -> -1 (its QTAIL lives in wlc), queue counters -> 0, in-box -> -1
+    if (!t->queue_ready || t->queue_dirty_ctr != wlc) {
+        PDM_CUDA(cudaMemsetAsync(t->queue, 0xFF, (size_t)(t->N + 1) * sizeof(int32_t), t->stream));
+        t->queue_ready = true; t->queue_dirty_ctr = wlc;
+    } else {
+        wl::k_queue_clean<<<296, 256, 0, t->stream>>>(t->queue, wlc, (long long)t->N);
+        PDM_LAUNCHED();
+    }
+    wl::k_queue_zero<<<1, 1, 0, t->stream>>>(wlc, 0);
+    PDM_LAUNCHED();
+    PDM_CUDA(cudaMemsetAsync(t->ts_slots, 0xFF, (size_t)t->ts_cap * sizeof(int32_t), t->stream));
+    pp.launches++;
+    unsigned long long *root = reinterpret_cast<unsigned long long *>(pp.all_ctl[0]);
+    k_wl_p2p_arrive<<<1, 1, 0, t->stream>>>(wlc, t->d_counters + CT_SOURCES, root + ts::TC_ARRIVED);
+    PDM_LAUNCHED();
+    DrainOp<3> op{t->link, t->cell, nullptr, (int32_t)t->C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w, 0};
+    op.own_lo = (int32_t)(w.lo * w.C); op.own_hi = (int32_t)(w.hi * w.C);
+    for (int side = 0; side < 2; side++) {
+        op.peer_cell[side] = nullptr; op.peer_ctr[side] = nullptr; op.peer_inbox[side] = nullptr; op.peer_cell0[side] = 0;
+        if (!pp.rec[side]) continue;
+        // above: the neighbour's last owned row; below: its first owned row
+        const long long prow = side == 0 ? pp.hi[0] - 1 : pp.lo[1];
+        op.peer_cell0[side] = (int32_t)(prow * w.C);
+        op.peer_cell[side] = reinterpret_cast<Cell *>(const_cast<void *>(pp.rec[side])) + prow * w.C;
+        char *ctl = reinterpret_cast<char *>(pp.ctl[side]);
+        op.peer_ctr[side] = reinterpret_cast<unsigned long long *>(ctl) + ts::TC_WLC;
+        op.peer_inbox[side] = reinterpret_cast<int32_t *>(ctl + pp.off_slots[side]);
+    }
+    wl::Queue q{t->queue, wlc, (long long)t->N, wlc + CT_SOURCES};
+    q = wl::tuned(q);
+    q.inbox = t->ts_slots; q.inbox_cap = (long long)t->ts_cap;
+    q.epoch = pp.launches;
+    q.arrived = root + ts::TC_ARRIVED; q.start_target = (unsigned long long)pp.world * pp.launches;
+    q.world = pp.world;
+    for (int r = 0; r < pp.world; r++) q.all_ctr[r] = reinterpret_cast<unsigned long long *>(pp.all_ctl[r]) + ts::TC_WLC;
+    wl::k_worklist<<<g_sweep_blocks_p2p, 256, 0, t->stream>>>(op, wl::DomainRange{w.lo * w.C, (w.hi - w.lo) * w.C}, q);
     PDM_LAUNCHED();
     return PDM_OK;
 }

@@ -962,7 +962,7 @@ static int ts_prepare(pdm_tile *t, Variant **out)
     const int64_t ntx = (w.C + v.tw - 1) / v.tw, nty = (w.hi - w.lo + v.th - 1) / v.th;
     const int64_t ntiles = ntx * nty;
     int64_t cap = 1024;
-    while (cap < 4 * ntiles) cap <<= 1;
+    while (cap < 4 * ntiles || cap < 2 * w.C + 64) cap <<= 1;   // (the slots also serve as the in-box of a multi-GPU work-list sweep: <= 2 C cells)
     if (t->ts_cap < cap || t->ts_ntiles_cap < ntiles) {
         if (t->p2p.on) { pdm_set_error("tile sweep: the control block is shared with peer GPUs and cannot grow; connect after the first sweep geometry is known"); return PDM_ERR_STATE; }
         if (t->ts_ctl) { cudaFree(t->ts_ctl); t->ts_ctl = nullptr; }
@@ -1085,49 +1085,70 @@ static int open_peer(const unsigned char *handle, long long off, void **map, voi
     return PDM_OK;
 }
 
-// up / down: the exports of the ranks holding the rows above / below (nullptr at the ends of the grid);
-// root: rank 0's export (nullptr on rank 0 itself)
-int pdm_ts_p2p_connect(pdm_tile *t, const P2PExport *up, const P2PExport *down, const P2PExport *root, int world, int rank)
+// ex[r]: the export of rank r (nullptr = not known; ex[rank] is ignored).  The row neighbours' records and
+// control blocks and rank 0's control block are needed; with every rank's control block mapped the work-list
+// sweep can span the GPUs as well (sweep.cu, pdm_launch_sweep_p2p).
+int pdm_ts_p2p_connect_ranks(pdm_tile *t, const P2PExport *const *ex, int world, int rank)
 {
     pdm_tile::P2P &q = t->p2p;
     if (q.on) { pdm_set_error("pdm_shard_p2p_connect: already connected"); return PDM_ERR_STATE; }
+    if (world > PDM_MAX_WORLD) { pdm_set_error("pdm_shard_p2p_connect: at most %d ranks", PDM_MAX_WORLD); return PDM_ERR_ARG; }
     Variant *v = nullptr;
     int rc = ts_prepare(t, &v);
     if (rc) return rc;
     memset(&q, 0, sizeof(q));
-    const P2PExport *nb[2] = {up, down};
     const long long me = (long long)getpid();
-    for (int side = 0; side < 2; side++) {
-        const P2PExport *e = nb[side];
+    for (int r = 0; r < world; r++) {
+        if (r == rank) { q.all_ctl[r] = t->ts_ctl; continue; }
+        const P2PExport *e = ex[r];
         if (!e) continue;
+        if (e->proc_tag == me) q.all_ctl[r] = e->raw_ctl;
+        else if ((rc = open_peer(e->h_ctl, e->off_ctl, &q.map_all[r], &q.all_ctl[r]))) return rc;   // (an allocation is opened once per process)
+    }
+    for (int side = 0; side < 2; side++) {
+        const int r = side == 0 ? rank - 1 : rank + 1;
+        if (r < 0 || r >= world) continue;
+        const P2PExport *e = ex[r];
+        if (!e) { pdm_set_error("pdm_shard_p2p_connect: the export of rank %d (a row neighbour) is missing", r); return PDM_ERR_ARG; }
         if (e->C != t->win.C) { pdm_set_error("pdm_shard_p2p_connect: the neighbour has %lld columns, this tile %lld", e->C, (long long)t->win.C); return PDM_ERR_ARG; }
-        if (e->proc_tag == me) { q.rec[side] = e->raw_rec; q.ctl[side] = e->raw_ctl; }
+        if (e->proc_tag == me) q.rec[side] = e->raw_rec;
         else {
             void *p = nullptr;
             if ((rc = open_peer(e->h_rec, e->off_rec, &q.map_rec[side], &p))) return rc;
             q.rec[side] = p;
-            if ((rc = open_peer(e->h_ctl, e->off_ctl, &q.map_ctl[side], &q.ctl[side]))) return rc;
         }
+        q.ctl[side] = q.all_ctl[r];
         q.off_flag[side] = e->off_flag; q.off_slots[side] = e->off_slots;
         q.lo[side] = e->lo; q.hi[side] = e->hi; q.nty[side] = e->nty; q.cap_mask[side] = e->cap_mask;
     }
-    if (root) {
-        if (root->proc_tag == me) q.root_ctl = root->raw_ctl;
-        else if (up && root->device == up->device && !memcmp(root->h_ctl, up->h_ctl, 64)) q.root_ctl = q.ctl[0];   // rank 1: rank 0 is the upper neighbour (an allocation is opened once)
-        else if ((rc = open_peer(root->h_ctl, root->off_ctl, &q.map_root, &q.root_ctl))) return rc;
+    if (rank > 0) {
+        if (!q.all_ctl[0]) { pdm_set_error("pdm_shard_p2p_connect: the export of rank 0 is missing"); return PDM_ERR_ARG; }
+        q.root_ctl = q.all_ctl[0];
     }
     q.world = world; q.rank = rank; q.launches = 0; q.on = 1;
     return PDM_OK;
 }
 
+// up / down: the exports of the ranks holding the rows above / below (nullptr at the ends of the grid);
+// root: rank 0's export (nullptr on rank 0 itself)
+int pdm_ts_p2p_connect(pdm_tile *t, const P2PExport *up, const P2PExport *down, const P2PExport *root, int world, int rank)
+{
+    if (world > PDM_MAX_WORLD) { pdm_set_error("pdm_shard_p2p_connect: at most %d ranks", PDM_MAX_WORLD); return PDM_ERR_ARG; }
+    const P2PExport *ex[PDM_MAX_WORLD];
+    for (int r = 0; r < PDM_MAX_WORLD; r++) ex[r] = nullptr;
+    if (rank > 0) ex[0] = root;
+    if (rank > 0) ex[rank - 1] = up;        // (rank 1: rank 0 is the neighbour above; the same export)
+    if (rank + 1 < world) ex[rank + 1] = down;
+    return pdm_ts_p2p_connect_ranks(t, ex, world, rank);
+}
+
 void pdm_ts_p2p_close(pdm_tile *t)
 {
     pdm_tile::P2P &q = t->p2p;
-    for (int side = 0; side < 2; side++) {
+    for (int side = 0; side < 2; side++)
         if (q.map_rec[side]) cudaIpcCloseMemHandle(q.map_rec[side]);
-        if (q.map_ctl[side]) cudaIpcCloseMemHandle(q.map_ctl[side]);
-    }
-    if (q.map_root) cudaIpcCloseMemHandle(q.map_root);
+    for (int r = 0; r < PDM_MAX_WORLD; r++)
+        if (q.map_all[r]) cudaIpcCloseMemHandle(q.map_all[r]);
     memset(&q, 0, sizeof(q));
 }
 

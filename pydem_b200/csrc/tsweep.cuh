@@ -25,7 +25,8 @@ enum {
     TC_HIST = 96,       // PYDEM_B200_TS_DEBUG timeline: per 100 us bucket {visits, cells completed} x 64
     TC_LATE = 96 + 128, // debug: phases {claim, load, count, flow, store, schedule} ns, visits, cells of the visits after dbg x 100 us
     TC_DBG2 = 96 + 128 + 8, // debug: cycles {busy turns total, inside the drain step, in the hand-over, looking for work} of the busiest-warp turns of late visits
-    TC_N = 96 + 128 + 16
+    TC_WLC = 96 + 128 + 16,  // counters (CT_*, pdm_internal.cuh) of a work-list sweep that spans the GPUs (sweep.cu, pdm_launch_sweep_p2p)
+    TC_N = 96 + 128 + 16 + CT_N
 };
 
 struct Args {

@@ -72,6 +72,7 @@ k_upd_border(const double *__restrict__ sdata, const uint8_t *__restrict__ sdone
 //   WHICH 1: seeds ST_TODOSEED, marks ST_REACH
 template <int WHICH>
 struct FloodOp {
+    static constexpr bool P2P = false;
     Cell *cell;
     uint8_t *st;
     int32_t C;

@@ -66,6 +66,14 @@ struct Queue {
     const unsigned long long *nseeds;  // device counter: exact number of seeds in the scan domain
     int32_t backoff_max;   // longest sleep of an idle warp between polls, ns (0: default)
     int32_t dbg;           // collect the CT_X_* diagnostics (PYDEM_B200_WL_DEBUG)
+    // ---- one sweep across the row shards of several GPUs (Op::P2P; see the block comment at p2p_service)
+    int32_t *inbox;                       // cells a peer GPU made ready, in arrival order (slots are -1 until written)
+    long long inbox_cap;
+    unsigned long long epoch;             // number of this multi-GPU sweep (CT_GTERM >= epoch: it is over everywhere)
+    const unsigned long long *arrived;    // start barrier on rank 0: ranks whose state is ready, summed over all sweeps
+    unsigned long long start_target;
+    int32_t world;
+    unsigned long long *all_ctr[PDM_MAX_WORLD];   // every rank's counters (own included), mapped peer memory
     __device__ __forceinline__ void push(int32_t cell) const
     {
         const unsigned long long slot = atomicAdd(&ctr[CT_QTAIL], 1ULL);
@@ -101,6 +109,100 @@ struct DomainBorder {
         return (int32_t)((1 + (u >> 1)) * C + ((u & 1) ? C - 1 : 0));
     }
 };
+
+// One sweep across the row shards of several GPUs (Op::P2P, drain_op.cuh MODE 3).  A cell whose receiver
+// belongs to the neighbouring rank adds into that rank's record and counts its in-degree down with
+// system-scope atomics over NVLink; the cell that brings a peer's counter to zero goes into the peer's
+// IN-BOX (CT_INBOX_TAIL + slot store).  Warp 0 of block 0 of every rank is the SERVICE warp: it
+//   * forwards in-box cells to the local queue (single consumer: no claim traffic, 32 cells per turn).
+//     Accounting: the in-box item counts as produced at CT_INBOX_TAIL (by the peer) and as finished at
+//     CT_QDONE once it has been re-pushed (CT_QTAIL), so that on every rank
+//     QDONE <= seeds dealt + QTAIL + INBOX_TAIL, all monotonic;
+//   * detects the end: when this rank looks quiescent it reads every rank's QDONE (first wave), then every
+//     rank's QTAIL, INBOX_TAIL and seed count (second wave, issued after the first has returned), each with a
+//     system-scope read-modify-write performed at the counter's home.  sum QDONE == sum (seeds + QTAIL +
+//     INBOX_TAIL) proves that at a moment between the waves nothing was running or queued anywhere (a push
+//     into a peer's in-box has returned before the pushing chain is counted as finished).  It then writes the
+//     sweep number into every rank's CT_GTERM -- which is never reset, so a rank that already prepares the
+//     next sweep cannot be confused by a late writer, and a rank whose own check reads a neighbour's freshly
+//     reset counters still leaves through its flag.
+// All other warps leave when their own CT_GTERM says so.
+static __device__ __forceinline__ void p2p_service(const Queue &q, unsigned long long nseeds)
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    unsigned long long head = 0, t_idle = 0;
+    unsigned polls = 0;
+    for (;;) {
+        unsigned long long tail = 0;
+        if (lane == 0) tail = ld_volatile_u64(q.ctr + CT_INBOX_TAIL);
+        tail = __shfl_sync(full, tail, 0);
+        if (tail > (unsigned long long)q.inbox_cap) { if (lane == 0) atomicExch(&q.ctr[CT_WATCHDOG], 2ULL); tail = head; }
+        while (head < tail) {
+            const int n = (int)(tail - head < 32ULL ? tail - head : 32ULL);
+            int32_t v = -1;
+            if (lane < n) {
+                // the peer bumps the counter first and stores the slot right after: a short wait at most
+                unsigned spins = 0;
+                while ((v = ld_volatile_i32(q.inbox + head + lane)) < 0 && ++spins < (1u << 24)) __nanosleep(50);
+            }
+            const unsigned ok = __ballot_sync(full, v >= 0);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&q.ctr[CT_QTAIL], (unsigned long long)__popc(ok));
+            base = __shfl_sync(full, base, 0);
+            if (v >= 0) st_volatile_i32(q.slots + base + __popc(ok & ((1u << lane) - 1u)), v);
+            __syncwarp(full);
+            // finished only after the re-push has been counted (base has returned: in-order issue)
+            if (lane == 0) atomicAdd(&q.ctr[CT_QDONE], (unsigned long long)n + dep_zero_u64(base));
+            if (__popc(ok) != n && lane == 0) atomicExch(&q.ctr[CT_WATCHDOG], 3ULL);   // a slot never arrived (cannot happen)
+            head += n;
+            t_idle = 0;
+        }
+        int term = 0;
+        if (lane == 0) {
+            if (ld_volatile_u64(q.ctr + CT_GTERM) >= q.epoch) term = 1;
+            else if (ld_volatile_u64(q.ctr + CT_WATCHDOG) != 0) term = 1;
+        }
+        if (__shfl_sync(full, term, 0)) break;
+        // cheap local filter (plain loads, QDONE first), then the two waves over all ranks
+        int quiet = 0;
+        if (lane == 0) {
+            const unsigned long long d = ld_volatile_u64(q.ctr + CT_QDONE);
+            const unsigned long long t = ld_volatile_u64(q.ctr + CT_QTAIL + dep_zero_u64(d));
+            const unsigned long long it = ld_volatile_u64(q.ctr + CT_INBOX_TAIL + dep_zero_u64(t));
+            quiet = (d == nseeds + t + it && it == head) ? 1 : 0;
+        }
+        quiet = __shfl_sync(full, quiet, 0);
+        if (quiet) {
+            unsigned long long d = 0, t = 0;
+            unsigned long long *c = lane < q.world ? q.all_ctr[lane] : nullptr;
+            if (c) d = atomicAdd_system(c + CT_QDONE, 0ULL);
+            for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(full, d, o);
+            __threadfence_system();
+            if (c) {
+                // second wave: its addresses depend on the first wave's sum (and the shuffles above were a
+                // convergence point), so it is issued after every QDONE has come back
+                const unsigned long long z = dep_zero_u64(d);
+                t = atomicAdd_system(c + CT_QTAIL + z, 0ULL) + atomicAdd_system(c + CT_INBOX_TAIL + z, 0ULL) +
+                    atomicAdd_system(c + CT_SOURCES + z, 0ULL);
+            }
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(full, t, o);
+            if (d == t) {
+                if (c) atomicMax_system(c + CT_GTERM, q.epoch);
+                break;
+            }
+            __nanosleep(1000);
+        } else {
+            __nanosleep(100);
+        }
+        // watchdog (never fires in a correct run): nothing arrived and nobody finished for 4 s
+        if ((++polls & 1023u) == 0 && lane == 0) {
+            const unsigned long long now = globaltimer_ns();
+            if (t_idle == 0) t_idle = now;
+            else if (now - t_idle > 8000000000ULL) atomicExch(&q.ctr[CT_WATCHDOG], 1ULL);
+        }
+    }
+}
 
 template <class Op, class Domain>
 __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
@@ -146,7 +248,23 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
     const unsigned backoff_max = q.backoff_max > 0 ? (unsigned)q.backoff_max : 200u;
     unsigned long long x_polls = 0, x_chain_ns = 0, x_chain_cells = 0, x_chain_calls = 0, x_team_ns = 0, x_team_steps = 0,
                        x_team_lanes = 0;
+    if constexpr (Op::P2P) {
+        // start barrier: nobody touches a peer's records or in-box before every rank has reset its own
+        // (each rank arrives on rank 0's counter after its set-up kernels, pdm_launch_sweep_p2p)
+        if (threadIdx.x == 0) {
+            while (ld_volatile_u64(q.arrived) < q.start_target) __nanosleep(200);
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
     if (lane == 0) atomicMin(&q.ctr[CT_T_START], globaltimer_ns());
+    if constexpr (Op::P2P) {
+        if (blockIdx.x == 0 && (threadIdx.x >> 5) == 0) {
+            p2p_service(q, nseeds);
+            if (lane == 0) atomicMax(&q.ctr[CT_T_END], globaltimer_ns());
+            return;
+        }
+    }
 
     for (;;) {
         // ---- a finished chain first continues with the lane's own stashed cell
@@ -228,7 +346,14 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
                 // counters are read only every 4th round so that polling does not slow the
                 // producers' atomics on the same lines
                 int term = 0;
-                if ((++idle_polls & 3u) == 0) {
+                if (Op::P2P) {
+                    // a sweep across GPUs ends when the service warp (p2p_service) has seen -- or been told --
+                    // that every rank is quiescent
+                    if ((++idle_polls & 3u) == 0) {
+                        if (lane == 0) term = ld_volatile_u64(q.ctr + CT_GTERM) >= q.epoch ? 1 : 0;
+                        term = __shfl_sync(full, term, 0);
+                    }
+                } else if ((++idle_polls & 3u) == 0) {
                     if (lane == 0) {
                         // the proof needs QDONE to be read before QTAIL.  The cheap filter reads both
                         // with plain volatile loads (the second address depends on the first value);
@@ -429,7 +554,7 @@ static __global__ void __launch_bounds__(256) k_queue_clean(int32_t *slots, cons
 }
 static __global__ void k_queue_zero(unsigned long long *ctr, int keep_drained)
 {
-    ctr[CT_QTAIL] = 0; ctr[CT_QHEAD] = 0; ctr[CT_QDONE] = 0; ctr[CT_PHASE1] = 0; ctr[CT_CHUNK] = 0;
+    ctr[CT_QTAIL] = 0; ctr[CT_QHEAD] = 0; ctr[CT_QDONE] = 0; ctr[CT_PHASE1] = 0; ctr[CT_CHUNK] = 0;   // (CT_GTERM is never reset)
     if (!keep_drained) ctr[CT_DRAINED] = 0;
     for (int k = CT_X_FIRST; k <= CT_X_LAST; k++) ctr[k] = 0;
     ctr[CT_T_START] = ~0ULL; ctr[CT_T_SCAN] = 0; ctr[CT_T_END] = 0; ctr[CT_DBG_DEALT] = 0; ctr[CT_DBG_TAKEN] = 0; ctr[CT_DBG_EXITS] = 0;
@@ -451,9 +576,9 @@ inline int check_watchdog(pdm_tile *t)
 // host: reset the queue state before a run (slots to -1, the queue counters to 0)
 inline int reset_queue(pdm_tile *t, int keep_drained = 0)
 {
-    if (!t->queue_ready) {
+    if (!t->queue_ready || (t->queue_dirty_ctr && t->queue_dirty_ctr != t->d_counters)) {
         PDM_CUDA(cudaMemsetAsync(t->queue, 0xFF, (size_t)(t->N + 1) * sizeof(int32_t), t->stream));
-        t->queue_ready = true;
+        t->queue_ready = true; t->queue_dirty_ctr = t->d_counters;
     } else {
         k_queue_clean<<<296, 256, 0, t->stream>>>(t->queue, t->d_counters, (long long)t->N);
         PDM_LAUNCHED();

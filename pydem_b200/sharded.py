@@ -136,9 +136,7 @@ class DistGroup(object):
         allb = [torch.empty_like(mine) for _ in range(self.world)]
         self.dist.all_gather(allb, mine)
         blobs = [bytes(b.cpu().numpy().tobytes()) for b in allb]
-        engine.p2p_connect(blobs[self.rank - 1] if self.rank > 0 else None,
-                           blobs[self.rank + 1] if self.rank < self.world - 1 else None,
-                           blobs[0] if self.rank > 0 else None, self.world, self.rank)
+        engine.p2p_connect_all(blobs, self.world, self.rank)
         self.dist.barrier()
 
 
@@ -182,6 +180,14 @@ class ShardEngine(object):
         import ctypes as ct
         keep = [ct.create_string_buffer(b, len(b)) if b is not None else None for b in (up, down, root)]
         self.T._lib.check(self.tile.L.pdm_shard_p2p_connect(self.tile.h, *keep, int(world), int(rank)))
+        self.p2p = True
+
+    def p2p_connect_all(self, blobs, world, rank):
+        """every rank's export: the work-list engine can then run the accumulation as one sweep across the GPUs"""
+        import ctypes as ct
+        joined = b"".join(blobs)
+        buf = ct.create_string_buffer(joined, len(joined))
+        self.T._lib.check(self.tile.L.pdm_shard_p2p_connect_all(self.tile.h, buf, int(world), int(rank)))
         self.p2p = True
 
     def rows(self, field):
