@@ -332,7 +332,10 @@ def gpu_arm(args):
         E = synth.conditioned_fractal_dem(n, 0, wrap_rows=True)
     else:
         E = synth.fractal_dem(n, 0)                      # secondary 'sinks' variant: raw fractal
-    pits_flag = 1 if (variant == "conditioned" and world == 1) else 0
+    # the reference's default drain_pits=True on the conditioned variant; on row shards it needs the multi-GPU
+    # work-list sweep over peer memory (pits drain across shard boundaries), i.e. not PYDEM_B200_SHARD_P2P=0
+    p2p_on = os.environ.get("PYDEM_B200_SHARD_P2P", "1") != "0" and not os.environ.get("PYDEM_B200_SHARD_SWEEP", "w").lower().startswith("t")
+    pits_flag = 1 if (variant == "conditioned" and (world == 1 or p2p_on)) else 0
     flags_txt = ("fill_flats=False, drain_pits_path=False, drain_pits=%s" % bool(pits_flag))
     if world == 1:
         stream = torch.cuda.current_stream().cuda_stream
@@ -369,6 +372,7 @@ def gpu_arm(args):
     else:
         from pydem_b200 import sharded
         sh = sharded.ShardedDEM(rows_per_rank=n, cols=n, spacing=SPACING, seed=0, profile=True, block=E)
+        sh.uca_flags = {"drain_pits": pits_flag}
         stats = {}
 
         def step():
@@ -378,7 +382,7 @@ def gpu_arm(args):
         cells_per_step = n * n * world
         workload = ("%dx%d DEM = the %dx%d block of the 1-GPU run (%s) repeated %d times vertically (periodic, "
                     "seamless), row-sharded over %d GPUs (%d rows each, halo rows over NCCL send/recv, UCA as one work-list sweep across the GPUs over NVLink peer memory), dX=dY=30 m, "
-                    "slope+aspect + UCA + TWI, %s (pit drains are not available on shards)"
+                    "slope+aspect + UCA + TWI, %s"
                     % (n * world, n, n, n, "conditioned fractal" if variant == "conditioned" else "raw fractal", world,
                        world, n, flags_txt))
         parallelism = "row-block x%d" % world

@@ -244,6 +244,16 @@ int pdm_shard_label_pack(pdm_tile *t, int64_t row, void *out_labels, void *out_e
 int pdm_shard_label_unpack(pdm_tile *t, int64_t row, const void *in_labels, const void *in_elev, void *changed);
 int pdm_shard_flats_extend(pdm_tile *t);
 int pdm_shard_links(pdm_tile *t, const pdm_uca_params *p);
+/* drain_pits on row shards (_mk_connectivity_pits, dem_processing.py:1269-1382; needs pdm_shard_p2p_connect_all):
+ * pdm_tile_set_global_spacing once (host arrays of R_global - 1 fences); per pass, between links and indeg:
+ * exchange strips of ELEV and FLAT0 (= the pit mask after links) -- the Hu / Hd = drain_pits_max_iter + 1 owned rows
+ * next to each boundary -- then pdm_shard_pits (device pointers to the received strips; in_up / in_dn: int32
+ * [Hin][C] out, pit edges that end on the neighbour's Hin rows next to the boundary, Hin >= drain_pits_max_dist),
+ * exchange in_up / in_dn, pdm_shard_pit_in_apply with what arrived. */
+int pdm_tile_set_global_spacing(pdm_tile *t, const double *dX, const double *dY, int64_t n);
+int pdm_shard_pits(pdm_tile *t, const pdm_uca_params *p, const void *E_up, const void *P_up, int64_t Hu,
+                   const void *E_dn, const void *P_dn, int64_t Hd, void *in_up, void *in_dn, int64_t Hin);
+int pdm_shard_pit_in_apply(pdm_tile *t, const void *from_up, const void *from_dn, int64_t Hin);
 int pdm_shard_indeg(pdm_tile *t);
 int pdm_shard_sweep(pdm_tile *t, int first);
 int pdm_shard_sweep_sent(pdm_tile *t, void *sent);

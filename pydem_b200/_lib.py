@@ -65,7 +65,7 @@ EXPORTS = [
     "pdm_tile_upload", "pdm_tile_download", "pdm_tile_download_async", "pdm_tile_device_ptr", "pdm_tile_mark_resident", "pdm_tile_set_stencil_parity", "pdm_tile_sync", "pdm_selftest_division",
     "pdm_tile_slopes_directions", "pdm_tile_find_flats", "pdm_tile_uca", "pdm_tile_pit_updates", "pdm_tile_uca_update",
     "pdm_tile_twi", "pdm_tile_set_keep_graph", "pdm_tile_set_window", "pdm_shard_slopes", "pdm_shard_ccl", "pdm_shard_label_pack",
-    "pdm_shard_label_unpack", "pdm_shard_flats_extend", "pdm_shard_links", "pdm_shard_indeg", "pdm_shard_sweep",
+    "pdm_shard_label_unpack", "pdm_shard_flats_extend", "pdm_shard_links", "pdm_tile_set_global_spacing", "pdm_shard_pits", "pdm_shard_pit_in_apply", "pdm_shard_indeg", "pdm_shard_sweep",
     "pdm_shard_sweep_sent", "pdm_shard_finalize",
     "pdm_slopes_directions", "pdm_uca", "pdm_uca_update", "pdm_twi",
     "pdm_default_cond_params", "pdm_tile_fill_pit_artifacts", "pdm_tile_fill_flats", "pdm_tile_pit_drain_paths",
@@ -126,6 +126,9 @@ def load():
     L.pdm_shard_label_pack.argtypes = [_vp, _i64, _vp, _vp]
     L.pdm_shard_label_unpack.argtypes = [_vp, _i64, _vp, _vp, _vp]
     L.pdm_shard_links.argtypes = [_vp, ct.POINTER(UcaParams)]
+    L.pdm_tile_set_global_spacing.argtypes = [_vp, _vp, _vp, _i64]
+    L.pdm_shard_pits.argtypes = [_vp, ct.POINTER(UcaParams), _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64]
+    L.pdm_shard_pit_in_apply.argtypes = [_vp, _vp, _vp, _i64]
     L.pdm_shard_sweep.argtypes = [_vp, ct.c_int]
     L.pdm_shard_p2p_export.argtypes = [_vp, _vp, ct.POINTER(_i64)]
     L.pdm_shard_p2p_connect.argtypes = [_vp, _vp, _vp, _vp, ct.c_int, ct.c_int]

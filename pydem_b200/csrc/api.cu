@@ -175,7 +175,7 @@ int pdm_tile_destroy(pdm_tile *t)
                     t->edge_todo, t->edge_done, t->section, t->label, t->queue, t->dX, t->dY, t->dg,
                     t->thA, t->thB, t->th_row, t->row_area, t->d_counters, t->pit_cell, t->pit_beg, t->pit_end,
                     t->pit_dst, t->pit_w, t->pit_scratch_i, t->pit_scratch_d, t->edge_buf_d, t->edge_buf_b,
-                    t->glabel, t->glelev, t->twi10, t->rdX, t->rdY, t->rdg, t->ts_ctl, t->ts_seen};
+                    t->glabel, t->glelev, t->twi10, t->rdX, t->rdY, t->rdg, t->ts_ctl, t->ts_seen, t->dXg, t->dYg};
     pdm_ts_p2p_close(t);
     for (void *p : ptrs) if (p) cudaFree(p);
     if (t->h_counters) cudaFreeHost(t->h_counters);
@@ -434,8 +434,7 @@ int pdm_tile_uca(pdm_tile *t, const pdm_uca_params *p_in, pdm_uca_stats *stats)
                 h[CT_X_TEAM_LANES] ? (double)h[CT_X_TEAM_NS] / (double)h[CT_X_TEAM_LANES] : 0.0, h[CT_X_POLLS], h[CT_QTAIL]);
     }
     if (st.n_undone > 0) {
-        // circular references: the reference restarts from the highest undone cells
-        // (dem_processing.py:951-964); replayed level-synchronously.
+        // dem_processing.py:951-964: unreachable for a DAG unless circular_ref_maxcount <= 1 switched the sweep off
         rc = pdm_restart_rounds(t, &p, &st);
         if (rc) return rc;
     }

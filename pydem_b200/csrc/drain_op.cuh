@@ -80,13 +80,18 @@ struct DrainOp {
     {
         const int side = r < own_lo ? 0 : 1;
         const int32_t col = r - (side == 0 ? own_lo - C : own_hi);
-        Cell *P = peer_cell[side] + col;
+        push_peer_at(side, peer_cell0[side] + col, da, dt, tt);
+    }
+    // idx: the cell's index on the neighbouring rank (boundary row: push_peer; any row: pit drains across the boundary)
+    __device__ __forceinline__ void push_peer_at(int side, int32_t idx, double da, double dt, bool tt) const
+    {
+        Cell *P = peer_cell[side] + (idx - peer_cell0[side]);
         atomicAdd_system(&P->area, da);
         if (tt) atomicAdd_system(&P->taint, dt);
         __threadfence_system();
         if (atomicAdd_system(&P->indeg, -1) == 1) {
             const unsigned long long s = atomicAdd_system(peer_ctr[side] + CT_INBOX_TAIL, 1ULL);
-            wl::st_volatile_i32(peer_inbox[side] + s, peer_cell0[side] + col);
+            wl::st_volatile_i32(peer_inbox[side] + s, idx);
         }
     }
     __device__ __forceinline__ bool skip(int32_t r) const { return MODE == 1 && (st[r] & ST_START); }
@@ -108,14 +113,20 @@ struct DrainOp {
             const int32_t e0 = pit_beg[slot], e1 = pit_end[slot];
             for (int32_t e = e0; e < e1; e++) {
                 const int32_t r = pit_dst[e];
-                if (skip(r)) continue;
                 const double w = pit_w[e];
+                if (MODE == 3 && r < 0) {
+                    // the drain is a cell of the neighbouring rank (pits.cu, k_pit_search<true>): ~r = side << 30 | its index there
+                    push_peer_at((~r) >> 30, (~r) & 0x3fffffff, __dmul_rn(ai, w), __dmul_rn(ti, w), ti != 0.0);
+                    continue;
+                }
+                if (skip(r)) continue;
                 atomicAdd(&cell[r].area, __dmul_rn(ai, w));
                 if (MODE != 1 && ti != 0.0) atomicAdd(&cell[r].taint, __dmul_rn(ti, w));
             }
             __threadfence();
             for (int32_t e = e0; e < e1; e++) {
                 const int32_t r = pit_dst[e];
+                if (MODE == 3 && r < 0) continue;
                 if (skip(r)) continue;
                 if (atomicSub(&cell[r].indeg, 1) == 1) {
                     if (nxt < 0) nxt = r; else q.push(r);

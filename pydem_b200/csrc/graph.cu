@@ -250,11 +250,12 @@ int pdm_graph_links_pits(pdm_tile *t, const pdm_uca_params *p)
                                            t->flat0, t->d_counters);
     PDM_LAUNCHED();
     t->n_pits = 0; t->n_pit_edges = 0;
+    t->shard_pits_wanted = false; t->shard_pits_done = false;
     if (p->drain_pits) {
         if (w.lo != 0 || w.hi != t->R || w.Rg != t->R) {
-            pdm_set_error("drain_pits=True is not supported on a row shard yet (the pit search needs a %d-row halo); "
-                          "run the sharded path with drain_pits=False", (int)p->drain_pits_max_iter + 1);
-            return PDM_ERR_ARG;
+            // row shard: the search needs the neighbours' strips of elevation and pit mask -> pdm_shard_pits (shard.cu)
+            t->shard_pits_wanted = true;
+            return PDM_OK;
         }
         int rc = pdm_launch_pits(t, p);
         if (rc) return rc;
@@ -270,7 +271,7 @@ int pdm_launch_indeg_todo(pdm_tile *t)
     dim3 block(32, 8);
     dim3 grid((unsigned)((w.C + 31) / 32), (unsigned)((t->R + 7) / 8));
     PDM_CUDA(cudaMemsetAsync(t->edge_todo, 0, (size_t)t->N, t->stream));
-    k_indeg<<<grid, block, 0, t->stream>>>(t->link, w, t->row_area, t->twi, t->n_pits ? t->label : nullptr, t->cell,
+    k_indeg<<<grid, block, 0, t->stream>>>(t->link, w, t->row_area, t->twi, (t->n_pits || t->shard_pits_done) ? t->label : nullptr, t->cell,
                                            t->d_counters);
     PDM_LAUNCHED();
     const int64_t per = 2 * w.C + 2 * (w.hi - w.lo);
@@ -302,7 +303,9 @@ int pdm_launch_graph(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *st)
     (void)st;
     int rc = pdm_graph_links_pits(t, p);
     if (rc) return rc;
-    return pdm_sweep_legacy() ? pdm_launch_indeg_todo(t) : pdm_launch_border_todo(t);
+    // circular_ref_maxcount <= 1: the reference's sweep loop never runs (see pdm_launch_sweep_full): the epilogue
+    // needs the initial records of the work-list graph
+    return (pdm_sweep_legacy() || p->circular_ref_maxcount <= 1) ? pdm_launch_indeg_todo(t) : pdm_launch_border_todo(t);
 }
 
 int pdm_launch_section_export(pdm_tile *t)

@@ -75,6 +75,7 @@ struct pdm_tile {
     // geometry
     double *dX, *dY, *dg, *thA, *thB, *th_row, *row_area;
     double *rdX, *rdY, *rdg;   // correctly rounded reciprocals of dX, dY, dg (fast stencil divisions)
+    double *dXg, *dYg;         // row shard: fences of the whole grid (pit drains across the shard boundary)
     double min_area;
     bool have_spacing, have_elev, have_slopes, have_flats, have_graph, have_uca;
     bool stencil_parity; // run the literal (slow) stencil formulation on this tile (tests)
@@ -120,6 +121,7 @@ struct pdm_tile {
         unsigned cap_mask[2];
     } p2p;
     bool legacy_graph;          // the graph on the tile was built for the legacy work-list sweep
+    bool shard_pits_wanted, shard_pits_done;   // row shard with drain_pits: pdm_shard_pits must run between pdm_shard_links and pdm_shard_indeg
 };
 
 // sweep state of one cell in the tile sweep (tsweep.cu): exactly one 32-byte DRAM sector, in the
@@ -169,7 +171,17 @@ int pdm_launch_pit_readback(pdm_tile *t, int32_t *cells, double *mag, uint8_t *f
 int pdm_launch_selftest_div(unsigned long long seed, int blocks, long long per_thread, unsigned long long *mismatch_host);
 int pdm_restart_rounds(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *st);
 int pdm_graph_links_pits(pdm_tile *t, const pdm_uca_params *p);
-int pdm_launch_pits(pdm_tile *t, const pdm_uca_params *p);
+// row shard: what the pit search sees of the neighbouring ranks (pdm_shard_pits, shard.cu)
+struct pdm_pit_shard {
+    const double *E_up, *E_dn;      // elevation of the Hu rows above / Hd rows below the owned rows (device)
+    const uint8_t *P_up, *P_dn;     // their pit mask
+    int64_t Hu, Hd;
+    int32_t *in_up, *in_dn;         // out: pit edges arriving at the neighbours' cells, [Hin][C] each
+    int64_t Hin;
+    int64_t peer_row[2];            // neighbour's local row = my local row + peer_row[side]
+    const double *dXg, *dYg;        // fences of the whole grid (device)
+};
+int pdm_launch_pits(pdm_tile *t, const pdm_uca_params *p, const pdm_pit_shard *sh = nullptr);
 // tile sweep (tsweep.cu)
 int pdm_ts_reset_state(pdm_tile *t);
 int pdm_launch_tsweep(pdm_tile *t, int first);

@@ -12,6 +12,8 @@
 // the region border as a compacted list that is rebuilt incrementally each iteration
 // (block-wide min reductions instead of np.setdiff1d + min over Python arrays).
 #include "pdm_internal.cuh"
+#include <string.h>
+
 #include "np_sum.cuh"
 
 #define PIT_THREADS 128
@@ -38,7 +40,46 @@ struct PitArgs {
     int max_iter, max_dist, min_border;
     double max_dist_xy;
     int W;                    // window radius = max_iter + 1
+    // ---- row shard (k_pit_search<true>): the search also sees H rows of the neighbouring ranks (strips of
+    //      elevation and pit mask received before the search); cells are addressed by an EXTENDED index
+    //      (local row - lo + H) * C + column, dX / dY are the fences of the whole grid
+    int64_t lo, hi, row_off, Rg;          // owned local rows, global row of local row 0, rows of the grid
+    int64_t H, Hu, Hd;                    // coordinate offset; strip rows available above / below
+    const double *E_up, *E_dn;
+    const uint8_t *P_up, *P_dn;
+    int32_t *in_up, *in_dn;               // pit edges arriving at the neighbours' cells: [Hin][C] each (rows next to the boundary)
+    int64_t Hin;
+    int64_t peer_row[2];                  // neighbour's local row = my local row + peer_row[side]
 };
+
+// cell access: plain local index on a stand-alone tile, extended index on a shard
+template <bool SHARD> __device__ __forceinline__ int64_t x_row(const PitArgs &a, int32_t c) { return SHARD ? (int64_t)c / a.C - a.H + a.lo : (int64_t)c / a.C; }
+template <bool SHARD> __device__ __forceinline__ int32_t x_idx(const PitArgs &a, int64_t i, int64_t j) { return SHARD ? (int32_t)((i - a.lo + a.H) * a.C + j) : (int32_t)(i * a.C + j); }
+template <bool SHARD> __device__ __forceinline__ double x_elev(const PitArgs &a, int32_t c)
+{
+    if (!SHARD) return a.E[c];
+    const int64_t i = x_row<true>(a, c), j = (int64_t)c % a.C;
+    if (i < a.lo) return a.E_up[(i - (a.lo - a.Hu)) * a.C + j];
+    if (i >= a.hi) return a.E_dn[(i - a.hi) * a.C + j];
+    return a.E[i * a.C + j];
+}
+template <bool SHARD> __device__ __forceinline__ bool x_pit(const PitArgs &a, int32_t c)
+{
+    if (!SHARD) return a.pitmask[c] != 0;
+    const int64_t i = x_row<true>(a, c), j = (int64_t)c % a.C;
+    if (i < a.lo) return a.P_up[(i - (a.lo - a.Hu)) * a.C + j] != 0;
+    if (i >= a.hi) return a.P_dn[(i - a.hi) * a.C + j] != 0;
+    return a.pitmask[i * a.C + j] != 0;
+}
+// is (ni, nj) a cell of the grid?  On a shard *beyond = true when it is, but lies outside the rows this rank can see
+template <bool SHARD> __device__ __forceinline__ bool x_inside(const PitArgs &a, int64_t ni, int64_t nj, bool *beyond)
+{
+    if (nj < 0 || nj >= a.C) return false;
+    if (!SHARD) return ni >= 0 && ni < a.R;
+    if (ni + a.row_off < 0 || ni + a.row_off >= a.Rg) return false;
+    if (ni < a.lo - a.Hu || ni >= a.hi + a.Hd) { *beyond = true; return false; }
+    return true;
+}
 
 // NaN-propagating min (np.min) over a block; every thread passes its partial
 // (value, saw_nan, count) and gets the block result.
@@ -62,6 +103,7 @@ __device__ __forceinline__ void acc_merge(MinAcc &a, const MinAcc &b)
     a.cnt += b.cnt;
 }
 
+template <bool SHARD>
 __global__ void __launch_bounds__(PIT_THREADS)
 k_pit_search(PitArgs a)
 {
@@ -70,7 +112,8 @@ k_pit_search(PitArgs a)
     __shared__ MinAcc s_red[3][PIT_THREADS / 32];
     __shared__ int s_flag;
     const int tid = threadIdx.x;
-    const int64_t R = a.R, C = a.C;
+    const int64_t C = a.C;
+    const int64_t Rg = SHARD ? a.Rg : a.R;      // rows of the whole grid
     const int W = a.W, WW = 2 * W + 1;
     const int nwords = (WW * WW + 31) / 32;
     int32_t *B[2] = {a.scratch_i + (size_t)blockIdx.x * 2 * PIT_CAP, a.scratch_i + (size_t)blockIdx.x * 2 * PIT_CAP + PIT_CAP};
@@ -92,11 +135,13 @@ k_pit_search(PitArgs a)
         __syncthreads();
         if (tid < 8) {
             const int64_t ni = ip + DR[tid], nj = jp + DC[tid];
-            if (ni >= 0 && ni < R && nj >= 0 && nj < C) {
+            bool beyond = false;
+            if (x_inside<SHARD>(a, ni, nj, &beyond)) {
                 const int bit = (int)(ni - ip + W) * WW + (int)(nj - jp + W);
                 atomicOr(&seen[bit >> 5], 1u << (bit & 31));
-                B[0][atomicAdd(&s_nb[0], 1)] = (int32_t)(ni * C + nj);
+                B[0][atomicAdd(&s_nb[0], 1)] = x_idx<SHARD>(a, ni, nj);
             }
+            if (beyond) s_flag = 2;
         }
         __syncthreads();
         const double epit = a.E[pit];
@@ -104,7 +149,7 @@ k_pit_search(PitArgs a)
         int cur = 0, mode = 0;
         if (a.min_border) {                                                  // 1292-1297
             MinAcc m = {0.0, 0, 0};
-            for (int t = tid; t < s_nb[0]; t += PIT_THREADS) acc_add(m, a.E[B[0][t]]);
+            for (int t = tid; t < s_nb[0]; t += PIT_THREADS) acc_add(m, x_elev<SHARD>(a, B[0][t]));
             for (int o = 16; o > 0; o >>= 1) {
                 MinAcc b = {__shfl_down_sync(0xffffffffu, m.v, o), __shfl_down_sync(0xffffffffu, m.nan, o), __shfl_down_sync(0xffffffffu, m.cnt, o)};
                 acc_merge(m, b);
@@ -123,9 +168,9 @@ k_pit_search(PitArgs a)
             MinAcc mall = {0.0, 0, 0}, mnp = {0.0, 0, 0}, mp = {0.0, 0, 0};
             for (int t = tid; t < nb; t += PIT_THREADS) {
                 const int32_t c = B[cur][t];
-                const double e = a.E[c];
+                const double e = x_elev<SHARD>(a, c);
                 acc_add(mall, e);
-                if (a.pitmask[c]) acc_add(mp, e); else acc_add(mnp, e);
+                if (x_pit<SHARD>(a, c)) acc_add(mp, e); else acc_add(mnp, e);
             }
             MinAcc *ms[3] = {&mall, &mnp, &mp};
             for (int k = 0; k < 3; k++) {
@@ -150,16 +195,17 @@ k_pit_search(PitArgs a)
             __syncthreads();
             for (int t = tid; t < nb; t += PIT_THREADS) {
                 const int32_t c = B[cur][t];
-                if (a.E[c] == emin) {
-                    const int64_t ci = c / C, cj = c % C;
+                if (x_elev<SHARD>(a, c) == emin) {
+                    const int64_t ci = x_row<SHARD>(a, c), cj = c % C;
                     for (int k = 0; k < 8; k++) {
                         const int64_t ni = ci + DR[k], nj = cj + DC[k];
-                        if (ni < 0 || ni >= R || nj < 0 || nj >= C) continue;
+                        bool beyond = false;
+                        if (!x_inside<SHARD>(a, ni, nj, &beyond)) { if (beyond) s_flag = 2; continue; }
                         const int bit = (int)(ni - ip + W) * WW + (int)(nj - jp + W);
                         const uint32_t mask = 1u << (bit & 31);
                         if (atomicOr(&seen[bit >> 5], mask) & mask) continue;
                         const int pos = atomicAdd(&s_nb[nxt], 1);
-                        if (pos < PIT_CAP) B[nxt][pos] = (int32_t)(ni * C + nj); else s_flag = 1;
+                        if (pos < PIT_CAP) B[nxt][pos] = x_idx<SHARD>(a, ni, nj); else s_flag = 1;
                     }
                 } else {
                     const int pos = atomicAdd(&s_nb[nxt], 1);
@@ -171,8 +217,8 @@ k_pit_search(PitArgs a)
             cur = nxt;
         }
         __syncthreads();
-        if (s_flag) {  // border list overflow: fail loudly on the host
-            if (tid == 0) atomicAdd(&a.ctr[CT_ABORT], 1ULL);
+        if (s_flag) {  // border list overflow (1) / region beyond the neighbours' strips (2): fail loudly on the host
+            if (tid == 0) atomicAdd(&a.ctr[CT_ABORT], s_flag == 2 ? (1ULL << 32) : 1ULL);
             __syncthreads();
             continue;
         }
@@ -188,11 +234,11 @@ k_pit_search(PitArgs a)
         __syncthreads();
         for (int t = tid; t < nb; t += PIT_THREADS) {
             const int32_t c = B[cur][t];
-            const double e = a.E[c];
-            const bool isp = a.pitmask[c] != 0;
+            const double e = x_elev<SHARD>(a, c);
+            const bool isp = x_pit<SHARD>(a, c);
             bool ok = (mode == 1) ? (!isp && e < epit_border) : (isp && e < epit);
             if (ok && a.max_dist > 0) {                                      // 1335-1343
-                const int64_t di = ip - c / C, dj = jp - c % C;
+                const int64_t di = ip - x_row<SHARD>(a, c), dj = jp - c % C;
                 ok = sqrt((double)(di * di + dj * dj)) <= (double)a.max_dist;
             }
             if (ok) B[oth][atomicAdd(&s_nb[oth], 1)] = c;
@@ -215,12 +261,14 @@ k_pit_search(PitArgs a)
                 a.pit_beg[slot] = 0; a.pit_end[slot] = 0;
             } else {
                 // real distances 1346-1349
+                // (rows of the whole grid: on a shard dX / dY are the grid's fences)
+                const int64_t gip = SHARD ? ip + a.row_off : ip;
                 for (int t = 0; t < n; t++) {
-                    const int64_t id = D[t] / C, jd = D[t] % C;
+                    const int64_t id = x_row<SHARD>(a, D[t]) + (SHARD ? a.row_off : 0), jd = D[t] % C;
                     double dxm, dy;
-                    if (ip == id) { dxm = a.dX[ip < R - 2 ? ip : R - 2]; dy = 0.0; }
+                    if (gip == id) { dxm = a.dX[gip < Rg - 2 ? gip : Rg - 2]; dy = 0.0; }
                     else {
-                        const int64_t lo = ip < id ? ip : id, hi = ip < id ? id : ip;
+                        const int64_t lo = gip < id ? gip : id, hi = gip < id ? id : gip;
                         dxm = __ddiv_rn(np_sum(a.dX + lo, hi - lo), (double)(hi - lo));
                         dy = np_sum(a.dY + lo, hi - lo);
                     }
@@ -237,13 +285,13 @@ k_pit_search(PitArgs a)
                     atomicAdd(&a.ctr[CT_PITS_UNDRAINED], 1ULL);
                     a.pit_beg[slot] = 0; a.pit_end[slot] = 0;
                 } else {
-                    for (int t = 0; t < n; t++) S[t] = __ddiv_rn(fabs(__dsub_rn(epit, a.E[D[t]])), S[t]);  // 1361
+                    for (int t = 0; t < n; t++) S[t] = __ddiv_rn(fabs(__dsub_rn(epit, x_elev<SHARD>(a, D[t]))), S[t]);  // 1361
                     const double ssum = np_sum(S, n);
                     // edges that survive the matrix filter (1136-1137): weight > 1e-8, not NaN
                     int kept = 0;
                     for (int t = 0; t < n; t++) {
                         const double w = __ddiv_rn(S[t], ssum);
-                        if (w > 1e-8 && a.E[D[t]] <= epit) kept++;
+                        if (w > 1e-8 && x_elev<SHARD>(a, D[t]) <= epit) kept++;
                     }
                     const unsigned long long base = atomicAdd(&a.ctr[CT_NPITEDGES], (unsigned long long)kept);
                     if ((int64_t)(base + kept) > a.edge_cap) {
@@ -253,10 +301,27 @@ k_pit_search(PitArgs a)
                         int k = 0;
                         for (int t = 0; t < n; t++) {
                             const double w = __ddiv_rn(S[t], ssum);                      // 1367
-                            if (w > 1e-8 && a.E[D[t]] <= epit) {
-                                a.pit_dst[base + k] = D[t];
+                            if (w > 1e-8 && x_elev<SHARD>(a, D[t]) <= epit) {
+                                int32_t dst = D[t];
+                                if (SHARD) {
+                                    // own cell: local index; a neighbour's cell: ~(side << 30 | its own index there), and
+                                    // the edge is counted in the strip that travels to that rank before its in-degrees are built
+                                    const int64_t di = x_row<true>(a, dst), dj = dst % C;
+                                    if (di < a.lo) {
+                                        dst = ~(int32_t)((di + a.peer_row[0]) * C + dj);
+                                        if (di >= a.lo - a.Hin) atomicAdd(a.in_up + (di - (a.lo - a.Hin)) * C + dj, 1); else atomicAdd(&a.ctr[CT_ABORT], 1ULL << 48);
+                                    } else if (di >= a.hi) {
+                                        dst = ~(int32_t)((1 << 30) | (int32_t)((di + a.peer_row[1]) * C + dj));
+                                        if (di < a.hi + a.Hin) atomicAdd(a.in_dn + (di - a.hi) * C + dj, 1); else atomicAdd(&a.ctr[CT_ABORT], 1ULL << 48);
+                                    } else {
+                                        dst = (int32_t)(di * C + dj);
+                                        atomicAdd(a.indeg + dst, 1);
+                                    }
+                                } else {
+                                    atomicAdd(a.indeg + dst, 1);
+                                }
+                                a.pit_dst[base + k] = dst;
                                 a.pit_w[base + k] = w;
-                                atomicAdd(a.indeg + D[t], 1);
                                 k++;
                             }
                         }
@@ -276,9 +341,9 @@ k_pit_search(PitArgs a)
 
 // compact the pit mask into a list (order is irrelevant to the result)
 __global__ void __launch_bounds__(256)
-k_pit_compact(const uint8_t *__restrict__ pitmask, int64_t N, int32_t *__restrict__ pit_cell, unsigned long long *ctr)
+k_pit_compact(const uint8_t *__restrict__ pitmask, int64_t n0, int64_t N, int32_t *__restrict__ pit_cell, unsigned long long *ctr)
 {
-    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = n0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // owned cells [n0, N)
     const bool is = n < N && pitmask[n];
     const unsigned m = __ballot_sync(0xffffffffu, is);
     if (!m) return;
@@ -330,7 +395,8 @@ static int read_ctr(pdm_tile *t)
 }
 
 // Called after k_links has written the pit mask into t->flat0 and counted it in CT_NPITS.
-int pdm_launch_pits(pdm_tile *t, const pdm_uca_params *p)
+// sh != nullptr: the tile is a row shard and the search also sees the neighbours' strips (pdm_shard_pits).
+int pdm_launch_pits(pdm_tile *t, const pdm_uca_params *p, const pdm_pit_shard *sh)
 {
     int rc = read_ctr(t);
     if (rc) return rc;
@@ -345,11 +411,12 @@ int pdm_launch_pits(pdm_tile *t, const pdm_uca_params *p)
                       (long long)p->drain_pits_max_iter);
         return PDM_ERR_ARG;
     }
-    PDM_CUDA(cudaFuncSetAttribute(k_pit_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void (*kernel)(PitArgs) = sh ? k_pit_search<true> : k_pit_search<false>;
+    PDM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 0, occ = 0;
     PDM_CUDA(cudaGetDevice(&dev));
     PDM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    PDM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pit_search, PIT_THREADS, smem));
+    PDM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, PIT_THREADS, smem));
     if (occ < 1) occ = 1;
     int64_t blocks = (int64_t)sms * occ;
     if (blocks > npits) blocks = npits;
@@ -375,24 +442,46 @@ int pdm_launch_pits(pdm_tile *t, const pdm_uca_params *p)
     // t->label (free after the flat labelling) counts the pit edges arriving at each cell
     PDM_CUDA(cudaMemsetAsync(t->label, 0, (size_t)t->N * sizeof(int32_t), t->stream));
     PDM_CUDA(cudaMemsetAsync(t->d_counters + CT_TMP0, 0, sizeof(unsigned long long), t->stream));
-    k_pit_compact<<<(unsigned)((t->N + 255) / 256), 256, 0, t->stream>>>(t->flat0, t->N, t->pit_cell, t->d_counters);
-    PDM_LAUNCHED();
+    {
+        const int64_t n0 = t->win.lo * t->C, n1 = t->win.hi * t->C;    // (halo rows of flat0 do not hold the pit mask)
+        k_pit_compact<<<(unsigned)((n1 - n0 + 255) / 256), 256, 0, t->stream>>>(t->flat0, n0, n1, t->pit_cell, t->d_counters);
+        PDM_LAUNCHED();
+    }
     for (int attempt = 0; attempt < 8; attempt++) {
         PDM_CUDA(cudaMemsetAsync(t->d_counters + CT_NPITEDGES, 0, sizeof(unsigned long long), t->stream));
         PDM_CUDA(cudaMemsetAsync(t->d_counters + CT_PITS_UNDRAINED, 0, sizeof(unsigned long long), t->stream));
         PDM_CUDA(cudaMemsetAsync(t->d_counters + CT_FLAG, 0, sizeof(unsigned long long), t->stream));
         PDM_CUDA(cudaMemsetAsync(t->d_counters + CT_ABORT, 0, sizeof(unsigned long long), t->stream));
         PitArgs a;
-        a.E = t->elev; a.pitmask = t->flat0; a.dX = t->dX; a.dY = t->dY; a.R = t->R; a.C = t->C; a.npits = npits;
+        memset(&a, 0, sizeof(a));
+        if (sh) {
+            a.lo = t->win.lo; a.hi = t->win.hi; a.row_off = t->win.row_off; a.Rg = t->win.Rg;
+            a.H = W; a.Hu = sh->Hu; a.Hd = sh->Hd;
+            a.E_up = sh->E_up; a.E_dn = sh->E_dn; a.P_up = sh->P_up; a.P_dn = sh->P_dn;
+            a.in_up = sh->in_up; a.in_dn = sh->in_dn; a.Hin = sh->Hin;
+            a.peer_row[0] = sh->peer_row[0]; a.peer_row[1] = sh->peer_row[1];
+            if (sh->Hin > 0) {
+                if (sh->in_up) PDM_CUDA(cudaMemsetAsync(sh->in_up, 0, (size_t)sh->Hin * t->C * 4, t->stream));
+                if (sh->in_dn) PDM_CUDA(cudaMemsetAsync(sh->in_dn, 0, (size_t)sh->Hin * t->C * 4, t->stream));
+            }
+        }
+        a.E = t->elev; a.pitmask = t->flat0; a.dX = sh ? sh->dXg : t->dX; a.dY = sh ? sh->dYg : t->dY; a.R = t->R; a.C = t->C; a.npits = npits;
         a.pit_cell = t->pit_cell; a.pit_beg = t->pit_beg; a.pit_end = t->pit_end; a.pit_dst = t->pit_dst; a.pit_w = t->pit_w;
         a.edge_cap = t->pit_edge_cap; a.scratch_i = t->pit_scratch_i; a.scratch_d = t->pit_scratch_d;
         a.flats = t->flats; a.link = t->link; a.mag = t->mag; a.prop = t->twi; a.indeg = t->label; a.ctr = t->d_counters;
         a.max_iter = (int)p->drain_pits_max_iter; a.max_dist = (int)p->drain_pits_max_dist;
         a.min_border = p->drain_pits_min_border; a.max_dist_xy = p->drain_pits_max_dist_xy; a.W = W;
-        k_pit_search<<<(unsigned)blocks, PIT_THREADS, smem, t->stream>>>(a);
+        kernel<<<(unsigned)blocks, PIT_THREADS, smem, t->stream>>>(a);
         PDM_LAUNCHED();
         rc = read_ctr(t);
         if (rc) return rc;
+        if (t->h_counters[CT_ABORT] >> 32) {
+            pdm_set_error("pit search on a row shard: %llu pit region(s) reach beyond the %lld / %lld rows of the neighbouring ranks this rank "
+                          "can see, %llu drain(s) lie farther than %lld rows across the boundary (shards need >= drain_pits_max_iter + 1 rows)",
+                          (t->h_counters[CT_ABORT] >> 32) & 0xffffULL, (long long)(sh ? sh->Hu : 0), (long long)(sh ? sh->Hd : 0),
+                          t->h_counters[CT_ABORT] >> 48, (long long)(sh ? sh->Hin : 0));
+            return PDM_ERR_ARG;
+        }
         if (t->h_counters[CT_ABORT]) {
             pdm_set_error("pit search: region border of %llu pit(s) exceeded %d cells", t->h_counters[CT_ABORT], PIT_CAP);
             return PDM_ERR_NOMEM;

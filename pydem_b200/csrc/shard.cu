@@ -21,6 +21,15 @@
 
 namespace {
 
+// pit edges that start on a neighbouring rank and end in my rows next to the boundary: add their counts to the
+// per-cell pit in-degree (t->label) before the in-degrees are built
+__global__ void __launch_bounds__(256)
+k_pit_in_apply(int32_t *__restrict__ pit_in, const int32_t *__restrict__ strip, int64_t n)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) { const int32_t v = strip[k]; if (v) pit_in[k] += v; }
+}
+
 __global__ void k_add_sent(const unsigned long long *ctr, long long *out) { *out += (long long)ctr[ts::TC_SENT]; }
 
 }  // namespace
@@ -118,10 +127,92 @@ int pdm_shard_links(pdm_tile *t, const pdm_uca_params *p_in)
     return pdm_graph_links_pits(t, &p);
 }
 
+// fences of the whole grid (host arrays of n = R_global - 1 doubles): pit drains of a row shard reach across
+// the shard boundary, their distances (_get_dX_mean / make_slice, dem_processing.py:1346-1349) need rows this rank does not own
+int pdm_tile_set_global_spacing(pdm_tile *t, const double *dX, const double *dY, int64_t n)
+{
+    if (!t || !dX || !dY || n != t->win.Rg - 1) { pdm_set_error("pdm_tile_set_global_spacing: need R_global - 1 = %lld fences (set the window first)", t ? (long long)(t->win.Rg - 1) : 0LL); return PDM_ERR_ARG; }
+    if (t->dXg) { cudaFree(t->dXg); cudaFree(t->dYg); t->dXg = t->dYg = nullptr; }
+    PDM_CUDA(cudaMalloc(&t->dXg, (size_t)n * 8));
+    PDM_CUDA(cudaMalloc(&t->dYg, (size_t)n * 8));
+    PDM_CUDA(cudaMemcpyAsync(t->dXg, dX, (size_t)n * 8, cudaMemcpyHostToDevice, t->stream));
+    PDM_CUDA(cudaMemcpyAsync(t->dYg, dY, (size_t)n * 8, cudaMemcpyHostToDevice, t->stream));
+    PDM_CUDA(cudaStreamSynchronize(t->stream));
+    return PDM_OK;
+}
+
+// a5 on a row shard (_mk_connectivity_pits, dem_processing.py:1269-1382), between pdm_shard_links and pdm_shard_indeg.
+// E_up / P_up: elevation and pit mask (pdm_tile field FLAT0 after pdm_shard_links) of the Hu rows above the owned rows,
+// i.e. the last Hu owned rows of the rank above, in order; E_dn / P_dn: the first Hd owned rows of the rank below (device
+// pointers; 0 rows and NULL at the ends of the grid).  A region may grow drain_pits_max_iter + 1 rows beyond a pit, so the
+// strips must be that deep (or the search fails loudly).  Pit edges that end on a neighbour are counted into in_up / in_dn
+// (int32 [Hin][C], the neighbour's rows next to the boundary, Hin >= drain_pits_max_dist): send them to the neighbours and
+// hand what arrives to pdm_shard_pit_in_apply.  The sweep then pushes along such an edge straight into the neighbour's
+// record, so this needs the multi-GPU work-list sweep (pdm_shard_p2p_connect_all).
+int pdm_shard_pits(pdm_tile *t, const pdm_uca_params *p_in, const void *E_up, const void *P_up, int64_t Hu,
+                   const void *E_dn, const void *P_dn, int64_t Hd, void *in_up, void *in_dn, int64_t Hin)
+{
+    if (!t || !p_in) { pdm_set_error("pdm_shard_pits: NULL argument"); return PDM_ERR_ARG; }
+    if (!t->shard_pits_wanted) { pdm_set_error("pdm_shard_pits: call pdm_shard_links with drain_pits set first"); return PDM_ERR_STATE; }
+    if (!pdm_shard_worklist_p2p(t)) {
+        pdm_set_error("drain_pits=True on a row shard needs the multi-GPU work-list sweep (pdm_shard_p2p_connect_all): a pit may drain into the neighbouring rank's cells");
+        return PDM_ERR_STATE;
+    }
+    if (!t->dXg) { pdm_set_error("pdm_shard_pits: pdm_tile_set_global_spacing first"); return PDM_ERR_STATE; }
+    const Win &w = t->win;
+    const bool up = w.lo > 0, dn = w.hi < t->R;
+    if ((up && (!E_up || !P_up || Hu < 1 || (Hin > 0 && !in_up))) || (dn && (!E_dn || !P_dn || Hd < 1 || (Hin > 0 && !in_dn))) || Hin < 0) {
+        pdm_set_error("pdm_shard_pits: strips of the neighbouring ranks are missing");
+        return PDM_ERR_ARG;
+    }
+    pdm_pit_shard sh;
+    memset(&sh, 0, sizeof(sh));
+    if (up) { sh.E_up = (const double *)E_up; sh.P_up = (const uint8_t *)P_up; sh.Hu = Hu; sh.in_up = (int32_t *)in_up; sh.peer_row[0] = t->p2p.hi[0] - w.lo; }
+    if (dn) { sh.E_dn = (const double *)E_dn; sh.P_dn = (const uint8_t *)P_dn; sh.Hd = Hd; sh.in_dn = (int32_t *)in_dn; sh.peer_row[1] = t->p2p.lo[1] - w.hi; }
+    sh.Hin = Hin; sh.dXg = t->dXg; sh.dYg = t->dYg;
+    const int64_t W = p_in->drain_pits_max_iter + 1;
+    if ((w.hi - w.lo + 2 * W) * w.C >= ((int64_t)1 << 31) || (up && t->p2p.hi[0] * w.C >= ((int64_t)1 << 30)) ||
+        (dn && (t->p2p.lo[1] + Hin) * w.C >= ((int64_t)1 << 30))) {
+        pdm_set_error("pdm_shard_pits: shard too large for the 32-bit extended cell index of the pit search");
+        return PDM_ERR_ARG;
+    }
+    PDM_CUDA(cudaMemsetAsync(t->label, 0, (size_t)t->N * sizeof(int32_t), t->stream));
+    if (Hin > 0 && up) PDM_CUDA(cudaMemsetAsync(in_up, 0, (size_t)Hin * w.C * 4, t->stream));
+    if (Hin > 0 && dn) PDM_CUDA(cudaMemsetAsync(in_dn, 0, (size_t)Hin * w.C * 4, t->stream));
+    int rc = pdm_launch_pits(t, p_in, &sh);
+    if (rc) return rc;
+    t->shard_pits_done = true;
+    return PDM_OK;
+}
+
+// from_up: what the rank above counted for my first Hin owned rows (its in_dn), from_dn: what the rank below counted
+// for my last Hin owned rows (its in_up)
+int pdm_shard_pit_in_apply(pdm_tile *t, const void *from_up, const void *from_dn, int64_t Hin)
+{
+    if (!t || !t->shard_pits_done) { pdm_set_error("pdm_shard_pit_in_apply: run pdm_shard_pits first"); return PDM_ERR_STATE; }
+    const Win &w = t->win;
+    if (Hin < 0 || Hin > w.hi - w.lo) { pdm_set_error("pdm_shard_pit_in_apply: Hin out of range"); return PDM_ERR_ARG; }
+    const int64_t n = Hin * w.C;
+    if (n == 0) return PDM_OK;
+    if (from_up && w.lo > 0) {
+        k_pit_in_apply<<<(unsigned)((n + 255) / 256), 256, 0, t->stream>>>(t->label + w.lo * w.C, (const int32_t *)from_up, n);
+        PDM_LAUNCHED();
+    }
+    if (from_dn && w.hi < t->R) {
+        k_pit_in_apply<<<(unsigned)((n + 255) / 256), 256, 0, t->stream>>>(t->label + (w.hi - Hin) * w.C, (const int32_t *)from_dn, n);
+        PDM_LAUNCHED();
+    }
+    return PDM_OK;
+}
+
 // inflow-border mask + fresh sweep state (link AND proportion halo rows must be in place)
 int pdm_shard_indeg(pdm_tile *t)
 {
     if (!t) return PDM_ERR_ARG;
+    if (t->shard_pits_wanted && !t->shard_pits_done) {
+        pdm_set_error("pdm_shard_indeg: drain_pits was requested in pdm_shard_links; run pdm_shard_pits (+ pdm_shard_pit_in_apply) first");
+        return PDM_ERR_STATE;
+    }
     if (pdm_shard_worklist_p2p(t)) return pdm_launch_indeg_todo(t);    // Cell records of the work-list sweep
     int rc = pdm_launch_border_todo(t);
     if (rc) return rc;
@@ -230,6 +321,8 @@ int pdm_shard_finalize(pdm_tile *t, const pdm_uca_params *p_in, pdm_uca_stats *s
         stats->n_undone = (int64_t)t->h_counters[CT_UNDONE];
         stats->n_edge_todo = (int64_t)t->h_counters[CT_EDGE_TODO];
         stats->min_area = t->min_area;
+        stats->n_pits = t->n_pits; stats->n_pit_edges = t->n_pit_edges;
+        stats->n_pits_undrained = t->n_pits ? (int64_t)t->h_counters[CT_PITS_UNDRAINED] : 0;
     }
     return PDM_OK;
 }

@@ -18,10 +18,16 @@
 //
 // For an acyclic graph this visits every cell exactly once and yields the reference's
 // sums up to fp64 re-association (the reference adds in (level, source index) order).
-// Cells on cycles never reach in-degree 0; they are counted (n_undone) and reported.  The
-// reference's restart heuristic for such circular references (dem_processing.py:951-964,
-// "should never occur") is not replayed: the filter elev[j] <= elev[i] only admits cycles of
-// equal-elevation cells, whose mutual flow has weight 0 and is filtered.
+// Circular references (dem_processing.py:951-964, "should never occur"): the reference restarts its
+// sweep from the highest undone cells up to circular_ref_maxcount times.  That path is unreachable:
+// an edge i -> j only survives the filter (1136-1137) if elev[j] <= elev[i] and its weight is > 1e-8,
+// so a cycle would have to consist of cells of equal elevation -- but a facet neighbour at the centre's
+// elevation always gets weight exactly 0 (s = 0 clamps the facet angle onto the other neighbour,
+// 1942-1991), and pit edges only go to strictly lower cells or to non-pit cells that drain strictly
+// downhill (1312-1320).  The graph is a DAG, one sweep finishes it, and the flag only matters through
+// the loop condition: circular_ref_maxcount <= 1 means "no sweep at all" (honoured in
+// pdm_launch_sweep_full, pinned against the reference in tests).  Should cells be left over after a
+// sweep anyway, pdm_tile_uca fails loudly instead of returning partial sums.
 //
 // Traffic per cell (sweep): one 32-byte sector for the cell's own record and one per receiver
 // (fp64 atomic on .area + int atomic on .indeg of the same sector); the kernel is bound by
@@ -225,8 +231,15 @@ int pdm_launch_sweep_full(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *s
 {
     (void)st;
     if (t->legacy_graph) {
-        int rc = pdm_launch_sweep_first(t);
-        if (rc) return rc;
+        // dem_processing.py:951-952: `while np.any(~done_) and count < self.circular_ref_maxcount ...` with count = 1:
+        // for circular_ref_maxcount <= 1 the reference never calls drain_area -- every cell keeps its own area, only
+        // the cells nobody drains into count as done.  One call (maxcount >= 2) drains a whole acyclic graph.
+        if (p->circular_ref_maxcount > 1) {
+            int rc = pdm_launch_sweep_first(t);
+            if (rc) return rc;
+        } else {
+            PDM_CUDA(cudaMemsetAsync(t->d_counters + CT_T_START, 0, 3 * sizeof(unsigned long long), t->stream));
+        }
         return pdm_launch_uca_finalize(t, p);
     }
     int rc = pdm_ts_reset_state(t);

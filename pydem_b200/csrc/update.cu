@@ -1,4 +1,4 @@
-// update.cu -- a8: edge-update mode of calc_uca and the circular-reference restart path.
+// update.cu -- a8: edge-update mode of calc_uca.
 //
 // Reference behaviour: calc_uca edge packing (dem_processing.py:719-744, 769-771) and
 // _calc_uca_chunk_update (778-862) with cyutils.drain_connections (cyutils.pyx:35-72) and
@@ -228,13 +228,16 @@ int pdm_launch_update(pdm_tile *t, const pdm_uca_params *p, const double *const 
     return PDM_OK;
 }
 
-// Circular references (cells that never reach in-degree 0).  The reference restarts its
-// level-synchronous sweep from the highest undone cells up to circular_ref_maxcount times
-// (dem_processing.py:951-964) -- "which should never occur" (dem_processing.py:149-151).
-// Not replayed yet: the partial sums of the first pass are returned and the count is reported.
+// Circular references: the reference's restart loop (dem_processing.py:951-964) is unreachable -- the drainage
+// graph is acyclic by construction (sweep.cu explains) -- so cells left over after a full sweep mean a broken
+// graph, not a case to replay: fail loudly.
 int pdm_restart_rounds(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *st)
 {
-    (void)t; (void)p;
+    (void)t;
     st->n_restarts = 0;
-    return PDM_OK;
+    if (p->circular_ref_maxcount <= 1) return PDM_OK;     // no sweep was asked for (the loop condition of 951-952)
+    pdm_set_error("pdm_tile_uca: %lld cells were not drained by a full sweep; the drainage graph of a DEM is acyclic "
+                  "(elev[j] <= elev[i] on every edge, zero weight between equal elevations), so this is an internal error",
+                  (long long)st->n_undone);
+    return PDM_ERR_STATE;
 }

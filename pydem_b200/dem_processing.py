@@ -419,7 +419,10 @@ class DEMProcessor(object):
                 if st.n_pits_undrained:
                     warnings.warn("Warning %d pits had no place to drain to in this chunk" % st.n_pits_undrained)
             if st.n_undone:
-                warnings.warn("%d cells are on circular references and were not drained" % st.n_undone)
+                # only reachable with circular_ref_maxcount <= 1 (the reference's sweep loop, dem_processing.py:951-952,
+                # then never runs); otherwise the library has raised
+                warnings.warn("circular_ref_maxcount=%d: the accumulation sweep did not run, %d cells keep their own area"
+                              % (int(self.circular_ref_maxcount), st.n_undone))
             outer = self._chain == 1
         finally:
             self._end()

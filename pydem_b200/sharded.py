@@ -165,6 +165,8 @@ class ShardEngine(object):
         self.flag = torch.zeros(1, dtype=torch.int64, device=dev)
         self.views = {}
         self.p2p = False
+        self._dXY = (np.ascontiguousarray(dX, "float64"), np.ascontiguousarray(dY, "float64"))   # fences of the whole grid
+        self._pit = None
 
     # ---- one sweep across GPUs (pdm_shard_p2p_*)
     def p2p_export(self):
@@ -189,6 +191,59 @@ class ShardEngine(object):
         buf = ct.create_string_buffer(joined, len(joined))
         self.T._lib.check(self.tile.L.pdm_shard_p2p_connect_all(self.tile.h, buf, int(world), int(rank)))
         self.p2p = True
+
+    # ---- drain_pits on a row shard (pdm_shard_pits): strips of the neighbours' elevation / pit mask in, counts of the
+    #      pit edges that end on a neighbour out
+    def pit_setup(self):
+        import ctypes as ct
+        p = self.tile._shard_params
+        H = int(p.drain_pits_max_iter) + 1
+        Hin = min(H, int(p.drain_pits_max_dist)) if int(p.drain_pits_max_dist) > 0 else H
+        if self._pit is not None and self._pit["H"] == H and self._pit["Hin"] == Hin:
+            return self._pit
+        s, torch = self.spec, self.torch
+        if s.r1 - s.r0 < H:
+            raise ValueError("drain_pits on row shards needs at least drain_pits_max_iter + 1 = %d rows per rank (have %d)"
+                             % (H, s.r1 - s.r0))
+        if self._pit is None:
+            dX, dY = self._dXY
+            self.T._lib.check(self.tile.L.pdm_tile_set_global_spacing(self.tile.h, self.T._lib.ptr(dX), self.T._lib.ptr(dY),
+                                                                      ct.c_int64(dX.size)))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        mk = lambda rows, dt, ok: torch.zeros((rows, s.C), dtype=dt, device=dev) if ok else None
+        b = dict(H=H, Hin=Hin)
+        for side, ok in (("up", s.halo_top), ("dn", s.halo_bot)):
+            b["E_" + side] = mk(H, torch.float64, ok)
+            b["P_" + side] = mk(H, torch.uint8, ok)
+            b["in_" + side] = mk(Hin, torch.int32, ok)
+            b["from_" + side] = mk(Hin, torch.int32, ok)
+        self._pit = b
+        return b
+
+    def pit_bufs(self, what):
+        """exchange buffers: 'E' / 'P' = my owned rows next to each boundary -> the neighbours' strips; 'in' = edge counts"""
+        s, b = self.spec, self._pit
+        if what == "in":
+            return dict(send_up=b["in_up"], recv_up=b["from_up"], send_down=b["in_dn"], recv_down=b["from_dn"])
+        v = self.rows(self.T.F_ELEV if what == "E" else self.T.F_FLAT0)
+        H = b["H"]
+        return dict(send_up=v[s.lo:s.lo + H] if s.halo_top else None, recv_up=b[what + "_up"],
+                    send_down=v[s.hi - H:s.hi] if s.halo_bot else None, recv_down=b[what + "_dn"])
+
+    def shard_pits(self):
+        import ctypes as ct
+        b = self._pit
+        dp = lambda x: ct.c_void_p(x.data_ptr()) if x is not None else None
+        Hu = b["H"] if b["E_up"] is not None else 0
+        Hd = b["H"] if b["E_dn"] is not None else 0
+        self.T._lib.check(self.tile.L.pdm_shard_pits(self.tile.h, ct.byref(self.tile._shard_params), dp(b["E_up"]), dp(b["P_up"]), Hu,
+                                                     dp(b["E_dn"]), dp(b["P_dn"]), Hd, dp(b["in_up"]), dp(b["in_dn"]), b["Hin"]))
+
+    def pit_in_apply(self):
+        import ctypes as ct
+        b = self._pit
+        dp = lambda x: ct.c_void_p(x.data_ptr()) if x is not None else None
+        self.T._lib.check(self.tile.L.pdm_shard_pit_in_apply(self.tile.h, dp(b["from_up"]), dp(b["from_dn"]), b["Hin"]))
 
     def rows(self, field):
         if field not in self.views:
@@ -291,6 +346,17 @@ def run_hot_path(engines, group, twi=True, profile=False, **uca_flags):
     # a3/a4: links, link halo, in-degree + inflow-border mask
     for e in engines:
         e.tile.shard_links(**uca_flags)
+    if uca_flags.get("drain_pits") and group.world > 1:
+        # a5 across shards: a pit's search region / drains may lie on the neighbouring rank
+        for e in engines:
+            e.pit_setup()
+        group.exchange([e.pit_bufs("E") for e in engines])
+        group.exchange([e.pit_bufs("P") for e in engines])
+        for e in engines:
+            e.shard_pits()
+        group.exchange([e.pit_bufs("in") for e in engines])
+        for e in engines:
+            e.pit_in_apply()
     group.exchange([e.halo_bufs(T.F_LINK) for e in engines])
     for e in engines:
         e.tile.shard_stage("indeg")
@@ -395,6 +461,7 @@ class ShardedDEM(object):
         if w > 1 and os.environ.get("PYDEM_B200_SHARD_P2P", "1") != "0":
             self.group.connect_p2p(self.engine)
         self.profile = profile
+        self.uca_flags = {}     # e.g. drain_pits=1 (needs the p2p connection)
         self.cells = (s.r1 - s.r0) * cols
         if noise:
             view = self.engine.rows(T.F_ELEV)                     # zero-copy torch view of the tile's elevation field
@@ -424,7 +491,7 @@ class ShardedDEM(object):
         self.engine.tile.close()
 
     def step(self):
-        return run_hot_path([self.engine], self.group, profile=self.profile)[0]
+        return run_hot_path([self.engine], self.group, profile=self.profile, **self.uca_flags)[0]
 
     def e2e(self, steps):
         """Same metric with the rank's rows uploaded from pinned host memory and its results
@@ -439,7 +506,7 @@ class ShardedDEM(object):
 
         def one():
             self.engine.tile.upload(T.F_ELEV, Eh)
-            run_hot_path([self.engine], self.group)
+            run_hot_path([self.engine], self.group, **self.uca_flags)
             for f, o in outs.items():
                 self.engine.tile.download(f, o)
         one()

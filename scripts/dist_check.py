@@ -15,6 +15,7 @@ from pydem_b200 import _lib, sharded, synth, tile as T, DEMProcessor
 _lib.init(local)
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 C = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+PITS = len(sys.argv) > 3 and sys.argv[3] == "pits"     # drain_pits=True (the reference default): pits search and drain across the shard boundaries
 g = sharded.DistGroup()
 E = synth.value_noise_dem(0, R, C, seed=7)
 E[R // 2 - 3:R // 2 + 3, 100:400] = E[R // 2 - 3:R // 2 + 3, 100:400].min()     # a lake on a shard boundary
@@ -25,8 +26,8 @@ if g.world > 1 and os.environ.get("PYDEM_B200_SHARD_P2P", "1") != "0":
     g.connect_p2p(eng)      # one sweep across the GPUs (peer memory) instead of exchange rounds
 loc = np.full((spec.Rl, C), np.nan); loc[spec.lo:spec.hi] = E[spec.r0:spec.r1]
 eng.tile.upload(T.F_ELEV, loc)
-st = sharded.run_hot_path([eng], g)[0]
-dp = DEMProcessor(elev=E, dX=30.0, dY=30.0, fill_flats=False, drain_pits_path=False, drain_pits=False)
+st = sharded.run_hot_path([eng], g, drain_pits=1)[0] if PITS else sharded.run_hot_path([eng], g)[0]
+dp = DEMProcessor(elev=E, dX=30.0, dY=30.0, fill_flats=False, drain_pits_path=False, drain_pits=PITS)
 dp.calc_twi()
 ok = True
 for name, f, exact in (("mag", T.F_MAG, True), ("direction", T.F_DIR, True), ("flats", T.F_FLATS, True),
@@ -43,6 +44,6 @@ for name, f, exact in (("mag", T.F_MAG, True), ("direction", T.F_DIR, True), ("f
 flag = torch.tensor([0 if ok else 1], device="cuda")
 dist.all_reduce(flag)
 if g.rank == 0:
-    print("dist_check", "OK" if flag.item() == 0 else "FAILED", "world", g.world, "rows", R, "cols", C, st, flush=True)
+    print("dist_check", "OK" if flag.item() == 0 else "FAILED", "world", g.world, "rows", R, "cols", C, "drain_pits", PITS, st, flush=True)
 dist.destroy_process_group()
 sys.exit(0 if flag.item() == 0 else 1)

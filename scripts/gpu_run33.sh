@@ -1,0 +1,13 @@
+cd $GRAFT_REPO_ROOT
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 scripts/dist_check.py 2048 1024 pits 2>&1 | grep -v "^\*\*\*\|OMP_NUM\|^$" | tail -8 | cut -c1-700
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29542 scripts/dist_check.py 4096 2048 pits 2>&1 | grep -v "^\*\*\*\|OMP_NUM\|^$" | tail -8 | cut -c1-700
+PDM_BENCH_VERBOSE=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 10 --warmup 3 --no-config4 > gpurun_out/r2_bench_n2_pits.json 2> gpurun_out/r2_bench_n2_pits.err; python - <<'PY'
+import json
+try:
+    d = json.loads([l for l in open("gpurun_out/r2_bench_n2_pits.json") if l.startswith("{")][0])
+    print("value", d["value"], "ms", d["ms_per_step"], "parity", d["parity"], "stages", d["stages"])
+    print(d["config"]["workload"])
+except Exception as e:
+    print("ERR", e)
+PY
+grep -v "^\*\*\*\|OMP_NUM\|^$" gpurun_out/r2_bench_n2_pits.err | tail -12 | cut -c1-300

@@ -50,6 +50,10 @@ def cases():
     out["frac96_xy"] = (synth.fractal_dem(96, 9), dict(dX=30.0, dY=30.0, drain_pits_max_dist_XY=70.0))
     out["odd_cols"] = (synth.fractal_dem(0, 10, shape=(67, 131)), dict(dX=10.0, dY=12.5))
     out["tiny3"] = (np.array([[3.0, 2.0, 3.0], [2.0, 1.0, 2.0], [3.0, 2.5, 3.0]]), {})
+    # circular_ref_maxcount only acts through the loop condition of dem_processing.py:951-952 (the drainage graph
+    # is acyclic): <= 1 switches the accumulation sweep off, 2 allows exactly the one call that is ever needed
+    out["frac96_maxcount1"] = (synth.fractal_dem(96, 13), dict(circular_ref_maxcount=1))
+    out["frac96_maxcount2"] = (synth.fractal_dem(96, 13), dict(circular_ref_maxcount=2, drain_pits=False))
     out["frac512_limits"] = (synth.fractal_dem(512, 11), dict(dX=30.0, dY=30.0, apply_uca_limit_edges=True,
                                                             apply_twi_limits=True, apply_twi_limits_on_uca=True))
     return out

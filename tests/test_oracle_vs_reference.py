@@ -11,7 +11,8 @@ from oracle.oracle import OracleDEMProcessor
 pytestmark = pytest.mark.skipif(not rh.reference_available(), reason="reference tree not present")
 
 NAMES = ["cone256", "frac128", "frac128_nopits", "frac256_dx30", "frac_rect_vardx", "nan_holes", "quantized",
-         "lakes", "lakes_minborder", "frac96_maxdist4", "frac96_xy", "odd_cols", "tiny3"]
+         "lakes", "lakes_minborder", "frac96_maxdist4", "frac96_xy", "odd_cols", "tiny3", "frac96_maxcount1",
+         "frac96_maxcount2"]
 
 
 @pytest.mark.parametrize("name", NAMES)
