@@ -272,6 +272,25 @@ int pdm_shard_p2p_connect_all(pdm_tile *t, const void *blobs, int world, int ran
 int pdm_shard_p2p_disconnect(pdm_tile *t);   /* unmap the peers' memory: all ranks, then a barrier, before any tile is destroyed */
 int pdm_shard_finalize(pdm_tile *t, const pdm_uca_params *p, pdm_uca_stats *stats);
 
+/* ---- the row-sharded path without any host-side framework (pdm_comm_init) ---------
+ * One process per GPU.  NCCL (loaded at run time) moves the halo rows, CUDA-IPC peer memory carries the
+ * accumulation sweep.  Call order on every rank:
+ *   pdm_init(device); rank 0: pdm_comm_unique_id(id) and hand the 128 bytes to every rank;
+ *   pdm_comm_init(rank, nranks, id); pdm_tile_create / pdm_tile_set_spacing / pdm_tile_set_window
+ *   (+ pdm_tile_set_global_spacing for drain_pits); pdm_shard_connect(t);
+ *   per pass: upload ELEV of the owned rows, pdm_shard_run(t, ...), download the owned rows of the results;
+ *   pdm_shard_disconnect(t); pdm_tile_destroy(t); pdm_comm_finalize().
+ * pdm_shard_run is the collective equivalent of DEMProcessor.calc_slopes_directions + calc_uca + calc_twi on the
+ * whole grid (pydem/dem_processing.py:587-776, 1647-1677): the result equals the single-tile result. */
+#define PDM_COMM_ID_BYTES 128
+int pdm_comm_unique_id(void *id_out);
+int pdm_comm_init(int rank, int nranks, const void *id);
+int pdm_comm_finalize(void);
+int pdm_comm_barrier(pdm_tile *t);
+int pdm_shard_connect(pdm_tile *t);
+int pdm_shard_disconnect(pdm_tile *t);
+int pdm_shard_run(pdm_tile *t, const pdm_uca_params *p, const pdm_twi_params *twi, pdm_uca_stats *stats, int *label_rounds);
+
 /* ---- one-shot host-buffer calls ---------------------------------------------------------- */
 /* DEMProcessor.calc_slopes_directions with the conditioning flags off. */
 int pdm_slopes_directions(const double *elev, int64_t R, int64_t C,

@@ -67,6 +67,7 @@ EXPORTS = [
     "pdm_tile_twi", "pdm_tile_set_keep_graph", "pdm_tile_set_window", "pdm_shard_slopes", "pdm_shard_ccl", "pdm_shard_label_pack",
     "pdm_shard_label_unpack", "pdm_shard_flats_extend", "pdm_shard_links", "pdm_tile_set_global_spacing", "pdm_shard_pits", "pdm_shard_pit_in_apply", "pdm_shard_indeg", "pdm_shard_sweep",
     "pdm_shard_sweep_sent", "pdm_shard_finalize",
+    "pdm_comm_unique_id", "pdm_comm_init", "pdm_comm_finalize", "pdm_comm_barrier", "pdm_shard_connect", "pdm_shard_disconnect", "pdm_shard_run",
     "pdm_slopes_directions", "pdm_uca", "pdm_uca_update", "pdm_twi",
     "pdm_default_cond_params", "pdm_tile_fill_pit_artifacts", "pdm_tile_fill_flats", "pdm_tile_pit_drain_paths",
 ]
@@ -136,6 +137,12 @@ def load():
     L.pdm_shard_p2p_disconnect.argtypes = [_vp]
     L.pdm_shard_sweep_sent.argtypes = [_vp, _vp]
     L.pdm_shard_finalize.argtypes = [_vp, ct.POINTER(UcaParams), ct.POINTER(UcaStats)]
+    L.pdm_comm_unique_id.argtypes = [_vp]
+    L.pdm_comm_init.argtypes = [ct.c_int, ct.c_int, _vp]
+    L.pdm_comm_barrier.argtypes = [_vp]
+    L.pdm_shard_connect.argtypes = [_vp]
+    L.pdm_shard_disconnect.argtypes = [_vp]
+    L.pdm_shard_run.argtypes = [_vp, ct.POINTER(UcaParams), ct.POINTER(TwiParams), ct.POINTER(UcaStats), ct.POINTER(ct.c_int)]
     L.pdm_slopes_directions.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
     L.pdm_uca.argtypes = [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
                           ct.POINTER(UcaParams), _vp, _vp, _vp, ct.POINTER(UcaStats)]

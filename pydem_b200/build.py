@@ -14,7 +14,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libpydem_b200.so")
-SOURCES = ["slopes.cu", "flats.cu", "graph.cu", "pits.cu", "sweep.cu", "tsweep.cu", "update.cu", "shard.cu", "condition.cu", "api.cu"]
+SOURCES = ["slopes.cu", "flats.cu", "graph.cu", "pits.cu", "sweep.cu", "tsweep.cu", "update.cu", "shard.cu", "comm.cu", "condition.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false",
               "-std=c++17", "-Xcompiler", "-fPIC", "-cudart", "static"]
 

@@ -177,6 +177,7 @@ int pdm_tile_destroy(pdm_tile *t)
                     t->pit_dst, t->pit_w, t->pit_scratch_i, t->pit_scratch_d, t->edge_buf_d, t->edge_buf_b,
                     t->glabel, t->glelev, t->twi10, t->rdX, t->rdY, t->rdg, t->ts_ctl, t->ts_seen, t->dXg, t->dYg};
     pdm_ts_p2p_close(t);
+    pdm_comm_scratch_free(t);
     for (void *p : ptrs) if (p) cudaFree(p);
     if (t->h_counters) cudaFreeHost(t->h_counters);
     if (t->ts_hctr) cudaFreeHost(t->ts_hctr);

@@ -120,6 +120,7 @@ struct pdm_tile {
         int nty[2];
         unsigned cap_mask[2];
     } p2p;
+    void *comm_scratch;         // device buffers of pdm_shard_run (comm.cu)
     bool legacy_graph;          // the graph on the tile was built for the legacy work-list sweep
     bool shard_pits_wanted, shard_pits_done;   // row shard with drain_pits: pdm_shard_pits must run between pdm_shard_links and pdm_shard_indeg
 };
@@ -191,6 +192,7 @@ void pdm_ts_p2p_close(pdm_tile *t);
 int pdm_launch_border_todo(pdm_tile *t);
 int pdm_launch_indeg_todo(pdm_tile *t);
 bool pdm_sweep_legacy();
+void pdm_comm_scratch_free(pdm_tile *t);
 bool pdm_shard_worklist_p2p(const pdm_tile *t);
 int pdm_launch_sweep_p2p(pdm_tile *t);
 int pdm_launch_sweep_first(pdm_tile *t);

@@ -58,8 +58,9 @@ def _ifd(buf, bo, off):
     return tags
 
 
-def read_geotiff(fn):
-    """-> dict(elev, transform, bounds, is_projected, ellipsoid)"""
+def read_geotiff(fn, projected=None):
+    """-> dict(elev, transform, bounds, is_projected, ellipsoid).  ``projected``: what to assume when a
+    georeferenced file carries no GTModelTypeGeoKey (None: raise)."""
     buf = open(fn, "rb").read()
     if buf[:2] == b"II":
         bo = "<"
@@ -109,9 +110,29 @@ def read_geotiff(fn):
         transform = Affine((1.0, 0.0, 0.0, 0.0, -1.0, 0.0))
     keys = t.get(34735, ())
     geokeys = {keys[i]: keys[i + 3] for i in range(4, len(keys) - 3, 4) if keys[i + 1] == 0}
-    model = geokeys.get(1024, 1 if 33550 not in t else 2)
-    gcs = geokeys.get(2048, 4326)
-    ellipsoid = {4326: "WGS-84", 4269: "GRS-80", 4258: "GRS-80", 4277: "Airy (1830)"}.get(gcs, "WGS-84")
+    # The reference asks rasterio for crs.is_projected and for the spheroid named in the WKT and fails when the file has no
+    # CRS (utils.py:132-151).  Here the same two facts come from the geokeys; anything that cannot be determined
+    # raises instead of silently producing geodesic spacings for metre coordinates (or the wrong ellipsoid).
+    georef = 33550 in t or 34264 in t
+    model = geokeys.get(1024)
+    if model is None and georef and projected is not None:
+        model = 1 if projected else 2
+        geokeys.setdefault(2048, 4326)
+    if model is None:
+        if georef:
+            raise ValueError("%s: georeferenced TIFF without a GTModelTypeGeoKey: cannot tell projected from geographic "
+                             "coordinates (pass projected=True/False)" % fn)
+        model = 1                                   # no georeferencing at all: pixel coordinates (unit spacing)
+    if model not in (1, 2):
+        raise ValueError("%s: GTModelTypeGeoKey %d (geocentric / user defined) is not supported" % (fn, model))
+    ellipsoid = "WGS-84"
+    if model == 2:
+        known = {4326: "WGS-84", 4269: "GRS-80", 4258: "GRS-80", 4277: "Airy (1830)"}
+        gcs = geokeys.get(2048)
+        if gcs not in known:
+            raise ValueError("%s: geographic CRS code %r: ellipsoid unknown (supported: EPSG %s)"
+                             % (fn, gcs, ", ".join(str(k) for k in sorted(known))))
+        ellipsoid = known[gcs]
     left, top = transform.c, transform.f
     bounds = (left, top + H * transform.e, left + W * transform.a, top)          # left, bottom, right, top
     return dict(elev=data.astype(data.dtype.newbyteorder("=")), transform=transform, bounds=bounds,

@@ -144,7 +144,10 @@ def test_big_endian_multi_strip_tiff(tmp_path):
     body += struct.pack(">16d", *M) + b"".join(strips)
     fn = str(tmp_path / "be.tif")
     open(fn, "wb").write(body)
-    r = rio.read_geotiff(fn)
+    with pytest.raises(ValueError, match="GTModelTypeGeoKey"):
+        rio.read_geotiff(fn)        # georeferenced, but nothing says whether the coordinates are metres or degrees
+    r = rio.read_geotiff(fn, projected=True)
+    assert r["is_projected"]
     np.testing.assert_array_equal(r["elev"], a.astype("f4"))
     assert tuple(r["transform"]) == (2.0, 0.0, 100.0, 0.0, -3.0, 50.0)
     assert r["bounds"] == (100.0, 50.0 - 3.0 * H, 100.0 + 2.0 * W, 50.0)
