@@ -183,6 +183,9 @@ int pdm_selftest_division(unsigned long long seed, long long n_pairs, unsigned l
  * (657-680) + the stamping of flats (611-613).  In: ELEV.  Out: MAG, DIR, FLATS. */
 int pdm_tile_slopes_directions(pdm_tile *t);
 /* DEMProcessor.find_flats (305-306): FLATS = (MAG == -1). */
+/* pdm_tile_upload(ELEV) + pdm_tile_slopes_directions in one call: the stencil of a row chunk runs while the next
+ * chunk is still on its way over PCIe (same results) */
+int pdm_tile_upload_slopes_directions(pdm_tile *t, const void *host_elev);
 int pdm_tile_find_flats(pdm_tile *t);
 /* a3..a7: _calc_uca_chunk (864-987) incl. _calc_uca_section_proportion (1021),
  * _mk_adjacency_matrix (1072), _mk_connectivity_pits (1269) and cyutils.drain_area.

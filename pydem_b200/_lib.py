@@ -63,7 +63,7 @@ EXPORTS = [
     "pdm_abi_version", "pdm_last_error", "pdm_init", "pdm_device_count", "pdm_default_uca_params",
     "pdm_default_twi_params", "pdm_launch_count", "pdm_shard_p2p_export", "pdm_shard_p2p_connect", "pdm_shard_p2p_connect_all", "pdm_shard_p2p_disconnect", "pdm_set_sweep_mode", "pdm_get_sweep_mode", "pdm_host_alloc", "pdm_host_free", "pdm_tile_create", "pdm_tile_destroy", "pdm_tile_set_spacing",
     "pdm_tile_upload", "pdm_tile_download", "pdm_tile_download_async", "pdm_tile_device_ptr", "pdm_tile_mark_resident", "pdm_tile_set_stencil_parity", "pdm_tile_sync", "pdm_selftest_division",
-    "pdm_tile_slopes_directions", "pdm_tile_find_flats", "pdm_tile_uca", "pdm_tile_pit_updates", "pdm_tile_uca_update",
+    "pdm_tile_slopes_directions", "pdm_tile_upload_slopes_directions", "pdm_tile_find_flats", "pdm_tile_uca", "pdm_tile_pit_updates", "pdm_tile_uca_update",
     "pdm_tile_twi", "pdm_tile_set_keep_graph", "pdm_tile_set_window", "pdm_shard_slopes", "pdm_shard_ccl", "pdm_shard_label_pack",
     "pdm_shard_label_unpack", "pdm_shard_flats_extend", "pdm_shard_links", "pdm_tile_set_global_spacing", "pdm_shard_pits", "pdm_shard_pit_in_apply", "pdm_shard_indeg", "pdm_shard_sweep",
     "pdm_shard_sweep_sent", "pdm_shard_finalize",
@@ -111,6 +111,7 @@ def load():
     L.pdm_tile_sync.argtypes = [_vp]
     L.pdm_selftest_division.argtypes = [ct.c_ulonglong, ct.c_longlong, ct.POINTER(ct.c_ulonglong)]
     L.pdm_tile_slopes_directions.argtypes = [_vp]
+    L.pdm_tile_upload_slopes_directions.argtypes = [_vp, _vp]
     L.pdm_tile_find_flats.argtypes = [_vp]
     L.pdm_tile_uca.argtypes = [_vp, ct.POINTER(UcaParams), ct.POINTER(UcaStats)]
     L.pdm_tile_pit_updates.argtypes = [_vp, _i64, _vp, _vp, _vp, ct.POINTER(_i64)]

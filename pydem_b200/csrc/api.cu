@@ -184,6 +184,7 @@ int pdm_tile_destroy(pdm_tile *t)
     for (int k = 0; k < 4; k++) if (t->ev[k]) cudaEventDestroy(t->ev[k]);
     if (t->copy_stream) { cudaStreamSynchronize(t->copy_stream); cudaStreamDestroy(t->copy_stream); }
     if (t->copy_ev) cudaEventDestroy(t->copy_ev);
+    for (int k = 0; k < 16; k++) if (t->up_ev[k]) cudaEventDestroy(t->up_ev[k]);
     delete t;
     return PDM_OK;
 }
@@ -327,6 +328,43 @@ int pdm_tile_slopes_directions(pdm_tile *t)
     rc = pdm_launch_flats(t);
     if (rc) return rc;
     t->have_slopes = true; t->have_flats = true; t->have_graph = false;
+    return PDM_OK;
+}
+
+// ELEV from the host and calc_slopes_directions in one call: the elevation goes up in row chunks on the copy stream
+// and the stencil of a chunk starts as soon as its rows (and the first row of the next chunk) have arrived, so the
+// stencil hides behind the host -> device copy (the copy is the longer of the two: ~55 GB/s PCIe vs ~0.2 TB/s stencil).
+// Same results as pdm_tile_upload + pdm_tile_slopes_directions.
+int pdm_tile_upload_slopes_directions(pdm_tile *t, const void *host_elev)
+{
+    if (!t || !host_elev) { pdm_set_error("pdm_tile_upload_slopes_directions: NULL argument"); return PDM_ERR_ARG; }
+    if (!t->have_spacing) { pdm_set_error("pdm_tile_upload_slopes_directions: set the spacing first"); return PDM_ERR_STATE; }
+    if (!standalone(t)) { pdm_set_error("pdm_tile_upload_slopes_directions: tile is a row shard; use the pdm_shard_* stages"); return PDM_ERR_STATE; }
+    const int64_t R = t->R, C = t->C;
+    int K = 8;
+    if (R < 64 * K) K = (int)(R / 64 > 0 ? R / 64 : 1);
+    const char *host = reinterpret_cast<const char *>(host_elev);
+    // the copy stream starts behind whatever still reads the old ELEV on the tile's stream
+    PDM_CUDA(cudaEventRecord(t->copy_ev, t->stream));
+    PDM_CUDA(cudaStreamWaitEvent(t->copy_stream, t->copy_ev, 0));
+    int64_t edge[17];
+    for (int k = 0; k <= K; k++) edge[k] = R * k / K;
+    for (int k = 0; k < K; k++) {
+        if (!t->up_ev[k]) PDM_CUDA(cudaEventCreateWithFlags(&t->up_ev[k], cudaEventDisableTiming));
+        PDM_CUDA(cudaMemcpyAsync(t->elev + edge[k] * C, host + (size_t)edge[k] * C * 8, (size_t)(edge[k + 1] - edge[k]) * C * 8,
+                                 cudaMemcpyHostToDevice, t->copy_stream));
+        PDM_CUDA(cudaEventRecord(t->up_ev[k], t->copy_stream));
+    }
+    t->have_elev = true; t->have_graph = false;
+    // chunk k computes rows [edge[k] - (k > 0), edge[k + 1] - (k < K - 1)): its last row needs the row below it
+    for (int k = 0; k < K; k++) {
+        PDM_CUDA(cudaStreamWaitEvent(t->stream, t->up_ev[k], 0));
+        const int64_t a = k > 0 ? edge[k] - 1 : 0, b = k < K - 1 ? edge[k + 1] - 1 : R;
+        if (b > a) { int rc = pdm_launch_slopes_rows(t, a, b); if (rc) return rc; }
+    }
+    int rc = pdm_launch_flats(t);
+    if (rc) return rc;
+    t->have_slopes = true; t->have_flats = true;
     return PDM_OK;
 }
 

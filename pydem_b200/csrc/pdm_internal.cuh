@@ -100,6 +100,7 @@ struct pdm_tile {
     cudaEvent_t ev[4];
     cudaStream_t copy_stream;   // device->host copies that overlap the next stage (pdm_tile_download_async)
     cudaEvent_t copy_ev;
+    cudaEvent_t up_ev[16];      // chunked upload of ELEV overlapping the stencil (pdm_tile_upload_slopes_directions)
     // tile sweep (tsweep.cu): ticket queue, per-tile state words, counters (+ pinned mirror), the
     // "already seen" bytes of the two halo rows of a shard
     void *ts_ctl;               // one allocation: [counters | tile flags | queue slots] (shared with peer GPUs through CUDA IPC)
@@ -159,6 +160,7 @@ extern unsigned long long g_pdm_launches;
 // kernels' launchers (each returns a pdm_status)
 int pdm_launch_geometry(pdm_tile *t);
 int pdm_launch_slopes(pdm_tile *t);
+int pdm_launch_slopes_rows(pdm_tile *t, int64_t row_lo, int64_t row_hi);
 int pdm_launch_flats(pdm_tile *t);
 int pdm_launch_find_flats(pdm_tile *t);
 int pdm_launch_ccl(pdm_tile *t);   // union-find labels of the mask in flat0 (label[] must hold own indices)

@@ -528,10 +528,16 @@ int pdm_launch_geometry(pdm_tile *t)
     return PDM_OK;
 }
 
-int pdm_launch_slopes(pdm_tile *t)
+int pdm_launch_slopes(pdm_tile *t) { return pdm_launch_slopes_rows(t, t->win.lo, t->win.hi); }
+
+// the stencil on the owned rows [row_lo, row_hi) only (rows row_lo - 1 and row_hi of ELEV must be in place): lets
+// the upload of a tile overlap its stencil, chunk by chunk (pdm_tile_upload_slopes_directions)
+int pdm_launch_slopes_rows(pdm_tile *t, int64_t row_lo, int64_t row_hi)
 {
     Geom g{t->dX, t->dY, t->dg, t->thA, t->thB, t->rdX, t->rdY, t->rdg};
-    const Win &w = t->win;
+    Win w = t->win;
+    if (row_lo < w.lo || row_hi > w.hi || row_lo >= row_hi) { pdm_set_error("pdm_launch_slopes_rows: bad row range"); return PDM_ERR_ARG; }
+    w.lo = row_lo; w.hi = row_hi;
     dim3 block(32, 8);
     dim3 grid((unsigned)((w.C + 31) / 32), (unsigned)((w.hi - w.lo + 7) / 8));
     // PYDEM_B200_STENCIL=parity runs the literal 8 x (3 div + atan2) formulation everywhere (tests

@@ -335,8 +335,19 @@ class DEMProcessor(object):
             L = self._lib()
             t = self._get_tile()
             self._spacing()
-            self._up(_lib.F_ELEV, "elev")
-            _lib.check(L.pdm_tile_slopes_directions(t))
+            if ("elev" in self._ondev or (self._chain and _lib.F_ELEV in self._resident)
+                    or os.environ.get("PYDEM_B200_CHUNKED_UPLOAD", "1") == "0"):
+                self._up(_lib.F_ELEV, "elev")
+                _lib.check(L.pdm_tile_slopes_directions(t))
+            else:
+                # elevation still on the host: upload it in row chunks and run the stencil of a chunk while the next one
+                # is on its way (same results as upload + stencil)
+                a = np.ascontiguousarray(np.asarray(self._host["elev"]), dtype=np.float64)
+                if a.shape != self._tile_shape:
+                    raise ValueError("elev has shape %s, expected %s" % (a.shape, self._tile_shape))
+                self._upload_keepalive = a
+                _lib.check(L.pdm_tile_upload_slopes_directions(t, _lib.ptr(a)))
+                self._resident.add(_lib.F_ELEV)
             self._resident.update((_lib.F_MAG, _lib.F_DIR, _lib.F_FLATS))
             self._produced("mag", "direction", "flats")
             outer = self._chain == 1

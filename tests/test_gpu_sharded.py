@@ -74,3 +74,26 @@ def test_sharded_2048_many_rounds(cuda_lib):
     E = helpers.synth.value_noise_dem(0, 2048, 1024, seed=3)
     out = check(E, 8, dX=30.0, dY=30.0)
     assert out["stats"][0]["sweep_rounds"] >= 2
+
+
+def _n_gpus(cuda_lib):
+    import ctypes as ct
+    n = ct.c_int(0)
+    cuda_lib.check(cuda_lib.load().pdm_device_count(ct.byref(n)))
+    return n.value
+
+
+@pytest.mark.parametrize("pits", [False, True])
+def test_c_abi_sharded_pass_on_two_gpus(cuda_lib, pits):
+    """Two processes, one per GPU, drive the sharded pass through the C ABI alone (pdm_comm_* over NCCL for the
+    halo rows, one work-list sweep across the GPUs over CUDA-IPC peer memory; with pits: pit regions and drains
+    across the shard boundary) and compare their rows with the single-tile result -- scripts/c_abi_shard_check.py.
+    Needs a box with >= 2 GPUs; the driver's N > 1 bench runs check the same path (bench.py, "parity")."""
+    if _n_gpus(cuda_lib) < 2:
+        pytest.skip("needs 2 GPUs")
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "scripts", "c_abi_shard_check.py"), "2", "1024", "768"] + (["pits"] if pits else [])
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=400)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "c_abi_shard_check OK" in r.stdout and "torch_loaded False" in r.stdout
