@@ -471,6 +471,11 @@ int pdm_tile_uca(pdm_tile *t, const pdm_uca_params *p_in, pdm_uca_stats *stats)
                 st.ms_sweep_kernel, st.ms_sweep_scan, h[CT_X_SCAN_CELLS], h[CT_X_CHAIN_CALLS], h[CT_X_CHAIN_CELLS],
                 h[CT_X_CHAIN_CELLS] ? (double)h[CT_X_CHAIN_NS] / (double)h[CT_X_CHAIN_CELLS] : 0.0, h[CT_X_TEAM_LANES],
                 h[CT_X_TEAM_LANES] ? (double)h[CT_X_TEAM_NS] / (double)h[CT_X_TEAM_LANES] : 0.0, h[CT_X_POLLS], h[CT_QTAIL]);
+        fprintf(stderr, "[wl] chased %llu (avg %.1f) | runs ended by the chase %llu, by in-degree 2: %llu, >= 3: %llu, <= 0: %llu\n", h[76],
+                h[CT_X_BURSTS] ? (double)h[76] / (double)h[CT_X_BURSTS] : 0.0, h[CT_DBG_DEALT], h[77], h[78], h[79]);
+        fprintf(stderr, "[wl] bursts %llu (failed %llu) cells %llu avg run %.1f | avg ns per burst %.0f of which chase %.0f\n", h[CT_X_BURSTS], h[CT_X_BURST_FAILS],
+                h[CT_X_BURST_CELLS], h[CT_X_BURSTS] ? (double)h[CT_X_BURST_CELLS] / (double)h[CT_X_BURSTS] : 0.0,
+                h[CT_X_BURSTS] ? (double)h[CT_X_BURST_NS] / (double)h[CT_X_BURSTS] : 0.0, h[CT_X_BURSTS] ? (double)h[CT_X_CHASE_NS] / (double)h[CT_X_BURSTS] : 0.0);
     }
     if (st.n_undone > 0) {
         // dem_processing.py:951-964: unreachable for a DAG unless circular_ref_maxcount <= 1 switched the sweep off

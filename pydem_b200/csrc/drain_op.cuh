@@ -49,6 +49,10 @@ __device__ __forceinline__ int atom_add_s32_if(bool on, int32_t *addr, int v)
     return old;
 }
 
+#ifndef PDM_BURST_MAX
+#define PDM_BURST_MAX 31
+#endif
+
 template <int MODE>
 struct DrainOp {
     static constexpr bool P2P = MODE == 3;
@@ -61,6 +65,8 @@ struct DrainOp {
     const int32_t *pit_dst;
     const double *pit_w;
     int32_t strict;        // hold the decrements back until the adds have returned (see process())
+    int32_t burst;         // the express chain advances by warp-wide bursts along single-receiver runs (chain_warp)
+    int32_t nrows;         // rows of the tile (chain_warp's L1 warm-up stays inside the link plane)
     // MODE 3 only
     int32_t own_lo, own_hi;              // owned cells [own_lo, own_hi); the rows next to them are halo rows
     Cell *peer_cell[2];                  // the neighbour's record behind column 0 of the halo row above / below
@@ -102,14 +108,16 @@ struct DrainOp {
         // the cell's whole sweep state is one 32-byte sector: two 16-byte L2 loads
         const double2 at = __ldcg(reinterpret_cast<const double2 *>(&cell[i].area));      // area, taint
         const longlong2 pm = __ldcg(reinterpret_cast<const longlong2 *>(&cell[i].prop));  // prop | indeg, link
-        const double ai = at.x;
-        const double ti = MODE != 1 ? at.y : 0.0;
-        const double p = __longlong_as_double(pm.x);
-        const uint8_t lk = (uint8_t)((unsigned long long)pm.y >> 32);
+        return drain(i, at.x, MODE != 1 ? at.y : 0.0, __longlong_as_double(pm.x), (uint8_t)((unsigned long long)pm.y >> 32), q, defer);
+    }
+
+    // the same with the cell's record (final area ai, taint ti, proportion p, link byte lk) already in registers
+    __device__ __forceinline__ int32_t drain(int32_t i, double ai, double ti, double p, uint8_t lk, const wl::Queue &q, int32_t &defer) const
+    {
         int32_t nxt = -1;
         if (lk & LK_PIT) {
             // long-range pit edges (_mk_connectivity_pits): rare, plain fence ordering
-            const int64_t slot = pm.x;
+            const int64_t slot = __double_as_longlong(p);
             const int32_t e0 = pit_beg[slot], e1 = pit_end[slot];
             for (int32_t e = e0; e < e1; e++) {
                 const int32_t r = pit_dst[e];
@@ -236,6 +244,202 @@ struct DrainOp {
             i = process(i, q, other);
         }
         cur = i;
+        return n;
+    }
+
+    // ---- Chain bursts: the express chain of a warp whose other lanes are idle, advanced by the WHOLE warp.
+    //
+    // The critical path of a conditioned DEM is a river of single-receiver cells (on the 4096^2 benchmark DEM 94 % of
+    // the 3896 cells of the longest flow path have one receiver, mostly with weight exactly 1) whose tributaries
+    // finished long ago: every cell on it waits for nothing but its predecessor.  Followed cell by cell it costs two
+    // dependent L2 operations + ~100 single-lane instructions per cell (~1.07 us); but along such a run the sweep is a
+    // linear recurrence  A[j] = S[j] + w[j] * A[j-1]  (S[j]: what the cell's record has accumulated = its own area +
+    // its finished tributaries, cyutils.pyx:161), which a warp evaluates for up to 31 cells at once:
+    //   1. the holder lane follows the static link bytes from its ready cell: R1, R2, ... (one L1/L2-hit byte load per
+    //      hop -- the link plane is read-only during the sweep) while every next cell has a single receiver;
+    //   2. lane t loads the record of R[t+1] with ONE 256-bit load.  A record with in-degree 1 is waiting for its
+    //      chain predecessor only (the predecessor is undone and counts, so nobody else is pending, and every donor
+    //      that has counted off did its adds before -- the ordering the sweep relies on anyway, see drain()); the
+    //      leading lanes with in-degree 1 form the run;
+    //   3. a warp scan composes the affine maps x -> S + w x over the run (area and taint), the lanes store the final
+    //      records (in-degree 0 = drained), and the holder continues from the last cell of the run with its record in
+    //      registers.  Nobody reads a record of the run again (all its donors have pushed; only the epilogue does).
+    // A run that fails at once costs one hop and one load and falls back to the ordinary step; the speculation length
+    // adapts (4..31).  Sums re-associate like the fp64 atomics of the bulk phase do (uca within the parity bar).
+    // PYDEM_B200_SWEEP_BURST=0 switches it off; the strict cross-check mode never uses it.
+    struct Rec32 { double area, taint, prop; int32_t indeg; uint8_t link; };
+    static __device__ __forceinline__ Rec32 ld_rec(const Cell *c)
+    {
+        unsigned long long a, b, pq, d;
+        asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(pq), "=l"(d) : "l"(c) : "memory");
+        Rec32 r;
+        r.area = __longlong_as_double((long long)a); r.taint = __longlong_as_double((long long)b);
+        r.prop = __longlong_as_double((long long)pq);
+        r.indeg = (int32_t)(d & 0xffffffffULL); r.link = (uint8_t)(d >> 32);
+        return r;
+    }
+    // the only receiver of a cell with link byte lk at index c, or -1 (no / two receivers, pit drain, outside the owned rows)
+    __device__ __forceinline__ int32_t single_receiver(int32_t c, uint8_t lk) const
+    {
+        if (lk & (LK_PIT | LK_NOSEC)) return -1;
+        const bool k1 = lk & LK_KEEP1, k2 = lk & LK_KEEP2;
+        if (k1 == k2) return -1;
+        const int sec = lk & LK_SEC_MASK;
+        const int32_t r = c + (k1 ? wl::off_e1(sec, C) : wl::off_e2(sec, C));
+        if (MODE == 3 && (r < own_lo || r >= own_hi)) return -1;
+        return r;
+    }
+
+    // offset from a cell with link byte lk to its only receiver, 0 if it has none or two (table s_off of k_worklist:
+    // the holder's chase is one dependent instruction chain, and the table turns ~25 ALU instructions per hop into one
+    // shared-memory load)
+    __device__ __forceinline__ int32_t chase_offset(uint8_t lk) const
+    {
+        if (lk & (LK_PIT | LK_NOSEC)) return 0;
+        const bool k1 = lk & LK_KEEP1, k2 = lk & LK_KEEP2;
+        if (k1 == k2) return 0;
+        const int sec = lk & LK_SEC_MASK;
+        return k1 ? wl::off_e1(sec, C) : wl::off_e2(sec, C);
+    }
+
+    // all 32 lanes call this; `holder` is the one lane with work (cur >= 0).  sh: 32 ints of shared memory of this warp.
+    // Returns the cells drained (on the holder lane; 0 elsewhere).
+    __device__ __forceinline__ unsigned long long chain_warp(int32_t &cur, int32_t &other, const wl::Queue &q, int holder, int32_t *sh, int &L, int &score, const int32_t *s_off) const
+    {
+        const unsigned full = 0xffffffffu;
+        const int lane = threadIdx.x & 31;
+        const bool H = lane == holder;
+        if ((MODE != 0 && MODE != 3) || strict || !burst) {
+            return H ? chain(cur, other, q) : 0ULL;
+        }
+        unsigned long long n = 0;
+        int32_t i = H ? cur : -1;
+        bool have = false;                 // holder: the record of i is in the registers below
+        double ai = 0.0, ti = 0.0, p = 0.0;
+        uint8_t lk = 0;
+        unsigned long long x_b = 0, x_bc = 0, x_bf = 0, x_cn = 0, x_bn = 0, x_nch = 0, x_f2 = 0, x_f3 = 0, x_f0 = 0, x_full = 0;     // diagnostics (q.dbg)
+        for (;;) {
+            const int go = __shfl_sync(full, (H && i >= 0 && other < 0) ? 1 : 0, holder);
+            if (!go) break;
+            int32_t r1 = -1;
+            if (H) {
+                if (!have) {
+                    const double2 at = __ldcg(reinterpret_cast<const double2 *>(&cell[i].area));
+                    const longlong2 pm = __ldcg(reinterpret_cast<const longlong2 *>(&cell[i].prop));
+                    ai = at.x; ti = at.y; p = __longlong_as_double(pm.x); lk = (uint8_t)((unsigned long long)pm.y >> 32);
+                    have = true;
+                }
+                r1 = single_receiver(i, lk);
+            }
+            int run = 0;
+            const unsigned long long x_t0 = q.dbg ? wl::globaltimer_ns() : 0;
+            // score (per warp, persists across calls, -64..64): how productive this warp's bursts have been.  On terrain
+            // without long single-receiver runs (a raw fractal: runs of ~1 cell) the bursts would only cost time: with a
+            // negative score only every 16th step tries one (L <= 0 counts the ordinary steps in between)
+            if (L <= 0) { L = L < -1 ? L + 1 : 4; r1 = -1; }
+            if (__shfl_sync(full, r1, holder) >= 0) {
+                // 1. follow the link bytes (holder): sh[t] = R[t+1]  (pulling the link bytes around the cell into L1 with
+                //    all lanes first made no difference: measured, dropped)
+                int nch = 0;
+                if (H) {
+                    int32_t c = r1;
+                    while (nch < L) {
+                        sh[nch++] = c;
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(cell + c));      // the lanes read these records next
+                        const int32_t o = s_off[__ldg(link + c) & 0x7f];
+                        if (o == 0) break;
+                        c += o;
+                        if (MODE == 3 && (c < own_lo || c >= own_hi)) break;
+                    }
+                }
+                __syncwarp(full);
+                if (q.dbg) x_cn += wl::globaltimer_ns() - x_t0;
+                nch = __shfl_sync(full, nch, holder);
+                // 2. the records of the chased cells, one lane each
+                const bool mine = lane < nch;
+                const int32_t c = mine ? sh[lane] : 0;
+                Rec32 rec;
+                rec.area = 0.0; rec.taint = 0.0; rec.prop = 0.0; rec.indeg = 0; rec.link = 0;
+                if (mine) rec = ld_rec(&cell[c]);
+                const unsigned vm = __ballot_sync(full, mine && rec.indeg == 1);
+                run = __ffs(~vm) - 1;                       // leading lanes waiting for their predecessor only
+                if (run < 0) run = 32;
+                // (the speculation length follows the runs: grow after a full hit, shrink after a miss)
+                if (run == nch && nch == L) { L = L * 2 < PDM_BURST_MAX ? L * 2 : PDM_BURST_MAX; }
+                else if (2 * run < nch) { L = L / 2 > 4 ? L / 2 : 4; }
+                score += run - 2;
+                score = score > 64 ? 64 : (score < -64 ? -64 : score);
+                if (score < 0 && run < 2) L = -16;
+                if (run > 0) {
+                    // 3. weight of the edge into my cell: its predecessor's proportion (the holder's cell for lane 0)
+                    const double hp = __shfl_sync(full, p, holder);
+                    const int hl = __shfl_sync(full, (int)lk, holder);
+                    double pp = __shfl_up_sync(full, rec.prop, 1);
+                    int pl = __shfl_up_sync(full, (int)rec.link, 1);
+                    if (lane == 0) { pp = hp; pl = hl; }
+                    double m = (pl & LK_KEEP1) ? pp : __dsub_rn(1.0, pp);       // dem_processing.py:1082
+                    double a = rec.area, t = rec.taint;
+                    // inclusive scan of the affine maps x -> a + m x (area) / t + m x (taint) over the lanes [0, run)
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const double m2 = __shfl_up_sync(full, m, d), a2 = __shfl_up_sync(full, a, d), t2 = __shfl_up_sync(full, t, d);
+                        if (lane >= d) {
+                            a = __dadd_rn(a, __dmul_rn(m, a2));
+                            t = __dadd_rn(t, __dmul_rn(m, t2));
+                            m = __dmul_rn(m, m2);
+                        }
+                    }
+                    const double a0 = __shfl_sync(full, ai, holder), t0 = __shfl_sync(full, ti, holder);
+                    const double A = __dadd_rn(a, __dmul_rn(m, a0));                                  // cyutils.pyx:161
+                    const double T = (t0 != 0.0) ? __dadd_rn(t, __dmul_rn(m, t0)) : t;                // cyutils.pyx:163-164
+                    // the last cell of the run becomes the holder's current cell (record in registers; it is the holder
+                    // who stores it: whoever gets that cell later got it from the holder)
+                    const int last = run - 1;
+                    const double la = __shfl_sync(full, A, last), lt = __shfl_sync(full, T, last), lp = __shfl_sync(full, rec.prop, last);
+                    const int ll = __shfl_sync(full, (int)rec.link, last);
+                    const int32_t lc = __shfl_sync(full, c, last);
+                    if (lane < last) {
+                        // drained: final sums, in-degree 0
+                        asm volatile("st.global.cg.v2.f64 [%0], {%1, %2};" :: "l"(&cell[c].area), "d"(A), "d"(T) : "memory");
+                        asm volatile("st.global.cg.s32 [%0], %1;" :: "l"(&cell[c].indeg), "r"(0) : "memory");
+                    }
+                    if (H) {
+                        asm volatile("st.global.cg.v2.f64 [%0], {%1, %2};" :: "l"(&cell[lc].area), "d"(la), "d"(lt) : "memory");
+                        asm volatile("st.global.cg.s32 [%0], %1;" :: "l"(&cell[lc].indeg), "r"(0) : "memory");
+                        i = lc; ai = la; ti = lt; p = lp; lk = (uint8_t)ll;
+                        n += (unsigned long long)run;
+                    }
+                }
+                __syncwarp(full);
+                if (q.dbg) {
+                    x_b++; x_bc += run; x_bf += run == 0; x_bn += wl::globaltimer_ns() - x_t0; x_nch += nch; x_full += run == nch;
+                    const int fi = __shfl_sync(full, rec.indeg, run < 31 ? run : 31);      // in-degree of the record that ended the run
+                    if (run < nch) { x_f2 += fi == 2; x_f3 += fi >= 3; x_f0 += fi <= 0; }
+                }
+            }
+            if (run == 0 && H) {
+                // the ordinary step (record in registers)
+                n++;
+                i = drain(i, ai, MODE != 1 ? ti : 0.0, p, lk, q, other);
+                have = false;
+                if (other >= 0 && score > 0) {
+                    // fork on a river (this warp's bursts have been productive): both receivers became ready at once.  The side branch of a D-infinity flow path usually ends
+                    // one cell later in a cell of the main path, so it is drained right here (a few ordinary steps) and
+                    // the main path goes on in bursts -- instead of leaving for the team loop of the warp.  What is left
+                    // of a longer side branch goes to the queue.
+                    int32_t sb = other, o2 = -1;
+                    other = -1;
+                    for (int k = 0; k < 3 && sb >= 0 && o2 < 0; k++) { n++; sb = process(sb, q, o2); }
+                    if (sb >= 0) q.push(sb);
+                    if (o2 >= 0) q.push(o2);
+                }
+            }
+        }
+        if (H) cur = i;
+        if (q.dbg && H) {
+            atomicAdd(&q.ctr[CT_X_BURSTS], x_b); atomicAdd(&q.ctr[CT_X_BURST_CELLS], x_bc); atomicAdd(&q.ctr[CT_X_BURST_FAILS], x_bf);
+            atomicAdd(&q.ctr[CT_X_CHASE_NS], x_cn); atomicAdd(&q.ctr[CT_X_BURST_NS], x_bn);
+            atomicAdd(&q.ctr[76], x_nch); atomicAdd(&q.ctr[77], x_f2); atomicAdd(&q.ctr[78], x_f3); atomicAdd(&q.ctr[79], x_f0); atomicAdd(&q.ctr[CT_DBG_DEALT], x_full);
+        }
         return n;
     }
 };

@@ -232,7 +232,8 @@ enum {
     CT_X_FIRST = 116,  // diagnostics of a work-list run (PYDEM_B200_WL_DEBUG)
     CT_X_CHAIN_CALLS = 116, CT_X_CHAIN_CELLS = 117, CT_X_CHAIN_NS = 118, CT_X_TEAM_LANES = 119, CT_X_TEAM_NS = 120,
     CT_X_POLLS = 121, CT_X_SCAN_CELLS = 122,
-    CT_X_LAST = 122,
+    CT_X_BURSTS = 123, CT_X_BURST_CELLS = 124, CT_X_BURST_FAILS = 125, CT_X_CHASE_NS = 126, CT_X_BURST_NS = 127,   // chain bursts (drain_op.cuh)
+    CT_X_LAST = 127,
     // one work-list sweep across the row shards of several GPUs (drain_op.cuh MODE 3): the counters then live in the
     // control block the peers have mapped (tsweep.cuh, TC_WLC)
     CT_INBOX_TAIL = 128,  // cells made ready by a peer GPU (it pushes them into this rank's in-box)

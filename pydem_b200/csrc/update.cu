@@ -103,6 +103,12 @@ struct FloodOp {
         cur = i;
         return n;
     }
+    __device__ __forceinline__ int32_t chase_offset(uint8_t) const { return 0; }
+    // (no warp-wide bursts for the floods: the holder lane runs the ordinary chain)
+    __device__ __forceinline__ unsigned long long chain_warp(int32_t &cur, int32_t &other, const wl::Queue &q, int holder, int32_t *, int &, int &, const int32_t *) const
+    {
+        return (int)(threadIdx.x & 31) == holder ? chain(cur, other, q) : 0ULL;
+    }
     __device__ __forceinline__ int32_t process(int32_t i, const wl::Queue &q, int32_t &defer) const
     {
         const longlong2 pm = *reinterpret_cast<const longlong2 *>(&cell[i].prop);   // prop | indeg, link (link, prop fixed)

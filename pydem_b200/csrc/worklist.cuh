@@ -207,6 +207,10 @@ static __device__ __forceinline__ void p2p_service(const Queue &q, unsigned long
 template <class Op, class Domain>
 __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
 {
+    __shared__ int32_t s_chain[8][32];   // per warp: the cells of a chain burst (Op::chain_warp)
+    __shared__ int32_t s_off[128];       // link byte -> offset of the cell's only receiver (0: none or two); Op::chase_offset
+    if (threadIdx.x < 128) s_off[threadIdx.x] = op.chase_offset((uint8_t)threadIdx.x);
+    __syncthreads();
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -234,6 +238,8 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
     int32_t cur = -1;
     int32_t stash = -1, stash2 = -1, stash3 = -1;   // ready receivers kept for after the current chain (see below)
     int chain_len = 0;
+    int burst_len = 16;      // speculation length of the chain bursts (warp-uniform, adapts to the runs; Op::chain_warp)
+    int burst_score = 8;     // how productive this warp's bursts have been (warp-uniform)
     long long ticket = -1;   // queue slot this lane is entitled to (fetch-and-add ticket, never fails)
     bool active = false;     // this lane owns an unfinished chain (current cell and/or stash)
     bool scan_stamped = false;
@@ -410,9 +416,11 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
             // express fast path: one lane has work and the warp has no seeds left to deal -> it
             // follows the chain in a tight single-lane loop (no warp collectives between cells:
             // the critical path pays memory round trips only) until the chain ends or forks
-            if (cur >= 0) {
-                const unsigned long long t0 = q.dbg ? globaltimer_ns() : 0;
-                const unsigned long long nc = op.chain(cur, defer, q);
+            // (all lanes go in: the idle ones help the chain along single-receiver runs, drain_op.cuh chain_warp)
+            const int holder = __ffs(work_mask) - 1;
+            const unsigned long long t0 = q.dbg ? globaltimer_ns() : 0;
+            const unsigned long long nc = op.chain_warp(cur, defer, q, holder, s_chain[threadIdx.x >> 5], burst_len, burst_score, s_off);
+            if (lane == holder) {
                 processed += nc;
                 if (q.dbg) { x_chain_ns += globaltimer_ns() - t0; x_chain_cells += nc; x_chain_calls++; }
                 if (cur < 0 && defer >= 0) { cur = defer; defer = -1; }
@@ -557,6 +565,7 @@ static __global__ void k_queue_zero(unsigned long long *ctr, int keep_drained)
     ctr[CT_QTAIL] = 0; ctr[CT_QHEAD] = 0; ctr[CT_QDONE] = 0; ctr[CT_PHASE1] = 0; ctr[CT_CHUNK] = 0;   // (CT_GTERM is never reset)
     if (!keep_drained) ctr[CT_DRAINED] = 0;
     for (int k = CT_X_FIRST; k <= CT_X_LAST; k++) ctr[k] = 0;
+    for (int k = 76; k < 80; k++) ctr[k] = 0;
     ctr[CT_T_START] = ~0ULL; ctr[CT_T_SCAN] = 0; ctr[CT_T_END] = 0; ctr[CT_DBG_DEALT] = 0; ctr[CT_DBG_TAKEN] = 0; ctr[CT_DBG_EXITS] = 0;
 }
 

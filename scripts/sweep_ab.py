@@ -36,7 +36,7 @@ from pydem_b200 import synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 opts = sys.argv[2:] or ["strict=0", "strict=1"]
 KEYS = {"sweep": "PYDEM_B200_SWEEP", "tile": "PYDEM_B200_TS_TILE", "legacy": "PYDEM_B200_SWEEP_LEGACY", "tocc": "PYDEM_B200_TS_OCC", "tdbg": "PYDEM_B200_TS_DEBUG",
-        "lib": "PYDEM_B200_LIB", "strict": "PYDEM_B200_SWEEP_STRICT", "backoff": "PYDEM_B200_WL_BACKOFF", "occ": "PYDEM_B200_WL_OCC", "dbg": "PYDEM_B200_WL_DEBUG"}
+        "lib": "PYDEM_B200_LIB", "burst": "PYDEM_B200_SWEEP_BURST", "strict": "PYDEM_B200_SWEEP_STRICT", "backoff": "PYDEM_B200_WL_BACKOFF", "occ": "PYDEM_B200_WL_OCC", "dbg": "PYDEM_B200_WL_DEBUG"}
 np.save("/tmp/ab_cond_%d.npy" % n, synth.conditioned_fractal_dem(n, 0))
 np.save("/tmp/ab_raw_%d.npy" % n, synth.fractal_dem(n, 0))
 for o in opts:
