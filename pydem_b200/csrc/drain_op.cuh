@@ -317,7 +317,6 @@ struct DrainOp {
         bool have = false;                 // holder: the record of i is in the registers below
         double ai = 0.0, ti = 0.0, p = 0.0;
         uint8_t lk = 0;
-        unsigned long long x_b = 0, x_bc = 0, x_bf = 0, x_cn = 0, x_bn = 0, x_nch = 0, x_f2 = 0, x_f3 = 0, x_f0 = 0, x_full = 0;     // diagnostics (q.dbg)
         for (;;) {
             const int go = __shfl_sync(full, (H && i >= 0 && other < 0) ? 1 : 0, holder);
             if (!go) break;
@@ -353,7 +352,7 @@ struct DrainOp {
                     }
                 }
                 __syncwarp(full);
-                if (q.dbg) x_cn += wl::globaltimer_ns() - x_t0;
+                if (q.dbg && H) atomicAdd(&q.ctr[CT_X_CHASE_NS], wl::globaltimer_ns() - x_t0);
                 nch = __shfl_sync(full, nch, holder);
                 // 2. the records of the chased cells, one lane each
                 const bool mine = lane < nch;
@@ -411,9 +410,18 @@ struct DrainOp {
                 }
                 __syncwarp(full);
                 if (q.dbg) {
-                    x_b++; x_bc += run; x_bf += run == 0; x_bn += wl::globaltimer_ns() - x_t0; x_nch += nch; x_full += run == nch;
+                    // diagnostics straight into the counters (no registers held across the loop)
                     const int fi = __shfl_sync(full, rec.indeg, run < 31 ? run : 31);      // in-degree of the record that ended the run
-                    if (run < nch) { x_f2 += fi == 2; x_f3 += fi >= 3; x_f0 += fi <= 0; }
+                    if (H) {
+                        atomicAdd(&q.ctr[CT_X_BURSTS], 1ULL); atomicAdd(&q.ctr[CT_X_BURST_CELLS], (unsigned long long)run);
+                        if (run == 0) atomicAdd(&q.ctr[CT_X_BURST_FAILS], 1ULL);
+                        atomicAdd(&q.ctr[CT_X_BURST_NS], wl::globaltimer_ns() - x_t0);
+                        atomicAdd(&q.ctr[76], (unsigned long long)nch);
+                        if (run == nch) atomicAdd(&q.ctr[CT_DBG_DEALT], 1ULL);
+                        else if (fi == 2) atomicAdd(&q.ctr[77], 1ULL);
+                        else if (fi >= 3) atomicAdd(&q.ctr[78], 1ULL);
+                        else atomicAdd(&q.ctr[79], 1ULL);
+                    }
                 }
             }
             if (run == 0 && H) {
@@ -435,11 +443,6 @@ struct DrainOp {
             }
         }
         if (H) cur = i;
-        if (q.dbg && H) {
-            atomicAdd(&q.ctr[CT_X_BURSTS], x_b); atomicAdd(&q.ctr[CT_X_BURST_CELLS], x_bc); atomicAdd(&q.ctr[CT_X_BURST_FAILS], x_bf);
-            atomicAdd(&q.ctr[CT_X_CHASE_NS], x_cn); atomicAdd(&q.ctr[CT_X_BURST_NS], x_bn);
-            atomicAdd(&q.ctr[76], x_nch); atomicAdd(&q.ctr[77], x_f2); atomicAdd(&q.ctr[78], x_f3); atomicAdd(&q.ctr[79], x_f0); atomicAdd(&q.ctr[CT_DBG_DEALT], x_full);
-        }
         return n;
     }
 };

@@ -229,10 +229,10 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
     //   * warp 0 of every block is express from the start (it never scans for seeds);
     //   * every other warp becomes express when its seed scan is exhausted;
     //   * a scanning warp hands a chain longer than HANDOFF cells to the queue.
-    const int HANDOFF = 16;
+    const int HANDOFF = 16, TEAM_HANDOFF = 4;
     const bool express_only = (threadIdx.x >> 5) == 0 && gridDim.x * (blockDim.x >> 5) > 8;
     bool scanning = nchunks > 0 && !express_only;
-    long long ch_next = 0, ch_end = 0;   // current batch [ch_next, ch_end)
+    int32_t ch_next = 0, ch_end = 0;     // current batch [ch_next, ch_end) (chunks of 32 cells: < 2^26 per tile)
     unsigned pend_mask = 0;  // lanes whose pend_cell is an unassigned seed
     int32_t pend_cell = -1;
     int32_t cur = -1;
@@ -240,11 +240,11 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
     int chain_len = 0;
     int burst_len = 16;      // speculation length of the chain bursts (warp-uniform, adapts to the runs; Op::chain_warp)
     int burst_score = 8;     // how productive this warp's bursts have been (warp-uniform)
-    long long ticket = -1;   // queue slot this lane is entitled to (fetch-and-add ticket, never fails)
+    int32_t ticket = -1;     // queue slot this lane is entitled to (fetch-and-add ticket, never fails; the queue has <= 2^31 slots)
     bool active = false;     // this lane owns an unfinished chain (current cell and/or stash)
     bool scan_stamped = false;
     const unsigned long long nseeds = *q.nseeds;
-    unsigned long long processed = 0;
+    unsigned processed = 0;              // cells this lane drained (a tile has < 2^31 cells)
     unsigned idle_polls = 0, iters = 0;
     unsigned long long push_dep = 0;
     unsigned done_acc = 0;   // chains this warp has finished but not yet added to CT_QDONE (warp-uniform)
@@ -252,8 +252,6 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
     const unsigned long long WATCHDOG_NS = 4000000000ULL;
     unsigned backoff = 200;
     const unsigned backoff_max = q.backoff_max > 0 ? (unsigned)q.backoff_max : 200u;
-    unsigned long long x_polls = 0, x_chain_ns = 0, x_chain_cells = 0, x_chain_calls = 0, x_team_ns = 0, x_team_steps = 0,
-                       x_team_lanes = 0;
     if constexpr (Op::P2P) {
         // start barrier: nobody touches a peer's records or in-box before every rank has reset its own
         // (each rank arrives on rank 0's counter after its set-up kernels, pdm_launch_sweep_p2p)
@@ -284,10 +282,10 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
                     if (lane == 0) b = (long long)atomicAdd(&q.ctr[CT_CHUNK], (unsigned long long)CHUNK_BATCH);
                     b = __shfl_sync(full, b, 0);
                     if (b >= nchunks) { scanning = false; break; }
-                    ch_next = b;
-                    ch_end = b + CHUNK_BATCH < nchunks ? b + CHUNK_BATCH : nchunks;
+                    ch_next = (int32_t)b;
+                    ch_end = (int32_t)(b + CHUNK_BATCH < nchunks ? b + CHUNK_BATCH : nchunks);
                 }
-                const int64_t t = (ch_next << 5) + lane;
+                const int64_t t = ((int64_t)ch_next << 5) + lane;
                 ch_next++;
                 pend_cell = t < dsize ? dom.cell(t) : -1;
                 pend_mask = __ballot_sync(full, pend_cell >= 0 && op.is_seed(pend_cell));
@@ -319,9 +317,9 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(&q.ctr[CT_QHEAD], (unsigned long long)__popc(need_mask));
             base = __shfl_sync(full, base, 0);
-            if (need_ticket) ticket = (long long)(base + __popc(need_mask & lt_mask));
+            if (need_ticket) { const unsigned long long tk = base + __popc(need_mask & lt_mask); ticket = tk < (unsigned long long)q.cap ? (int32_t)tk : 0x7fffffff; }
         }
-        if (cur < 0 && ticket >= 0 && ticket < q.cap) {
+        if (cur < 0 && ticket >= 0 && ticket != 0x7fffffff) {
             const int32_t v = ld_volatile_i32(q.slots + ticket);
             if (v >= 0) {
                 cur = v; active = true; ticket = -1; chain_len = 0;
@@ -333,7 +331,7 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
         // ---- statistics only: when did the last warp run out of seeds
         if (!scanning && !scan_stamped) {
             if (lane == 0) atomicMax(&q.ctr[CT_T_SCAN], globaltimer_ns());
-            if (q.dbg) atomicAdd(&q.ctr[CT_X_SCAN_CELLS], processed);
+            if (q.dbg) atomicAdd(&q.ctr[CT_X_SCAN_CELLS], (unsigned long long)processed);
             scan_stamped = true;
         }
         // ---- nothing to do in this warp: terminate on global quiescence, else back off
@@ -398,7 +396,7 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
                 // slices the working chains' atomics go through
                 __nanosleep(backoff);
                 if (backoff < backoff_max) backoff <<= 1;
-                if (q.dbg && lane == 0) x_polls++;
+                if (q.dbg && lane == 0) atomicAdd(&q.ctr[CT_X_POLLS], 1ULL);
             }
             continue;
         }
@@ -412,6 +410,7 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
         // ---- one step per working lane
         bool finished_q = false;
         int32_t defer = -1;  // second ready receiver: dealt to an idle lane of this warp or handed to the queue
+        bool handoff = false;   // defer is this lane's own long chain on its way to an express warp
         if (!scanning && (work_mask & (work_mask - 1)) == 0) {
             // express fast path: one lane has work and the warp has no seeds left to deal -> it
             // follows the chain in a tight single-lane loop (no warp collectives between cells:
@@ -421,8 +420,8 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
             const unsigned long long t0 = q.dbg ? globaltimer_ns() : 0;
             const unsigned long long nc = op.chain_warp(cur, defer, q, holder, s_chain[threadIdx.x >> 5], burst_len, burst_score, s_off);
             if (lane == holder) {
-                processed += nc;
-                if (q.dbg) { x_chain_ns += globaltimer_ns() - t0; x_chain_cells += nc; x_chain_calls++; }
+                processed += (unsigned)nc;
+                if (q.dbg) { atomicAdd(&q.ctr[CT_X_CHAIN_NS], globaltimer_ns() - t0); atomicAdd(&q.ctr[CT_X_CHAIN_CELLS], nc); atomicAdd(&q.ctr[CT_X_CHAIN_CALLS], 1ULL); }
                 if (cur < 0 && defer >= 0) { cur = defer; defer = -1; }
                 if (cur < 0 && stash < 0) { finished_q = active; active = false; }
             }
@@ -432,7 +431,7 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
             chain_len++;
             const unsigned long long t0 = (q.dbg && !scanning) ? globaltimer_ns() : 0;
             const int32_t nxt = op.process(cur, q, defer);
-            if (q.dbg && !scanning) { x_team_ns += globaltimer_ns() - t0; x_team_lanes++; }
+            if (q.dbg && !scanning) { atomicAdd(&q.ctr[CT_X_TEAM_NS], globaltimer_ns() - t0); atomicAdd(&q.ctr[CT_X_TEAM_LANES], 1ULL); }
             cur = nxt;
             // a second ready receiver waits in the lane's stash (no queue traffic) unless the
             // stash is taken; a long chain hands its stash to the queue so that it cannot sit on
@@ -443,9 +442,11 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
                 if (stash < 0) stash = defer; else if (stash2 < 0) stash2 = defer; else stash3 = defer;
                 defer = -1;
             }
-            // bulk phase: a long chain moves to an express warp; its stash follows one cell per step
-            if (scanning && defer < 0 && chain_len > HANDOFF) {
-                if (cur >= 0) { defer = cur; cur = -1; chain_len = 0; }
+            // bulk phase: a long chain moves to an express warp; its stash follows one cell per step.  The same in a
+            // team (several chains in lock step, after the scan): a chain that keeps going is a river, and an idle warp
+            // that takes it from the queue advances it in bursts (Op::chain_warp) instead of ~3 us per cell here
+            if (defer < 0 && chain_len > (scanning ? HANDOFF : TEAM_HANDOFF)) {
+                if (cur >= 0) { defer = cur; cur = -1; chain_len = 0; handoff = true; }
             }
             if (cur < 0 && stash < 0) { finished_q = active; active = false; }
         }
@@ -458,7 +459,7 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
         //      it belongs to the giving chain's accounting, which is only reported when the whole
         //      warp has run dry.
         if (!scanning) {
-            const unsigned dm = __ballot_sync(full, defer >= 0);
+            const unsigned dm = __ballot_sync(full, defer >= 0 && !handoff);      // (a handed-off chain goes to the queue)
             if (dm) {
                 const bool idle = cur < 0 && stash < 0 && ticket < 0;
                 const unsigned im = __ballot_sync(full, idle);
@@ -467,7 +468,7 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
                 const bool take = idle && k < nd;
                 const int src = take ? (int)__fns(dm, 0, k + 1) : 0;
                 const int32_t c = __shfl_sync(full, defer, src);
-                if (defer >= 0 && __popc(dm & lt_mask) < ni) defer = -1;   // given away
+                if (defer >= 0 && !handoff && __popc(dm & lt_mask) < ni) defer = -1;   // given away
                 if (take) { cur = c; chain_len = 0; }
             }
         }
@@ -485,19 +486,10 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
         done_acc += __popc(fq);
         if (pm) push_dep = base;
     }
-    if (q.dbg) {
-        // diagnostics: single-lane chains (calls, cells, ns), team steps (lane-steps, lane-ns), idle polls
-        atomicAdd(&q.ctr[CT_X_CHAIN_CALLS], x_chain_calls);
-        atomicAdd(&q.ctr[CT_X_CHAIN_CELLS], x_chain_cells);
-        atomicAdd(&q.ctr[CT_X_CHAIN_NS], x_chain_ns);
-        atomicAdd(&q.ctr[CT_X_TEAM_LANES], x_team_lanes);
-        atomicAdd(&q.ctr[CT_X_TEAM_NS], x_team_ns);
-        atomicAdd(&q.ctr[CT_X_POLLS], x_polls);
-        (void)x_team_steps;
-    }
-    for (int o = 16; o > 0; o >>= 1) processed += __shfl_down_sync(full, processed, o);
+    unsigned long long processed_w = processed;
+    for (int o = 16; o > 0; o >>= 1) processed_w += __shfl_down_sync(full, processed_w, o);
     if (lane == 0) {
-        if (processed) atomicAdd(&q.ctr[CT_DRAINED], processed);
+        if (processed_w) atomicAdd(&q.ctr[CT_DRAINED], processed_w);
         atomicMax(&q.ctr[CT_T_END], globaltimer_ns());
     }
 }
