@@ -86,3 +86,22 @@ def test_numpy_pairwise_sum_restatement():
     for n in (0, 1, 2, 7, 8, 9, 15, 16, 17, 31, 33, 127, 128, 129, 130, 257, 1000):
         a = rng.standard_normal(n) * 10.0 ** rng.integers(-3, 4, n)
         assert orc.lib().orc_np_sum(np.ascontiguousarray(a), n) == float(np.sum(a))
+
+
+@pytest.mark.parametrize("name", ["frac128", "frac128_nopits", "nan_holes", "quantized", "lakes", "lakes_minborder", "frac_rect_vardx",
+                                  "frac96_maxdist4", "odd_cols", "cone256"])
+def test_drainage_graph_is_acyclic(name):
+    """The circular-reference restart of the reference (dem_processing.py:951-964) never fires: one call of
+    drain_area finishes every cell, because an edge needs elev[j] <= elev[i] AND a weight > 1e-8, and a facet
+    neighbour at the centre's own elevation always gets weight 0.  The CUDA path relies on it
+    (cells left over after a sweep are an error there, not a case to replay)."""
+    import warnings
+    from oracle.oracle import OracleDEMProcessor
+    E, kw = helpers.cases()[name]
+    k = dict(helpers.HOT); k.update(kw)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        dp = OracleDEMProcessor(E, **k)
+        dp.calc_slopes_directions()
+        dp.calc_uca()
+    assert dp.done.all() and dp.stats["restarts"] == 0
