@@ -1,4 +1,3 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python scripts/sweep_ab.py 4096 sweep=worklist,burst=1,dbg=1 > gpurun_out/r2_ab41.log 2>&1
-grep -E '^\{|rror|assert|Trace' gpurun_out/r2_ab41.log | cut -c1-330
-grep '^\[wl\]' gpurun_out/r2_ab41.log | head -3 | cut -c1-300
+timeout 900 python scripts/sweep_ab.py 4096 sweep=worklist,burst=1 sweep=worklist,burst=0 sweep=worklist,burst=1 > gpurun_out/r2_ab41.log 2>&1
+grep -E '^\{|rror|assert|Trace|^cond|^raw' gpurun_out/r2_ab41.log | cut -c1-330
