@@ -175,7 +175,7 @@ int pdm_tile_destroy(pdm_tile *t)
                     t->edge_todo, t->edge_done, t->section, t->label, t->queue, t->dX, t->dY, t->dg,
                     t->thA, t->thB, t->th_row, t->row_area, t->d_counters, t->pit_cell, t->pit_beg, t->pit_end,
                     t->pit_dst, t->pit_w, t->pit_scratch_i, t->pit_scratch_d, t->edge_buf_d, t->edge_buf_b,
-                    t->glabel, t->glelev, t->twi10, t->rdX, t->rdY, t->rdg, t->ts_ctl, t->ts_seen, t->dXg, t->dYg, t->chase};
+                    t->glabel, t->glelev, t->twi10, t->rdX, t->rdY, t->rdg, t->ts_ctl, t->ts_seen, t->dXg, t->dYg};
     pdm_ts_p2p_close(t);
     pdm_comm_scratch_free(t);
     for (void *p : ptrs) if (p) cudaFree(p);

@@ -66,9 +66,7 @@ struct DrainOp {
     const double *pit_w;
     int32_t strict;        // hold the decrements back until the adds have returned (see process())
     int32_t burst;         // the express chain advances by warp-wide bursts along single-receiver runs (chain_warp)
-    int32_t nrows;         // rows of the tile
-    const uint8_t *chase;  // the link bytes in 8 x 16-cell tiles (k_indeg); tiles per tile row
-    int32_t chase_tpr;
+    int32_t nrows;         // rows of the tile (chain_warp's L1 warm-up stays inside the link plane)
     // MODE 3 only
     int32_t own_lo, own_hi;              // owned cells [own_lo, own_hi); the rows next to them are halo rows
     Cell *peer_cell[2];                  // the neighbour's record behind column 0 of the halo row above / below
@@ -268,6 +266,8 @@ struct DrainOp {
     //      registers.  Nobody reads a record of the run again (all its donors have pushed; only the epilogue does).
     // A run that fails at once costs one hop and one load and falls back to the ordinary step; the speculation length
     // adapts (4..31).  Sums re-associate like the fp64 atomics of the bulk phase do (uca within the parity bar).
+    // Measured without effect and dropped: following a copy of the link bytes laid out in 8 x 16-cell tiles of 128 B
+    // (so that a hop mostly stays in one L1 line) -- the chase is not what bounds a burst.
     // PYDEM_B200_SWEEP_BURST=0 switches it off; the strict cross-check mode never uses it.
     struct Rec32 { double area, taint, prop; int32_t indeg; uint8_t link; };
     static __device__ __forceinline__ Rec32 ld_rec(const Cell *c)
@@ -295,17 +295,13 @@ struct DrainOp {
     // offset from a cell with link byte lk to its only receiver, 0 if it has none or two (table s_off of k_worklist:
     // the holder's chase is one dependent instruction chain, and the table turns ~25 ALU instructions per hop into one
     // shared-memory load)
-    // table entry: (row step + 1) | (column step + 1) << 2 | 16, or 0
     __device__ __forceinline__ int32_t chase_offset(uint8_t lk) const
     {
         if (lk & (LK_PIT | LK_NOSEC)) return 0;
         const bool k1 = lk & LK_KEEP1, k2 = lk & LK_KEEP2;
         if (k1 == k2) return 0;
         const int sec = lk & LK_SEC_MASK;
-        int dr, dc;
-        if (k1) { dr = ((0x6941 >> (2 * sec)) & 3) - 1; dc = ((0x9416 >> (2 * sec)) & 3) - 1; }      // wl::off_e1
-        else { dr = ((sec >> 1) & 2) - 1; dc = 1 - (((sec + 2) >> 1) & 2); }                           // wl::off_e2
-        return (dr + 1) | ((dc + 1) << 2) | 16;
+        return k1 ? wl::off_e1(sec, C) : wl::off_e2(sec, C);
     }
 
     // all 32 lanes call this; `holder` is the one lane with work (cur >= 0).  sh: 32 ints of shared memory of this warp.
@@ -348,15 +344,12 @@ struct DrainOp {
                 int nch = 0;
                 if (H) {
                     int32_t c = r1;
-                    int32_t rr = c / C, cc = c - rr * C;
                     while (nch < L) {
                         sh[nch++] = c;
                         asm volatile("prefetch.global.L2 [%0];" :: "l"(cell + c));      // the lanes read these records next
-                        // the link byte from the tiled copy: a hop to a neighbour mostly stays in the same 128-byte L1 line
-                        const int32_t e = s_off[__ldg(chase + ((((rr >> 3) * chase_tpr + (cc >> 4)) << 7) + ((rr & 7) << 4) + (cc & 15))) & 0x7f];
-                        if (e == 0) break;
-                        rr += (e & 3) - 1; cc += ((e >> 2) & 3) - 1;
-                        c = rr * C + cc;
+                        const int32_t o = s_off[__ldg(link + c) & 0x7f];
+                        if (o == 0) break;
+                        c += o;
                         if (MODE == 3 && (c < own_lo || c >= own_hi)) break;
                     }
                 }

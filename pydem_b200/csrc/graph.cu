@@ -111,8 +111,7 @@ __device__ __forceinline__ int drains_in(uint8_t lk, uint8_t keepbit, uint32_t s
 // shard (the out-boxes of the sweep) start at zero.
 __global__ void __launch_bounds__(256)
 k_indeg(uint8_t *__restrict__ link, Win w, const double *__restrict__ row_area, const double *__restrict__ prop,
-        const int32_t *__restrict__ pit_in, Cell *__restrict__ cell, unsigned long long *counters,
-        uint8_t *__restrict__ chase, int64_t chase_tpr)
+        const int32_t *__restrict__ pit_in, Cell *__restrict__ cell, unsigned long long *counters)
 {
     const int64_t C = w.C;
     const int64_t j = (int64_t)blockIdx.x * 32 + threadIdx.x;
@@ -126,9 +125,6 @@ k_indeg(uint8_t *__restrict__ link, Win w, const double *__restrict__ row_area, 
         Cell rec;
         rec.taint = 0.0; rec.pad[0] = rec.pad[1] = rec.pad[2] = 0;
         rec.link = link[n];
-        // copy of the link byte in 8 x 16-cell tiles of 128 bytes: what the chain bursts of the sweep follow
-        // (drain_op.cuh, chain_warp: a hop to a neighbouring cell then mostly stays in the same L1 line)
-        if (chase) chase[(((i >> 3) * chase_tpr + (j >> 4)) << 7) + ((i & 7) << 4) + (j & 15)] = rec.link;
         if (own) {
             const bool up = w.row_in_grid(i - 1), dn = w.row_in_grid(i + 1), lf = j > 0, rt = j < C - 1;
             // all eight neighbour bytes are loaded unconditionally (a missing neighbour reads the
@@ -275,10 +271,8 @@ int pdm_launch_indeg_todo(pdm_tile *t)
     dim3 block(32, 8);
     dim3 grid((unsigned)((w.C + 31) / 32), (unsigned)((t->R + 7) / 8));
     PDM_CUDA(cudaMemsetAsync(t->edge_todo, 0, (size_t)t->N, t->stream));
-    const int64_t tpr = (w.C + 15) >> 4;
-    if (!t->chase) PDM_CUDA(cudaMalloc(&t->chase, (size_t)((t->R + 7) >> 3) * tpr * 128));
     k_indeg<<<grid, block, 0, t->stream>>>(t->link, w, t->row_area, t->twi, (t->n_pits || t->shard_pits_done) ? t->label : nullptr, t->cell,
-                                           t->d_counters, t->chase, tpr);
+                                           t->d_counters);
     PDM_LAUNCHED();
     const int64_t per = 2 * w.C + 2 * (w.hi - w.lo);
     k_border_todo<true><<<(unsigned)((per + 255) / 256), 256, 0, t->stream>>>(

@@ -68,7 +68,6 @@ struct pdm_tile {
     double *twi10;       // 10 * twi (what DEMProcessor.twi stores), allocated on first download request
     Cell *cell;
     uint8_t *flats, *flat0, *link, *edge_todo, *edge_done;
-    uint8_t *chase;      // link bytes again, in 8 x 16-cell tiles of 128 B (written by k_indeg, followed by the sweep's chain bursts)
     int8_t *section;  // only materialised on download of PDM_F_SECTION
     int32_t *label, *queue;
     long long *glabel;   // sharded mode: global minimum cell index of each flat region (at its local root)

@@ -150,7 +150,7 @@ int pdm_launch_sweep_first(pdm_tile *t)
     int rc = wl::reset_queue(t);
     if (rc) return rc;
     const Win &w = t->win;
-    DrainOp<0> op{t->link, t->cell, nullptr, (int32_t)t->C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w, sweep_strict(), (sweep_strict() || !t->chase) ? 0 : sweep_burst(), (int32_t)t->R, t->chase, (int32_t)((t->C + 15) >> 4)};
+    DrainOp<0> op{t->link, t->cell, nullptr, (int32_t)t->C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w, sweep_strict(), sweep_strict() ? 0 : sweep_burst(), (int32_t)t->R};
     wl::k_worklist<<<g_sweep_blocks, 256, 0, t->stream>>>(op, wl::DomainRange{w.lo * w.C, (w.hi - w.lo) * w.C},
                                                           wl::tuned(wl::Queue{t->queue, t->d_counters, (long long)t->N, t->d_counters + CT_SOURCES}));
     PDM_LAUNCHED();
@@ -197,7 +197,7 @@ int pdm_launch_sweep_p2p(pdm_tile *t)
     unsigned long long *root = reinterpret_cast<unsigned long long *>(pp.all_ctl[0]);
     k_wl_p2p_arrive<<<1, 1, 0, t->stream>>>(wlc, t->d_counters + CT_SOURCES, root + ts::TC_ARRIVED);
     PDM_LAUNCHED();
-    DrainOp<3> op{t->link, t->cell, nullptr, (int32_t)t->C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w, 0, t->chase ? sweep_burst() : 0, (int32_t)t->R, t->chase, (int32_t)((t->C + 15) >> 4)};
+    DrainOp<3> op{t->link, t->cell, nullptr, (int32_t)t->C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w, 0, sweep_burst(), (int32_t)t->R};
     op.own_lo = (int32_t)(w.lo * w.C); op.own_hi = (int32_t)(w.hi * w.C);
     for (int side = 0; side < 2; side++) {
         op.peer_cell[side] = nullptr; op.peer_ctr[side] = nullptr; op.peer_inbox[side] = nullptr; op.peer_cell0[side] = 0;
