@@ -267,7 +267,10 @@ struct DrainOp {
     // A run that fails at once costs one hop and one load and falls back to the ordinary step; the speculation length
     // adapts (4..31).  Sums re-associate like the fp64 atomics of the bulk phase do (uca within the parity bar).
     // Measured without effect and dropped: following a copy of the link bytes laid out in 8 x 16-cell tiles of 128 B
-    // (so that a hop mostly stays in one L1 line) -- the chase is not what bounds a burst.
+    // (so that a hop mostly stays in one L1 line), and copying the 32 x 32 window of link bytes around the cell into
+    // shared memory with all lanes before the chase (2.82-2.90 vs 2.72 ms).  A cycle-accounting build (clock64 per
+    // phase, holder lanes summed) gave per burst: own record + chase ~5400 cycles, records ~1900, scan + stores ~800,
+    // and ~2600 per ordinary step at the end of a run.
     // PYDEM_B200_SWEEP_BURST=0 switches it off; the strict cross-check mode never uses it.
     struct Rec32 { double area, taint, prop; int32_t indeg; uint8_t link; };
     static __device__ __forceinline__ Rec32 ld_rec(const Cell *c)
