@@ -228,8 +228,16 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
     // DEM: thousands of cells) therefore run in EXPRESS mode: one chain per warp, lane 0 only.
     //   * warp 0 of every block is express from the start (it never scans for seeds);
     //   * every other warp becomes express when its seed scan is exhausted;
-    //   * a scanning warp hands a chain longer than HANDOFF cells to the queue.
-    const int HANDOFF = 16, TEAM_HANDOFF = 4;
+    //   * a scanning warp hands a chain longer than HANDOFF cells to the queue, a team one longer than TEAM_HANDOFF.
+// (thresholds A/B-ed on one B200 at 4096^2, conditioned / raw sweep in ms: team 4, scan 16: 2.70 / 1.12; 8: 2.58 / 1.00; 16: 2.50 / 0.99;
+//  16, 32: 2.44 / 0.98; 32, 64: 2.35 / 0.99; 64, 64: 2.37 / 1.00; 32, 128: 2.35 / 0.97; no team hand-off at all: 3.1-4.1, unstable)
+#ifndef PDM_HANDOFF
+#define PDM_HANDOFF 64
+#endif
+#ifndef PDM_TEAM_HANDOFF
+#define PDM_TEAM_HANDOFF 32
+#endif
+    const int HANDOFF = PDM_HANDOFF, TEAM_HANDOFF = PDM_TEAM_HANDOFF;
     const bool express_only = (threadIdx.x >> 5) == 0 && gridDim.x * (blockDim.x >> 5) > 8;
     bool scanning = nchunks > 0 && !express_only;
     int32_t ch_next = 0, ch_end = 0;     // current batch [ch_next, ch_end) (chunks of 32 cells: < 2^26 per tile)
