@@ -144,14 +144,14 @@ extern "C" int pdm_get_sweep_mode(void) { return pdm_sweep_legacy() ? 0 : 1; }
 int pdm_launch_sweep_first(pdm_tile *t)
 {
     if (!g_sweep_blocks) {
-        int rc = wl::grid_for(wl::k_worklist<DrainOp<0>, wl::DomainRange>, &g_sweep_blocks);
+        int rc = wl::grid_for(wl::k_worklist<DrainOp<0>, wl::DomainPatches>, &g_sweep_blocks);
         if (rc) return rc;
     }
     int rc = wl::reset_queue(t);
     if (rc) return rc;
     const Win &w = t->win;
     DrainOp<0> op{t->link, t->cell, nullptr, (int32_t)t->C, t->pit_beg, t->pit_end, t->pit_dst, t->pit_w, sweep_strict(), sweep_strict() ? 0 : sweep_burst(), (int32_t)t->R};
-    wl::k_worklist<<<g_sweep_blocks, 256, 0, t->stream>>>(op, wl::DomainRange{w.lo * w.C, (w.hi - w.lo) * w.C},
+    wl::k_worklist<<<g_sweep_blocks, 256, 0, t->stream>>>(op, wl::DomainPatches{w.lo, w.hi - w.lo, w.C},
                                                           wl::tuned(wl::Queue{t->queue, t->d_counters, (long long)t->N, t->d_counters + CT_SOURCES}));
     PDM_LAUNCHED();
     return PDM_OK;
@@ -176,7 +176,7 @@ int pdm_launch_sweep_p2p(pdm_tile *t)
 {
     if (!pdm_shard_worklist_p2p(t)) { pdm_set_error("pdm_launch_sweep_p2p: the tile is not connected to every rank"); return PDM_ERR_STATE; }
     if (!g_sweep_blocks_p2p) {
-        int rc = wl::grid_for(wl::k_worklist<DrainOp<3>, wl::DomainRange>, &g_sweep_blocks_p2p);
+        int rc = wl::grid_for(wl::k_worklist<DrainOp<3>, wl::DomainPatches>, &g_sweep_blocks_p2p);
         if (rc) return rc;
     }
     pdm_tile::P2P &pp = t->p2p;
@@ -217,7 +217,7 @@ int pdm_launch_sweep_p2p(pdm_tile *t)
     q.arrived = root + ts::TC_ARRIVED; q.start_target = (unsigned long long)pp.world * pp.launches;
     q.world = pp.world;
     for (int r = 0; r < pp.world; r++) q.all_ctr[r] = reinterpret_cast<unsigned long long *>(pp.all_ctl[r]) + ts::TC_WLC;
-    wl::k_worklist<<<g_sweep_blocks_p2p, 256, 0, t->stream>>>(op, wl::DomainRange{w.lo * w.C, (w.hi - w.lo) * w.C}, q);
+    wl::k_worklist<<<g_sweep_blocks_p2p, 256, 0, t->stream>>>(op, wl::DomainPatches{w.lo, w.hi - w.lo, w.C}, q);
     PDM_LAUNCHED();
     return PDM_OK;
 }

@@ -82,21 +82,45 @@ struct Queue {
 };
 
 // scan domains: index -> cell
+#ifndef PDM_CHUNK_BATCH
+#define PDM_CHUNK_BATCH 16     // chunks a warp reserves at a time = rows of a patch of DomainPatches
+#endif
+// (the seed scan walks a domain in chunks of 32 entries: nchunks() chunks, chunk_cell(chunk, lane) = the lane's cell or -1)
+#define WL_LINEAR_CHUNKS                                                                                          \
+    __device__ __forceinline__ long long nchunks() const { return (long long)((size() + 31) >> 5); }              \
+    __device__ __forceinline__ int32_t chunk_cell(long long ch, int lane) const { const int64_t t = (ch << 5) + lane; return t < size() ? cell(t) : -1; }
 struct DomainAll {
     int64_t N;
     __device__ __forceinline__ int64_t size() const { return N; }
     __device__ __forceinline__ int32_t cell(int64_t t) const { return (int32_t)t; }
+    WL_LINEAR_CHUNKS
 };
 struct DomainRange {   // cells [first, first + n): the owned rows of a shard
     int64_t first, n;
     __device__ __forceinline__ int64_t size() const { return n; }
     __device__ __forceinline__ int32_t cell(int64_t t) const { return (int32_t)(first + t); }
+    WL_LINEAR_CHUNKS
+};
+// the owned rows [row0, row0 + nrows) of a tile with C columns, walked in patches of 16 rows x 32 columns: a batch of 16 (PDM_CHUNK_BATCH)
+// chunks (what a warp reserves at a time) is one patch, so the cells a warp drains back to back are neighbours in both
+// directions and their receivers' records are still in L2 when the next row of the patch pushes into them
+struct DomainPatches {
+    int64_t row0, nrows, C;
+    __device__ __forceinline__ long long tpr() const { return (long long)((C + 31) >> 5); }
+    __device__ __forceinline__ long long nchunks() const { return ((nrows + PDM_CHUNK_BATCH - 1) / PDM_CHUNK_BATCH) * tpr() * PDM_CHUNK_BATCH; }
+    __device__ __forceinline__ int32_t chunk_cell(long long ch, int lane) const
+    {
+        const long long patch = ch / PDM_CHUNK_BATCH, t = tpr();
+        const long long row = (patch / t) * PDM_CHUNK_BATCH + (ch % PDM_CHUNK_BATCH), col = (patch % t) * 32 + lane;
+        return (row < nrows && col < C) ? (int32_t)((row0 + row) * C + col) : -1;
+    }
 };
 struct DomainList {    // explicit seed list; its length lives in device memory
     const int32_t *cells;
     const unsigned long long *count;
     __device__ __forceinline__ int64_t size() const { return (int64_t)*count; }
     __device__ __forceinline__ int32_t cell(int64_t t) const { return cells[t]; }
+    WL_LINEAR_CHUNKS
 };
 struct DomainBorder {
     int64_t R, C;
@@ -108,6 +132,7 @@ struct DomainBorder {
         const int64_t u = t - 2 * C;
         return (int32_t)((1 + (u >> 1)) * C + ((u & 1) ? C - 1 : 0));
     }
+    WL_LINEAR_CHUNKS
 };
 
 // One sweep across the row shards of several GPUs (Op::P2P, drain_op.cuh MODE 3).  A cell whose receiver
@@ -215,13 +240,12 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-    const int64_t dsize = dom.size();
-    const long long nchunks = (long long)((dsize + 31) >> 5);
+    const long long nchunks = dom.nchunks();
     // seed scan state (warp-uniform): the scan domain is cut into chunks of 32 consecutive
     // entries; a warp reserves a batch of CHUNK_BATCH chunks with one fetch-and-add (a per-chunk
     // counter was the hottest address of the kernel), tests a chunk with one coalesced load,
     // keeps the mask of seeds not yet given to a lane, and moves on when it is empty
-    const int CHUNK_BATCH = 16;
+    const int CHUNK_BATCH = PDM_CHUNK_BATCH;
     // Critical path.  All lanes of a warp advance in lock step, so a chain that shares its warp
     // with 31 other busy lanes pays the slowest lane's memory latency three times per cell
     // (measured ~7 us per cell against ~1 us alone).  Long flow paths (rivers of a conditioned
@@ -293,9 +317,8 @@ __global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
                     ch_next = (int32_t)b;
                     ch_end = (int32_t)(b + CHUNK_BATCH < nchunks ? b + CHUNK_BATCH : nchunks);
                 }
-                const int64_t t = ((int64_t)ch_next << 5) + lane;
+                pend_cell = dom.chunk_cell((long long)ch_next, lane);
                 ch_next++;
-                pend_cell = t < dsize ? dom.cell(t) : -1;
                 pend_mask = __ballot_sync(full, pend_cell >= 0 && op.is_seed(pend_cell));
                 if (pend_mask == 0) continue;
             }
