@@ -52,6 +52,12 @@ __device__ __forceinline__ int atom_add_s32_if(bool on, int32_t *addr, int v)
 #ifndef PDM_BURST_MAX
 #define PDM_BURST_MAX 31
 #endif
+#ifndef PDM_FORK_STEPS
+#define PDM_FORK_STEPS 3     // cells of a side branch drained in place at a fork on a river
+#endif
+#ifndef PDM_BURST_MIN
+#define PDM_BURST_MIN 4
+#endif
 
 template <int MODE>
 struct DrainOp {
@@ -349,7 +355,9 @@ struct DrainOp {
                     int32_t c = r1;
                     while (nch < L) {
                         sh[nch++] = c;
+#ifndef PDM_NO_PREFETCH
                         asm volatile("prefetch.global.L2 [%0];" :: "l"(cell + c));      // the lanes read these records next
+#endif
                         const int32_t o = s_off[__ldg(link + c) & 0x7f];
                         if (o == 0) break;
                         c += o;
@@ -370,7 +378,7 @@ struct DrainOp {
                 if (run < 0) run = 32;
                 // (the speculation length follows the runs: grow after a full hit, shrink after a miss)
                 if (run == nch && nch == L) { L = L * 2 < PDM_BURST_MAX ? L * 2 : PDM_BURST_MAX; }
-                else if (2 * run < nch) { L = L / 2 > 4 ? L / 2 : 4; }
+                else if (2 * run < nch) { L = L / 2 > PDM_BURST_MIN ? L / 2 : PDM_BURST_MIN; }
                 score += run - 2;
                 score = score > 64 ? 64 : (score < -64 ? -64 : score);
                 if (score < 0 && run < 2) L = -16;
@@ -441,7 +449,7 @@ struct DrainOp {
                     // of a longer side branch goes to the queue.
                     int32_t sb = other, o2 = -1;
                     other = -1;
-                    for (int k = 0; k < 3 && sb >= 0 && o2 < 0; k++) { n++; sb = process(sb, q, o2); }
+                    for (int k = 0; k < PDM_FORK_STEPS && sb >= 0 && o2 < 0; k++) { n++; sb = process(sb, q, o2); }
                     if (sb >= 0) q.push(sb);
                     if (o2 >= 0) q.push(o2);
                 }

@@ -31,6 +31,7 @@ k_pit_in_apply(int32_t *__restrict__ pit_in, const int32_t *__restrict__ strip, 
 }
 
 __global__ void k_add_sent(const unsigned long long *ctr, long long *out) { *out += (long long)ctr[ts::TC_SENT]; }
+__global__ void k_add_counter(const unsigned long long *ctr, long long *out) { *out += (long long)*ctr; }
 
 }  // namespace
 
@@ -92,7 +93,8 @@ int pdm_shard_label_pack(pdm_tile *t, int64_t row, void *out_labels, void *out_e
     return pdm_launch_label_pack(t, row, (long long *)out_labels, (double *)out_elev);
 }
 
-// changed (device pointer, int64) accumulates the number of regions whose label went down
+// changed (device pointer, int64) accumulates the number of regions whose label went down (on the device: no host
+// synchronisation; the driver all-reduces it)
 int pdm_shard_label_unpack(pdm_tile *t, int64_t row, const void *in_labels, const void *in_elev, void *changed)
 {
     if (!t || !t->glabel || row < 0 || row >= t->R) { pdm_set_error("pdm_shard_label_unpack: bad state/row"); return PDM_ERR_ARG; }
@@ -100,12 +102,8 @@ int pdm_shard_label_unpack(pdm_tile *t, int64_t row, const void *in_labels, cons
     int rc = pdm_launch_label_unpack(t, row, (const long long *)in_labels, (const double *)in_elev);
     if (rc) return rc;
     if (changed) {
-        rc = read_ctr(t);
-        if (rc) return rc;
-        long long add = (long long)t->h_counters[CT_FLAG], cur = 0;
-        PDM_CUDA(cudaMemcpy(&cur, changed, sizeof(cur), cudaMemcpyDeviceToHost));
-        cur += add;
-        PDM_CUDA(cudaMemcpy(changed, &cur, sizeof(cur), cudaMemcpyHostToDevice));
+        k_add_counter<<<1, 1, 0, t->stream>>>(t->d_counters + CT_FLAG, (long long *)changed);
+        PDM_LAUNCHED();
     }
     return PDM_OK;
 }
