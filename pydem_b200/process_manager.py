@@ -30,6 +30,9 @@ and the order in which tiles were corrected).
 """
 import warnings
 
+import json
+import os
+
 import numpy as np
 
 SIDES = ("left", "right", "top", "bottom")
@@ -143,7 +146,7 @@ class ProcessManager(object):
     per-tile arrays.  dem_proc_kwargs: flags forwarded to every DEMProcessor (reference trait of
     the same name).  dem_processor: operator class (default: the CUDA DEMProcessor)."""
 
-    def __init__(self, tiles, boxes, spacing=None, dem_proc_kwargs=None, dem_processor=None, n_workers=1, group=None):
+    def __init__(self, tiles, boxes, spacing=None, dem_proc_kwargs=None, dem_processor=None, n_workers=1, group=None, out_path=None):
         """group: None (one process) or an object with `rank`, `world` and `all_gather(obj) -> list`
         (see `TorchGroup`); tile k belongs to rank k % world.  Every rank passes the same `boxes`;
         a rank may pass None for the elevation of tiles it does not own."""
@@ -181,6 +184,11 @@ class ProcessManager(object):
         self.uca_edge_metrics = np.zeros((self.n_inputs, 2))
         self.success = np.zeros((self.n_inputs, 4), bool)
         self.correction_log = []       # tiles in the order process_uca_edges corrected them
+        # out_path: a directory store of the per-tile results with the reference's resume semantics (its zarr
+        # arrays + the `success` array, process_manager.py:362-381, 998-1007): every stage writes what it produced
+        # and marks the tile; a manager created on an existing store skips what is already there
+        self.out_path = out_path
+        self.edges_done = False
         self.georef = None             # set by from_directory: extreme bounds of the inputs
         self.compute_grid()
         self.compute_grid_overlaps()
@@ -193,6 +201,74 @@ class ProcessManager(object):
                     shared = (o.box[3] - t.box[2]) if dj < 0 else (t.box[3] - o.box[2]) if dj > 0 else \
                              (o.box[1] - t.box[0]) if di < 0 else (t.box[1] - o.box[0])
                     self.ring_w = max(self.ring_w, int(shared))
+
+        if self.out_path is not None:
+            self._store_load()
+
+    # ------------------------------------------------------------------------------------
+    # directory store + resume (the reference keeps every result in zarr arrays and a `success` array of
+    # n_inputs x 4 stages, and queue_processes skips what is marked: process_manager.py:998-1007, 1251-1288)
+    # ------------------------------------------------------------------------------------
+    STAGE_KEYS = (("elev",), ("aspect", "slope"), ("aspect", "slope", "uca", "uca_edges", "edge_todo", "edge_done"), ("twi",))
+
+    def _store_file(self, key, i):
+        return os.path.join(self.out_path, key, "%05d.npy" % i)
+
+    def _store_save(self, i, keys):
+        t = self.tiles[i]
+        if not self._mine(t):
+            return
+        for key in keys:
+            a = getattr(t, key)
+            if a is None or isinstance(a, _RingArray):
+                continue
+            fn = self._store_file(key, i)
+            os.makedirs(os.path.dirname(fn), exist_ok=True)
+            with open(fn + ".tmp", "wb") as f:
+                np.save(f, np.asarray(a))
+            os.replace(fn + ".tmp", fn)               # a reader never sees a half-written array
+
+    def _store_mark(self):
+        if self.rank == 0 or self.group is None:
+            with open(os.path.join(self.out_path, "success.npy.tmp"), "wb") as f:
+                np.save(f, self.success)
+            os.replace(os.path.join(self.out_path, "success.npy.tmp"), os.path.join(self.out_path, "success.npy"))
+            with open(os.path.join(self.out_path, "edges.json.tmp"), "w") as f:
+                json.dump({"edges_done": bool(self.edges_done), "correction_log": [int(k) for k in self.correction_log]}, f)
+            os.replace(os.path.join(self.out_path, "edges.json.tmp"), os.path.join(self.out_path, "edges.json"))
+
+    def _store_load(self):
+        os.makedirs(self.out_path, exist_ok=True)
+        fn = os.path.join(self.out_path, "success.npy")
+        if not os.path.exists(fn):
+            return
+        ok = np.load(fn)
+        if ok.shape != self.success.shape:
+            raise ValueError("%s holds the results of another tiling (%s tiles)" % (self.out_path, ok.shape[0]))
+        for i, t in enumerate(self.tiles):
+            for col in range(4):
+                if not ok[i, col]:
+                    break                                   # a stage needs the ones before it
+                if self._mine(t):
+                    for key in self.STAGE_KEYS[col]:
+                        f = self._store_file(key, i)
+                        if not os.path.exists(f):
+                            ok[i, col:] = False
+                            break
+                        a = np.load(f)
+                        if a.shape != t.shape:
+                            raise ValueError("%s: shape %s does not match tile %d %s" % (f, a.shape, i, t.shape))
+                        setattr(t, key, a)
+                    else:
+                        continue
+                    break
+        self.success = ok
+        ej = os.path.join(self.out_path, "edges.json")
+        if os.path.exists(ej) and self.success[:, 2].all():
+            with open(ej) as f:
+                d = json.load(f)
+            self.edges_done = bool(d.get("edges_done"))
+            self.correction_log = [int(k) for k in d.get("correction_log", [])]
 
     INPUT_FILE_TYPES = ("tif", "tiff")      # of the reference's _INPUT_FILE_TYPES (:462-463), what raster_io reads
 
@@ -487,7 +563,11 @@ class ProcessManager(object):
         for i, t in enumerate(self.tiles):
             if self._mine(t) and not self.success[i, col]:
                 fn(t)
+                if self.out_path is not None:
+                    self._store_save(i, self.STAGE_KEYS[col])
             self.success[i, col] = True
+        if self.out_path is not None:
+            self._store_mark()
         return self.success[:, col].copy()
 
     def process_elevation(self):
@@ -526,6 +606,8 @@ class ProcessManager(object):
         it and its rings are refreshed -- the result is the serial loop's by construction.  (This
         stage does not parallelise under the reference's semantics, see process_uca_edges_rounds.)"""
         mets = self.update_uca_edge_metrics()
+        if self.edges_done:                 # resumed from a store whose corrections had finished
+            return mets
         I = self._order(mets, mets_type)
         I_old = np.zeros_like(I)
         count = 0
@@ -545,6 +627,11 @@ class ProcessManager(object):
                     chk.add(self.tiles.index(o))
             mets = self.update_uca_edge_metrics(sorted(chk))
             I = self._order(mets, mets_type)
+        self.edges_done = True
+        if self.out_path is not None:
+            for i in range(self.n_inputs):
+                self._store_save(i, ("uca_edges", "edge_todo", "edge_done"))
+            self._store_mark()
         return mets
 
     def process_uca_edges_rounds(self, max_rounds=100000):
@@ -732,6 +819,8 @@ class ResidentProcessManager(ProcessManager):
     def __init__(self, *a, **kw):
         if kw.get("dem_processor") is not None:
             raise ValueError("ResidentProcessManager drives the CUDA tiles directly; dem_processor cannot be replaced")
+        if kw.get("out_path") is not None:
+            raise ValueError("ResidentProcessManager keeps the results in HBM; use ProcessManager(out_path=...) for a store that can resume")
         ProcessManager.__init__(self, *a, **kw)
         import torch
         from . import tile as T

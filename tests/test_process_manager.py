@@ -139,3 +139,55 @@ def test_operator_drops_in_under_the_reference_process_manager(name):
         np.testing.assert_array_equal(r[key], G["%s_%s" % (name, key)])
     np.testing.assert_allclose(r["aspect"], G[name + "_aspect"], atol=1e-12)
     np.testing.assert_allclose(r["uca"] + r["uca_edges"], G[name + "_uca"] + G[name + "_uca_edges"], rtol=1e-9, equal_nan=True)
+
+
+@pytest.mark.parametrize("stop_after", [0, 1, 2, "edges", 3])
+def test_directory_store_resumes_like_the_reference(tmp_path, stop_after):
+    """out_path: every stage writes the per-tile arrays it produced and marks the tile in `success` (the reference's
+    zarr arrays + success array, process_manager.py:362-381, 998-1007, 1251-1288).  A manager created on the store of
+    an interrupted run does not repeat a finished stage and ends with the same arrays, the same mosaic and the same
+    order of corrections as an uninterrupted run."""
+    name = sorted(CASES)[0]
+    E, nx, ny, ov, kw = CASES[name]
+    boxes = [tuple(b) for b in G[name + "_boxes"].tolist()]
+    tiles = [E[b[0]:b[1], b[2]:b[3]] for b in boxes]
+    calls = []
+
+    def counting_factory(**k):
+        calls.append(1)
+        return oracle_factory(**k)
+
+    store = str(tmp_path / "store")
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        ref = run_pm(E, boxes, kw, oracle_factory)                         # uninterrupted, no store
+        pm1 = ProcessManager(tiles, boxes, dem_proc_kwargs=kw, dem_processor=counting_factory, out_path=store)
+        pm1.process_elevation()
+        if stop_after != 0:
+            pm1.process_aspect_slope()
+        if stop_after in (2, "edges", 3):
+            pm1.process_uca()
+        if stop_after in ("edges", 3):
+            pm1.process_uca_edges()
+        if stop_after == 3:
+            pm1.process_twi()
+        n1 = len(calls)
+        del pm1                                                            # "the process died here"
+        pm2 = ProcessManager(tiles, boxes, dem_proc_kwargs=kw, dem_processor=counting_factory, out_path=store)
+        done_cols = {0: 1, 1: 2, 2: 3, "edges": 3, 3: 4}[stop_after]
+        assert pm2.success[:, :done_cols].all() and not pm2.success[:, done_cols:].any()
+        pm2.process_twi()
+        n2 = len(calls) - n1
+        pm_fresh_calls = []
+        pm3 = ProcessManager(tiles, boxes, dem_proc_kwargs=kw, dem_processor=lambda **k: (pm_fresh_calls.append(1), oracle_factory(**k))[1])
+        pm3.process_twi()
+    assert n1 + n2 == len(pm_fresh_calls)                                  # nothing was computed twice
+    if stop_after == 3:
+        assert n2 == 0
+    assert pm2.success.all() and pm2.correction_log == ref.correction_log
+    for key in ("elev", "aspect", "slope", "uca", "uca_edges", "edge_todo", "edge_done", "twi"):
+        for a, b in zip(pm2.tiles, ref.tiles):
+            np.testing.assert_array_equal(np.asarray(getattr(a, key)), np.asarray(getattr(b, key)), err_msg=key)
+    np.testing.assert_array_equal(pm2.mosaic("uca"), ref.mosaic("uca"))
+    with pytest.raises(ValueError):
+        ProcessManager(tiles[:-1], boxes[:-1], dem_proc_kwargs=kw, dem_processor=oracle_factory, out_path=store)
