@@ -15,6 +15,7 @@ from pydem_b200 import _lib, sharded, synth, tile as T, DEMProcessor
 _lib.init(local)
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 C = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+REPS = int(sys.argv[4]) if len(sys.argv) > 4 else 1     # stress: repeat the sharded pass, every result must equal the first
 PITS = len(sys.argv) > 3 and sys.argv[3] == "pits"     # drain_pits=True (the reference default): pits search and drain across the shard boundaries
 g = sharded.DistGroup()
 E = synth.value_noise_dem(0, R, C, seed=7)
@@ -27,9 +28,19 @@ if g.world > 1 and os.environ.get("PYDEM_B200_SHARD_P2P", "1") != "0":
 loc = np.full((spec.Rl, C), np.nan); loc[spec.lo:spec.hi] = E[spec.r0:spec.r1]
 eng.tile.upload(T.F_ELEV, loc)
 st = sharded.run_hot_path([eng], g, drain_pits=1)[0] if PITS else sharded.run_hot_path([eng], g)[0]
+first = eng.tile.download(T.F_UCA)[spec.lo:spec.hi].copy()
+stress_bad = 0
+for rep in range(1, REPS):
+    eng.tile.upload(T.F_ELEV, loc)
+    st = sharded.run_hot_path([eng], g, drain_pits=1)[0] if PITS else sharded.run_hot_path([eng], g)[0]
+    u = eng.tile.download(T.F_UCA)[spec.lo:spec.hi]
+    if st["n_undone"] != 0 or not np.allclose(u, first, rtol=1e-10, equal_nan=True):
+        stress_bad += 1
 dp = DEMProcessor(elev=E, dX=30.0, dY=30.0, fill_flats=False, drain_pits_path=False, drain_pits=PITS)
 dp.calc_twi()
-ok = True
+ok = stress_bad == 0
+if stress_bad:
+    print("rank", g.rank, "STRESS: %d of %d repeated passes differ" % (stress_bad, REPS - 1), flush=True)
 for name, f, exact in (("mag", T.F_MAG, True), ("direction", T.F_DIR, True), ("flats", T.F_FLATS, True),
                        ("edge_todo", T.F_EDGE_TODO, True), ("edge_done", T.F_EDGE_DONE, True), ("uca", T.F_UCA, False)):
     a = eng.tile.download(f)[spec.lo:spec.hi]
@@ -44,6 +55,6 @@ for name, f, exact in (("mag", T.F_MAG, True), ("direction", T.F_DIR, True), ("f
 flag = torch.tensor([0 if ok else 1], device="cuda")
 dist.all_reduce(flag)
 if g.rank == 0:
-    print("dist_check", "OK" if flag.item() == 0 else "FAILED", "world", g.world, "rows", R, "cols", C, "drain_pits", PITS, st, flush=True)
+    print("dist_check", "OK" if flag.item() == 0 else "FAILED", "world", g.world, "rows", R, "cols", C, "drain_pits", PITS, "passes", REPS, st, flush=True)
 dist.destroy_process_group()
 sys.exit(0 if flag.item() == 0 else 1)
