@@ -468,6 +468,9 @@ def gpu_arm(args):
     _note("e2e done")
 
     config4 = None
+    if world == 1 and args.config4:
+        dt.close()
+        config4 = config4_single(args)
     if world > 1 and not args.no_config4:
         sh.close()
         config4 = config4_leg(args, world, rank)
@@ -525,12 +528,52 @@ def gpu_arm(args):
             line["parity"]["against"] = "oracle (oracle/pdm_oracle.c) on the whole benchmark DEM, same flags"
     else:
         line["parity"] = shard_parity
-        if config4 is not None:
-            line["config4"] = config4
+    if config4 is not None:
+        line["config4"] = config4
     print(json.dumps(line), flush=True)
     if line.get("parity") and not line["parity"].get("ok", True):
         print("bench.py: PARITY FAILURE: %s" % json.dumps(line["parity"]), file=sys.stderr, flush=True)
         sys.exit(3)
+
+
+def config4_single(args):
+    """The per-GPU share of config 4 (one shard's worth: config4_rows x config4_cols of the same value-noise terrain,
+    rows 0..) as ONE stand-alone tile on one GPU -- the N = 1 point of that shape's weak scaling (opt-in: --config4)."""
+    import torch
+    from pydem_b200 import synth, tile as T
+    rows, cols = args.config4_rows, args.config4_cols
+    t0 = time.perf_counter()
+    dt = T.DeviceTile(rows, cols, stream=torch.cuda.current_stream().cuda_stream)
+    dt.set_spacing(SPACING, SPACING)
+    synth.value_noise_dem_torch(dt.as_torch(T.F_ELEV), 0, seed=11)
+    dt.mark_resident(T.F_ELEV)
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t0
+    stats = {}
+
+    def step():
+        dt.slopes_directions()
+        stats.update(dt.uca(drain_pits=0))
+        dt.twi()
+    step()
+    torch.cuda.synchronize()
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.config4_steps):
+        step()
+    ev1.record(); torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.config4_steps
+    uca = dt.as_torch(T.F_UCA); fl = dt.as_torch(T.F_FLATS)
+    bad = [int(stats.get("n_undone", 0)), int((torch.isnan(uca) != (fl != 0)).sum().item()),
+           int((uca[~torch.isnan(uca)] < SPACING * SPACING).sum().item())]
+    out = {"workload": "%dx%d value-noise DEM (8 octaves, seed 11; the first shard of the config-4 terrain) as one stand-alone tile, "
+                       "dX=dY=30 m, slope+aspect + UCA + TWI, fill_flats=False, drain_pits_path=False, drain_pits=False" % (rows, cols),
+           "value": rows * cols / (ms * 1e-3) / 1e6, "unit": "Mcells/s", "ms_per_step": ms, "steps": args.config4_steps, "n_gpus": 1,
+           "cells": rows * cols, "seconds_setup": t_gen,
+           "stages": {k: stats.get(k) for k in ("ms_graph", "ms_sweep", "ms_sweep_kernel", "ms_sweep_scan", "n_sources", "n_queue_items")},
+           "checks": {"undone_cells": bad[0], "nan_pattern_vs_flats_mismatches": bad[1], "uca_below_one_cell": bad[2], "ok": sum(bad) == 0}}
+    dt.close()
+    return out
 
 
 def config4_leg(args, world, rank):
@@ -651,6 +694,7 @@ def main():
                          "sinks: raw fractal with drain_pits=False")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle / single-tile check of the GPU arm's outputs")
     ap.add_argument("--no-config4", action="store_true", help="N > 1: skip the extra run of BASELINE configs[3] at its own shape")
+    ap.add_argument("--config4", action="store_true", help="N = 1: also run one GPU's share of config 4 as a stand-alone tile")
     ap.add_argument("--config4-rows", type=int, default=8192, help="rows per GPU of the config-4 run")
     ap.add_argument("--config4-cols", type=int, default=65536)
     ap.add_argument("--config4-steps", type=int, default=3)
