@@ -230,7 +230,7 @@ static __device__ __forceinline__ void p2p_service(const Queue &q, unsigned long
 }
 
 template <class Op, class Domain>
-__global__ void __launch_bounds__(256) k_worklist(Op op, Domain dom, Queue q)
+__global__ void __launch_bounds__(256, 4) k_worklist(Op op, Domain dom, Queue q)
 {
     __shared__ int32_t s_chain[8][32];   // per warp: the cells of a chain burst (Op::chain_warp)
     __shared__ int32_t s_off[128];       // link byte -> offset of the cell's only receiver (0: none or two); Op::chase_offset
