@@ -679,7 +679,7 @@ def sharded_check(sh, block, world, rank, pits_flag):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the sweep kernel, one launch (profiles/, per size)
-PROFILE_TRAFFIC = {4096: 1.4625e9}   # profiles/r2_n1_kernels_4096_conditioned_final_ncu_full.csv: 921.5 MB read + 541.0 MB written
+PROFILE_TRAFFIC = {4096: 1.3952e9}   # profiles/r2_n1_kernels_4096_conditioned_final_ncu_full.csv: 868.0 MB read + 527.2 MB written
 
 
 def main():
