@@ -82,3 +82,19 @@ def test_operator_surface_matches_reference():
         assert list(inspect.signature(getattr(DEMProcessor, meth)).parameters) == ["self"]
     with pytest.raises(RuntimeError):                                   # no device here, and no CPU fallback
         DEMProcessor(elev=np.ones((5, 5))).calc_slopes_directions()      # default flags: conditioning runs first
+
+
+def test_header_is_plain_c_and_the_c_host_links(lib, tmp_path):
+    """include/pydem_b200.h must be usable from C (the boundary is a C ABI): examples/shard_host.c -- the sharded pass
+    driven from plain C, INTEGRATION.md section 5 -- compiles as C99 with -Wall -Wextra and links against the library."""
+    import os, shutil, subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "shard_host")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"),
+                        os.path.join(root, "examples", "shard_host.c"), "-L", os.path.join(root, "pydem_b200"),
+                        "-lpydem_b200", "-lm", "-o", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert os.path.exists(out)
