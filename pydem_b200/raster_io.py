@@ -199,7 +199,7 @@ def dem_processor_from_raster_kwargs(fn):
     return dict(dX=dX, dY=dY, elev=r["elev"], bounds=r["bounds"], transform=r["transform"], dX2=dX2, dY2=dY2)
 
 
-def write_geotiff(fn, data, transform, projected=False, tile=None):
+def write_geotiff(fn, data, transform, projected=False, tile=None, gcs=4326, model=None):
     """Minimal writer (uncompressed, one band, little endian; strips or `tile` x `tile` tiles) --
     what utils.save_raster produces for the reference's tests.  Used by this repo's tests."""
     data = np.ascontiguousarray(data)
@@ -227,7 +227,8 @@ def write_geotiff(fn, data, transform, projected=False, tile=None):
         off_tag, cnt_tag = 273, 279
     ent(33550, 12, [transform.a, -transform.e, 0.0])
     ent(33922, 12, [0.0, 0.0, 0.0, transform.c, transform.f, 0.0])
-    ent(34735, 3, [1, 1, 0, 2, 1024, 0, 1, 1 if projected else 2, 2048, 0, 1, 4326])
+    # (gcs / model: tests write files whose CRS the reader must refuse)
+    ent(34735, 3, [1, 1, 0, 2, 1024, 0, 1, (1 if projected else 2) if model is None else model, 2048, 0, 1, gcs])
     n = len(entries) + 2
     head = 8 + 2 + 12 * n + 4
     extra = b""

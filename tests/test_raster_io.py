@@ -179,3 +179,23 @@ def test_from_directory_keeps_the_rasters_spacing(tmp_path):
     assert worst["elev"] == 0 and worst["edge_todo"] == 0 and worst["edge_done"] == 0, worst
     assert worst["slope"] <= 1e-13 * 1e6 and worst["aspect"] <= 1e-12 and worst["uca"] <= 1e-9, worst
     assert pm.correction_log == G[name + "_order"].tolist()
+
+
+def test_undeterminable_crs_is_refused(tmp_path):
+    """The reader must not guess: a geographic file whose ellipsoid is unknown, or a model type that is neither
+    projected nor geographic, raises instead of silently producing WGS-84 geodesic spacings (the reference fails too
+    when rasterio cannot give it `crs.is_projected` / a spheroid name, utils.py:132-151)."""
+    a = np.arange(12, dtype="f4").reshape(3, 4)
+    tr = rio.Affine((0.01, 0.0, -72.0, 0.0, -0.01, 45.0))
+    ok = str(tmp_path / "ok.tif"); rio.write_geotiff(ok, a, tr)
+    assert rio.read_geotiff(ok)["ellipsoid"] == "WGS-84" and not rio.read_geotiff(ok)["is_projected"]
+    nad83 = str(tmp_path / "nad83.tif"); rio.write_geotiff(nad83, a, tr, gcs=4269)
+    assert rio.read_geotiff(nad83)["ellipsoid"] == "GRS-80"
+    bad_gcs = str(tmp_path / "gcs.tif"); rio.write_geotiff(bad_gcs, a, tr, gcs=4267)           # NAD27: Clarke 1866, not in the table
+    with pytest.raises(ValueError, match="ellipsoid unknown"):
+        rio.read_geotiff(bad_gcs)
+    geocentric = str(tmp_path / "geoc.tif"); rio.write_geotiff(geocentric, a, tr, model=3)
+    with pytest.raises(ValueError, match="not supported"):
+        rio.read_geotiff(geocentric)
+    projected = str(tmp_path / "proj.tif"); rio.write_geotiff(projected, a, rio.Affine((30.0, 0.0, 5e5, 0.0, -30.0, 4e6)), projected=True, gcs=4267)
+    assert rio.read_geotiff(projected)["is_projected"]            # metres: the ellipsoid does not matter
